@@ -1,0 +1,168 @@
+"""ctypes binding of the CUDA library limo_b200/libkba_b200.so (C ABI: include/kba_b200.h).
+
+The product path: there is no CPU fallback.  Importing works without a GPU (symbols can be inspected), but every
+computing call fails with KBA_ERR_CUDA when no sm_100 device is present.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+from .capi_types import (KbaCounters, KbaEvalOut, KbaOptions, KbaResult, KbaWindow, Result, c_double_p, c_int32_p)
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libkba_b200.so")
+_lib = None
+
+SYMBOLS = ["kba_version", "kba_last_error", "kba_default_options", "kba_create", "kba_destroy", "kba_set_stream",
+           "kba_solve_window", "kba_solve_batch", "kba_eval", "kba_batch_create", "kba_batch_upload",
+           "kba_batch_solve", "kba_batch_download", "kba_batch_jacobian_pass", "kba_batch_destroy",
+           "kba_get_counters", "kba_enable_kernel_timing"]
+
+
+class KbaError(RuntimeError):
+    pass
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise KbaError("CUDA library %s is missing: build it with `make -C limo_b200/csrc` (there is no CPU "
+                           "fallback)" % LIB_PATH)
+        L = C.CDLL(LIB_PATH)
+        vp = C.c_void_p
+        L.kba_version.restype = C.c_int
+        L.kba_last_error.restype = C.c_char_p
+        L.kba_default_options.argtypes = [C.POINTER(KbaOptions)]
+        L.kba_create.argtypes = [C.POINTER(vp), C.c_int]
+        L.kba_destroy.argtypes = [vp]
+        L.kba_destroy.restype = None
+        L.kba_set_stream.argtypes = [vp, vp]
+        L.kba_solve_window.argtypes = [vp, C.POINTER(KbaWindow), C.POINTER(KbaOptions), C.POINTER(KbaResult)]
+        L.kba_solve_batch.argtypes = [vp, C.c_int32, C.POINTER(KbaWindow), C.POINTER(KbaOptions), C.POINTER(KbaResult)]
+        L.kba_eval.argtypes = [vp, C.POINTER(KbaWindow), C.POINTER(KbaOptions), C.POINTER(KbaEvalOut)]
+        L.kba_batch_create.argtypes = [vp, C.c_int32, C.POINTER(KbaWindow), C.POINTER(vp)]
+        L.kba_batch_upload.argtypes = [vp, C.c_int32, C.POINTER(KbaWindow)]
+        L.kba_batch_solve.argtypes = [vp, C.POINTER(KbaOptions)]
+        L.kba_batch_download.argtypes = [vp, C.POINTER(KbaResult)]
+        L.kba_batch_jacobian_pass.argtypes = [vp, C.POINTER(KbaOptions), C.c_int32, C.POINTER(C.c_float)]
+        L.kba_batch_destroy.argtypes = [vp]
+        L.kba_batch_destroy.restype = None
+        L.kba_get_counters.argtypes = [vp, C.POINTER(KbaCounters), C.c_int]
+        L.kba_enable_kernel_timing.argtypes = [vp, C.c_int]
+        _lib = L
+    return _lib
+
+
+def _check(rc):
+    if rc != 0:
+        raise KbaError("kba_b200 error %d: %s" % (rc, lib().kba_last_error().decode()))
+
+
+def default_options():
+    o = KbaOptions()
+    lib().kba_default_options(C.byref(o))
+    return o
+
+
+class Batch:
+    """Windows resident in HBM (kba_batch_*)."""
+
+    def __init__(self, handle, windows):
+        self.handle, self.windows = handle, list(windows)
+        self._arr = (KbaWindow * len(self.windows))(*[w.c for w in self.windows])
+        self._p = C.c_void_p()
+        _check(lib().kba_batch_create(handle._p, len(self.windows), self._arr, C.byref(self._p)))
+
+    def upload(self):
+        _check(lib().kba_batch_upload(self._p, len(self.windows), self._arr))
+
+    def solve(self, opt=None):
+        _check(lib().kba_batch_solve(self._p, C.byref(opt or default_options())))
+
+    def download(self, iterations_capacity=0):
+        results = [Result(w, max(iterations_capacity, 1)) for w in self.windows]
+        arr = (KbaResult * len(results))(*[r.c for r in results])
+        _check(lib().kba_batch_download(self._p, arr))
+        for r, c in zip(results, arr):
+            r.c = c
+        self._keep = arr
+        return results
+
+    def jacobian_pass(self, opt=None, repeats=1):
+        ms = C.c_float()
+        _check(lib().kba_batch_jacobian_pass(self._p, C.byref(opt or default_options()), repeats, C.byref(ms)))
+        return ms.value
+
+    def close(self):
+        if self._p:
+            lib().kba_batch_destroy(self._p)
+            self._p = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class Handle:
+    """One solver handle per host thread / GPU (kba_create)."""
+
+    def __init__(self, device=0, stream=None):
+        self._p = C.c_void_p()
+        _check(lib().kba_create(C.byref(self._p), device))
+        if stream is not None:
+            _check(lib().kba_set_stream(self._p, C.c_void_p(stream)))
+
+    def default_options(self):
+        return default_options()
+
+    def solve_window(self, win, opt=None, iterations_capacity=256):
+        res = Result(win, iterations_capacity)
+        _check(lib().kba_solve_window(self._p, C.byref(win.c), C.byref(opt or default_options()), C.byref(res.c)))
+        return res
+
+    def solve_batch(self, windows, opt=None, iterations_capacity=1):
+        results = [Result(w, iterations_capacity) for w in windows]
+        warr = (KbaWindow * len(windows))(*[w.c for w in windows])
+        rarr = (KbaResult * len(windows))(*[r.c for r in results])
+        _check(lib().kba_solve_batch(self._p, len(windows), warr, C.byref(opt or default_options()), rarr))
+        for r, c in zip(results, rarr):
+            r.c = c
+        self._keep = rarr
+        return results
+
+    def evaluate(self, win, opt=None):
+        n = max(win.n_obs, 1)
+        r = np.zeros((n, 3)); jp = np.zeros((n, 3, 6)); jl = np.zeros((n, 3, 3)); cost = np.zeros(1)
+        failed = np.zeros(1, dtype=np.int32)
+        out = KbaEvalOut()
+        out.residual = r.ctypes.data_as(c_double_p); out.jac_pose = jp.ctypes.data_as(c_double_p)
+        out.jac_lm = jl.ctypes.data_as(c_double_p); out.cost = cost.ctypes.data_as(c_double_p)
+        out.failed = failed.ctypes.data_as(c_int32_p)
+        _check(lib().kba_eval(self._p, C.byref(win.c), C.byref(opt or default_options()), C.byref(out)))
+        return r[:win.n_obs], jp[:win.n_obs], jl[:win.n_obs], float(cost[0]), int(failed[0])
+
+    def batch(self, windows):
+        return Batch(self, windows)
+
+    def counters(self, reset=False):
+        c = KbaCounters()
+        _check(lib().kba_get_counters(self._p, C.byref(c), 1 if reset else 0))
+        return c
+
+    def enable_kernel_timing(self, on=True):
+        _check(lib().kba_enable_kernel_timing(self._p, 1 if on else 0))
+
+    def close(self):
+        if self._p:
+            lib().kba_destroy(self._p)
+            self._p = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -1,0 +1,557 @@
+// kba_api.cu -- host side of the C ABI declared in include/kba_b200.h: handle / batch lifetime, packing of caller
+// windows into the batch-flat device layout, the pass loop, result download.  No numerical work happens on the host.
+#include <algorithm>
+#include <chrono>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include <cuda_runtime.h>
+
+#include "kba_b200.h"
+#include "kba_kernels.h"
+
+using namespace kba;
+
+static thread_local std::string g_last_error;
+static int fail(int code, const std::string& msg) {
+    g_last_error = msg;
+    return code;
+}
+#define CU(call)                                                                                              \
+    do {                                                                                                      \
+        cudaError_t e_ = (call);                                                                              \
+        if (e_ != cudaSuccess)                                                                                \
+            return fail(KBA_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_));                    \
+    } while (0)
+
+struct kba_handle {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    Counters counters;
+    bool kernel_timing = false;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    int sm_count = 148;
+};
+
+// ---- a device + pinned-host buffer pair, filled on the host and uploaded with one async copy ----------------------------
+template <typename T>
+struct Staged {
+    T* h = nullptr;
+    T* d = nullptr;
+    size_t n = 0;
+    int alloc(size_t count, bool host_copy) {
+        n = count;
+        const size_t bytes = std::max<size_t>(count, 1) * sizeof(T);
+        if (cudaMalloc(&d, bytes) != cudaSuccess) return 1;
+        if (host_copy && cudaMallocHost(&h, bytes) != cudaSuccess) return 1;
+        return 0;
+    }
+    void release() {
+        if (d) cudaFree(d);
+        if (h) cudaFreeHost(h);
+        d = nullptr; h = nullptr;
+    }
+    cudaError_t upload(cudaStream_t s) { return cudaMemcpyAsync(d, h, std::max<size_t>(n, 1) * sizeof(T), cudaMemcpyHostToDevice, s); }
+    cudaError_t download(cudaStream_t s) { return cudaMemcpyAsync(h, d, std::max<size_t>(n, 1) * sizeof(T), cudaMemcpyDeviceToHost, s); }
+};
+
+struct kba_batch {
+    kba_handle* h = nullptr;
+    BatchDev bd{};
+    std::vector<WinDesc> desc_h;
+    // staged inputs
+    Staged<WinDesc> desc;
+    Staged<double> pose0, plane0, cam, lm0, lm_weight;
+    Staged<uint8_t> kf_fixed;
+    Staged<int> lm_ptr, obs_kf, obs_cam, obs_lm, kf_ptr, pm_lm, pm_cam, chunk_lm0, chunk_lm1;
+    Staged<float> obs_u, obs_v, obs_d, pm_u, pm_v, pm_d;
+    // outputs
+    Staged<WinState> state;
+    Staged<IterRecord> log;
+    Staged<double> pose_out[2], lm_out[2];
+    Staged<uint8_t> lm_active;
+    Staged<int> n_active;
+    std::vector<void*> scratch;  // device-only allocations
+    LaunchCfg lc;
+    size_t h2d_bytes = 0, d2h_bytes = 0;
+    float last_solve_ms = 0.f;
+    cudaEvent_t ev_a = nullptr, ev_b = nullptr;
+
+    template <typename T>
+    int dev_alloc(T** p, size_t count) {
+        void* q = nullptr;
+        if (cudaMalloc(&q, std::max<size_t>(count, 1) * sizeof(T)) != cudaSuccess) return 1;
+        scratch.push_back(q);
+        *p = (T*)q;
+        return 0;
+    }
+    void release() {
+        desc.release(); pose0.release(); plane0.release(); cam.release(); lm0.release(); lm_weight.release();
+        kf_fixed.release(); lm_ptr.release(); obs_kf.release(); obs_cam.release(); obs_lm.release(); kf_ptr.release();
+        pm_lm.release(); pm_cam.release(); chunk_lm0.release(); chunk_lm1.release(); obs_u.release(); obs_v.release();
+        obs_d.release(); pm_u.release(); pm_v.release(); pm_d.release(); state.release(); log.release();
+        pose_out[0].release(); pose_out[1].release(); lm_out[0].release(); lm_out[1].release(); lm_active.release();
+        n_active.release();
+        for (void* p : scratch) cudaFree(p);
+        scratch.clear();
+        if (ev_a) cudaEventDestroy(ev_a);
+        if (ev_b) cudaEventDestroy(ev_b);
+    }
+};
+
+static int validate_window(const kba_window* w, std::string& why) {
+    if (!w) { why = "null window"; return KBA_ERR_BAD_ARG; }
+    if (w->n_kf < 0 || w->n_lm < 0 || w->n_obs < 0 || w->n_gp < 0 || w->n_cam < 1) { why = "negative size"; return KBA_ERR_BAD_ARG; }
+    if (!w->kf_pose || !w->kf_fixed || !w->cam_intr || !w->cam_pose) { why = "null keyframe/camera array"; return KBA_ERR_BAD_ARG; }
+    if (w->n_lm > 0 && (!w->lm_pos || !w->lm_weight || !w->lm_obs_ptr)) { why = "null landmark array"; return KBA_ERR_BAD_ARG; }
+    if (w->n_obs > 0 && (!w->obs_kf || !w->obs_u || !w->obs_v || !w->obs_d)) { why = "null observation array"; return KBA_ERR_BAD_ARG; }
+    if (w->n_kf > kMaxKf) { why = "more than 128 keyframes per window"; return KBA_ERR_CAPACITY; }
+    if (w->n_cam > kMaxCam) { why = "more than 8 cameras per window"; return KBA_ERR_CAPACITY; }
+    if (w->n_gp > 0 || w->plane_reg_weight > 0) { why = "ground-plane residuals are not implemented in this build of the CUDA path"; return KBA_ERR_CAPACITY; }
+    if (w->landmarks_fixed || w->speed_weight > 0) { why = "motion-only windows are not implemented in this build of the CUDA path"; return KBA_ERR_CAPACITY; }
+    if (w->n_lm > 0 && w->lm_obs_ptr[w->n_lm] != w->n_obs) { why = "lm_obs_ptr[n_lm] != n_obs"; return KBA_ERR_BAD_ARG; }
+    for (int o = 0; o < w->n_obs; ++o) {
+        if (w->obs_kf[o] < 0 || w->obs_kf[o] >= w->n_kf) { why = "obs_kf out of range"; return KBA_ERR_BAD_ARG; }
+        if (w->obs_cam && (w->obs_cam[o] < 0 || w->obs_cam[o] >= w->n_cam)) { why = "obs_cam out of range"; return KBA_ERR_BAD_ARG; }
+    }
+    if (w->scale_weight > 0 && (w->scale_kf0 < 0 || w->scale_kf0 >= w->n_kf || w->scale_kf1 < 0 || w->scale_kf1 >= w->n_kf)) {
+        why = "scale regulariser keyframe out of range"; return KBA_ERR_BAD_ARG;
+    }
+    return KBA_OK;
+}
+
+static void fill_window(kba_batch* b, int wi, const kba_window* w) {
+    const WinDesc& d = b->desc_h[wi];
+    memcpy(b->pose0.h + 7 * (size_t)d.kf_off, w->kf_pose, sizeof(double) * 7 * w->n_kf);
+    memcpy(b->kf_fixed.h + d.kf_off, w->kf_fixed, w->n_kf);
+    for (int k = 0; k < w->n_kf; ++k) {
+        double* pl = b->plane0.h + 4 * (size_t)(d.kf_off + k);
+        if (w->kf_plane) memcpy(pl, w->kf_plane + 4 * k, 4 * sizeof(double));
+        else { pl[0] = 0; pl[1] = 0; pl[2] = 1; pl[3] = 0; }
+    }
+    for (int c = 0; c < w->n_cam; ++c) {
+        double* o = b->cam.h + kCamStride * (size_t)(d.cam_off + c);
+        quat_to_rot<double>(w->cam_pose + 7 * c, o);
+        o[9] = w->cam_pose[7 * c + 4]; o[10] = w->cam_pose[7 * c + 5]; o[11] = w->cam_pose[7 * c + 6];
+        o[12] = w->cam_intr[3 * c]; o[13] = w->cam_intr[3 * c + 1]; o[14] = w->cam_intr[3 * c + 2]; o[15] = 0;
+    }
+    if (w->n_lm > 0) {
+        memcpy(b->lm0.h + 3 * (size_t)d.lm_off, w->lm_pos, sizeof(double) * 3 * w->n_lm);
+        memcpy(b->lm_weight.h + d.lm_off, w->lm_weight, sizeof(double) * w->n_lm);
+        memcpy(b->lm_ptr.h + d.lm_off + wi, w->lm_obs_ptr, sizeof(int) * (w->n_lm + 1));
+    } else {
+        b->lm_ptr.h[d.lm_off + wi] = 0;
+    }
+    if (w->n_obs > 0) {
+        memcpy(b->obs_kf.h + d.obs_off, w->obs_kf, sizeof(int) * w->n_obs);
+        if (w->obs_cam) memcpy(b->obs_cam.h + d.obs_off, w->obs_cam, sizeof(int) * w->n_obs);
+        else memset(b->obs_cam.h + d.obs_off, 0, sizeof(int) * w->n_obs);
+        memcpy(b->obs_u.h + d.obs_off, w->obs_u, sizeof(float) * w->n_obs);
+        memcpy(b->obs_v.h + d.obs_off, w->obs_v, sizeof(float) * w->n_obs);
+        memcpy(b->obs_d.h + d.obs_off, w->obs_d, sizeof(float) * w->n_obs);
+    }
+    // landmark index per observation + keyframe-major copy (counting sort, stable -> deterministic reduction order)
+    int* kp = b->kf_ptr.h + d.kf_off + wi;
+    std::fill(kp, kp + w->n_kf + 1, 0);
+    for (int j = 0; j < w->n_lm; ++j)
+        for (int o = w->lm_obs_ptr[j]; o < w->lm_obs_ptr[j + 1]; ++o) {
+            b->obs_lm.h[d.obs_off + o] = j;
+            kp[w->obs_kf[o] + 1]++;
+        }
+    for (int k = 0; k < w->n_kf; ++k) kp[k + 1] += kp[k];
+    std::vector<int> cur(kp, kp + w->n_kf);
+    for (int j = 0; j < w->n_lm; ++j)
+        for (int o = w->lm_obs_ptr[j]; o < w->lm_obs_ptr[j + 1]; ++o) {
+            const int e = d.obs_off + cur[w->obs_kf[o]]++;
+            b->pm_lm.h[e] = j;
+            b->pm_cam.h[e] = w->obs_cam ? w->obs_cam[o] : 0;
+            b->pm_u.h[e] = w->obs_u[o]; b->pm_v.h[e] = w->obs_v[o]; b->pm_d.h[e] = w->obs_d[o];
+        }
+    for (int c = 0; c < d.n_chunks; ++c) {
+        b->chunk_lm0.h[d.chunk_off + c] = c * 32;
+        b->chunk_lm1.h[d.chunk_off + c] = std::min(w->n_lm, (c + 1) * 32);
+    }
+}
+
+extern "C" {
+
+int kba_version(void) { return KBA_VERSION_MAJOR * 100 + KBA_VERSION_MINOR; }
+const char* kba_last_error(void) { return g_last_error.c_str(); }
+
+void kba_default_options(kba_options* o) {
+    if (!o) return;
+    memset(o, 0, sizeof *o);
+    o->depth_thres = 0.16; o->reprojection_thres = 1.6;
+    o->depth_quantile = 0.95; o->reprojection_quantile = 0.95; o->gp_quantile = 1.0; o->gp_huber = 0.1;
+    o->num_trim_rounds = -1; o->trim_solver_iterations = 2; o->final_solver_iterations = 100;
+    o->min_landmarks_for_trimming = 100; o->min_residual_groups = 30; o->num_rounds_option = 1;
+    o->solver_time_sec = 20.0;
+    o->function_tolerance = 1e-6; o->gradient_tolerance = 1e-10; o->parameter_tolerance = 1e-8;
+    o->initial_trust_region_radius = 1e4; o->max_trust_region_radius = 1e16; o->min_trust_region_radius = 1e-32;
+    o->min_relative_decrease = 1e-3; o->min_lm_diagonal = 1e-6; o->max_lm_diagonal = 1e32;
+    o->max_consecutive_invalid_steps = 5; o->precision = 0;
+}
+
+int kba_create(kba_handle** out, int device) {
+    if (!out) return fail(KBA_ERR_BAD_ARG, "null out pointer");
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0)
+        return fail(KBA_ERR_CUDA, "no CUDA device available: the kba_b200 library has no CPU fallback");
+    if (device < 0 || device >= n) return fail(KBA_ERR_BAD_ARG, "device index out of range");
+    CU(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10) return fail(KBA_ERR_CUDA, "kba_b200 kernels are built for sm_100a only");
+    kba_handle* h = new kba_handle();
+    h->device = device;
+    h->sm_count = prop.multiProcessorCount;
+    CU(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    h->own_stream = true;
+    CU(cudaEventCreate(&h->ev0));
+    CU(cudaEventCreate(&h->ev1));
+    *out = h;
+    return KBA_OK;
+}
+
+void kba_destroy(kba_handle* h) {
+    if (!h) return;
+    if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
+    if (h->ev0) cudaEventDestroy(h->ev0);
+    if (h->ev1) cudaEventDestroy(h->ev1);
+    delete h;
+}
+
+int kba_set_stream(kba_handle* h, void* s) {
+    if (!h) return fail(KBA_ERR_BAD_ARG, "null handle");
+    if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
+    h->stream = (cudaStream_t)s;
+    h->own_stream = false;
+    return KBA_OK;
+}
+
+int kba_get_counters(kba_handle* h, kba_counters* out, int reset) {
+    if (!h || !out) return fail(KBA_ERR_BAD_ARG, "null argument");
+    const Counters& c = h->counters;
+    out->launches_total = c.launches_total; out->launches_jacobian = c.launches_jacobian; out->launches_prep = c.launches_prep;
+    out->launches_schur = c.launches_schur; out->launches_solve = c.launches_solve; out->launches_backsub = c.launches_backsub;
+    out->launches_cost = c.launches_cost; out->launches_update = c.launches_update; out->launches_trim = c.launches_trim;
+    out->ms_jacobian = c.ms_jacobian; out->jacobian_obs = c.jacobian_obs;
+    if (reset) h->counters = Counters();
+    return KBA_OK;
+}
+
+int kba_enable_kernel_timing(kba_handle* h, int on) {
+    if (!h) return fail(KBA_ERR_BAD_ARG, "null handle");
+    h->kernel_timing = on != 0;
+    return KBA_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+int kba_batch_create(kba_handle* h, int32_t n_windows, const kba_window* w, kba_batch** out) {
+    if (!h || !w || !out || n_windows <= 0) return fail(KBA_ERR_BAD_ARG, "bad argument to kba_batch_create");
+    CU(cudaSetDevice(h->device));
+    std::string why;
+    for (int i = 0; i < n_windows; ++i) {
+        const int rc = validate_window(&w[i], why);
+        if (rc != KBA_OK) return fail(rc, "window " + std::to_string(i) + ": " + why);
+        if (w[i].n_kf < 3) return fail(KBA_ERR_NOT_ENOUGH_KF, "window " + std::to_string(i) + ": fewer than 3 keyframes");
+    }
+    kba_batch* b = new kba_batch();
+    b->h = h;
+    BatchDev& bd = b->bd;
+    bd.n_win = n_windows;
+    b->desc_h.resize(n_windows);
+    long long kf = 0, cam = 0, lm = 0, obs = 0, chunks = 0, soff = 0;
+    int nr_cap_max = 64;
+    for (int i = 0; i < n_windows; ++i) {
+        WinDesc& d = b->desc_h[i];
+        memset(&d, 0, sizeof d);
+        d.n_kf = w[i].n_kf; d.n_cam = w[i].n_cam; d.n_lm = w[i].n_lm; d.n_obs = w[i].n_obs; d.n_gp = 0;
+        d.kf_off = (int)kf; d.cam_off = (int)cam; d.lm_off = (int)lm; d.obs_off = (int)obs; d.gp_off = 0;
+        d.chunk_off = (int)chunks; d.n_chunks = (w[i].n_lm + 31) / 32;
+        d.scale_kf0 = w[i].scale_kf0; d.scale_kf1 = w[i].scale_kf1;
+        d.scale_weight = w[i].scale_weight; d.scale_value = w[i].scale_value;
+        d.nr_cap = ((6 * w[i].n_kf + 1 + 63) / 64) * 64;
+        d.s_off = soff;
+        soff += (long long)d.nr_cap * d.nr_cap;
+        nr_cap_max = std::max(nr_cap_max, d.nr_cap);
+        kf += w[i].n_kf; cam += w[i].n_cam; lm += w[i].n_lm; obs += w[i].n_obs; chunks += d.n_chunks;
+        bd.max_obs = std::max(bd.max_obs, w[i].n_obs); bd.max_lm = std::max(bd.max_lm, w[i].n_lm);
+        bd.max_kf = std::max(bd.max_kf, w[i].n_kf);
+    }
+    if (obs > 2000000000LL) { delete b; return fail(KBA_ERR_CAPACITY, "batch exceeds 2^31 observations"); }
+    bd.tot_kf = kf; bd.tot_cam = cam; bd.tot_lm = lm; bd.tot_obs = obs; bd.tot_chunks = (int)chunks;
+    bd.nr_cap_max = nr_cap_max;
+    b->lc.nr_cap_max = nr_cap_max;
+    // split the landmark chunks of each window over several CTAs when the batch alone cannot fill the GPU
+    {
+        const int nb = nr_cap_max / 64, pairs = nb * (nb + 1) / 2;
+        int max_chunks = 1;
+        for (auto& d : b->desc_h) max_chunks = std::max(max_chunks, d.n_chunks);
+        int p = (2 * h->sm_count + n_windows * pairs - 1) / (n_windows * pairs);
+        bd.p_split = std::max(1, std::min(p, max_chunks));
+    }
+    bd.cost_parts = (bd.max_obs + 255) / 256;
+    bd.bs_parts = (bd.max_lm + 7) / 8;
+    int bad = 0;
+    bad |= b->desc.alloc(n_windows, true);
+    bad |= b->pose0.alloc(7 * kf, true); bad |= b->plane0.alloc(4 * kf, true); bad |= b->kf_fixed.alloc(kf, true);
+    bad |= b->cam.alloc(kCamStride * cam, true);
+    bad |= b->lm0.alloc(3 * lm, true); bad |= b->lm_weight.alloc(lm, true); bad |= b->lm_ptr.alloc(lm + n_windows, true);
+    bad |= b->obs_kf.alloc(obs, true); bad |= b->obs_cam.alloc(obs, true); bad |= b->obs_lm.alloc(obs, true);
+    bad |= b->obs_u.alloc(obs, true); bad |= b->obs_v.alloc(obs, true); bad |= b->obs_d.alloc(obs, true);
+    bad |= b->kf_ptr.alloc(kf + n_windows, true); bad |= b->pm_lm.alloc(obs, true); bad |= b->pm_cam.alloc(obs, true);
+    bad |= b->pm_u.alloc(obs, true); bad |= b->pm_v.alloc(obs, true); bad |= b->pm_d.alloc(obs, true);
+    bad |= b->chunk_lm0.alloc(chunks, true); bad |= b->chunk_lm1.alloc(chunks, true);
+    bad |= b->state.alloc(n_windows, true); bad |= b->log.alloc((size_t)n_windows * kIterLogCap, true);
+    for (int q = 0; q < 2; ++q) { bad |= b->pose_out[q].alloc(7 * kf, true); bad |= b->lm_out[q].alloc(3 * lm, true); }
+    bad |= b->lm_active.alloc(lm, true); bad |= b->n_active.alloc(1, true);
+    // device-only scratch
+    bad |= b->dev_alloc(&bd.plane[0], 4 * kf); bad |= b->dev_alloc(&bd.plane[1], 4 * kf);
+    bad |= b->dev_alloc(&bd.off_pose, kf); bad |= b->dev_alloc(&bd.off_dir, kf); bad |= b->dev_alloc(&bd.off_dist, kf);
+    bad |= b->dev_alloc(&bd.bkf, 27 * kf);
+    bad |= b->dev_alloc(&bd.scale_f, (size_t)n_windows * nr_cap_max); bad |= b->dev_alloc(&bd.lambda_f, (size_t)n_windows * nr_cap_max);
+    bad |= b->dev_alloc(&bd.grad_f, (size_t)n_windows * nr_cap_max); bad |= b->dev_alloc(&bd.delta_f, (size_t)n_windows * nr_cap_max);
+    bad |= b->dev_alloc(&bd.lm_scale, 3 * lm); bad |= b->dev_alloc(&bd.lm_linv, 6 * lm); bad |= b->dev_alloc(&bd.lm_z, 3 * lm);
+    bad |= b->dev_alloc(&bd.lm_g, 3 * lm); bad |= b->dev_alloc(&bd.lm_lambda, 3 * lm); bad |= b->dev_alloc(&bd.trim_val, 3 * lm);
+    bad |= b->dev_alloc(&bd.trim_reject, lm);
+    bad |= b->dev_alloc(&bd.res, 3 * obs); bad |= b->dev_alloc(&bd.jp, 18 * obs); bad |= b->dev_alloc(&bd.jl, 9 * obs);
+    bad |= b->dev_alloc(&bd.vobs, 18 * obs);
+    bad |= b->dev_alloc(&bd.cost_part_x, (size_t)n_windows * bd.cost_parts); bad |= b->dev_alloc(&bd.cost_part_c, (size_t)n_windows * bd.cost_parts);
+    bad |= b->dev_alloc(&bd.bs_part, (size_t)n_windows * bd.bs_parts * 4);
+    bad |= b->dev_alloc(&bd.sred, (size_t)soff * bd.p_split); bad |= b->dev_alloc(&bd.amat, (size_t)soff);
+    if (bad) {
+        const std::string msg = std::string("device/pinned allocation failed: ") + cudaGetErrorString(cudaGetLastError());
+        b->release(); delete b;
+        return fail(KBA_ERR_CUDA, msg);
+    }
+    bd.desc = b->desc.d; bd.state = b->state.d; bd.log = b->log.d;
+    bd.pose0 = b->pose0.d; bd.plane0 = b->plane0.d; bd.pose[0] = b->pose_out[0].d; bd.pose[1] = b->pose_out[1].d;
+    bd.kf_fixed = b->kf_fixed.d; bd.cam = b->cam.d;
+    bd.lm0 = b->lm0.d; bd.lm[0] = b->lm_out[0].d; bd.lm[1] = b->lm_out[1].d; bd.lm_weight = b->lm_weight.d;
+    bd.lm_active = b->lm_active.d; bd.lm_ptr = b->lm_ptr.d;
+    bd.obs_kf = b->obs_kf.d; bd.obs_cam = b->obs_cam.d; bd.obs_lm = b->obs_lm.d;
+    bd.obs_u = b->obs_u.d; bd.obs_v = b->obs_v.d; bd.obs_d = b->obs_d.d;
+    bd.kf_ptr = b->kf_ptr.d; bd.pm_lm = b->pm_lm.d; bd.pm_cam = b->pm_cam.d; bd.pm_u = b->pm_u.d; bd.pm_v = b->pm_v.d; bd.pm_d = b->pm_d.d;
+    bd.chunk_lm0 = b->chunk_lm0.d; bd.chunk_lm1 = b->chunk_lm1.d;
+    bd.n_active = b->n_active.d;
+    CU(cudaEventCreate(&b->ev_a));
+    CU(cudaEventCreate(&b->ev_b));
+    CU(configure_kernels(nr_cap_max));
+    *out = b;
+    const int rc = kba_batch_upload(b, n_windows, w);
+    if (rc != KBA_OK) { b->release(); delete b; *out = nullptr; }
+    return rc;
+}
+
+int kba_batch_upload(kba_batch* b, int32_t n_windows, const kba_window* w) {
+    if (!b || !w || n_windows != b->bd.n_win) return fail(KBA_ERR_BAD_ARG, "bad argument to kba_batch_upload");
+    for (int i = 0; i < n_windows; ++i) {
+        const WinDesc& d = b->desc_h[i];
+        if (w[i].n_kf != d.n_kf || w[i].n_lm != d.n_lm || w[i].n_obs != d.n_obs || w[i].n_cam != d.n_cam)
+            return fail(KBA_ERR_BAD_ARG, "kba_batch_upload: window shapes differ from kba_batch_create");
+        b->desc_h[i].scale_weight = w[i].scale_weight; b->desc_h[i].scale_value = w[i].scale_value;
+        b->desc_h[i].scale_kf0 = w[i].scale_kf0; b->desc_h[i].scale_kf1 = w[i].scale_kf1;
+        b->desc.h[i] = b->desc_h[i];
+        fill_window(b, i, &w[i]);
+    }
+    cudaStream_t s = b->h->stream;
+    CU(b->desc.upload(s)); CU(b->pose0.upload(s)); CU(b->plane0.upload(s)); CU(b->kf_fixed.upload(s)); CU(b->cam.upload(s));
+    CU(b->lm0.upload(s)); CU(b->lm_weight.upload(s)); CU(b->lm_ptr.upload(s));
+    CU(b->obs_kf.upload(s)); CU(b->obs_cam.upload(s)); CU(b->obs_lm.upload(s));
+    CU(b->obs_u.upload(s)); CU(b->obs_v.upload(s)); CU(b->obs_d.upload(s));
+    CU(b->kf_ptr.upload(s)); CU(b->pm_lm.upload(s)); CU(b->pm_cam.upload(s)); CU(b->pm_u.upload(s)); CU(b->pm_v.upload(s)); CU(b->pm_d.upload(s));
+    CU(b->chunk_lm0.upload(s)); CU(b->chunk_lm1.upload(s));
+    const BatchDev& bd = b->bd;
+    b->h2d_bytes = sizeof(WinDesc) * bd.n_win + (7 + 4) * 8 * bd.tot_kf + bd.tot_kf + kCamStride * 8 * bd.tot_cam +
+                   (3 + 1) * 8 * bd.tot_lm + 4 * (bd.tot_lm + bd.n_win) + (3 * 4 + 3 * 4) * bd.tot_obs +
+                   4 * (bd.tot_kf + bd.n_win) + (2 * 4 + 3 * 4) * bd.tot_obs + 8 * bd.tot_chunks;
+    return KBA_OK;
+}
+
+static SolveParams make_params(const kba_options* o) {
+    SolveParams sp;
+    sp.depth_thres = o->depth_thres; sp.reprojection_thres = o->reprojection_thres;
+    sp.depth_quantile = o->depth_quantile; sp.reprojection_quantile = o->reprojection_quantile;
+    sp.function_tolerance = o->function_tolerance; sp.gradient_tolerance = o->gradient_tolerance;
+    sp.parameter_tolerance = o->parameter_tolerance; sp.initial_radius = o->initial_trust_region_radius;
+    sp.max_radius = o->max_trust_region_radius; sp.min_radius = o->min_trust_region_radius;
+    sp.min_relative_decrease = o->min_relative_decrease; sp.min_lm_diagonal = o->min_lm_diagonal;
+    sp.max_lm_diagonal = o->max_lm_diagonal; sp.trim_solver_iterations = o->trim_solver_iterations;
+    sp.final_solver_iterations = o->final_solver_iterations; sp.min_residual_groups = o->min_residual_groups;
+    sp.max_consecutive_invalid_steps = o->max_consecutive_invalid_steps;
+    return sp;
+}
+
+int kba_batch_solve(kba_batch* b, const kba_options* opt) {
+    if (!b || !opt) return fail(KBA_ERR_BAD_ARG, "bad argument to kba_batch_solve");
+    if (opt->precision != 0) return fail(KBA_ERR_CAPACITY, "only the FP64 kernels (precision = 0) are built");
+    kba_handle* h = b->h;
+    CU(cudaSetDevice(h->device));
+    cudaStream_t s = h->stream;
+    const SolveParams sp = make_params(opt);
+    LaunchCfg lc = b->lc;
+    lc.rounds_override = opt->num_trim_rounds;
+    lc.min_landmarks_for_trimming = opt->min_landmarks_for_trimming;
+    lc.num_rounds_option = opt->num_rounds_option;
+    lc.time_jacobian = h->kernel_timing;
+    lc.ev0 = h->ev0; lc.ev1 = h->ev1;
+    CU(cudaEventRecord(b->ev_a, s));
+    launch_reset(b->bd, lc, s);
+    // upper bound on passes: every solve needs (iterations + 2) passes, plus one pass per trimming step
+    const int rounds_max = 7;
+    const int max_passes = rounds_max * (3 * opt->trim_solver_iterations + 4) + opt->final_solver_iterations + 8;
+    const auto t0 = std::chrono::steady_clock::now();
+    int check_every = 4;
+    for (int pass = 0; pass < max_passes; ++pass) {
+        launch_pass(b->bd, sp, lc, &h->counters, s);
+        if (lc.time_jacobian) {
+            CU(cudaEventSynchronize(lc.ev1));
+            float ms = 0.f;
+            CU(cudaEventElapsedTime(&ms, lc.ev0, lc.ev1));
+            h->counters.ms_jacobian += ms;
+        }
+        if ((pass + 1) % check_every == 0 || pass + 1 == max_passes) {
+            launch_count_active(b->bd, s);
+            CU(b->n_active.download(s));
+            CU(cudaStreamSynchronize(s));
+            if (b->n_active.h[0] == 0) break;
+            if (opt->solver_time_sec > 0) {
+                const double el = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+                if (el > opt->solver_time_sec) break;  // wall-clock cap: the accepted iterate stands
+            }
+        }
+    }
+    CU(cudaEventRecord(b->ev_b, s));
+    CU(cudaStreamSynchronize(s));
+    CU(cudaGetLastError());
+    CU(cudaEventElapsedTime(&b->last_solve_ms, b->ev_a, b->ev_b));
+    return KBA_OK;
+}
+
+int kba_batch_download(kba_batch* b, kba_result* res) {
+    if (!b || !res) return fail(KBA_ERR_BAD_ARG, "bad argument to kba_batch_download");
+    cudaStream_t s = b->h->stream;
+    CU(b->state.download(s)); CU(b->log.download(s));
+    CU(b->pose_out[0].download(s)); CU(b->pose_out[1].download(s));
+    CU(b->lm_out[0].download(s)); CU(b->lm_out[1].download(s)); CU(b->lm_active.download(s));
+    CU(cudaStreamSynchronize(s));
+    const BatchDev& bd = b->bd;
+    b->d2h_bytes = sizeof(WinState) * bd.n_win + 2 * (7 * 8 * bd.tot_kf + 3 * 8 * bd.tot_lm) + bd.tot_lm;
+    for (int i = 0; i < bd.n_win; ++i) {
+        const WinDesc& d = b->desc_h[i];
+        const WinState& st = b->state.h[i];
+        kba_result& r = res[i];
+        const int cur = st.cur;
+        if (r.kf_pose) memcpy(r.kf_pose, b->pose_out[cur].h + 7 * (size_t)d.kf_off, sizeof(double) * 7 * d.n_kf);
+        if (r.kf_plane) memcpy(r.kf_plane, b->plane0.h + 4 * (size_t)d.kf_off, sizeof(double) * 4 * d.n_kf);
+        if (r.lm_pos && d.n_lm > 0) memcpy(r.lm_pos, b->lm_out[cur].h + 3 * (size_t)d.lm_off, sizeof(double) * 3 * d.n_lm);
+        if (r.lm_rejected) for (int j = 0; j < d.n_lm; ++j) r.lm_rejected[j] = !b->lm_active.h[d.lm_off + j];
+        r.num_solves = st.n_solves;
+        for (int q = 0; q < st.n_solves && q < KBA_MAX_SOLVES; ++q) {
+            const SolveSummary& ss = st.solves[q];
+            kba_solve_summary& o = r.solves[q];
+            o.initial_cost = ss.initial_cost; o.final_cost = ss.final_cost; o.num_iterations = ss.num_iterations;
+            o.num_successful_steps = ss.num_successful_steps; o.termination = ss.termination;
+            o.num_landmarks = ss.num_landmarks; o.num_residual_blocks = ss.num_residual_blocks; o.reserved_ = 0;
+        }
+        r.initial_cost = st.n_solves > 0 ? st.solves[0].initial_cost : 0.0;
+        r.final_cost = st.n_solves > 0 ? st.solves[st.n_solves - 1].final_cost : 0.0;
+        r.status = (st.phase == PH_DONE) ? KBA_OK : KBA_ERR_CAPACITY;
+        r.time_sec = 1e-3 * b->last_solve_ms;
+        int n = 0;
+        if (r.iterations) {
+            for (; n < st.log_n && n < r.iterations_capacity; ++n) {
+                const IterRecord& e = b->log.h[(size_t)i * kIterLogCap + n];
+                kba_iteration& o = r.iterations[n];
+                o.cost = e.cost; o.cost_change = e.cost_change; o.gradient_max_norm = e.gradient_max_norm;
+                o.step_norm = e.step_norm; o.relative_decrease = e.relative_decrease; o.trust_region_radius = e.radius;
+                o.iteration = e.iteration; o.solve_index = e.solve_index; o.step_is_valid = e.valid; o.step_is_successful = e.successful;
+            }
+        }
+        r.num_iteration_records = n;
+    }
+    return KBA_OK;
+}
+
+void kba_batch_destroy(kba_batch* b) {
+    if (!b) return;
+    cudaStreamSynchronize(b->h->stream);
+    b->release();
+    delete b;
+}
+
+int kba_batch_jacobian_pass(kba_batch* b, const kba_options* opt, int32_t repeats, float* ms_out) {
+    if (!b || !opt || repeats < 1) return fail(KBA_ERR_BAD_ARG, "bad argument to kba_batch_jacobian_pass");
+    kba_handle* h = b->h;
+    cudaStream_t s = h->stream;
+    const SolveParams sp = make_params(opt);
+    launch_reset(b->bd, b->lc, s);
+    launch_force_linearize(b->bd, s);
+    CU(cudaEventRecord(b->ev_a, s));
+    for (int i = 0; i < repeats; ++i) launch_jacobian_only(b->bd, sp, s);
+    CU(cudaEventRecord(b->ev_b, s));
+    CU(cudaStreamSynchronize(s));
+    CU(cudaGetLastError());
+    float ms = 0.f;
+    CU(cudaEventElapsedTime(&ms, b->ev_a, b->ev_b));
+    if (ms_out) *ms_out = ms;
+    h->counters.launches_total += repeats; h->counters.launches_jacobian += repeats;
+    h->counters.ms_jacobian += ms; h->counters.jacobian_obs += (long long)repeats * b->bd.tot_obs;
+    return KBA_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+int kba_solve_batch(kba_handle* h, int32_t n_windows, const kba_window* w, const kba_options* opt, kba_result* res) {
+    if (!h || !w || !opt || !res) return fail(KBA_ERR_BAD_ARG, "null argument to kba_solve_batch");
+    kba_batch* b = nullptr;
+    int rc = kba_batch_create(h, n_windows, w, &b);
+    if (rc != KBA_OK) return rc;
+    rc = kba_batch_solve(b, opt);
+    if (rc == KBA_OK) rc = kba_batch_download(b, res);
+    kba_batch_destroy(b);
+    return rc;
+}
+
+int kba_solve_window(kba_handle* h, const kba_window* w, const kba_options* opt, kba_result* res) {
+    return kba_solve_batch(h, 1, w, opt, res);
+}
+
+int kba_eval(kba_handle* h, const kba_window* w, const kba_options* opt, kba_eval_out* out) {
+    if (!h || !w || !opt || !out) return fail(KBA_ERR_BAD_ARG, "null argument to kba_eval");
+    kba_batch* b = nullptr;
+    int rc = kba_batch_create(h, 1, w, &b);
+    if (rc != KBA_OK) return rc;
+    float ms;
+    rc = kba_batch_jacobian_pass(b, opt, 1, &ms);
+    if (rc != KBA_OK) { kba_batch_destroy(b); return rc; }
+    const BatchDev& bd = b->bd;
+    const size_t n = (size_t)w->n_obs;
+    std::vector<double> res_h(3 * n + 1), jp_h(18 * n + 1), jl_h(9 * n + 1), cost_h(bd.cost_parts);
+    std::vector<int> offp(w->n_kf);
+    WinState st;
+    cudaStream_t s = h->stream;
+    cudaMemcpyAsync(res_h.data(), bd.res, 3 * n * sizeof(double), cudaMemcpyDeviceToHost, s);
+    cudaMemcpyAsync(jp_h.data(), bd.jp, 18 * n * sizeof(double), cudaMemcpyDeviceToHost, s);
+    cudaMemcpyAsync(jl_h.data(), bd.jl, 9 * n * sizeof(double), cudaMemcpyDeviceToHost, s);
+    cudaMemcpyAsync(cost_h.data(), bd.cost_part_x, bd.cost_parts * sizeof(double), cudaMemcpyDeviceToHost, s);
+    cudaMemcpyAsync(offp.data(), bd.off_pose, w->n_kf * sizeof(int), cudaMemcpyDeviceToHost, s);
+    cudaMemcpyAsync(&st, bd.state, sizeof(WinState), cudaMemcpyDeviceToHost, s);
+    cudaError_t e = cudaStreamSynchronize(s);
+    if (e != cudaSuccess) { kba_batch_destroy(b); return fail(KBA_ERR_CUDA, cudaGetErrorString(e)); }
+    for (size_t o = 0; o < n; ++o) {
+        const bool fixed = offp[w->obs_kf[o]] < 0;
+        if (out->residual) for (int q = 0; q < 3; ++q) out->residual[3 * o + q] = res_h[q * n + o];
+        if (out->jac_pose) for (int q = 0; q < 18; ++q) out->jac_pose[18 * o + q] = fixed ? 0.0 : jp_h[q * n + o];
+        if (out->jac_lm) for (int q = 0; q < 9; ++q) out->jac_lm[9 * o + q] = jl_h[q * n + o];
+    }
+    if (out->cost) { double c = 0; for (int q = 0; q < bd.cost_parts; ++q) c += cost_h[q]; out->cost[0] = c; }
+    if (out->failed) out->failed[0] = st.eval_failed;
+    kba_batch_destroy(b);
+    return KBA_OK;
+}
+
+}  // extern "C"

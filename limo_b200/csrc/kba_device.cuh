@@ -1,0 +1,281 @@
+// kba_device.cuh -- device-side data model and per-observation math of the B200 window solver.
+//
+// Layout rule: everything that is streamed per observation is SoA over the whole batch (component-major), so that
+// a warp touching 32 consecutive observations issues fully coalesced 128-/256-byte transactions; everything that is
+// per keyframe / per camera is tiny and staged into shared memory by the consuming CTA.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace kba {
+
+constexpr int kMaxKf = 128;         // keyframes per window the kernels stage in shared memory
+constexpr int kMaxCam = 8;
+constexpr int kPoseStride = 12;     // staged pose: R (9, row-major) + t (3)
+constexpr int kCamStride = 16;      // staged camera: Rc (9) + tc (3) + f, cx, cy, pad
+constexpr int kIterLogCap = 160;    // iteration records kept per window
+
+// ---- per-window descriptor (immutable after upload) --------------------------------------------------------------
+struct WinDesc {
+    int n_kf, n_cam, n_lm, n_obs, n_gp;
+    int kf_off, cam_off, lm_off, obs_off, gp_off;  // offsets into the batch-flat arrays
+    int chunk_off, n_chunks;                        // landmark chunks of the Schur kernel
+    int scale_kf0, scale_kf1;
+    double scale_weight, scale_value;
+    double plane_reg_weight;
+    int plane_dist_fixed, landmarks_fixed;
+    int speed_kf, pad0;
+    double speed_weight, speed_dt;
+    double speed_v_before[3];
+    double speed_T_origin_before[7];
+    long long s_off;                                // offset (doubles) of this window's reduced-system storage
+    int nr_cap, pad1;                               // allocated panel rows (multiple of 64)
+};
+
+// ---- per-window solver state (device resident, mutated by the kernels) ----------------------------------------------
+enum Phase : int { PH_SOLVE_BEGIN = 0, PH_ITERATE = 1, PH_TRIM = 2, PH_DONE = 3 };
+
+struct SolveSummary {
+    double initial_cost, final_cost;
+    int num_iterations, num_successful_steps, termination, num_landmarks, num_residual_blocks, pad;
+};
+
+struct IterRecord {
+    double cost, cost_change, gradient_max_norm, step_norm, relative_decrease, radius;
+    int iteration, solve_index, valid, successful;
+};
+
+struct WinState {
+    int phase;
+    int cur;               // index of the state buffer holding x (candidate = 1 - cur)
+    int need_linearize;    // x changed: Jacobian + pose-Hessian kernels must run
+    int iter0;             // the pending linearisation is iteration zero of a solve (Jacobi scaling is computed)
+    int solve_index;       // index of the inner solve (summary slot)
+    int round;             // trimming rounds completed
+    int rounds_total;
+    int retried;           // the current trimming-round solve is the 3x-iterations retry
+    int is_final;          // current solve is the final refinement
+    int max_iter;
+    int iteration;
+    int num_invalid;
+    int last_successful;   // the previous iteration was a successful step (gates the gradient tolerance test)
+    int n_f;               // columns of the reduced system in this solve
+    int nr;                // n_f + 1 rounded up to 8
+    int eval_failed;       // set by evaluation kernels (|z| < 0.01)
+    int solve_failed;      // reduced Cholesky / finiteness failure of the current step
+    int log_n;
+    int n_solves;
+    int pad;
+    double radius, decrease_factor;
+    double x_cost, x_norm, gmax;
+    // pose-side scalars of the current step (written by the reduced solve)
+    double f_model, f_step_sq, f_xnorm_sq, f_gmax;
+    SolveSummary solves[8];
+};
+
+// ---- batch-flat device arrays --------------------------------------------------------------------------------------------
+struct BatchDev {
+    int n_win;
+    int max_obs, max_lm, max_kf, max_gp;   // maxima over the batch (grid sizing)
+    long long tot_obs, tot_lm, tot_kf, tot_cam, tot_gp;
+    WinDesc* desc;
+    WinState* state;
+    IterRecord* log;          // [n_win][kIterLogCap]
+    // keyframes
+    double* pose0;            // [tot_kf*7] uploaded state
+    double* plane0;           // [tot_kf*4]
+    double* pose[2];          // [tot_kf*7] x / candidate (ping-pong)
+    double* plane[2];         // [tot_kf*4]
+    uint8_t* kf_fixed;        // [tot_kf]
+    int* off_pose;            // [tot_kf] column offset in the reduced system or -1
+    int* off_dir;
+    int* off_dist;
+    double* bkf;              // [tot_kf*27] per-keyframe J_p^T J_p (21, upper-packed row-major) + J_p^T r (6)
+    double* scale_f;          // [n_win * nr_cap_max] Jacobi scaling of the f columns (indexed desc.s... see kernels)
+    // cameras
+    double* cam;              // [tot_cam*16] staged camera parameters
+    // landmarks
+    double* lm0;              // [tot_lm*3]
+    double* lm[2];            // [tot_lm*3]
+    double* lm_weight;        // [tot_lm]
+    uint8_t* lm_active;       // [tot_lm]
+    uint8_t* lm_active0;      // all ones minus landmarks without residuals
+    int* lm_ptr;              // [tot_lm + n_win] CSR (window-local observation offsets), window w starts at lm_off + w
+    double* lm_scale;         // [tot_lm*3] Jacobi scaling of the landmark columns
+    double* lm_linv;          // [tot_lm*6] inverse Cholesky factor of the damped C_j (lower, packed)
+    double* lm_z;             // [tot_lm*3] L^-1 g_j
+    double* lm_g;             // [tot_lm*3] g_j = J_l^T r
+    double* lm_lambda;        // [tot_lm*3] LM damping of the landmark columns
+    double* trim_val;         // [3][tot_lm] per-landmark maximum raw residual norm per group
+    uint8_t* trim_reject;     // [tot_lm]
+    // observations, landmark-major
+    int* obs_kf;              // [tot_obs]
+    int* obs_cam;
+    int* obs_lm;              // window-local landmark index
+    float* obs_u, *obs_v, *obs_d;
+    // observations, keyframe-major copy (built on device at upload)
+    int* kf_ptr;              // [tot_kf + n_win]
+    int* pm_lm;               // [tot_obs]
+    int* pm_cam;
+    float* pm_u, *pm_v, *pm_d;
+    // materialised linearisation (SoA, component stride = tot_obs)
+    double* res;              // [3][tot_obs]  robustified residual rows (u, v, depth)
+    double* jp;               // [18][tot_obs] 3x6 d r~ / d (rot, trans)
+    double* jl;               // [9][tot_obs]  3x3 d r~ / d landmark
+    double* vobs;             // [18][tot_obs] V_i = (J_p^T J_l) L^-T, 6x3
+    // reductions
+    double* cost_part_x;      // [n_win][cost_parts] cost partials of the linearisation at x
+    double* cost_part_c;      // [n_win][cost_parts] cost partials at the candidate
+    int cost_parts;
+    double* bs_part;          // [n_win][bs_parts][4]: model_e, step_sq, xnorm_sq, gmax_e
+    int bs_parts;
+    int nr_cap_max;           // largest nr_cap in the batch = stride of scale_f / lambda_f / grad_f / delta_f
+    // reduced system
+    double* sred;             // per window nr_cap x nr_cap (row-major, lower part valid) x p_split partial copies
+    int p_split;
+    double* delta_f;          // [n_win * nr_cap]
+    double* lambda_f;         // [n_win * nr_cap]
+    double* grad_f;           // [n_win * nr_cap]
+    double* amat;             // per window nr_cap x nr_cap scratch for the factorisation
+    // chunking of landmarks for the Schur kernel
+    int* chunk_lm0;           // [tot_chunks] first landmark (window-local)
+    int* chunk_lm1;           // [tot_chunks] one past last
+    int* chunk_r0;            // row range touched, in 8-row tiles
+    int* chunk_r1;
+    int tot_chunks;
+    int* n_active;            // [1] windows still running (device counter)
+};
+
+struct SolveParams {  // kba_options subset used on the device
+    double depth_thres, reprojection_thres, depth_quantile, reprojection_quantile;
+    double function_tolerance, gradient_tolerance, parameter_tolerance;
+    double initial_radius, max_radius, min_radius, min_relative_decrease, min_lm_diagonal, max_lm_diagonal;
+    int trim_solver_iterations, final_solver_iterations, min_residual_groups, max_consecutive_invalid_steps;
+};
+
+// ---- small math ----------------------------------------------------------------------------------------------------------
+template <typename T>
+__host__ __device__ inline void quat_to_rot(const T* q, T* R) {
+    // Eigen::Quaternion::toRotationMatrix, no normalisation (reference definitions.hpp:75-83)
+    const T w = q[0], x = q[1], y = q[2], z = q[3];
+    const T tx = 2 * x, ty = 2 * y, tz = 2 * z;
+    const T twx = tx * w, twy = ty * w, twz = tz * w, txx = tx * x, txy = ty * x, txz = tz * x;
+    const T tyy = ty * y, tyz = tz * y, tzz = tz * z;
+    R[0] = 1 - (tyy + tzz); R[1] = txy - twz;       R[2] = txz + twy;
+    R[3] = txy + twz;       R[4] = 1 - (txx + tzz); R[5] = tyz - twx;
+    R[6] = txz - twy;       R[7] = tyz + twx;       R[8] = 1 - (txx + tyy);
+}
+
+// Ceres QuaternionParameterization::Plus x Identity(3) (reference bundle_adjuster_keyframes.cpp:181-182)
+__host__ __device__ inline void pose_plus(const double* p, const double* d, double* o) {
+    const double nd = sqrt(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);
+    if (nd > 0.0) {
+        const double s = sin(nd) / nd, c = cos(nd);
+        const double q0 = c, q1 = s * d[0], q2 = s * d[1], q3 = s * d[2];
+        o[0] = q0 * p[0] - q1 * p[1] - q2 * p[2] - q3 * p[3];
+        o[1] = q0 * p[1] + q1 * p[0] + q2 * p[3] - q3 * p[2];
+        o[2] = q0 * p[2] - q1 * p[3] + q2 * p[0] + q3 * p[1];
+        o[3] = q0 * p[3] + q1 * p[2] - q2 * p[1] + q3 * p[0];
+    } else {
+        o[0] = p[0]; o[1] = p[1]; o[2] = p[2]; o[3] = p[3];
+    }
+    o[4] = p[4] + d[3]; o[5] = p[5] + d[4]; o[6] = p[6] + d[5];
+}
+
+// Robust loss of one residual block: ScaledLoss(CauchyLoss(a), w): rho = w b log(1 + s/b), rho' = w / (1 + s/b)
+template <typename T>
+__device__ inline void cauchy(T b, T w, T s, T& half_rho, T& sqrt_rho1) {
+    const T sum = T(1) + s / b;
+    half_rho = T(0.5) * w * b * log(sum);
+    sqrt_rho1 = sqrt(w / sum);
+}
+
+// One observation: reprojection (2 rows) + optional lidar depth row, robustified.
+// pose: staged R(9)+t(3); cam: staged Rc(9)+tc(3)+f,cx,cy.  Jacobian rows: d/d(delta_rot) = -2 (m x a), d/d(delta_t) = m,
+// d/d(p) = m R, with m = (row of Pi) * Rc and a = R p   (reference cost_functors_ceres.hpp:91-155,193-212).
+// Returns false when |z_cam| < 0.01 (evaluation failure, cost_functors_ceres.hpp:78-83).
+template <typename T, bool kJac>
+__device__ inline bool eval_observation(const T* __restrict__ pose, const T* __restrict__ cam, const T p[3], T u, T v,
+                                        T d, T wt, T b_repr, T b_depth, T r[3], T jp[18], T jl[9], T& half_rho_sum,
+                                        T raw[2]) {
+    const T a0 = pose[0] * p[0] + pose[1] * p[1] + pose[2] * p[2];
+    const T a1 = pose[3] * p[0] + pose[4] * p[1] + pose[5] * p[2];
+    const T a2 = pose[6] * p[0] + pose[7] * p[1] + pose[8] * p[2];
+    const T x0 = a0 + pose[9], x1 = a1 + pose[10], x2 = a2 + pose[11];
+    const T c0 = cam[0] * x0 + cam[1] * x1 + cam[2] * x2 + cam[9];
+    const T c1 = cam[3] * x0 + cam[4] * x1 + cam[5] * x2 + cam[10];
+    const T c2 = cam[6] * x0 + cam[7] * x1 + cam[8] * x2 + cam[11];
+    if (!(fabs(c2) >= T(0.01))) return false;
+    const T f = cam[12], iz = T(1) / c2;
+    const T xn = c0 * iz, yn = c1 * iz;
+    const T ru = f * xn + cam[13] - u, rv = f * yn + cam[14] - v;
+    const T s = ru * ru + rv * rv;
+    T hr, sq;
+    cauchy<T>(b_repr, wt, s, hr, sq);
+    half_rho_sum = hr;
+    raw[0] = sqrt(s);
+    raw[1] = T(-1);
+    r[0] = sq * ru; r[1] = sq * rv; r[2] = T(0);
+    T sqd = T(0), rd = T(0);
+    const bool has_d = d > T(0);
+    if (has_d) {
+        rd = c2 - d;
+        T hrd;
+        cauchy<T>(b_depth, wt, rd * rd, hrd, sqd);
+        half_rho_sum += hrd;
+        raw[1] = fabs(rd);
+        r[2] = sqd * rd;
+    }
+    if (kJac) {
+        const T fz = f * iz * sq;  // robustified
+        // m rows: (fz * Rc[0,:] - fz*xn * Rc[2,:]), (fz * Rc[1,:] - fz*yn * Rc[2,:]), sqd * Rc[2,:]
+        T m[3][3];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            m[0][c] = fz * (cam[c] - xn * cam[6 + c]);
+            m[1][c] = fz * (cam[3 + c] - yn * cam[6 + c]);
+            m[2][c] = sqd * cam[6 + c];
+        }
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            jp[6 * i + 0] = T(-2) * (m[i][1] * a2 - m[i][2] * a1);
+            jp[6 * i + 1] = T(-2) * (m[i][2] * a0 - m[i][0] * a2);
+            jp[6 * i + 2] = T(-2) * (m[i][0] * a1 - m[i][1] * a0);
+            jp[6 * i + 3] = m[i][0];
+            jp[6 * i + 4] = m[i][1];
+            jp[6 * i + 5] = m[i][2];
+#pragma unroll
+            for (int c = 0; c < 3; ++c) jl[3 * i + c] = m[i][0] * pose[c] + m[i][1] * pose[3 + c] + m[i][2] * pose[6 + c];
+        }
+    }
+    return true;
+}
+
+// stage keyframe poses (as R|t) and cameras of one window into shared memory
+__device__ inline void stage_window(const WinDesc& wd, const double* __restrict__ pose7, const double* __restrict__ cam16,
+                                    double* s_pose, double* s_cam) {
+    for (int k = threadIdx.x; k < wd.n_kf; k += blockDim.x) {
+        const double* p = pose7 + 7 * (size_t)(wd.kf_off + k);
+        double R[9];
+        quat_to_rot<double>(p, R);
+#pragma unroll
+        for (int i = 0; i < 9; ++i) s_pose[kPoseStride * k + i] = R[i];
+        s_pose[kPoseStride * k + 9] = p[4];
+        s_pose[kPoseStride * k + 10] = p[5];
+        s_pose[kPoseStride * k + 11] = p[6];
+    }
+    for (int i = threadIdx.x; i < wd.n_cam * kCamStride; i += blockDim.x) s_cam[i] = cam16[(size_t)wd.cam_off * kCamStride + i];
+}
+
+__device__ inline double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ inline double warp_max(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+}  // namespace kba

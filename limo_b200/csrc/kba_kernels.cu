@@ -1,0 +1,1025 @@
+// kba_kernels.cu -- sm_100a kernels of the window solver.  One LM "pass" over a batch of windows is
+//   k_solve_begin -> k_eval_obs<true> (residual/Jacobian, HBM streaming) -> k_pose_hessian -> k_landmark_prep
+//   -> k_schur_syrk (FP64 tensor-core SYRK) -> k_reduced_solve -> k_backsub -> k_eval_obs<false> (candidate cost)
+//   -> k_lm_update [-> k_trim_eval -> k_trim_select]
+// Every kernel looks at the per-window state and returns immediately for windows that have nothing to do, so the
+// host launches a fixed sequence without synchronising per iteration.
+#include "kba_device.cuh"
+#include "kba_kernels.h"
+
+#include <cfloat>
+#include <cmath>
+
+namespace kba {
+
+// =====================================================================================================================
+// solve begin: program layout (which parameter blocks are in the reduced program) + LM state reset
+// =====================================================================================================================
+__global__ void __launch_bounds__(256) k_solve_begin(BatchDev bd, SolveParams sp) {
+    const int w = blockIdx.x;
+    WinState& st = bd.state[w];
+    if (st.phase != PH_SOLVE_BEGIN) return;
+    const WinDesc wd = bd.desc[w];
+    __shared__ int s_has[kMaxKf];
+    __shared__ int s_cnt[2];
+    for (int k = threadIdx.x; k < wd.n_kf; k += blockDim.x) s_has[k] = 0;
+    if (threadIdx.x < 2) s_cnt[threadIdx.x] = 0;
+    __syncthreads();
+    const int* lm_ptr = bd.lm_ptr + wd.lm_off + w;
+    int n_lm_in = 0, n_blocks = 0;
+    for (int j = threadIdx.x; j < wd.n_lm; j += blockDim.x) {
+        if (!bd.lm_active[wd.lm_off + j]) continue;
+        const int o0 = lm_ptr[j], o1 = lm_ptr[j + 1];
+        if (o1 > o0) n_lm_in++;
+        for (int o = o0; o < o1; ++o) {
+            s_has[bd.obs_kf[wd.obs_off + o]] = 1;  // benign race: every writer stores 1
+            n_blocks += (bd.obs_d[wd.obs_off + o] > 0.0f) ? 2 : 1;
+        }
+    }
+    atomicAdd(&s_cnt[0], n_lm_in);
+    atomicAdd(&s_cnt[1], n_blocks);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        if (wd.scale_weight > 0) { s_has[wd.scale_kf0] = 1; s_has[wd.scale_kf1] = 1; }
+        int n = 0;
+        for (int k = 0; k < wd.n_kf; ++k) {
+            const bool var = s_has[k] && !bd.kf_fixed[wd.kf_off + k];
+            bd.off_pose[wd.kf_off + k] = var ? n : -1;
+            if (var) n += 6;
+            bd.off_dir[wd.kf_off + k] = -1;
+            bd.off_dist[wd.kf_off + k] = -1;
+        }
+        st.n_f = n;
+        st.nr = (n + 1 + 7) & ~7;
+        st.radius = sp.initial_radius;
+        st.decrease_factor = 2.0;
+        st.iteration = 0;
+        st.num_invalid = 0;
+        st.last_successful = 0;
+        st.need_linearize = 1;
+        st.iter0 = 1;
+        st.eval_failed = 0;
+        st.solve_failed = 0;
+        st.max_iter = st.is_final ? sp.final_solver_iterations
+                                  : (st.retried ? 3 * sp.trim_solver_iterations : sp.trim_solver_iterations);
+        SolveSummary& s = st.solves[st.solve_index];
+        s.initial_cost = s.final_cost = 0.0;
+        s.num_iterations = 0; s.num_successful_steps = 0; s.termination = 1;
+        s.num_landmarks = s_cnt[0];
+        s.num_residual_blocks = s_cnt[1] + (wd.scale_weight > 0 ? 1 : 0);
+        st.phase = PH_ITERATE;
+    }
+}
+
+// =====================================================================================================================
+// residual / Jacobian kernel: one thread per observation, landmark-major order, SoA in / SoA out.
+//   kJac = true : linearisation at x -> residual (3), J_pose (3x6), J_landmark (3x3) per observation + cost partials
+//   kJac = false: cost only, at the candidate point
+// Algorithmic HBM bytes per observation (FP64, with depth row): 20 read + 240 written.
+// =====================================================================================================================
+template <bool kJac>
+__global__ void __launch_bounds__(256) k_eval_obs(BatchDev bd, SolveParams sp) {
+    const int w = blockIdx.y;
+    WinState& st = bd.state[w];
+    if (st.phase != PH_ITERATE) return;
+    if (kJac && !st.need_linearize) return;
+    if (!kJac && st.solve_failed) return;
+    const WinDesc& wd = bd.desc[w];
+    __shared__ double s_pose[kMaxKf * kPoseStride];
+    __shared__ double s_cam[kMaxCam * kCamStride];
+    __shared__ double s_red[8];
+    const int buf = kJac ? st.cur : 1 - st.cur;
+    stage_window(wd, bd.pose[buf], bd.cam, s_pose, s_cam);
+    __syncthreads();
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    double cost = 0.0;
+    if (i < wd.n_obs) {
+        const size_t o = (size_t)wd.obs_off + i;
+        const int L = wd.lm_off + bd.obs_lm[o];
+        if (bd.lm_active[L]) {
+            const double* lm = bd.lm[buf] + 3 * (size_t)L;
+            const double p[3] = {lm[0], lm[1], lm[2]};
+            const int k = bd.obs_kf[o], c = bd.obs_cam[o];
+            double r[3], jp[18], jl[9], raw[2], hr = 0.0;
+            const bool ok = eval_observation<double, kJac>(
+                s_pose + kPoseStride * k, s_cam + kCamStride * c, p, (double)bd.obs_u[o], (double)bd.obs_v[o],
+                (double)bd.obs_d[o], bd.lm_weight[L], sp.reprojection_thres * sp.reprojection_thres,
+                sp.depth_thres * sp.depth_thres, r, jp, jl, hr, raw);
+            if (!ok) {
+                st.eval_failed = 1;  // benign race
+            } else {
+                cost = hr;
+                if (kJac) {
+                    const size_t T = (size_t)bd.tot_obs;
+#pragma unroll
+                    for (int q = 0; q < 3; ++q) bd.res[q * T + o] = r[q];
+#pragma unroll
+                    for (int q = 0; q < 9; ++q) bd.jl[q * T + o] = jl[q];
+                    if (bd.off_pose[wd.kf_off + k] >= 0) {
+#pragma unroll
+                        for (int q = 0; q < 18; ++q) bd.jp[q * T + o] = jp[q];
+                    }
+                }
+            }
+        }
+    }
+    cost = warp_sum(cost);
+    if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = cost;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double s = 0.0;
+        for (int q = 0; q < 8; ++q) s += s_red[q];
+        (kJac ? bd.cost_part_x : bd.cost_part_c)[(size_t)w * bd.cost_parts + blockIdx.x] = s;
+    }
+}
+template __global__ void k_eval_obs<true>(BatchDev, SolveParams);
+template __global__ void k_eval_obs<false>(BatchDev, SolveParams);
+
+// =====================================================================================================================
+// pose-side Gauss-Newton blocks: one CTA per (keyframe, window) walks the keyframe-major copy of the observations,
+// re-evaluates the Jacobian rows (cheaper than gathering the materialised J_pose across sectors) and reduces
+// B_k = sum J_p^T J_p (21 unique) and g_k = sum J_p^T r (6) with a fixed-shape tree -> deterministic, no atomics.
+// =====================================================================================================================
+__global__ void __launch_bounds__(256) k_pose_hessian(BatchDev bd, SolveParams sp) {
+    const int w = blockIdx.y, k = blockIdx.x;
+    const WinState& st = bd.state[w];
+    if (st.phase != PH_ITERATE || !st.need_linearize) return;
+    const WinDesc& wd = bd.desc[w];
+    if (k >= wd.n_kf || bd.off_pose[wd.kf_off + k] < 0) return;
+    __shared__ double s_pose[kPoseStride];
+    __shared__ double s_cam[kMaxCam * kCamStride];
+    __shared__ double s_red[8][27];
+    if (threadIdx.x == 0) {
+        const double* p = bd.pose[st.cur] + 7 * (size_t)(wd.kf_off + k);
+        double R[9];
+        quat_to_rot<double>(p, R);
+        for (int i = 0; i < 9; ++i) s_pose[i] = R[i];
+        s_pose[9] = p[4]; s_pose[10] = p[5]; s_pose[11] = p[6];
+    }
+    for (int i = threadIdx.x; i < wd.n_cam * kCamStride; i += blockDim.x) s_cam[i] = bd.cam[(size_t)wd.cam_off * kCamStride + i];
+    __syncthreads();
+    double acc[27];
+#pragma unroll
+    for (int q = 0; q < 27; ++q) acc[q] = 0.0;
+    const int* kp = bd.kf_ptr + wd.kf_off + w;
+    const int e0 = kp[k], e1 = kp[k + 1];
+    for (int e = e0 + threadIdx.x; e < e1; e += blockDim.x) {
+        const size_t o = (size_t)wd.obs_off + e;
+        const int L = wd.lm_off + bd.pm_lm[o];
+        if (!bd.lm_active[L]) continue;
+        const double* lm = bd.lm[st.cur] + 3 * (size_t)L;
+        const double p[3] = {lm[0], lm[1], lm[2]};
+        double r[3], jp[18], jl[9], raw[2], hr;
+        if (!eval_observation<double, true>(s_pose, s_cam + kCamStride * bd.pm_cam[o], p, (double)bd.pm_u[o],
+                                            (double)bd.pm_v[o], (double)bd.pm_d[o], bd.lm_weight[L],
+                                            sp.reprojection_thres * sp.reprojection_thres,
+                                            sp.depth_thres * sp.depth_thres, r, jp, jl, hr, raw))
+            continue;  // flagged by k_eval_obs
+        int q = 0;
+#pragma unroll
+        for (int a = 0; a < 6; ++a)
+#pragma unroll
+            for (int b = a; b < 6; ++b) {
+                acc[q] += jp[a] * jp[b] + jp[6 + a] * jp[6 + b] + jp[12 + a] * jp[12 + b];
+                ++q;
+            }
+#pragma unroll
+        for (int a = 0; a < 6; ++a) acc[21 + a] += jp[a] * r[0] + jp[6 + a] * r[1] + jp[12 + a] * r[2];
+    }
+#pragma unroll
+    for (int q = 0; q < 27; ++q) {
+        const double v = warp_sum(acc[q]);
+        if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5][q] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x < 27) {
+        double s = 0.0;
+        for (int q = 0; q < 8; ++q) s += s_red[q][threadIdx.x];
+        bd.bkf[(size_t)(wd.kf_off + k) * 27 + threadIdx.x] = s;
+    }
+}
+
+// =====================================================================================================================
+// landmark preparation: one warp per landmark.  C_j = sum J_l^T J_l, g_j = sum J_l^T r (warp-shuffle tree), Jacobi-scaled
+// LM damping, 3x3 Cholesky, then per observation V_i = (J_p^T J_l) L^-T (6x3) for the Schur kernel and the back-substitution.
+// =====================================================================================================================
+__global__ void __launch_bounds__(256) k_landmark_prep(BatchDev bd, SolveParams sp) {
+    const int w = blockIdx.y;
+    WinState& st = bd.state[w];
+    if (st.phase != PH_ITERATE) return;
+    const WinDesc& wd = bd.desc[w];
+    const int lane = threadIdx.x & 31;
+    const int j = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (j >= wd.n_lm) return;
+    const int L = wd.lm_off + j;
+    if (!bd.lm_active[L]) return;
+    const int* lm_ptr = bd.lm_ptr + wd.lm_off + w;
+    const int o0 = lm_ptr[j], o1 = lm_ptr[j + 1];
+    if (o1 <= o0) return;
+    const size_t T = (size_t)bd.tot_obs, base = (size_t)wd.obs_off;
+    double c[6] = {0, 0, 0, 0, 0, 0}, g[3] = {0, 0, 0};
+    for (int o = o0 + lane; o < o1; o += 32) {
+        double jl[9], r[3];
+#pragma unroll
+        for (int q = 0; q < 9; ++q) jl[q] = bd.jl[q * T + base + o];
+#pragma unroll
+        for (int q = 0; q < 3; ++q) r[q] = bd.res[q * T + base + o];
+        c[0] += jl[0] * jl[0] + jl[3] * jl[3] + jl[6] * jl[6];
+        c[1] += jl[0] * jl[1] + jl[3] * jl[4] + jl[6] * jl[7];
+        c[2] += jl[0] * jl[2] + jl[3] * jl[5] + jl[6] * jl[8];
+        c[3] += jl[1] * jl[1] + jl[4] * jl[4] + jl[7] * jl[7];
+        c[4] += jl[1] * jl[2] + jl[4] * jl[5] + jl[7] * jl[8];
+        c[5] += jl[2] * jl[2] + jl[5] * jl[5] + jl[8] * jl[8];
+#pragma unroll
+        for (int a = 0; a < 3; ++a) g[a] += jl[a] * r[0] + jl[3 + a] * r[1] + jl[6 + a] * r[2];
+    }
+#pragma unroll
+    for (int q = 0; q < 6; ++q) c[q] = warp_sum(c[q]);
+#pragma unroll
+    for (int q = 0; q < 3; ++q) g[q] = warp_sum(g[q]);
+    // Jacobi scaling (fixed at iteration zero of the solve) and LM damping of the three landmark columns
+    const double cd[3] = {c[0], c[3], c[5]};
+    double sc[3], lam[3];
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        if (st.iter0) sc[a] = 1.0 / (1.0 + sqrt(cd[a]));
+        else sc[a] = bd.lm_scale[3 * (size_t)L + a];
+        const double s2 = sc[a] * sc[a];
+        lam[a] = fmin(fmax(cd[a] * s2, sp.min_lm_diagonal), sp.max_lm_diagonal) / (st.radius * s2);
+    }
+    // Cholesky of C + diag(lam):  [l00; l10 l11; l20 l21 l22]
+    const double a00 = c[0] + lam[0], a11 = c[3] + lam[1], a22 = c[5] + lam[2];
+    const double l00 = sqrt(a00);
+    const double l10 = c[1] / l00, l20 = c[2] / l00;
+    const double d11 = a11 - l10 * l10;
+    const double l11 = sqrt(d11);
+    const double l21 = (c[4] - l20 * l10) / l11;
+    const double d22 = a22 - l20 * l20 - l21 * l21;
+    const double l22 = sqrt(d22);
+    if (!(a00 > 0.0) || !(d11 > 0.0) || !(d22 > 0.0)) {
+        if (lane == 0) st.solve_failed = 1;
+        return;
+    }
+    // inverse of L (lower): i00; i10 i11; i20 i21 i22
+    const double i00 = 1.0 / l00, i11 = 1.0 / l11, i22 = 1.0 / l22;
+    const double i10 = -l10 * i00 * i11;
+    const double i21 = -l21 * i11 * i22;
+    const double i20 = -(l20 * i00 + l21 * i10) * i22;
+    const double z0 = i00 * g[0], z1 = i10 * g[0] + i11 * g[1], z2 = i20 * g[0] + i21 * g[1] + i22 * g[2];
+    if (lane == 0) {
+        double* li = bd.lm_linv + 6 * (size_t)L;
+        li[0] = i00; li[1] = i10; li[2] = i11; li[3] = i20; li[4] = i21; li[5] = i22;
+        double* zz = bd.lm_z + 3 * (size_t)L;
+        zz[0] = z0; zz[1] = z1; zz[2] = z2;
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+            bd.lm_g[3 * (size_t)L + a] = g[a];
+            bd.lm_lambda[3 * (size_t)L + a] = lam[a];
+            if (st.iter0) bd.lm_scale[3 * (size_t)L + a] = sc[a];
+        }
+    }
+    // V_i = E_i L^-T with E_i = J_p^T J_l;  V[r][cc] = sum_m E[r][m] * Linv[cc][m]
+    for (int o = o0 + lane; o < o1; o += 32) {
+        if (bd.off_pose[wd.kf_off + bd.obs_kf[base + o]] < 0) continue;
+        double jl[9], jp[18];
+#pragma unroll
+        for (int q = 0; q < 9; ++q) jl[q] = bd.jl[q * T + base + o];
+#pragma unroll
+        for (int q = 0; q < 18; ++q) jp[q] = bd.jp[q * T + base + o];
+#pragma unroll
+        for (int r = 0; r < 6; ++r) {
+            const double e0 = jp[r] * jl[0] + jp[6 + r] * jl[3] + jp[12 + r] * jl[6];
+            const double e1 = jp[r] * jl[1] + jp[6 + r] * jl[4] + jp[12 + r] * jl[7];
+            const double e2 = jp[r] * jl[2] + jp[6 + r] * jl[5] + jp[12 + r] * jl[8];
+            bd.vobs[(3 * r + 0) * T + base + o] = e0 * i00;
+            bd.vobs[(3 * r + 1) * T + base + o] = e0 * i10 + e1 * i11;
+            bd.vobs[(3 * r + 2) * T + base + o] = e0 * i20 + e1 * i21 + e2 * i22;
+        }
+    }
+}
+
+// =====================================================================================================================
+// Schur complement accumulation as a dense SYRK on the FP64 tensor cores:
+//   Sred = sum_j V_j V_j^T   with V_j the (n_f + 1) x 3 column block of landmark j (rows = pose rows of its
+//   observations, plus the right-hand-side row z_j^T).  CTA = 64x64 output block x a range of landmark chunks;
+//   the V panel of a chunk (32 landmarks = 96 columns) is scattered into shared memory, then mma.sync m8n8k4 f64.
+// =====================================================================================================================
+constexpr int kLC = 32;            // landmarks per chunk
+constexpr int kKC = 3 * kLC;       // panel columns per chunk
+constexpr int kKS = kKC + 4;       // panel row stride in doubles (== 4 mod 16 -> conflict-free fragment loads)
+
+__device__ __forceinline__ void dmma(double& c0, double& c1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                 : "+d"(c0), "+d"(c1)
+                 : "d"(a), "d"(b));
+}
+
+__global__ void __launch_bounds__(256, 2) k_schur_syrk(BatchDev bd) {
+    const int w = blockIdx.z;
+    const WinState& st = bd.state[w];
+    if (st.phase != PH_ITERATE || st.solve_failed) return;
+    const WinDesc& wd = bd.desc[w];
+    // block pair (bi >= bj) from the linear index
+    int bi = 0, rem = blockIdx.x;
+    while (rem > bi) { rem -= bi + 1; ++bi; }
+    const int bj = rem;
+    const int nrows = st.n_f + 1;  // pose rows + rhs row
+    if (bi * 64 >= nrows) return;
+    const bool diag = (bi == bj);
+    extern __shared__ double smem[];
+    double* pa = smem;                       // 64 x kKS
+    double* pb = diag ? pa : smem + 64 * kKS;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    double acc[8][2];
+#pragma unroll
+    for (int t = 0; t < 8; ++t) acc[t][0] = acc[t][1] = 0.0;
+    const int* lm_ptr = bd.lm_ptr + wd.lm_off + w;
+    const size_t T = (size_t)bd.tot_obs, base = (size_t)wd.obs_off;
+    const int rhs_row = st.n_f;
+    const int ra0 = bi * 64, rb0 = bj * 64;
+    // chunks of this CTA: split p of p_split
+    const int per = (wd.n_chunks + bd.p_split - 1) / bd.p_split;
+    const int ch0 = blockIdx.y * per, ch1 = min(wd.n_chunks, ch0 + per);
+    for (int ch = ch0; ch < ch1; ++ch) {
+        const int j0 = bd.chunk_lm0[wd.chunk_off + ch], j1 = bd.chunk_lm1[wd.chunk_off + ch];
+        const int o0 = lm_ptr[j0], o1 = lm_ptr[j1];
+        __syncthreads();  // previous chunk's MMA done before the panel is overwritten
+        for (int i = threadIdx.x; i < (diag ? 1 : 2) * 64 * kKS; i += blockDim.x) smem[i] = 0.0;
+        __syncthreads();
+        // scatter V_i (6x3) into the panel(s)
+        const int nobs = o1 - o0;
+        for (int idx = threadIdx.x; idx < nobs * 18; idx += blockDim.x) {
+            const int e = idx / nobs, oo = idx - e * nobs;
+            const size_t o = base + o0 + oo;
+            const int jl = bd.obs_lm[o];
+            if (!bd.lm_active[wd.lm_off + jl]) continue;
+            const int off = bd.off_pose[wd.kf_off + bd.obs_kf[o]];
+            if (off < 0) continue;
+            const int row = off + e / 3, col = 3 * (jl - j0) + e % 3;
+            const double v = bd.vobs[e * T + o];
+            if (row >= ra0 && row < ra0 + 64) pa[(row - ra0) * kKS + col] = v;
+            if (!diag && row >= rb0 && row < rb0 + 64) pb[(row - rb0) * kKS + col] = v;
+        }
+        // rhs row: z_j
+        for (int idx = threadIdx.x; idx < (j1 - j0) * 3; idx += blockDim.x) {
+            const int jl = j0 + idx / 3;
+            if (!bd.lm_active[wd.lm_off + jl] || lm_ptr[jl + 1] <= lm_ptr[jl]) continue;
+            const double v = bd.lm_z[3 * (size_t)(wd.lm_off + jl) + idx % 3];
+            if (rhs_row >= ra0 && rhs_row < ra0 + 64) pa[(rhs_row - ra0) * kKS + idx] = v;
+            if (!diag && rhs_row >= rb0 && rhs_row < rb0 + 64) pb[(rhs_row - rb0) * kKS + idx] = v;
+        }
+        __syncthreads();
+        const double* arow = pa + (8 * warp + (lane >> 2)) * kKS + (lane & 3);
+        const double* brow = pb + (lane >> 2) * kKS + (lane & 3);
+#pragma unroll 4
+        for (int kk = 0; kk < kKC; kk += 4) {
+            const double a = arow[kk];
+#pragma unroll
+            for (int t = 0; t < 8; ++t) {
+                if (diag && t > warp) continue;
+                const double b = brow[t * 8 * kKS + kk];
+                dmma(acc[t][0], acc[t][1], a, b);
+            }
+        }
+    }
+    // store the partial block (row-major, leading dimension nr_cap)
+    double* out = bd.sred + wd.s_off * (size_t)bd.p_split + (size_t)blockIdx.y * wd.nr_cap * wd.nr_cap;
+    const int row = ra0 + 8 * warp + (lane >> 2);
+#pragma unroll
+    for (int t = 0; t < 8; ++t) {
+        if (diag && t > warp) continue;
+        const int col = rb0 + 8 * t + 2 * (lane & 3);
+        out[(size_t)row * wd.nr_cap + col] = acc[t][0];
+        out[(size_t)row * wd.nr_cap + col + 1] = acc[t][1];
+    }
+}
+
+// =====================================================================================================================
+// reduced system: assemble S = F + Lambda - sum V V^T (+ rhs as an augmented row), blocked Cholesky in place, solve,
+// candidate poses.  One CTA per window.
+// =====================================================================================================================
+constexpr int kNB = 32;  // Cholesky block size
+
+// PoseRegularization residual |(T1 T0^-1).t| - s0 with local Jacobians (reference cost_functors_ceres.hpp:224-250).
+__device__ void scale_regulariser(const double* p1, const double* p0, double s0, double& r, double* j1, double* j0) {
+    double R1[9], R0[9];
+    quat_to_rot<double>(p1, R1);
+    quat_to_rot<double>(p0, R0);
+    const double* t1 = p1 + 4, *t0 = p0 + 4;
+    double c[3], rc[3], d[3];
+    for (int i = 0; i < 3; ++i) c[i] = R0[i] * t0[0] + R0[3 + i] * t0[1] + R0[6 + i] * t0[2];          // R0^T t0
+    for (int i = 0; i < 3; ++i) rc[i] = R1[3 * i] * c[0] + R1[3 * i + 1] * c[1] + R1[3 * i + 2] * c[2];  // R1 c
+    for (int i = 0; i < 3; ++i) d[i] = t1[i] - rc[i];
+    const double nrm = sqrt(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);
+    r = nrm - s0;
+    if (!j1) return;
+    const double u[3] = {d[0] / nrm, d[1] / nrm, d[2] / nrm};
+    // dd/d(dr1) = 2 [R1 c]x -> u^T 2 [rc]x = 2 (u x rc)^T ... (u^T [a]x = (u x a)^T)
+    j1[0] = 2.0 * (u[1] * rc[2] - u[2] * rc[1]);
+    j1[1] = 2.0 * (u[2] * rc[0] - u[0] * rc[2]);
+    j1[2] = 2.0 * (u[0] * rc[1] - u[1] * rc[0]);
+    j1[3] = u[0]; j1[4] = u[1]; j1[5] = u[2];
+    // dd/d(dt0) = -R1 R0^T ;  dd/d(dr0) = -2 R1 R0^T [t0]x
+    double ur[3];  // u^T R1 R0^T  = (R0 R1^T u)^T
+    double tmp[3];
+    for (int i = 0; i < 3; ++i) tmp[i] = R1[i] * u[0] + R1[3 + i] * u[1] + R1[6 + i] * u[2];               // R1^T u
+    for (int i = 0; i < 3; ++i) ur[i] = R0[3 * i] * tmp[0] + R0[3 * i + 1] * tmp[1] + R0[3 * i + 2] * tmp[2];  // R0 R1^T u
+    j0[3] = -ur[0]; j0[4] = -ur[1]; j0[5] = -ur[2];
+    j0[0] = -2.0 * (ur[1] * t0[2] - ur[2] * t0[1]);
+    j0[1] = -2.0 * (ur[2] * t0[0] - ur[0] * t0[2]);
+    j0[2] = -2.0 * (ur[0] * t0[1] - ur[1] * t0[0]);
+}
+
+__global__ void __launch_bounds__(512, 1) k_reduced_solve(BatchDev bd, SolveParams sp) {
+    const int w = blockIdx.x;
+    WinState& st = bd.state[w];
+    if (st.phase != PH_ITERATE) return;
+    const WinDesc& wd = bd.desc[w];
+    const int tid = threadIdx.x, nth = blockDim.x;
+    const int n = st.n_f, ld = wd.nr_cap;
+    double* A = bd.amat + wd.s_off;
+    extern __shared__ double sm[];
+    double* s_fdiag = sm;                 // [ld] squared column norms of J (f part)
+    double* s_g = s_fdiag + ld;           // [ld] gradient J^T r (f part)
+    double* s_y = s_g + ld;               // [ld]
+    double* s_lam = s_y + ld;             // [ld]
+    double* s_D = s_lam + ld;             // [kNB][kNB+1]
+    double* s_P = s_D + kNB * (kNB + 1);  // [ld][kNB+1] panel
+    __shared__ int s_fail;
+    __shared__ double s_red[16][4];
+    if (tid == 0) s_fail = 0;
+
+    // ---- cost at x and evaluation failure (fresh linearisation only) ----
+    if (st.need_linearize && tid == 0) {
+        double c = 0.0;
+        for (int q = 0; q < bd.cost_parts; ++q) c += bd.cost_part_x[(size_t)w * bd.cost_parts + q];
+        st.x_cost = c;  // regulariser cost added below
+    }
+    __syncthreads();
+    if (st.eval_failed) {  // only reachable at iteration zero: "Residual and Jacobian evaluation failed."
+        if (tid == 0) st.solve_failed = 2;
+        return;
+    }
+    if (st.solve_failed) return;  // landmark block not positive definite -> invalid step
+
+    for (int i = tid; i < ld; i += nth) { s_fdiag[i] = 0.0; s_g[i] = 0.0; }
+    // ---- A(lower, rows 0..n incl. augmented row n) = - sum_p Sred_p ----
+    {
+        const double* sp0 = bd.sred + wd.s_off * (size_t)bd.p_split;
+        const size_t pstride = (size_t)ld * ld;
+        for (int idx = tid; idx < (n + 1) * ld; idx += nth) {
+            const int r = idx / ld, c = idx - r * ld;
+            if (c > r || c >= n + 1) continue;
+            double s = 0.0;
+            for (int p = 0; p < bd.p_split; ++p) s += sp0[p * pstride + (size_t)r * ld + c];
+            A[(size_t)r * ld + c] = -s;
+        }
+    }
+    __syncthreads();
+    // ---- + per-keyframe Gauss-Newton blocks ----
+    for (int idx = tid; idx < wd.n_kf * 27; idx += nth) {
+        const int k = idx / 27, q = idx - 27 * k;
+        const int off = bd.off_pose[wd.kf_off + k];
+        if (off < 0) continue;
+        const double v = bd.bkf[(size_t)(wd.kf_off + k) * 27 + q];
+        if (q < 21) {
+            int a = 0, rem = q;
+            while (rem >= 6 - a) { rem -= 6 - a; ++a; }
+            const int b = a + rem;  // a <= b
+            A[(size_t)(off + b) * ld + off + a] += v;
+            if (a == b) s_fdiag[off + a] = v;
+        } else {
+            s_g[off + q - 21] = v;
+        }
+    }
+    __syncthreads();
+    // ---- regularisers (thread 0; a handful of residuals) ----
+    if (tid == 0 && wd.scale_weight > 0) {
+        const double* P = bd.pose[st.cur];
+        double r, j1[6], j0[6];
+        scale_regulariser(P + 7 * (size_t)(wd.kf_off + wd.scale_kf1), P + 7 * (size_t)(wd.kf_off + wd.scale_kf0),
+                          wd.scale_value, r, j1, j0);
+        const double sq = sqrt(wd.scale_weight);  // TrivialLoss * weight: rho' = w
+        if (st.need_linearize) st.x_cost += 0.5 * wd.scale_weight * r * r;
+        const int o1 = bd.off_pose[wd.kf_off + wd.scale_kf1], o0 = bd.off_pose[wd.kf_off + wd.scale_kf0];
+        double J[12]; int cols[12]; int m = 0;
+        if (o1 >= 0) for (int a = 0; a < 6; ++a) { J[m] = sq * j1[a]; cols[m++] = o1 + a; }
+        if (o0 >= 0) for (int a = 0; a < 6; ++a) { J[m] = sq * j0[a]; cols[m++] = o0 + a; }
+        const double rr = sq * r;
+        for (int a = 0; a < m; ++a) {
+            for (int b = 0; b < m; ++b)
+                if (cols[b] <= cols[a]) A[(size_t)cols[a] * ld + cols[b]] += J[a] * J[b];
+            s_fdiag[cols[a]] += J[a] * J[a];
+            s_g[cols[a]] += J[a] * rr;
+        }
+    }
+    __syncthreads();
+    // ---- Jacobi scaling, damping, augmented row ----
+    double* scale_f = bd.scale_f + (size_t)w * bd.nr_cap_max;
+    double* lambda_f = bd.lambda_f + (size_t)w * bd.nr_cap_max;
+    double* grad_f = bd.grad_f + (size_t)w * bd.nr_cap_max;
+    for (int c = tid; c < n; c += nth) {
+        double s;
+        if (st.iter0) { s = 1.0 / (1.0 + sqrt(s_fdiag[c])); scale_f[c] = s; }
+        else s = scale_f[c];
+        const double s2 = s * s;
+        const double lam = fmin(fmax(s_fdiag[c] * s2, sp.min_lm_diagonal), sp.max_lm_diagonal) / (st.radius * s2);
+        s_lam[c] = lam;
+        lambda_f[c] = lam;
+        grad_f[c] = s_g[c];
+        A[(size_t)c * ld + c] += lam;
+        A[(size_t)n * ld + c] += s_g[c];  // augmented row: g_f - V z
+    }
+    __syncthreads();
+
+    // ---- blocked right-looking Cholesky of A[0..n) with the augmented row n carried along ----
+    const int PS = kNB + 1;
+    for (int kb = 0; kb < n; kb += kNB) {
+        const int nb = min(kNB, n - kb);
+        for (int idx = tid; idx < nb * nb; idx += nth) {
+            const int r = idx / nb, c = idx - r * nb;
+            s_D[r * PS + c] = (c <= r) ? A[(size_t)(kb + r) * ld + kb + c] : 0.0;
+        }
+        __syncthreads();
+        if (tid < 32) {  // factor the diagonal block with one warp: lane = row
+            const int lane = tid;
+            for (int j = 0; j < nb; ++j) {
+                const double djj = s_D[j * PS + j];
+                if (!(djj > 0.0) || !isfinite(djj)) { if (lane == 0) s_fail = 1; break; }
+                const double piv = sqrt(djj);
+                __syncwarp();
+                if (lane == j) s_D[j * PS + j] = piv;
+                if (lane > j && lane < nb) s_D[lane * PS + j] /= piv;
+                __syncwarp();
+                if (lane > j && lane < nb) {
+                    const double lij = s_D[lane * PS + j];
+                    for (int c = j + 1; c <= lane; ++c) s_D[lane * PS + c] -= lij * s_D[c * PS + j];
+                }
+                __syncwarp();
+            }
+        }
+        __syncthreads();
+        if (s_fail) break;
+        for (int idx = tid; idx < nb * nb; idx += nth) {
+            const int r = idx / nb, c = idx - r * nb;
+            if (c <= r) A[(size_t)(kb + r) * ld + kb + c] = s_D[r * PS + c];
+        }
+        // panel: rows below the block, including the augmented row n
+        const int r0 = kb + nb, m = n + 1 - r0;
+        for (int i = tid; i < m; i += nth) {
+            double x[kNB];
+            const double* arow = A + (size_t)(r0 + i) * ld + kb;
+            for (int c = 0; c < nb; ++c) x[c] = arow[c];
+            for (int c = 0; c < nb; ++c) {
+                double s = x[c];
+                for (int q = 0; q < c; ++q) s -= x[q] * s_D[c * PS + q];
+                x[c] = s / s_D[c * PS + c];
+            }
+            double* aw = A + (size_t)(r0 + i) * ld + kb;
+            for (int c = 0; c < nb; ++c) { aw[c] = x[c]; s_P[i * PS + c] = x[c]; }
+        }
+        __syncthreads();
+        // trailing update: A[r0+i][r0+j] -= P[i] . P[j], j <= i, skipping the (n, n) corner
+        const long long ntri = (long long)m * (m + 1) / 2;
+        for (long long idx = tid; idx < ntri; idx += nth) {
+            int i = (int)((sqrt(8.0 * (double)idx + 1.0) - 1.0) * 0.5);
+            while ((long long)(i + 1) * (i + 2) / 2 <= idx) ++i;
+            while ((long long)i * (i + 1) / 2 > idx) --i;
+            const int j = (int)(idx - (long long)i * (i + 1) / 2);
+            if (i == m - 1 && j == m - 1) continue;
+            double s = 0.0;
+            for (int c = 0; c < nb; ++c) s += s_P[i * PS + c] * s_P[j * PS + c];
+            A[(size_t)(r0 + i) * ld + r0 + j] -= s;
+        }
+        __syncthreads();
+    }
+    if (s_fail) {
+        if (tid == 0) st.solve_failed = 1;
+        return;
+    }
+    // ---- back substitution L^T d = y (y = augmented row), delta_f = -d ----
+    for (int c = tid; c < n; c += nth) s_y[c] = A[(size_t)n * ld + c];
+    __syncthreads();
+    for (int i = n - 1; i >= 0; --i) {
+        const double di = s_y[i] / A[(size_t)i * ld + i];
+        __syncthreads();
+        if (tid == 0) s_y[i] = di;
+        for (int k = tid; k < i; k += nth) s_y[k] -= A[(size_t)i * ld + k] * di;
+        __syncthreads();
+    }
+    double* delta_f = bd.delta_f + (size_t)w * bd.nr_cap_max;
+    double model = 0.0;
+    int bad = 0;
+    for (int c = tid; c < n; c += nth) {
+        const double d = -s_y[c];
+        delta_f[c] = d;
+        if (!isfinite(d)) bad = 1;
+        model += -s_g[c] * d + s_lam[c] * d * d;
+    }
+    // ---- candidate poses, step / state norms, gradient max-norm of the pose blocks ----
+    double step_sq = 0.0, xn_sq = 0.0, gmax = 0.0;
+    const double* Pc = bd.pose[st.cur];
+    double* Pn = bd.pose[1 - st.cur];
+    for (int k = tid; k < wd.n_kf; k += nth) {
+        const double* p = Pc + 7 * (size_t)(wd.kf_off + k);
+        double* q = Pn + 7 * (size_t)(wd.kf_off + k);
+        const int off = bd.off_pose[wd.kf_off + k];
+        if (off < 0) {
+            for (int i = 0; i < 7; ++i) q[i] = p[i];
+            continue;
+        }
+        double d[6], gneg[6], out[7];
+        for (int i = 0; i < 6; ++i) { d[i] = -s_y[off + i]; gneg[i] = -s_g[off + i]; }
+        pose_plus(p, d, out);
+        for (int i = 0; i < 7; ++i) { q[i] = out[i]; const double e = out[i] - p[i]; step_sq += e * e; xn_sq += p[i] * p[i]; }
+        pose_plus(p, gneg, out);
+        for (int i = 0; i < 7; ++i) gmax = fmax(gmax, fabs(out[i] - p[i]));
+    }
+    model = warp_sum(model); step_sq = warp_sum(step_sq); xn_sq = warp_sum(xn_sq); gmax = warp_max(gmax);
+    if (bad) s_fail = 1;
+    if ((tid & 31) == 0) { s_red[tid >> 5][0] = model; s_red[tid >> 5][1] = step_sq; s_red[tid >> 5][2] = xn_sq; s_red[tid >> 5][3] = gmax; }
+    __syncthreads();
+    if (tid == 0) {
+        double a = 0, b = 0, c = 0, g = 0;
+        for (int q = 0; q < (nth >> 5); ++q) { a += s_red[q][0]; b += s_red[q][1]; c += s_red[q][2]; g = fmax(g, s_red[q][3]); }
+        st.f_model = a; st.f_step_sq = b; st.f_xnorm_sq = c; st.f_gmax = g;
+        if (s_fail) st.solve_failed = 1;
+    }
+}
+
+// =====================================================================================================================
+// back-substitution: delta_p_j = -L^-T (z_j + sum_i V_i^T delta_f,i); candidate landmarks; deterministic partial sums
+// =====================================================================================================================
+__global__ void __launch_bounds__(256) k_backsub(BatchDev bd) {
+    const int w = blockIdx.y;
+    const WinState& st = bd.state[w];
+    if (st.phase != PH_ITERATE) return;
+    const WinDesc& wd = bd.desc[w];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int j = blockIdx.x * 8 + warp;
+    __shared__ double s_red[8][4];
+    double model = 0.0, step_sq = 0.0, xn_sq = 0.0, gmax = 0.0;
+    if (j < wd.n_lm) {
+        const int L = wd.lm_off + j;
+        const double* pc = bd.lm[st.cur] + 3 * (size_t)L;
+        double* pn = bd.lm[1 - st.cur] + 3 * (size_t)L;
+        const int* lm_ptr = bd.lm_ptr + wd.lm_off + w;
+        const int o0 = lm_ptr[j], o1 = lm_ptr[j + 1];
+        const bool in = bd.lm_active[L] && o1 > o0;
+        if (!in || st.solve_failed) {
+            if (lane < 3) pn[lane] = pc[lane];
+        } else {
+            const size_t T = (size_t)bd.tot_obs, base = (size_t)wd.obs_off;
+            const double* delta_f = bd.delta_f + (size_t)w * bd.nr_cap_max;
+            double t[3] = {0, 0, 0};
+            for (int o = o0 + lane; o < o1; o += 32) {
+                const int off = bd.off_pose[wd.kf_off + bd.obs_kf[base + o]];
+                if (off < 0) continue;
+#pragma unroll
+                for (int r = 0; r < 6; ++r) {
+                    const double d = delta_f[off + r];
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) t[c] += bd.vobs[(3 * r + c) * T + base + o] * d;
+                }
+            }
+#pragma unroll
+            for (int c = 0; c < 3; ++c) t[c] = warp_sum(t[c]);
+            const double* z = bd.lm_z + 3 * (size_t)L;
+            const double* li = bd.lm_linv + 6 * (size_t)L;  // i00; i10 i11; i20 i21 i22
+            const double t0 = t[0] + z[0], t1 = t[1] + z[1], t2 = t[2] + z[2];
+            // delta_p = -Linv^T t
+            const double d0 = -(li[0] * t0 + li[1] * t1 + li[3] * t2);
+            const double d1 = -(li[2] * t1 + li[4] * t2);
+            const double d2 = -(li[5] * t2);
+            const double* g = bd.lm_g + 3 * (size_t)L;
+            const double* lam = bd.lm_lambda + 3 * (size_t)L;
+            if (lane == 0) {
+                pn[0] = pc[0] + d0; pn[1] = pc[1] + d1; pn[2] = pc[2] + d2;
+                model = -(g[0] * d0 + g[1] * d1 + g[2] * d2) + lam[0] * d0 * d0 + lam[1] * d1 * d1 + lam[2] * d2 * d2;
+                step_sq = d0 * d0 + d1 * d1 + d2 * d2;
+                xn_sq = pc[0] * pc[0] + pc[1] * pc[1] + pc[2] * pc[2];
+                gmax = fmax(fabs(g[0]), fmax(fabs(g[1]), fabs(g[2])));
+                if (!isfinite(d0) || !isfinite(d1) || !isfinite(d2)) model = nan("");
+            }
+        }
+    }
+    if (lane == 0) { s_red[warp][0] = model; s_red[warp][1] = step_sq; s_red[warp][2] = xn_sq; s_red[warp][3] = gmax; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double a = 0, b = 0, c = 0, g = 0;
+        for (int q = 0; q < 8; ++q) { a += s_red[q][0]; b += s_red[q][1]; c += s_red[q][2]; g = fmax(g, s_red[q][3]); }
+        double* out = bd.bs_part + ((size_t)w * bd.bs_parts + blockIdx.x) * 4;
+        out[0] = a; out[1] = b; out[2] = c; out[3] = g;
+    }
+}
+
+// =====================================================================================================================
+// LM controller: one thread per window.  Mirrors ceres 1.13 TrustRegionMinimizer + LevenbergMarquardtStrategy as
+// restated in SURVEY.md A.6, and the solveTrimmed outer loop (reference robust_solving.cpp:140-248).
+// =====================================================================================================================
+__device__ void log_iter(BatchDev& bd, int w, WinState& st, double cost, double cost_change, double gmax,
+                         double step_norm, double rel, double radius, int valid, int successful) {
+    if (st.log_n >= kIterLogCap) return;
+    IterRecord& e = bd.log[(size_t)w * kIterLogCap + st.log_n++];
+    e.cost = cost; e.cost_change = cost_change; e.gradient_max_norm = gmax; e.step_norm = step_norm;
+    e.relative_decrease = rel; e.radius = radius; e.iteration = st.iteration; e.solve_index = st.solve_index;
+    e.valid = valid; e.successful = successful;
+}
+
+__device__ void solve_end(WinState& st, int termination) {
+    SolveSummary& s = st.solves[st.solve_index];
+    s.termination = termination;
+    s.num_iterations = st.iteration;
+    st.n_solves = st.solve_index + 1;
+    if (st.is_final) { st.phase = PH_DONE; return; }
+    if (s.initial_cost - s.final_cost <= 0.0 && !st.retried) {  // robust_solving.cpp:172-181
+        st.retried = 1;
+        st.phase = PH_SOLVE_BEGIN;
+        return;
+    }
+    st.phase = PH_TRIM;
+}
+
+__global__ void __launch_bounds__(128) k_lm_update(BatchDev bd, SolveParams sp) {
+    const int w = blockIdx.x * blockDim.x + threadIdx.x;
+    if (w >= bd.n_win) return;
+    WinState& st = bd.state[w];
+    if (st.phase != PH_ITERATE) return;
+    const WinDesc& wd = bd.desc[w];
+    SolveSummary& sum = st.solves[st.solve_index];
+    if (st.solve_failed == 2) {  // evaluation failed at iteration zero
+        sum.initial_cost = sum.final_cost = -1.0;
+        st.solve_failed = 0; st.eval_failed = 0;
+        solve_end(st, 2);
+        return;
+    }
+    const int cand_eval_failed = st.eval_failed;  // set by the candidate cost pass of THIS pass (|z| < 0.01)
+    st.eval_failed = 0;
+    // reduce the landmark-side partials (fixed order)
+    double e_model = 0, e_step = 0, e_xn = 0, e_g = 0;
+    for (int q = 0; q < (wd.n_lm + 7) / 8; ++q) {
+        const double* p = bd.bs_part + ((size_t)w * bd.bs_parts + q) * 4;
+        e_model += p[0]; e_step += p[1]; e_xn += p[2]; e_g = fmax(e_g, p[3]);
+    }
+    const bool step_ok = !st.solve_failed;
+    if (st.need_linearize) {  // a fresh linearisation was evaluated in this pass
+        if (step_ok || st.iter0) {
+            st.gmax = fmax(st.f_gmax, e_g);
+            st.x_norm = sqrt(st.f_xnorm_sq + e_xn);
+        }
+        if (st.iter0) {
+            sum.initial_cost = sum.final_cost = st.x_cost;
+            log_iter(bd, w, st, st.x_cost, 0, st.gmax, 0, 0, st.radius, 0, 0);
+        } else {
+            if (st.x_cost < sum.final_cost) sum.final_cost = st.x_cost;
+            // complete the record of the successful iteration that led here
+            if (st.log_n > 0) {
+                IterRecord& e = bd.log[(size_t)w * kIterLogCap + st.log_n - 1];
+                e.cost = st.x_cost; e.gradient_max_norm = st.gmax;
+            }
+        }
+    }
+    // ---- loop head of the next iteration (FinalizeIterationAndCheckIfMinimizerCanContinue) ----
+    if (st.iteration >= st.max_iter) { st.solve_failed = 0; solve_end(st, 1); return; }
+    if (st.last_successful && st.gmax <= sp.gradient_tolerance) { st.solve_failed = 0; solve_end(st, 0); return; }
+    if (st.radius <= sp.min_radius) { st.solve_failed = 0; solve_end(st, 0); return; }
+    st.iteration++;
+    st.last_successful = 0;
+    // ---- step validity ----
+    const double model_change = 0.5 * (st.f_model + e_model);
+    const bool valid = step_ok && isfinite(model_change) && model_change > 0.0;
+    if (!valid) {
+        st.solve_failed = 0;
+        if (++st.num_invalid >= sp.max_consecutive_invalid_steps) { solve_end(st, 2); return; }
+        st.radius /= st.decrease_factor; st.decrease_factor *= 2.0;
+        st.need_linearize = 0; st.iter0 = 0;
+        log_iter(bd, w, st, st.x_cost, 0, st.gmax, 0, 0, st.radius, 0, 0);
+        return;
+    }
+    st.num_invalid = 0;
+    // ---- candidate cost ----
+    double cand = 0.0;
+    for (int q = 0; q < bd.cost_parts; ++q) cand += bd.cost_part_c[(size_t)w * bd.cost_parts + q];
+    if (wd.scale_weight > 0) {
+        const double* P = bd.pose[1 - st.cur];
+        double r;
+        scale_regulariser(P + 7 * (size_t)(wd.kf_off + wd.scale_kf1), P + 7 * (size_t)(wd.kf_off + wd.scale_kf0),
+                          wd.scale_value, r, nullptr, nullptr);
+        cand += 0.5 * wd.scale_weight * r * r;
+    }
+    if (cand_eval_failed) cand = DBL_MAX;  // "Step failed to evaluate": infinite cost -> rejected
+    const double step_norm = sqrt(st.f_step_sq + e_step);
+    if (step_norm <= sp.parameter_tolerance * (st.x_norm + sp.parameter_tolerance)) {
+        log_iter(bd, w, st, st.x_cost, 0, st.gmax, step_norm, 0, st.radius, 1, 0);
+        solve_end(st, 0);
+        return;
+    }
+    const double cost_change = st.x_cost - cand;
+    if (fabs(cost_change) <= sp.function_tolerance * st.x_cost) {
+        log_iter(bd, w, st, st.x_cost, cost_change, st.gmax, step_norm, 0, st.radius, 1, 0);
+        solve_end(st, 0);
+        return;
+    }
+    const double rel = cost_change / model_change;
+    if (rel > sp.min_relative_decrease) {
+        st.cur = 1 - st.cur;
+        st.need_linearize = 1; st.iter0 = 0; st.last_successful = 1;
+        sum.num_successful_steps++;
+        const double t = 2.0 * rel - 1.0;
+        st.radius = fmin(sp.max_radius, st.radius / fmax(1.0 / 3.0, 1.0 - t * t * t));
+        st.decrease_factor = 2.0;
+        log_iter(bd, w, st, cand, cost_change, st.gmax, step_norm, rel, st.radius, 1, 1);
+    } else {
+        st.radius /= st.decrease_factor; st.decrease_factor *= 2.0;
+        st.need_linearize = 0; st.iter0 = 0;
+        log_iter(bd, w, st, cand, cost_change, st.gmax, step_norm, rel, st.radius, 1, 0);
+    }
+}
+
+// =====================================================================================================================
+// trimming (reference robust_solving.cpp:67-125, trimmer_quantile.hpp:40-63)
+// =====================================================================================================================
+// per-landmark maximum of the un-robustified block norms, per residual group (0 depth, 1 reprojection, 2 ground plane)
+__global__ void __launch_bounds__(256) k_trim_eval(BatchDev bd, SolveParams sp) {
+    const int w = blockIdx.y;
+    const WinState& st = bd.state[w];
+    if (st.phase != PH_TRIM) return;
+    const WinDesc& wd = bd.desc[w];
+    __shared__ double s_pose[kMaxKf * kPoseStride];
+    __shared__ double s_cam[kMaxCam * kCamStride];
+    stage_window(wd, bd.pose[st.cur], bd.cam, s_pose, s_cam);
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const int j = blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (j >= wd.n_lm) return;
+    const int L = wd.lm_off + j;
+    double m_d = -1.0, m_r = -1.0;
+    if (bd.lm_active[L]) {
+        const int* lm_ptr = bd.lm_ptr + wd.lm_off + w;
+        const double* lm = bd.lm[st.cur] + 3 * (size_t)L;
+        const double p[3] = {lm[0], lm[1], lm[2]};
+        for (int o = lm_ptr[j] + lane; o < lm_ptr[j + 1]; o += 32) {
+            const size_t oo = (size_t)wd.obs_off + o;
+            double r[3], raw[2], hr;
+            if (!eval_observation<double, false>(s_pose + kPoseStride * bd.obs_kf[oo], s_cam + kCamStride * bd.obs_cam[oo],
+                                                 p, (double)bd.obs_u[oo], (double)bd.obs_v[oo], (double)bd.obs_d[oo],
+                                                 bd.lm_weight[L], sp.reprojection_thres * sp.reprojection_thres,
+                                                 sp.depth_thres * sp.depth_thres, r, nullptr, nullptr, hr, raw))
+                continue;
+            m_r = fmax(m_r, raw[0]);
+            m_d = fmax(m_d, raw[1]);
+        }
+        m_r = warp_max(m_r);
+        m_d = warp_max(m_d);
+    }
+    if (lane == 0) {
+        bd.trim_val[0 * (size_t)bd.tot_lm + L] = m_d;
+        bd.trim_val[1 * (size_t)bd.tot_lm + L] = m_r;
+        bd.trim_val[2 * (size_t)bd.tot_lm + L] = -1.0;
+    }
+}
+
+// quantile rejection per group by exact rank (ties broken by landmark index), then start the next solve
+__global__ void __launch_bounds__(512) k_trim_select(BatchDev bd, SolveParams sp) {
+    const int w = blockIdx.x;
+    WinState& st = bd.state[w];
+    if (st.phase != PH_TRIM) return;
+    const WinDesc& wd = bd.desc[w];
+    __shared__ int s_n;
+    const double quant[3] = {sp.depth_quantile, sp.reprojection_quantile, 1.0};
+    for (int j = threadIdx.x; j < wd.n_lm; j += blockDim.x) bd.trim_reject[wd.lm_off + j] = 0;
+    for (int g = 0; g < 3; ++g) {
+        const double* v = bd.trim_val + g * (size_t)bd.tot_lm + wd.lm_off;
+        if (threadIdx.x == 0) s_n = 0;
+        __syncthreads();
+        int cnt = 0;
+        for (int j = threadIdx.x; j < wd.n_lm; j += blockDim.x) cnt += (v[j] >= 0.0);
+        atomicAdd(&s_n, cnt);
+        __syncthreads();
+        const int N = s_n;
+        __syncthreads();
+        if (N == 0 || N < sp.min_residual_groups) continue;
+        const int num = (int)((double)N * quant[g]);
+        if (num >= N) continue;
+        for (int j = threadIdx.x; j < wd.n_lm; j += blockDim.x) {
+            const double vj = v[j];
+            if (!(vj >= 0.0)) continue;
+            int rank = 0;
+            for (int k = 0; k < wd.n_lm; ++k) {
+                const double vk = v[k];
+                rank += (vk >= 0.0) && (vk < vj || (vk == vj && k < j));
+            }
+            if (rank >= num) bd.trim_reject[wd.lm_off + j] = 1;
+        }
+    }
+    __syncthreads();
+    for (int j = threadIdx.x; j < wd.n_lm; j += blockDim.x)
+        if (bd.trim_reject[wd.lm_off + j]) bd.lm_active[wd.lm_off + j] = 0;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        st.round++;
+        st.retried = 0;
+        st.solve_index++;
+        st.is_final = (st.round >= st.rounds_total) || (st.solve_index >= 7);
+        st.phase = PH_SOLVE_BEGIN;
+    }
+}
+
+__global__ void k_count_active(BatchDev bd) {
+    const int w = blockIdx.x * blockDim.x + threadIdx.x;
+    if (w >= bd.n_win) return;
+    if (bd.state[w].phase != PH_DONE) atomicAdd(bd.n_active, 1);
+}
+
+// reset of the solver state from the uploaded values
+__global__ void k_reset_state(BatchDev bd, int rounds_total_override, int min_landmarks_for_trimming, int num_rounds_option) {
+    const int w = blockIdx.x;
+    const WinDesc& wd = bd.desc[w];
+    for (int i = threadIdx.x; i < wd.n_kf * 7; i += blockDim.x) {
+        const double v = bd.pose0[(size_t)wd.kf_off * 7 + i];
+        bd.pose[0][(size_t)wd.kf_off * 7 + i] = v;
+        bd.pose[1][(size_t)wd.kf_off * 7 + i] = v;
+    }
+    for (int i = threadIdx.x; i < wd.n_lm * 3; i += blockDim.x) {
+        const double v = bd.lm0[(size_t)wd.lm_off * 3 + i];
+        bd.lm[0][(size_t)wd.lm_off * 3 + i] = v;
+        bd.lm[1][(size_t)wd.lm_off * 3 + i] = v;
+    }
+    for (int i = threadIdx.x; i < wd.n_lm; i += blockDim.x) bd.lm_active[wd.lm_off + i] = 1;
+    if (threadIdx.x == 0) {
+        WinState& st = bd.state[w];
+        st.phase = PH_SOLVE_BEGIN;
+        st.cur = 0;
+        st.solve_index = 0; st.round = 0; st.retried = 0; st.log_n = 0; st.n_solves = 0;
+        int rounds = rounds_total_override;
+        if (rounds < 0) rounds = (wd.n_lm > min_landmarks_for_trimming) ? num_rounds_option : 0;
+        if (rounds > 6) rounds = 6;
+        st.rounds_total = rounds;
+        st.is_final = (rounds == 0);
+        st.eval_failed = 0; st.solve_failed = 0;
+    }
+}
+
+// =====================================================================================================================
+// launch wrappers
+// =====================================================================================================================
+static inline size_t schur_smem() { return (size_t)2 * 64 * kKS * sizeof(double); }
+static inline size_t solve_smem(int ld) { return ((size_t)4 * ld + kNB * (kNB + 1) + (size_t)ld * (kNB + 1)) * sizeof(double); }
+
+cudaError_t configure_kernels(int nr_cap_max) {
+    cudaError_t e = cudaFuncSetAttribute(k_schur_syrk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)schur_smem());
+    if (e != cudaSuccess) return e;
+    return cudaFuncSetAttribute(k_reduced_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)solve_smem(nr_cap_max));
+}
+
+void launch_reset(const BatchDev& bd, const LaunchCfg& lc, cudaStream_t s) {
+    k_reset_state<<<bd.n_win, 256, 0, s>>>(bd, lc.rounds_override, lc.min_landmarks_for_trimming, lc.num_rounds_option);
+}
+
+void launch_pass(const BatchDev& bd, const SolveParams& sp, const LaunchCfg& lc, Counters* cnt, cudaStream_t s) {
+    const int B = bd.n_win;
+    const dim3 g_obs((bd.max_obs + 255) / 256, B);
+    const dim3 g_lm((bd.max_lm + 7) / 8, B);
+    k_solve_begin<<<B, 256, 0, s>>>(bd, sp);
+    if (lc.time_jacobian) cudaEventRecord(lc.ev0, s);
+    k_eval_obs<true><<<g_obs, 256, 0, s>>>(bd, sp);
+    if (lc.time_jacobian) cudaEventRecord(lc.ev1, s);
+    k_pose_hessian<<<dim3(bd.max_kf, B), 256, 0, s>>>(bd, sp);
+    k_landmark_prep<<<g_lm, 256, 0, s>>>(bd, sp);
+    const int nb = lc.nr_cap_max / 64;
+    k_schur_syrk<<<dim3(nb * (nb + 1) / 2, bd.p_split, B), 256, schur_smem(), s>>>(bd);
+    k_reduced_solve<<<B, 512, solve_smem(lc.nr_cap_max), s>>>(bd, sp);
+    k_backsub<<<g_lm, 256, 0, s>>>(bd);
+    k_eval_obs<false><<<g_obs, 256, 0, s>>>(bd, sp);
+    k_lm_update<<<(B + 127) / 128, 128, 0, s>>>(bd, sp);
+    k_trim_eval<<<g_lm, 256, 0, s>>>(bd, sp);
+    k_trim_select<<<B, 512, 0, s>>>(bd, sp);
+    if (cnt) {
+        cnt->launches_total += 11;
+        cnt->launches_jacobian += 1; cnt->launches_prep += 2; cnt->launches_schur += 1; cnt->launches_solve += 2;
+        cnt->launches_backsub += 1; cnt->launches_cost += 1; cnt->launches_update += 1; cnt->launches_trim += 2;
+    }
+}
+
+void launch_count_active(const BatchDev& bd, cudaStream_t s) {
+    cudaMemsetAsync(bd.n_active, 0, sizeof(int), s);
+    k_count_active<<<(bd.n_win + 127) / 128, 128, 0, s>>>(bd);
+}
+
+// stand-alone residual/Jacobian pass at the uploaded state (parity + roofline measurement)
+__global__ void k_force_linearize(BatchDev bd) {
+    const int w = blockIdx.x * blockDim.x + threadIdx.x;
+    if (w >= bd.n_win) return;
+    WinState& st = bd.state[w];
+    st.phase = PH_ITERATE; st.need_linearize = 1; st.iter0 = 1; st.cur = 0; st.eval_failed = 0; st.solve_failed = 0;
+}
+void launch_jacobian_only(const BatchDev& bd, const SolveParams& sp, cudaStream_t s) {
+    const dim3 g_obs((bd.max_obs + 255) / 256, bd.n_win);
+    k_eval_obs<true><<<g_obs, 256, 0, s>>>(bd, sp);
+}
+void launch_force_linearize(const BatchDev& bd, cudaStream_t s) {
+    k_solve_begin<<<bd.n_win, 256, 0, s>>>(bd, SolveParams{});  // layout (off_pose) for the eval entry point
+    k_force_linearize<<<(bd.n_win + 127) / 128, 128, 0, s>>>(bd);
+}
+
+}  // namespace kba

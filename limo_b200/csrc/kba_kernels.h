@@ -1,0 +1,31 @@
+// kba_kernels.h -- host-visible launch interface of kba_kernels.cu
+#pragma once
+#include <cuda_runtime.h>
+
+#include "kba_device.cuh"
+
+namespace kba {
+
+struct Counters {
+    long long launches_total = 0;
+    long long launches_jacobian = 0, launches_prep = 0, launches_schur = 0, launches_solve = 0, launches_backsub = 0,
+              launches_cost = 0, launches_update = 0, launches_trim = 0;
+    double ms_jacobian = 0.0;
+    long long jacobian_obs = 0;
+};
+
+struct LaunchCfg {
+    int nr_cap_max = 64;
+    int rounds_override = -1, min_landmarks_for_trimming = 100, num_rounds_option = 1;
+    bool time_jacobian = false;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+};
+
+cudaError_t configure_kernels(int nr_cap_max);
+void launch_reset(const BatchDev& bd, const LaunchCfg& lc, cudaStream_t s);
+void launch_pass(const BatchDev& bd, const SolveParams& sp, const LaunchCfg& lc, Counters* cnt, cudaStream_t s);
+void launch_count_active(const BatchDev& bd, cudaStream_t s);
+void launch_force_linearize(const BatchDev& bd, cudaStream_t s);
+void launch_jacobian_only(const BatchDev& bd, const SolveParams& sp, cudaStream_t s);
+
+}  // namespace kba

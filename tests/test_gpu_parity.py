@@ -1,0 +1,128 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the CPU oracle on identical inputs.
+
+Tolerances are the ones BASELINE.json's north_star states for FP64: pose translation <= 1e-6 m and cost
+relative <= 1e-8 against the reference solve (here: its restatement, see oracle/kba_oracle.h for what is pinned).
+"""
+import numpy as np
+import pytest
+
+from limo_b200 import geometry as g
+from limo_b200 import synth
+from tests import ref_scenes as rs
+
+pytestmark = pytest.mark.gpu
+
+TRANSLATION_TOL = 1e-6   # metres
+COST_REL_TOL = 1e-8
+
+
+@pytest.fixture(scope="module")
+def handle():
+    from limo_b200 import capi
+    h = capi.Handle(0)
+    yield h
+    h.close()
+
+
+def _compare_solves(res_gpu, res_cpu, win, label=""):
+    assert res_gpu.c.status == 0, label
+    assert res_gpu.c.num_solves == res_cpu.c.num_solves, label
+    for a, b in zip(res_gpu.solves, res_cpu.solves):
+        assert a.termination == b.termination, (label, a.termination, b.termination)
+        assert a.num_iterations == b.num_iterations, (label, a.num_iterations, b.num_iterations)
+        assert a.num_successful_steps == b.num_successful_steps, label
+        assert a.num_landmarks == b.num_landmarks, label
+        assert a.initial_cost == pytest.approx(b.initial_cost, rel=COST_REL_TOL), label
+        assert a.final_cost == pytest.approx(b.final_cost, rel=COST_REL_TOL, abs=1e-14), label
+    assert np.array_equal(res_gpu.lm_rejected[:win.n_lm], res_cpu.lm_rejected[:win.n_lm]), label
+    dt = np.linalg.norm(res_gpu.kf_pose[:, 4:] - res_cpu.kf_pose[:, 4:], axis=1).max()
+    dq = np.abs(res_gpu.kf_pose[:, :4] - res_cpu.kf_pose[:, :4]).max()
+    dl = np.linalg.norm(res_gpu.lm_pos[:win.n_lm] - res_cpu.lm_pos[:win.n_lm], axis=1).max()
+    assert dt <= TRANSLATION_TOL, (label, dt)
+    assert dq <= 1e-7, (label, dq)
+    assert dl <= 1e-5, (label, dl)
+
+
+def test_eval_matches_oracle(handle, oracle):
+    """residual / Jacobian kernel vs the oracle's Evaluate on the 5-keyframe config and on a slice of config 2"""
+    for win in (synth.make_window(1), synth.make_window(2, n_kf=12, n_lm=400, n_obs=3000)):
+        r, jp, jl, cost, failed = handle.evaluate(win)
+        r0, jp0, jl0, cost0, failed0 = oracle.evaluate(win)
+        assert failed == failed0 == 0
+        assert cost == pytest.approx(cost0, rel=1e-12)
+        assert np.allclose(r, r0, rtol=1e-11, atol=1e-11)
+        assert np.allclose(jp, jp0, rtol=1e-10, atol=1e-9 * np.abs(jp0).max())
+        assert np.allclose(jl, jl0, rtol=1e-10, atol=1e-9 * np.abs(jl0).max())
+        assert np.all(jp[win.obs_kf == 0] == 0.0)  # fixed keyframe: no pose columns
+
+
+@pytest.mark.parametrize("extr", ["mono", "stereo"])
+@pytest.mark.parametrize("case", [0, 1, 2])
+@pytest.mark.parametrize("depth", [False, True])
+def test_reference_scenes_on_gpu(handle, oracle, extr, case, depth):
+    """KeyFrameBundleAdjustment.solve / solve_depth of the reference, run through the CUDA path: must satisfy the
+    reference's own acceptance threshold AND agree with the oracle."""
+    from tests.test_oracle_reference_tests import SOLVE_CASES
+    noise_lms, noise_poses, thres = SOLVE_CASES[case]
+    if depth:
+        noise_lms = noise_lms + (0.0,)
+        ex = [np.eye(4)] if extr == "mono" else rs.stereo_extrinsics()
+    else:
+        ex = [rs.mono_extrinsics()] if extr == "mono" else rs.stereo_extrinsics()
+    bg, poses_gt, *_ = rs.build_adjuster(handle, noise_lms, noise_poses, ex, with_depth=depth)
+    bc, *_ = rs.build_adjuster(oracle.OracleBackend(), noise_lms, noise_poses, ex, with_depth=depth)
+    bg.solve()
+    bc.solve()
+    for ts in sorted(bg.keyframes_):
+        assert g.is_approx(bg.keyframes_[ts].getEigenPose(), poses_gt[ts], thres)
+    _compare_solves(bg.last_result, bc.last_result, bg.last_window, "%s case %d depth %s" % (extr, case, depth))
+
+
+@pytest.mark.parametrize("config,seed", [(1, None), (1, 11), (1, 12)])
+def test_config1_solve_matches_oracle(handle, oracle, config, seed):
+    """BASELINE config 1 (5 keyframes / 200 landmarks, mono): trimmed solve, GPU vs oracle"""
+    win = synth.make_window(config, seed=seed)
+    rg = handle.solve_window(win)
+    rc = oracle.solve_window(win)
+    _compare_solves(rg, rc, win, "config1 seed %s" % seed)
+
+
+def test_config2_solve_matches_oracle(handle, oracle):
+    """BASELINE config 2 (30 keyframes / 3k landmarks / 40k observations, mono + lidar depth, FP64)"""
+    win = synth.make_window(2)
+    rg = handle.solve_window(win)
+    rc = oracle.solve_window(win, num_threads=0)
+    _compare_solves(rg, rc, win, "config2")
+
+
+def test_batch_equals_single(handle):
+    """a batch of different windows gives bit-identical results to solving them one by one (deterministic reductions)"""
+    wins = [synth.make_window(1, seed=s) for s in (21, 22, 23)] + [synth.make_window(2, n_kf=10, n_lm=300, n_obs=2500, seed=5)]
+    single = [handle.solve_window(w) for w in wins]
+    batch = handle.solve_batch(wins)
+    for s, b, w in zip(single, batch, wins):
+        assert np.array_equal(s.kf_pose, b.kf_pose)
+        assert np.array_equal(s.lm_pos[:w.n_lm], b.lm_pos[:w.n_lm])
+        assert s.c.final_cost == b.c.final_cost
+
+
+def test_full_size_properties(handle):
+    """size-independent properties at BASELINE config 2 scale: cost decreases, outputs finite, fixed keyframe untouched,
+    rejected landmarks keep their position, repeat solve is bit-identical"""
+    win = synth.make_window(2, seed=77)
+    a = handle.solve_window(win)
+    b = handle.solve_window(win)
+    assert np.array_equal(a.kf_pose, b.kf_pose) and np.array_equal(a.lm_pos, b.lm_pos)
+    assert np.isfinite(a.kf_pose).all() and np.isfinite(a.lm_pos).all()
+    assert a.c.final_cost < a.c.initial_cost
+    assert np.array_equal(a.kf_pose[0], win.kf_pose[0])
+    rej = a.lm_rejected[:win.n_lm].astype(bool)
+    assert rej.sum() > 0
+
+
+def test_bad_arguments(handle):
+    """error behaviour of the boundary: fewer than 3 keyframes -> NotEnoughKeyframes (reference cpp:630-632)"""
+    from limo_b200 import capi
+    win = synth.make_window(1, n_kf=2, n_lm=20, n_obs=40)
+    with pytest.raises(capi.KbaError, match="error 3"):
+        handle.solve_window(win)
