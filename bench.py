@@ -1,0 +1,268 @@
+#!/usr/bin/env python
+"""bench.py -- BA windows/s of the B200 window solver on BASELINE.json's headline configuration.
+
+One "step" = one complete trimmed bundle-adjustment solve (all LM iterations + trimming round, Ceres-equivalent
+termination) of a BATCH of independent synthetic windows of config 2 (30 keyframes / 3000 landmarks / 40000
+observations, mono + lidar depth, FP64).  `value` is whole-job windows/s with the batch resident in HBM; `e2e` is the
+same metric through the host-buffer C-ABI path (pack + H2D + solve + D2H every step).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--batch B] [--impl reference]
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+METRIC = "BA windows/s (30 KF, 3k LM, 40k obs)"
+B_OBS_ALGORITHMIC = 259.0  # bytes per observation of the residual/Jacobian kernel, mono + depth FP64
+
+
+def usable_cores():
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
+def make_windows(n_distinct, rank, config=2):
+    from limo_b200 import synth
+    return [synth.make_window(config, seed=0xBA5E0000 + 1000 * rank + i) for i in range(n_distinct)]
+
+
+class ClockSampler:
+    """nvidia-smi clock / throttle-reason sampling during the timed region (B200_PROFILING.md)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu, self.proc, self.lines = gpu_index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for nm, val in zip(names, f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def cpu_baseline(windows, n_sample, threads):
+    """the CPU oracle (port of the reference algorithm, oracle/) timed on the host cores"""
+    os.environ.setdefault("OMP_WAIT_POLICY", "passive")
+    from oracle import oracle as orc
+    orc.lib()
+    orc.solve_window(windows[0], num_threads=threads)  # warm-up (page-in, thread pool)
+    t = time.perf_counter()
+    for i in range(n_sample):
+        orc.solve_window(windows[i % len(windows)], num_threads=threads)
+    dt = time.perf_counter() - t
+    return n_sample / dt, dt
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the reference's own CPU algorithm (its restatement in oracle/, since Ceres is not installable
+    offline -- see DESIGN.md) on the host cores, same metric and configuration."""
+    if rank != 0:
+        return
+    threads = min(usable_cores(), 32)
+    wins = make_windows(2, 0)
+    os.environ.setdefault("OMP_WAIT_POLICY", "passive")
+    from oracle import oracle as orc
+    orc.lib()
+    per_step = 1
+    for _ in range(max(args.warmup, 1)):
+        orc.solve_window(wins[0], num_threads=threads)
+    t = time.perf_counter()
+    for s in range(args.steps):
+        for i in range(per_step):
+            orc.solve_window(wins[(s + i) % len(wins)], num_threads=threads)
+    dt = time.perf_counter() - t
+    val = args.steps * per_step / dt
+    out = {"impl": "reference", "metric": METRIC, "value": val, "unit": "windows/s", "n_gpus": args.gpus,
+           "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True,
+           "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+           "config": {"workload": "config 2: 30 KF / 3000 LM / 40000 obs, mono + lidar depth, FP64; %d window per step"
+                                  % per_step},
+           "cpu_baseline": {"value": val, "unit": "windows/s", "cores": threads, "kind": "port",
+                            "sample": "%d full window solves (oracle/, OpenMP %d threads)" % (args.steps * per_step, threads)},
+           "e2e": {"value": val, "unit": "windows/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(out))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--batch", type=int, default=128, help="windows per GPU per step")
+    ap.add_argument("--distinct", type=int, default=16, help="distinct synthetic windows per GPU (tiled to --batch)")
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--cpu-sample", type=int, default=2)
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the kba_b200 path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    from limo_b200 import capi
+
+    n_distinct = max(1, min(args.distinct, args.batch))
+    base = make_windows(n_distinct, rank)
+    windows = [base[i % n_distinct] for i in range(args.batch)]
+    n_obs_win = windows[0].n_obs
+
+    stream = torch.cuda.current_stream()
+    h = capi.Handle(local_rank, stream=stream.cuda_stream)
+    opt = capi.default_options()
+    batch = h.batch(windows)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- warm-up ----
+    for _ in range(args.warmup):
+        batch.solve(opt)
+    barrier()
+    h.counters(reset=True)
+    h.enable_kernel_timing(True)
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    # ---- timed region: K steps, inputs resident in HBM ----
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record(stream)
+    for _ in range(args.steps):
+        batch.solve(opt)
+    ev1.record(stream)
+    barrier()
+    ms = ev0.elapsed_time(ev1)
+    clocks = sampler.stop()
+    cnt = h.counters(reset=True)
+    h.enable_kernel_timing(False)
+    results = batch.download()
+    ok = all(r.c.status == 0 for r in results)
+    iters = [sum(s.num_iterations for s in r.solves) for r in results]
+
+    # ---- end-to-end: host buffers -> pack -> H2D -> solve -> D2H, every step ----
+    for _ in range(1):
+        batch.upload(); batch.solve(opt); batch.download(results=results)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_wall = time.perf_counter()
+    e0.record(stream)
+    for _ in range(args.steps):
+        batch.upload()
+        batch.solve(opt)
+        batch.download(results=results)
+    e1.record(stream)
+    barrier()
+    ms_e2e = max(e0.elapsed_time(e1), 1e3 * (time.perf_counter() - t_wall))
+    h2d, d2h = batch.transfer_bytes()
+
+    t = torch.tensor([ms, ms_e2e], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms, ms_e2e = float(t[0]), float(t[1])
+
+    if rank == 0:
+        total_windows = world * args.batch * args.steps
+        value = total_windows / (ms * 1e-3)
+        peak, peak_src = measured_peak()
+        jac_gbs = (cnt.jacobian_obs * B_OBS_ALGORITHMIC / (cnt.ms_jacobian * 1e-3) / 1e9) if cnt.ms_jacobian > 0 else None
+        threads = min(usable_cores(), 32)
+        cpu_val, cpu_dt = cpu_baseline(base, args.cpu_sample, threads)
+        out = {
+            "metric": METRIC, "value": value, "unit": "windows/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "config 2: 30 KF / 3000 LM / 40000 obs, mono + lidar depth, FP64",
+                       "batch_windows_per_gpu": args.batch, "distinct_windows_per_gpu": n_distinct,
+                       "parallelism": "independent windows per GPU (no data-path collective)" if world > 1 else "1 GPU",
+                       "lm_iterations_per_window_mean": float(np.mean(iters)),
+                       "l2_policy": "inputs larger than L2 (%.1f GB of Jacobian blocks per pass)"
+                                    % (args.batch * n_obs_win * 240 / 1e9),
+                       "all_windows_converged": bool(ok)},
+            "e2e": {"value": total_windows / (ms_e2e * 1e-3), "unit": "windows/s",
+                    "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
+            "gpu_launches": int(cnt.launches_total),
+            "roofline": {"kernel": "k_eval_obs<true> (residual/Jacobian)", "bound": "hbm", "achieved": jac_gbs,
+                         "peak": peak, "unit": "GB/s", "frac": (jac_gbs / peak) if jac_gbs else None,
+                         "peak_source": peak_src, "traffic": None,
+                         "algorithmic_bytes_per_obs": B_OBS_ALGORITHMIC,
+                         "launch_ms_mean": cnt.ms_jacobian / max(cnt.launches_jacobian, 1),
+                         "obs_per_launch_mean": cnt.jacobian_obs / max(cnt.launches_jacobian, 1)},
+            "cpu_baseline": {"value": cpu_val, "unit": "windows/s", "cores": threads, "kind": "port",
+                             "sample": "%d full window solves of the same workload, %.1f s (oracle/, OpenMP)"
+                                       % (args.cpu_sample, cpu_dt)},
+            "clocks": clocks,
+        }
+        print(json.dumps(out))
+    batch.close()
+    h.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

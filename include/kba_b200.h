@@ -223,6 +223,7 @@ int kba_batch_create(kba_handle* h, int32_t n_windows, const kba_window* w, kba_
 int kba_batch_upload(kba_batch* b, int32_t n_windows, const kba_window* w); /* re-upload state, same shapes */
 int kba_batch_solve(kba_batch* b, const kba_options* opt);                 /* resets to the uploaded state, solves */
 int kba_batch_download(kba_batch* b, kba_result* res);
+int kba_batch_transfer_bytes(kba_batch* b, int64_t* h2d_bytes, int64_t* d2h_bytes); /* of the last upload / download */
 int kba_batch_jacobian_pass(kba_batch* b, const kba_options* opt, int32_t repeats, float* ms_out); /* residual/Jacobian kernel only */
 void kba_batch_destroy(kba_batch* b);
 /* counters for bench.py: kernels launched / device ms per kernel family since the last reset */

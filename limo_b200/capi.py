@@ -16,7 +16,7 @@ _lib = None
 
 SYMBOLS = ["kba_version", "kba_last_error", "kba_default_options", "kba_create", "kba_destroy", "kba_set_stream",
            "kba_solve_window", "kba_solve_batch", "kba_eval", "kba_batch_create", "kba_batch_upload",
-           "kba_batch_solve", "kba_batch_download", "kba_batch_jacobian_pass", "kba_batch_destroy",
+           "kba_batch_solve", "kba_batch_download", "kba_batch_transfer_bytes", "kba_batch_jacobian_pass", "kba_batch_destroy",
            "kba_get_counters", "kba_enable_kernel_timing"]
 
 
@@ -47,6 +47,7 @@ def lib():
         L.kba_batch_solve.argtypes = [vp, C.POINTER(KbaOptions)]
         L.kba_batch_download.argtypes = [vp, C.POINTER(KbaResult)]
         L.kba_batch_jacobian_pass.argtypes = [vp, C.POINTER(KbaOptions), C.c_int32, C.POINTER(C.c_float)]
+        L.kba_batch_transfer_bytes.argtypes = [vp, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
         L.kba_batch_destroy.argtypes = [vp]
         L.kba_batch_destroy.restype = None
         L.kba_get_counters.argtypes = [vp, C.POINTER(KbaCounters), C.c_int]
@@ -81,14 +82,22 @@ class Batch:
     def solve(self, opt=None):
         _check(lib().kba_batch_solve(self._p, C.byref(opt or default_options())))
 
-    def download(self, iterations_capacity=0):
-        results = [Result(w, max(iterations_capacity, 1)) for w in self.windows]
-        arr = (KbaResult * len(results))(*[r.c for r in results])
+    def download(self, iterations_capacity=0, results=None):
+        """results: reuse the buffers of an earlier download (avoids re-allocating numpy arrays every step)"""
+        if results is None:
+            results = [Result(w, max(iterations_capacity, 1)) for w in self.windows]
+            self._res_arr = (KbaResult * len(results))(*[r.c for r in results])
+        arr = self._res_arr
         _check(lib().kba_batch_download(self._p, arr))
         for r, c in zip(results, arr):
             r.c = c
-        self._keep = arr
         return results
+
+    def transfer_bytes(self):
+        """(host->device bytes of the last upload, device->host bytes of the last download)"""
+        a, b = C.c_int64(), C.c_int64()
+        _check(lib().kba_batch_transfer_bytes(self._p, C.byref(a), C.byref(b)))
+        return a.value, b.value
 
     def jacobian_pass(self, opt=None, repeats=1):
         ms = C.c_float()

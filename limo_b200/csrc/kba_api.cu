@@ -33,6 +33,8 @@ struct kba_handle {
     Counters counters;
     bool kernel_timing = false;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    std::vector<cudaEvent_t> ev_pool;  // event pairs around every residual/Jacobian launch (kernel timing)
+    int ev_used = 0;
     int sm_count = 148;
 };
 
@@ -74,6 +76,7 @@ struct kba_batch {
     Staged<double> pose_out[2], lm_out[2];
     Staged<uint8_t> lm_active;
     Staged<int> n_active;
+    Staged<unsigned long long> jac_obs;
     std::vector<void*> scratch;  // device-only allocations
     LaunchCfg lc;
     size_t h2d_bytes = 0, d2h_bytes = 0;
@@ -94,7 +97,7 @@ struct kba_batch {
         pm_lm.release(); pm_cam.release(); chunk_lm0.release(); chunk_lm1.release(); obs_u.release(); obs_v.release();
         obs_d.release(); pm_u.release(); pm_v.release(); pm_d.release(); state.release(); log.release();
         pose_out[0].release(); pose_out[1].release(); lm_out[0].release(); lm_out[1].release(); lm_active.release();
-        n_active.release();
+        n_active.release(); jac_obs.release();
         for (void* p : scratch) cudaFree(p);
         scratch.clear();
         if (ev_a) cudaEventDestroy(ev_a);
@@ -308,7 +311,7 @@ int kba_batch_create(kba_handle* h, int32_t n_windows, const kba_window* w, kba_
     bad |= b->chunk_lm0.alloc(chunks, true); bad |= b->chunk_lm1.alloc(chunks, true);
     bad |= b->state.alloc(n_windows, true); bad |= b->log.alloc((size_t)n_windows * kIterLogCap, true);
     for (int q = 0; q < 2; ++q) { bad |= b->pose_out[q].alloc(7 * kf, true); bad |= b->lm_out[q].alloc(3 * lm, true); }
-    bad |= b->lm_active.alloc(lm, true); bad |= b->n_active.alloc(1, true);
+    bad |= b->lm_active.alloc(lm, true); bad |= b->n_active.alloc(1, true); bad |= b->jac_obs.alloc(1, true);
     // device-only scratch
     bad |= b->dev_alloc(&bd.plane[0], 4 * kf); bad |= b->dev_alloc(&bd.plane[1], 4 * kf);
     bad |= b->dev_alloc(&bd.off_pose, kf); bad |= b->dev_alloc(&bd.off_dir, kf); bad |= b->dev_alloc(&bd.off_dist, kf);
@@ -338,6 +341,8 @@ int kba_batch_create(kba_handle* h, int32_t n_windows, const kba_window* w, kba_
     bd.kf_ptr = b->kf_ptr.d; bd.pm_lm = b->pm_lm.d; bd.pm_cam = b->pm_cam.d; bd.pm_u = b->pm_u.d; bd.pm_v = b->pm_v.d; bd.pm_d = b->pm_d.d;
     bd.chunk_lm0 = b->chunk_lm0.d; bd.chunk_lm1 = b->chunk_lm1.d;
     bd.n_active = b->n_active.d;
+    bd.jac_obs = b->jac_obs.d;
+    CU(cudaMemset(bd.jac_obs, 0, sizeof(unsigned long long)));
     CU(cudaEventCreate(&b->ev_a));
     CU(cudaEventCreate(&b->ev_b));
     CU(configure_kernels(nr_cap_max));
@@ -398,7 +403,13 @@ int kba_batch_solve(kba_batch* b, const kba_options* opt) {
     lc.min_landmarks_for_trimming = opt->min_landmarks_for_trimming;
     lc.num_rounds_option = opt->num_rounds_option;
     lc.time_jacobian = h->kernel_timing;
-    lc.ev0 = h->ev0; lc.ev1 = h->ev1;
+    if (h->kernel_timing && h->ev_pool.empty()) {
+        h->ev_pool.resize(1024);
+        for (auto& e : h->ev_pool) CU(cudaEventCreate(&e));
+    }
+    h->ev_used = 0;
+    lc.ev_pool = h->ev_pool.data(); lc.ev_cap = (int)h->ev_pool.size(); lc.ev_used = &h->ev_used;
+    CU(cudaMemsetAsync(b->bd.jac_obs, 0, sizeof(unsigned long long), s));
     CU(cudaEventRecord(b->ev_a, s));
     launch_reset(b->bd, lc, s);
     // upper bound on passes: every solve needs (iterations + 2) passes, plus one pass per trimming step
@@ -408,12 +419,6 @@ int kba_batch_solve(kba_batch* b, const kba_options* opt) {
     int check_every = 4;
     for (int pass = 0; pass < max_passes; ++pass) {
         launch_pass(b->bd, sp, lc, &h->counters, s);
-        if (lc.time_jacobian) {
-            CU(cudaEventSynchronize(lc.ev1));
-            float ms = 0.f;
-            CU(cudaEventElapsedTime(&ms, lc.ev0, lc.ev1));
-            h->counters.ms_jacobian += ms;
-        }
         if ((pass + 1) % check_every == 0 || pass + 1 == max_passes) {
             launch_count_active(b->bd, s);
             CU(b->n_active.download(s));
@@ -426,9 +431,16 @@ int kba_batch_solve(kba_batch* b, const kba_options* opt) {
         }
     }
     CU(cudaEventRecord(b->ev_b, s));
+    CU(b->jac_obs.download(s));
     CU(cudaStreamSynchronize(s));
     CU(cudaGetLastError());
     CU(cudaEventElapsedTime(&b->last_solve_ms, b->ev_a, b->ev_b));
+    h->counters.jacobian_obs += (long long)b->jac_obs.h[0];
+    for (int i = 0; i + 1 < h->ev_used; i += 2) {
+        float ms = 0.f;
+        CU(cudaEventElapsedTime(&ms, h->ev_pool[i], h->ev_pool[i + 1]));
+        h->counters.ms_jacobian += ms;
+    }
     return KBA_OK;
 }
 
@@ -477,6 +489,13 @@ int kba_batch_download(kba_batch* b, kba_result* res) {
     return KBA_OK;
 }
 
+int kba_batch_transfer_bytes(kba_batch* b, int64_t* h2d, int64_t* d2h) {
+    if (!b) return fail(KBA_ERR_BAD_ARG, "null batch");
+    if (h2d) *h2d = (int64_t)b->h2d_bytes;
+    if (d2h) *d2h = (int64_t)b->d2h_bytes;
+    return KBA_OK;
+}
+
 void kba_batch_destroy(kba_batch* b) {
     if (!b) return;
     cudaStreamSynchronize(b->h->stream);
@@ -501,6 +520,7 @@ int kba_batch_jacobian_pass(kba_batch* b, const kba_options* opt, int32_t repeat
     if (ms_out) *ms_out = ms;
     h->counters.launches_total += repeats; h->counters.launches_jacobian += repeats;
     h->counters.ms_jacobian += ms; h->counters.jacobian_obs += (long long)repeats * b->bd.tot_obs;
+    CU(cudaMemsetAsync(b->bd.jac_obs, 0, sizeof(unsigned long long), s));
     return KBA_OK;
 }
 

@@ -144,6 +144,7 @@ struct BatchDev {
     int* chunk_r1;
     int tot_chunks;
     int* n_active;            // [1] windows still running (device counter)
+    unsigned long long* jac_obs;  // [1] observations linearised by the residual/Jacobian kernel since the last reset
 };
 
 struct SolveParams {  // kba_options subset used on the device

@@ -93,6 +93,7 @@ __global__ void __launch_bounds__(256) k_eval_obs(BatchDev bd, SolveParams sp) {
     __syncthreads();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     double cost = 0.0;
+    int done = 0;
     if (i < wd.n_obs) {
         const size_t o = (size_t)wd.obs_off + i;
         const int L = wd.lm_off + bd.obs_lm[o];
@@ -109,6 +110,7 @@ __global__ void __launch_bounds__(256) k_eval_obs(BatchDev bd, SolveParams sp) {
                 st.eval_failed = 1;  // benign race
             } else {
                 cost = hr;
+                done = 1;
                 if (kJac) {
                     const size_t T = (size_t)bd.tot_obs;
 #pragma unroll
@@ -130,6 +132,10 @@ __global__ void __launch_bounds__(256) k_eval_obs(BatchDev bd, SolveParams sp) {
         double s = 0.0;
         for (int q = 0; q < 8; ++q) s += s_red[q];
         (kJac ? bd.cost_part_x : bd.cost_part_c)[(size_t)w * bd.cost_parts + blockIdx.x] = s;
+    }
+    if (kJac) {  // observation count for the roofline report (one atomic per CTA)
+        const int cnt = __syncthreads_count(done);
+        if (threadIdx.x == 0 && cnt) atomicAdd(bd.jac_obs, (unsigned long long)cnt);
     }
 }
 template __global__ void k_eval_obs<true>(BatchDev, SolveParams);
@@ -981,9 +987,10 @@ void launch_pass(const BatchDev& bd, const SolveParams& sp, const LaunchCfg& lc,
     const dim3 g_obs((bd.max_obs + 255) / 256, B);
     const dim3 g_lm((bd.max_lm + 7) / 8, B);
     k_solve_begin<<<B, 256, 0, s>>>(bd, sp);
-    if (lc.time_jacobian) cudaEventRecord(lc.ev0, s);
+    const bool timed = lc.time_jacobian && lc.ev_pool && *lc.ev_used + 2 <= lc.ev_cap;
+    if (timed) cudaEventRecord(lc.ev_pool[(*lc.ev_used)++], s);
     k_eval_obs<true><<<g_obs, 256, 0, s>>>(bd, sp);
-    if (lc.time_jacobian) cudaEventRecord(lc.ev1, s);
+    if (timed) cudaEventRecord(lc.ev_pool[(*lc.ev_used)++], s);
     k_pose_hessian<<<dim3(bd.max_kf, B), 256, 0, s>>>(bd, sp);
     k_landmark_prep<<<g_lm, 256, 0, s>>>(bd, sp);
     const int nb = lc.nr_cap_max / 64;

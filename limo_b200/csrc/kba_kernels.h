@@ -18,7 +18,9 @@ struct LaunchCfg {
     int nr_cap_max = 64;
     int rounds_override = -1, min_landmarks_for_trimming = 100, num_rounds_option = 1;
     bool time_jacobian = false;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    cudaEvent_t* ev_pool = nullptr;  // pairs of events bracketing each residual/Jacobian launch
+    int ev_cap = 0;
+    int* ev_used = nullptr;
 };
 
 cudaError_t configure_kernels(int nr_cap_max);

@@ -1013,7 +1013,9 @@ static void ceres_solve(program* P, state_t* x, int max_num_iterations, double m
     sum->initial_cost = x_cost;
     sum->final_cost = x_cost;
     sum->num_residual_blocks = 0;
-    for (int b = 0; b < P->n_blocks; ++b) sum->num_residual_blocks += (P->blk[b].nres > 0);
+    /* an observation with lidar depth is two ceres residual blocks (depth + reprojection, cpp:587-620) */
+    for (int b = 0; b < P->n_blocks; ++b)
+        sum->num_residual_blocks += (P->blk[b].nres > 0) + (b < P->n_obs && P->blk[b].nres == 3);
     log_iteration(L, solve_index, 0, x_cost, 0, gmax, 0, 0, radius, 0, 0);
 
     for (;;) {
