@@ -68,7 +68,7 @@ struct kba_batch {
     Staged<WinDesc> desc;
     Staged<double> pose0, plane0, cam, lm0, lm_weight;
     Staged<uint8_t> kf_fixed;
-    Staged<int> lm_ptr, obs_kf, obs_cam, obs_lm, kf_ptr, pm_lm, pm_cam, chunk_lm0, chunk_lm1;
+    Staged<int> lm_ptr, obs_kf, obs_cam, obs_lm, kf_ptr, pm_lm, pm_cam, chunk_lm0, chunk_lm1, chunk_k0, chunk_k1, lm_orig, obs_orig;
     Staged<float> obs_u, obs_v, obs_d, pm_u, pm_v, pm_d;
     // outputs
     Staged<WinState> state;
@@ -94,7 +94,8 @@ struct kba_batch {
     void release() {
         desc.release(); pose0.release(); plane0.release(); cam.release(); lm0.release(); lm_weight.release();
         kf_fixed.release(); lm_ptr.release(); obs_kf.release(); obs_cam.release(); obs_lm.release(); kf_ptr.release();
-        pm_lm.release(); pm_cam.release(); chunk_lm0.release(); chunk_lm1.release(); obs_u.release(); obs_v.release();
+        pm_lm.release(); pm_cam.release(); chunk_lm0.release(); chunk_lm1.release(); chunk_k0.release(); chunk_k1.release();
+        lm_orig.release(); obs_orig.release(); obs_u.release(); obs_v.release();
         obs_d.release(); pm_u.release(); pm_v.release(); pm_d.release(); state.release(); log.release();
         pose_out[0].release(); pose_out[1].release(); lm_out[0].release(); lm_out[1].release(); lm_active.release();
         n_active.release(); jac_obs.release();
@@ -141,41 +142,62 @@ static void fill_window(kba_batch* b, int wi, const kba_window* w) {
         o[9] = w->cam_pose[7 * c + 4]; o[10] = w->cam_pose[7 * c + 5]; o[11] = w->cam_pose[7 * c + 6];
         o[12] = w->cam_intr[3 * c]; o[13] = w->cam_intr[3 * c + 1]; o[14] = w->cam_intr[3 * c + 2]; o[15] = 0;
     }
-    if (w->n_lm > 0) {
-        memcpy(b->lm0.h + 3 * (size_t)d.lm_off, w->lm_pos, sizeof(double) * 3 * w->n_lm);
-        memcpy(b->lm_weight.h + d.lm_off, w->lm_weight, sizeof(double) * w->n_lm);
-        memcpy(b->lm_ptr.h + d.lm_off + wi, w->lm_obs_ptr, sizeof(int) * (w->n_lm + 1));
-    } else {
-        b->lm_ptr.h[d.lm_off + wi] = 0;
+    // Landmarks are stored sorted by (first keyframe, last keyframe): consecutive landmarks then touch the same rows of
+    // the reduced system, which is what lets the Schur kernel skip most tiles.  lm_orig maps back to the caller's order.
+    const int nl = w->n_lm;
+    int* orig = b->lm_orig.h + d.lm_off;
+    {
+        std::vector<long long> key(nl);
+        for (int j = 0; j < nl; ++j) {
+            const int o0 = w->lm_obs_ptr[j], o1 = w->lm_obs_ptr[j + 1];
+            const int k0 = o1 > o0 ? w->obs_kf[o0] : w->n_kf, k1 = o1 > o0 ? w->obs_kf[o1 - 1] : w->n_kf;
+            key[j] = ((long long)k0 << 40) | ((long long)k1 << 20) | 0;
+            orig[j] = j;
+        }
+        std::stable_sort(orig, orig + nl, [&](int a, int c) { return key[a] < key[c]; });
     }
-    if (w->n_obs > 0) {
-        memcpy(b->obs_kf.h + d.obs_off, w->obs_kf, sizeof(int) * w->n_obs);
-        if (w->obs_cam) memcpy(b->obs_cam.h + d.obs_off, w->obs_cam, sizeof(int) * w->n_obs);
-        else memset(b->obs_cam.h + d.obs_off, 0, sizeof(int) * w->n_obs);
-        memcpy(b->obs_u.h + d.obs_off, w->obs_u, sizeof(float) * w->n_obs);
-        memcpy(b->obs_v.h + d.obs_off, w->obs_v, sizeof(float) * w->n_obs);
-        memcpy(b->obs_d.h + d.obs_off, w->obs_d, sizeof(float) * w->n_obs);
-    }
-    // landmark index per observation + keyframe-major copy (counting sort, stable -> deterministic reduction order)
+    int* lp = b->lm_ptr.h + d.lm_off + wi;
     int* kp = b->kf_ptr.h + d.kf_off + wi;
     std::fill(kp, kp + w->n_kf + 1, 0);
-    for (int j = 0; j < w->n_lm; ++j)
-        for (int o = w->lm_obs_ptr[j]; o < w->lm_obs_ptr[j + 1]; ++o) {
-            b->obs_lm.h[d.obs_off + o] = j;
+    int pos = 0;
+    lp[0] = 0;
+    for (int jn = 0; jn < nl; ++jn) {
+        const int jo = orig[jn];
+        memcpy(b->lm0.h + 3 * (size_t)(d.lm_off + jn), w->lm_pos + 3 * (size_t)jo, 3 * sizeof(double));
+        b->lm_weight.h[d.lm_off + jn] = w->lm_weight[jo];
+        for (int o = w->lm_obs_ptr[jo]; o < w->lm_obs_ptr[jo + 1]; ++o, ++pos) {
+            const size_t e = (size_t)d.obs_off + pos;
+            b->obs_kf.h[e] = w->obs_kf[o];
+            b->obs_cam.h[e] = w->obs_cam ? w->obs_cam[o] : 0;
+            b->obs_lm.h[e] = jn;
+            b->obs_u.h[e] = w->obs_u[o]; b->obs_v.h[e] = w->obs_v[o]; b->obs_d.h[e] = w->obs_d[o];
+            b->obs_orig.h[e] = o;
             kp[w->obs_kf[o] + 1]++;
         }
+        lp[jn + 1] = pos;
+    }
+    // keyframe-major copy (counting sort, stable -> deterministic reduction order)
     for (int k = 0; k < w->n_kf; ++k) kp[k + 1] += kp[k];
     std::vector<int> cur(kp, kp + w->n_kf);
-    for (int j = 0; j < w->n_lm; ++j)
-        for (int o = w->lm_obs_ptr[j]; o < w->lm_obs_ptr[j + 1]; ++o) {
-            const int e = d.obs_off + cur[w->obs_kf[o]]++;
-            b->pm_lm.h[e] = j;
-            b->pm_cam.h[e] = w->obs_cam ? w->obs_cam[o] : 0;
-            b->pm_u.h[e] = w->obs_u[o]; b->pm_v.h[e] = w->obs_v[o]; b->pm_d.h[e] = w->obs_d[o];
+    for (int jn = 0; jn < nl; ++jn)
+        for (int o = lp[jn]; o < lp[jn + 1]; ++o) {
+            const size_t src = (size_t)d.obs_off + o;
+            const size_t e = (size_t)d.obs_off + cur[b->obs_kf.h[src]]++;
+            b->pm_lm.h[e] = jn;
+            b->pm_cam.h[e] = b->obs_cam.h[src];
+            b->pm_u.h[e] = b->obs_u.h[src]; b->pm_v.h[e] = b->obs_v.h[src]; b->pm_d.h[e] = b->obs_d.h[src];
         }
     for (int c = 0; c < d.n_chunks; ++c) {
-        b->chunk_lm0.h[d.chunk_off + c] = c * 32;
-        b->chunk_lm1.h[d.chunk_off + c] = std::min(w->n_lm, (c + 1) * 32);
+        const int j0 = c * 32, j1 = std::min(nl, (c + 1) * 32);
+        b->chunk_lm0.h[d.chunk_off + c] = j0;
+        b->chunk_lm1.h[d.chunk_off + c] = j1;
+        int k0 = w->n_kf, k1 = -1;
+        for (int o = lp[j0]; o < lp[j1]; ++o) {
+            const int k = b->obs_kf.h[(size_t)d.obs_off + o];
+            k0 = std::min(k0, k); k1 = std::max(k1, k);
+        }
+        b->chunk_k0.h[d.chunk_off + c] = k0;
+        b->chunk_k1.h[d.chunk_off + c] = k1;
     }
 }
 
@@ -295,6 +317,8 @@ int kba_batch_create(kba_handle* h, int32_t n_windows, const kba_window* w, kba_
         int max_chunks = 1;
         for (auto& d : b->desc_h) max_chunks = std::max(max_chunks, d.n_chunks);
         int p = (2 * h->sm_count + n_windows * pairs - 1) / (n_windows * pairs);
+        b->lc.small_syrk = (6 * bd.max_kf + 1 <= 184);
+        if (b->lc.small_syrk) p = (h->sm_count + n_windows - 1) / n_windows;  // one CTA per SM, each owning all tiles
         bd.p_split = std::max(1, std::min(p, max_chunks));
     }
     bd.cost_parts = (bd.max_obs + 255) / 256;
@@ -309,6 +333,9 @@ int kba_batch_create(kba_handle* h, int32_t n_windows, const kba_window* w, kba_
     bad |= b->kf_ptr.alloc(kf + n_windows, true); bad |= b->pm_lm.alloc(obs, true); bad |= b->pm_cam.alloc(obs, true);
     bad |= b->pm_u.alloc(obs, true); bad |= b->pm_v.alloc(obs, true); bad |= b->pm_d.alloc(obs, true);
     bad |= b->chunk_lm0.alloc(chunks, true); bad |= b->chunk_lm1.alloc(chunks, true);
+    bad |= b->chunk_k0.alloc(chunks, true); bad |= b->chunk_k1.alloc(chunks, true);
+    bad |= b->lm_orig.alloc(lm, true); bad |= b->obs_orig.alloc(obs, true);
+    bad |= b->dev_alloc(&bd.chunk_t0, chunks); bad |= b->dev_alloc(&bd.chunk_t1, chunks); bad |= b->dev_alloc(&bd.obs_row, obs);
     bad |= b->state.alloc(n_windows, true); bad |= b->log.alloc((size_t)n_windows * kIterLogCap, true);
     for (int q = 0; q < 2; ++q) { bad |= b->pose_out[q].alloc(7 * kf, true); bad |= b->lm_out[q].alloc(3 * lm, true); }
     bad |= b->lm_active.alloc(lm, true); bad |= b->n_active.alloc(1, true); bad |= b->jac_obs.alloc(1, true);
@@ -339,7 +366,8 @@ int kba_batch_create(kba_handle* h, int32_t n_windows, const kba_window* w, kba_
     bd.obs_kf = b->obs_kf.d; bd.obs_cam = b->obs_cam.d; bd.obs_lm = b->obs_lm.d;
     bd.obs_u = b->obs_u.d; bd.obs_v = b->obs_v.d; bd.obs_d = b->obs_d.d;
     bd.kf_ptr = b->kf_ptr.d; bd.pm_lm = b->pm_lm.d; bd.pm_cam = b->pm_cam.d; bd.pm_u = b->pm_u.d; bd.pm_v = b->pm_v.d; bd.pm_d = b->pm_d.d;
-    bd.chunk_lm0 = b->chunk_lm0.d; bd.chunk_lm1 = b->chunk_lm1.d;
+    bd.chunk_lm0 = b->chunk_lm0.d; bd.chunk_lm1 = b->chunk_lm1.d; bd.chunk_k0 = b->chunk_k0.d; bd.chunk_k1 = b->chunk_k1.d;
+    bd.lm_orig = b->lm_orig.d;
     bd.n_active = b->n_active.d;
     bd.jac_obs = b->jac_obs.d;
     CU(cudaMemset(bd.jac_obs, 0, sizeof(unsigned long long)));
@@ -369,7 +397,8 @@ int kba_batch_upload(kba_batch* b, int32_t n_windows, const kba_window* w) {
     CU(b->obs_kf.upload(s)); CU(b->obs_cam.upload(s)); CU(b->obs_lm.upload(s));
     CU(b->obs_u.upload(s)); CU(b->obs_v.upload(s)); CU(b->obs_d.upload(s));
     CU(b->kf_ptr.upload(s)); CU(b->pm_lm.upload(s)); CU(b->pm_cam.upload(s)); CU(b->pm_u.upload(s)); CU(b->pm_v.upload(s)); CU(b->pm_d.upload(s));
-    CU(b->chunk_lm0.upload(s)); CU(b->chunk_lm1.upload(s));
+    CU(b->chunk_lm0.upload(s)); CU(b->chunk_lm1.upload(s)); CU(b->chunk_k0.upload(s)); CU(b->chunk_k1.upload(s));
+    CU(b->lm_orig.upload(s));
     const BatchDev& bd = b->bd;
     b->h2d_bytes = sizeof(WinDesc) * bd.n_win + (7 + 4) * 8 * bd.tot_kf + bd.tot_kf + kCamStride * 8 * bd.tot_cam +
                    (3 + 1) * 8 * bd.tot_lm + 4 * (bd.tot_lm + bd.n_win) + (3 * 4 + 3 * 4) * bd.tot_obs +
@@ -460,8 +489,10 @@ int kba_batch_download(kba_batch* b, kba_result* res) {
         const int cur = st.cur;
         if (r.kf_pose) memcpy(r.kf_pose, b->pose_out[cur].h + 7 * (size_t)d.kf_off, sizeof(double) * 7 * d.n_kf);
         if (r.kf_plane) memcpy(r.kf_plane, b->plane0.h + 4 * (size_t)d.kf_off, sizeof(double) * 4 * d.n_kf);
-        if (r.lm_pos && d.n_lm > 0) memcpy(r.lm_pos, b->lm_out[cur].h + 3 * (size_t)d.lm_off, sizeof(double) * 3 * d.n_lm);
-        if (r.lm_rejected) for (int j = 0; j < d.n_lm; ++j) r.lm_rejected[j] = !b->lm_active.h[d.lm_off + j];
+        const int* orig = b->lm_orig.h + d.lm_off;
+        if (r.lm_pos)
+            for (int j = 0; j < d.n_lm; ++j) memcpy(r.lm_pos + 3 * (size_t)orig[j], b->lm_out[cur].h + 3 * (size_t)(d.lm_off + j), 3 * sizeof(double));
+        if (r.lm_rejected) for (int j = 0; j < d.n_lm; ++j) r.lm_rejected[orig[j]] = !b->lm_active.h[d.lm_off + j];
         r.num_solves = st.n_solves;
         for (int q = 0; q < st.n_solves && q < KBA_MAX_SOLVES; ++q) {
             const SolveSummary& ss = st.solves[q];
@@ -562,11 +593,12 @@ int kba_eval(kba_handle* h, const kba_window* w, const kba_options* opt, kba_eva
     cudaMemcpyAsync(&st, bd.state, sizeof(WinState), cudaMemcpyDeviceToHost, s);
     cudaError_t e = cudaStreamSynchronize(s);
     if (e != cudaSuccess) { kba_batch_destroy(b); return fail(KBA_ERR_CUDA, cudaGetErrorString(e)); }
-    for (size_t o = 0; o < n; ++o) {
+    for (size_t e = 0; e < n; ++e) {  // e: internal (sorted) observation slot, o: the caller's observation index
+        const size_t o = (size_t)b->obs_orig.h[e];
         const bool fixed = offp[w->obs_kf[o]] < 0;
-        if (out->residual) for (int q = 0; q < 3; ++q) out->residual[3 * o + q] = res_h[q * n + o];
-        if (out->jac_pose) for (int q = 0; q < 18; ++q) out->jac_pose[18 * o + q] = fixed ? 0.0 : jp_h[q * n + o];
-        if (out->jac_lm) for (int q = 0; q < 9; ++q) out->jac_lm[9 * o + q] = jl_h[q * n + o];
+        if (out->residual) for (int q = 0; q < 3; ++q) out->residual[3 * o + q] = res_h[q * n + e];
+        if (out->jac_pose) for (int q = 0; q < 18; ++q) out->jac_pose[18 * o + q] = fixed ? 0.0 : jp_h[q * n + e];
+        if (out->jac_lm) for (int q = 0; q < 9; ++q) out->jac_lm[9 * o + q] = jl_h[q * n + e];
     }
     if (out->cost) { double c = 0; for (int q = 0; q < bd.cost_parts; ++q) c += cost_h[q]; out->cost[0] = c; }
     if (out->failed) out->failed[0] = st.eval_failed;

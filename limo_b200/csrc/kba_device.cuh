@@ -140,8 +140,12 @@ struct BatchDev {
     // chunking of landmarks for the Schur kernel
     int* chunk_lm0;           // [tot_chunks] first landmark (window-local)
     int* chunk_lm1;           // [tot_chunks] one past last
-    int* chunk_r0;            // row range touched, in 8-row tiles
-    int* chunk_r1;
+    int* chunk_k0;            // [tot_chunks] first / last keyframe observed by the chunk's landmarks (host, static)
+    int* chunk_k1;
+    int* chunk_t0;            // [tot_chunks] 8-row tile range [t0, t1) of the reduced system the chunk touches (per solve)
+    int* chunk_t1;
+    int* obs_row;             // [tot_obs] first reduced-system row of the observation's pose block, -1: constant / inactive
+    int* lm_orig;             // [tot_lm] caller's landmark index (landmarks are stored sorted by first keyframe)
     int tot_chunks;
     int* n_active;            // [1] windows still running (device counter)
     unsigned long long* jac_obs;  // [1] observations linearised by the residual/Jacobian kernel since the last reset

@@ -69,6 +69,23 @@ __global__ void __launch_bounds__(256) k_solve_begin(BatchDev bd, SolveParams sp
         s.num_residual_blocks = s_cnt[1] + (wd.scale_weight > 0 ? 1 : 0);
         st.phase = PH_ITERATE;
     }
+    __syncthreads();
+    // per-observation row of the pose block in the reduced system (one load instead of a 4-deep dependent chain later)
+    for (int o = threadIdx.x; o < wd.n_obs; o += blockDim.x) {
+        const size_t oo = (size_t)wd.obs_off + o;
+        const bool act = bd.lm_active[wd.lm_off + bd.obs_lm[oo]];
+        bd.obs_row[oo] = act ? bd.off_pose[wd.kf_off + bd.obs_kf[oo]] : -1;
+    }
+    // 8-row tile range of the reduced system each landmark chunk touches (landmarks are sorted by first keyframe)
+    for (int c = threadIdx.x; c < wd.n_chunks; c += blockDim.x) {
+        int r0 = 1 << 30, r1 = -1;
+        for (int k = bd.chunk_k0[wd.chunk_off + c]; k <= bd.chunk_k1[wd.chunk_off + c]; ++k) {
+            const int off = bd.off_pose[wd.kf_off + k];
+            if (off >= 0) { r0 = min(r0, off); r1 = max(r1, off + 6); }
+        }
+        bd.chunk_t0[wd.chunk_off + c] = (r1 < 0) ? 0 : r0 / 8;
+        bd.chunk_t1[wd.chunk_off + c] = (r1 < 0) ? 0 : (r1 + 7) / 8;
+    }
 }
 
 // =====================================================================================================================
@@ -397,6 +414,93 @@ __global__ void __launch_bounds__(256, 2) k_schur_syrk(BatchDev bd) {
         const int col = rb0 + 8 * t + 2 * (lane & 3);
         out[(size_t)row * wd.nr_cap + col] = acc[t][0];
         out[(size_t)row * wd.nr_cap + col + 1] = acc[t][1];
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Register-resident variant for reduced systems of up to 184 rows (<= 30 free keyframes): ONE CTA owns the whole lower
+// triangle of Sred as 8x8 accumulator tiles spread cyclically over 16 warps (<= 18 tiles = 36 FP64 registers per lane),
+// so the V panel of a chunk is scattered into shared memory once (not once per 64x64 block), and only the tiles inside
+// the chunk's row range [t0, t1) (+ the rhs tile row) are multiplied.  Landmarks are stored sorted by first keyframe,
+// which makes those ranges tight.  grid = (p_split, windows); each CTA handles a contiguous range of chunks.
+// ---------------------------------------------------------------------------------------------------------------------
+constexpr int kSmallTiles = 23;               // tile rows (184 rows)
+constexpr int kSmallSlots = 18;               // ceil(23*24/2 / 16)
+
+__global__ void __launch_bounds__(512, 1) k_schur_syrk_small(BatchDev bd) {
+    const int w = blockIdx.y;
+    const WinState& st = bd.state[w];
+    if (st.phase != PH_ITERATE || st.solve_failed) return;
+    const WinDesc& wd = bd.desc[w];
+    extern __shared__ double panel[];  // [kSmallTiles*8][kKS]
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int nt = (st.n_f + 1 + 7) >> 3, trhs = st.n_f >> 3, rhs_row = st.n_f;
+    double acc[kSmallSlots][2];
+#pragma unroll
+    for (int s = 0; s < kSmallSlots; ++s) acc[s][0] = acc[s][1] = 0.0;
+    const int* lm_ptr = bd.lm_ptr + wd.lm_off + w;
+    const size_t T = (size_t)bd.tot_obs, base = (size_t)wd.obs_off;
+    const int per = (wd.n_chunks + bd.p_split - 1) / bd.p_split;
+    const int ch0 = blockIdx.x * per, ch1 = min(wd.n_chunks, ch0 + per);
+    const int fr = lane >> 2, fc = lane & 3;  // fragment row / k index of this lane
+    for (int ch = ch0; ch < ch1; ++ch) {
+        const int t0 = bd.chunk_t0[wd.chunk_off + ch], t1 = bd.chunk_t1[wd.chunk_off + ch];
+        if (t1 <= t0) continue;  // the chunk's landmarks are seen by constant keyframes only
+        const int j0 = bd.chunk_lm0[wd.chunk_off + ch], j1 = bd.chunk_lm1[wd.chunk_off + ch];
+        const int o0 = lm_ptr[j0], o1 = lm_ptr[j1];
+        __syncthreads();  // MMA of the previous chunk finished
+        {
+            double* z0 = panel + (size_t)8 * t0 * kKS;
+            const int nz = 8 * (t1 - t0) * kKS;
+            for (int i = threadIdx.x; i < nz; i += blockDim.x) z0[i] = 0.0;
+            if (trhs < t0 || trhs >= t1) {
+                double* z1 = panel + (size_t)8 * trhs * kKS;
+                for (int i = threadIdx.x; i < 8 * kKS; i += blockDim.x) z1[i] = 0.0;
+            }
+        }
+        __syncthreads();
+        const int nobs = o1 - o0;
+        for (int idx = threadIdx.x; idx < nobs * 18; idx += blockDim.x) {
+            const int e = idx / nobs, oo = idx - e * nobs;
+            const size_t o = base + o0 + oo;
+            const int row0 = bd.obs_row[o];
+            if (row0 < 0) continue;
+            panel[(row0 + e / 3) * kKS + 3 * (bd.obs_lm[o] - j0) + e % 3] = bd.vobs[e * T + o];
+        }
+        for (int idx = threadIdx.x; idx < (j1 - j0) * 3; idx += blockDim.x) {
+            const int jl = j0 + idx / 3;
+            if (!bd.lm_active[wd.lm_off + jl] || lm_ptr[jl + 1] <= lm_ptr[jl]) continue;
+            panel[rhs_row * kKS + idx] = bd.lm_z[3 * (size_t)(wd.lm_off + jl) + idx % 3];
+        }
+        __syncthreads();
+#pragma unroll
+        for (int s = 0; s < kSmallSlots; ++s) {
+            const int t = s * 16 + warp;
+            int i = (int)((sqrtf(8.0f * (float)t + 1.0f) - 1.0f) * 0.5f);
+            while ((i + 1) * (i + 2) / 2 <= t) ++i;
+            while (i * (i + 1) / 2 > t) --i;
+            const int j = t - i * (i + 1) / 2;
+            if (i >= nt) continue;
+            const bool ai = (i >= t0 && i < t1) || i == trhs, aj = (j >= t0 && j < t1) || j == trhs;
+            if (!(ai && aj)) continue;
+            const double* arow = panel + (8 * i + fr) * kKS + fc;
+            const double* brow = panel + (8 * j + fr) * kKS + fc;
+#pragma unroll 8
+            for (int kk = 0; kk < kKC; kk += 4) dmma(acc[s][0], acc[s][1], arow[kk], brow[kk]);
+        }
+    }
+    double* out = bd.sred + wd.s_off * (size_t)bd.p_split + (size_t)blockIdx.x * wd.nr_cap * wd.nr_cap;
+#pragma unroll
+    for (int s = 0; s < kSmallSlots; ++s) {
+        const int t = s * 16 + warp;
+        int i = (int)((sqrtf(8.0f * (float)t + 1.0f) - 1.0f) * 0.5f);
+        while ((i + 1) * (i + 2) / 2 <= t) ++i;
+        while (i * (i + 1) / 2 > t) --i;
+        const int j = t - i * (i + 1) / 2;
+        if (i >= nt) continue;
+        double* o = out + (size_t)(8 * i + fr) * wd.nr_cap + 8 * j + 2 * fc;
+        o[0] = acc[s][0];
+        o[1] = acc[s][1];
     }
 }
 
@@ -911,9 +1015,11 @@ __global__ void __launch_bounds__(512) k_trim_select(BatchDev bd, SolveParams sp
             const double vj = v[j];
             if (!(vj >= 0.0)) continue;
             int rank = 0;
+            const int* orig = bd.lm_orig + wd.lm_off;  // ties are broken by the caller's landmark index
+            const int oj = orig[j];
             for (int k = 0; k < wd.n_lm; ++k) {
                 const double vk = v[k];
-                rank += (vk >= 0.0) && (vk < vj || (vk == vj && k < j));
+                rank += (vk >= 0.0) && (vk < vj || (vk == vj && orig[k] < oj));
             }
             if (rank >= num) bd.trim_reject[wd.lm_off + j] = 1;
         }
@@ -970,10 +1076,13 @@ __global__ void k_reset_state(BatchDev bd, int rounds_total_override, int min_la
 // launch wrappers
 // =====================================================================================================================
 static inline size_t schur_smem() { return (size_t)2 * 64 * kKS * sizeof(double); }
+static inline size_t schur_small_smem() { return (size_t)kSmallTiles * 8 * kKS * sizeof(double); }
 static inline size_t solve_smem(int ld) { return ((size_t)4 * ld + kNB * (kNB + 1) + (size_t)ld * (kNB + 1)) * sizeof(double); }
 
 cudaError_t configure_kernels(int nr_cap_max) {
     cudaError_t e = cudaFuncSetAttribute(k_schur_syrk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)schur_smem());
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(k_schur_syrk_small, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)schur_small_smem());
     if (e != cudaSuccess) return e;
     return cudaFuncSetAttribute(k_reduced_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)solve_smem(nr_cap_max));
 }
@@ -993,8 +1102,12 @@ void launch_pass(const BatchDev& bd, const SolveParams& sp, const LaunchCfg& lc,
     if (timed) cudaEventRecord(lc.ev_pool[(*lc.ev_used)++], s);
     k_pose_hessian<<<dim3(bd.max_kf, B), 256, 0, s>>>(bd, sp);
     k_landmark_prep<<<g_lm, 256, 0, s>>>(bd, sp);
-    const int nb = lc.nr_cap_max / 64;
-    k_schur_syrk<<<dim3(nb * (nb + 1) / 2, bd.p_split, B), 256, schur_smem(), s>>>(bd);
+    if (lc.small_syrk) {
+        k_schur_syrk_small<<<dim3(bd.p_split, B), 512, schur_small_smem(), s>>>(bd);
+    } else {
+        const int nb = lc.nr_cap_max / 64;
+        k_schur_syrk<<<dim3(nb * (nb + 1) / 2, bd.p_split, B), 256, schur_smem(), s>>>(bd);
+    }
     k_reduced_solve<<<B, 512, solve_smem(lc.nr_cap_max), s>>>(bd, sp);
     k_backsub<<<g_lm, 256, 0, s>>>(bd);
     k_eval_obs<false><<<g_obs, 256, 0, s>>>(bd, sp);
