@@ -256,6 +256,62 @@ __device__ inline bool eval_observation(const T* __restrict__ pose, const T* __r
     return true;
 }
 
+// Streaming form of eval_observation for the residual/Jacobian kernel: every Jacobian row is written to its SoA slot
+// as soon as it is formed, so at most one 3-vector m and the rotated point a stay live (64 registers -> 4 CTAs/SM).
+// res/jp/jl point at this observation's slot of component 0; `stride` is the component stride (total observations).
+template <typename T>
+__device__ inline bool eval_observation_store(const T* __restrict__ pose, const T* __restrict__ cam, const T p[3], T u,
+                                              T v, T d, T wt, T b_repr, T b_depth, T* __restrict__ res,
+                                              T* __restrict__ jp, T* __restrict__ jl, size_t stride, bool write_jp,
+                                              T& half_rho_sum) {
+    const T a0 = pose[0] * p[0] + pose[1] * p[1] + pose[2] * p[2];
+    const T a1 = pose[3] * p[0] + pose[4] * p[1] + pose[5] * p[2];
+    const T a2 = pose[6] * p[0] + pose[7] * p[1] + pose[8] * p[2];
+    const T x0 = a0 + pose[9], x1 = a1 + pose[10], x2 = a2 + pose[11];
+    const T c0 = cam[0] * x0 + cam[1] * x1 + cam[2] * x2 + cam[9];
+    const T c1 = cam[3] * x0 + cam[4] * x1 + cam[5] * x2 + cam[10];
+    const T c2 = cam[6] * x0 + cam[7] * x1 + cam[8] * x2 + cam[11];
+    if (!(fabs(c2) >= T(0.01))) return false;
+    const T f = cam[12], iz = T(1) / c2;
+    const T xn = c0 * iz, yn = c1 * iz;
+    const T ru = f * xn + cam[13] - u, rv = f * yn + cam[14] - v;
+    T hr, sq;
+    cauchy<T>(b_repr, wt, ru * ru + rv * rv, hr, sq);
+    half_rho_sum = hr;
+    T sqd = T(0), rd = T(0);
+    if (d > T(0)) {
+        rd = c2 - d;
+        T hrd;
+        cauchy<T>(b_depth, wt, rd * rd, hrd, sqd);
+        half_rho_sum += hrd;
+    }
+    res[0] = sq * ru;
+    res[stride] = sq * rv;
+    res[2 * stride] = sqd * rd;
+    const T fz = f * iz * sq;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        T m0, m1, m2;
+        if (i == 0) { m0 = fz * (cam[0] - xn * cam[6]); m1 = fz * (cam[1] - xn * cam[7]); m2 = fz * (cam[2] - xn * cam[8]); }
+        else if (i == 1) { m0 = fz * (cam[3] - yn * cam[6]); m1 = fz * (cam[4] - yn * cam[7]); m2 = fz * (cam[5] - yn * cam[8]); }
+        else { m0 = sqd * cam[6]; m1 = sqd * cam[7]; m2 = sqd * cam[8]; }
+        if (write_jp) {
+            T* o = jp + (size_t)(6 * i) * stride;
+            o[0] = T(-2) * (m1 * a2 - m2 * a1);
+            o[stride] = T(-2) * (m2 * a0 - m0 * a2);
+            o[2 * stride] = T(-2) * (m0 * a1 - m1 * a0);
+            o[3 * stride] = m0;
+            o[4 * stride] = m1;
+            o[5 * stride] = m2;
+        }
+        T* q = jl + (size_t)(3 * i) * stride;
+        q[0] = m0 * pose[0] + m1 * pose[3] + m2 * pose[6];
+        q[stride] = m0 * pose[1] + m1 * pose[4] + m2 * pose[7];
+        q[2 * stride] = m0 * pose[2] + m1 * pose[5] + m2 * pose[8];
+    }
+    return true;
+}
+
 // stage keyframe poses (as R|t) and cameras of one window into shared memory
 __device__ inline void stage_window(const WinDesc& wd, const double* __restrict__ pose7, const double* __restrict__ cam16,
                                     double* s_pose, double* s_cam) {

@@ -95,7 +95,7 @@ __global__ void __launch_bounds__(256) k_solve_begin(BatchDev bd, SolveParams sp
 // Algorithmic HBM bytes per observation (FP64, with depth row): 20 read + 240 written.
 // =====================================================================================================================
 template <bool kJac>
-__global__ void __launch_bounds__(256) k_eval_obs(BatchDev bd, SolveParams sp) {
+__global__ void __launch_bounds__(256, 4) k_eval_obs(BatchDev bd, SolveParams sp) {
     const int w = blockIdx.y;
     WinState& st = bd.state[w];
     if (st.phase != PH_ITERATE) return;
@@ -118,27 +118,26 @@ __global__ void __launch_bounds__(256) k_eval_obs(BatchDev bd, SolveParams sp) {
             const double* lm = bd.lm[buf] + 3 * (size_t)L;
             const double p[3] = {lm[0], lm[1], lm[2]};
             const int k = bd.obs_kf[o], c = bd.obs_cam[o];
-            double r[3], jp[18], jl[9], raw[2], hr = 0.0;
-            const bool ok = eval_observation<double, kJac>(
-                s_pose + kPoseStride * k, s_cam + kCamStride * c, p, (double)bd.obs_u[o], (double)bd.obs_v[o],
-                (double)bd.obs_d[o], bd.lm_weight[L], sp.reprojection_thres * sp.reprojection_thres,
-                sp.depth_thres * sp.depth_thres, r, jp, jl, hr, raw);
+            double hr = 0.0;
+            bool ok;
+            if (kJac) {  // rows are stored to their SoA slots as they are formed
+                ok = eval_observation_store<double>(
+                    s_pose + kPoseStride * k, s_cam + kCamStride * c, p, (double)bd.obs_u[o], (double)bd.obs_v[o],
+                    (double)bd.obs_d[o], bd.lm_weight[L], sp.reprojection_thres * sp.reprojection_thres,
+                    sp.depth_thres * sp.depth_thres, bd.res + o, bd.jp + o, bd.jl + o, (size_t)bd.tot_obs,
+                    bd.off_pose[wd.kf_off + k] >= 0, hr);
+            } else {
+                double r[3], raw[2];
+                ok = eval_observation<double, false>(
+                    s_pose + kPoseStride * k, s_cam + kCamStride * c, p, (double)bd.obs_u[o], (double)bd.obs_v[o],
+                    (double)bd.obs_d[o], bd.lm_weight[L], sp.reprojection_thres * sp.reprojection_thres,
+                    sp.depth_thres * sp.depth_thres, r, nullptr, nullptr, hr, raw);
+            }
             if (!ok) {
                 st.eval_failed = 1;  // benign race
             } else {
                 cost = hr;
                 done = 1;
-                if (kJac) {
-                    const size_t T = (size_t)bd.tot_obs;
-#pragma unroll
-                    for (int q = 0; q < 3; ++q) bd.res[q * T + o] = r[q];
-#pragma unroll
-                    for (int q = 0; q < 9; ++q) bd.jl[q * T + o] = jl[q];
-                    if (bd.off_pose[wd.kf_off + k] >= 0) {
-#pragma unroll
-                        for (int q = 0; q < 18; ++q) bd.jp[q * T + o] = jp[q];
-                    }
-                }
             }
         }
     }
