@@ -73,7 +73,9 @@ struct kba_batch {
     // outputs
     Staged<WinState> state;
     Staged<IterRecord> log;
-    Staged<double> pose_out[2], lm_out[2];
+    Staged<double> pose_out[2], lm_out[2], plane_out[2];
+    Staged<int> gp_lm, gp_kf, gp_of_lm;
+    Staged<double> gp_weight;
     Staged<uint8_t> lm_active;
     Staged<int> n_active;
     Staged<unsigned long long> jac_obs;
@@ -98,7 +100,8 @@ struct kba_batch {
         lm_orig.release(); obs_orig.release(); obs_u.release(); obs_v.release();
         obs_d.release(); pm_u.release(); pm_v.release(); pm_d.release(); state.release(); log.release();
         pose_out[0].release(); pose_out[1].release(); lm_out[0].release(); lm_out[1].release(); lm_active.release();
-        n_active.release(); jac_obs.release();
+        n_active.release(); jac_obs.release(); plane_out[0].release(); plane_out[1].release();
+        gp_lm.release(); gp_kf.release(); gp_of_lm.release(); gp_weight.release();
         for (void* p : scratch) cudaFree(p);
         scratch.clear();
         if (ev_a) cudaEventDestroy(ev_a);
@@ -114,8 +117,11 @@ static int validate_window(const kba_window* w, std::string& why) {
     if (w->n_obs > 0 && (!w->obs_kf || !w->obs_u || !w->obs_v || !w->obs_d)) { why = "null observation array"; return KBA_ERR_BAD_ARG; }
     if (w->n_kf > kMaxKf) { why = "more than 128 keyframes per window"; return KBA_ERR_CAPACITY; }
     if (w->n_cam > kMaxCam) { why = "more than 8 cameras per window"; return KBA_ERR_CAPACITY; }
-    if (w->n_gp > 0 || w->plane_reg_weight > 0) { why = "ground-plane residuals are not implemented in this build of the CUDA path"; return KBA_ERR_CAPACITY; }
-    if (w->landmarks_fixed || w->speed_weight > 0) { why = "motion-only windows are not implemented in this build of the CUDA path"; return KBA_ERR_CAPACITY; }
+    if ((w->n_gp > 0 || w->plane_reg_weight > 0) && !w->kf_plane) { why = "ground-plane residuals need kf_plane"; return KBA_ERR_BAD_ARG; }
+    if (w->n_gp > 0 && (!w->gp_lm || !w->gp_kf || !w->gp_weight)) { why = "null ground-plane array"; return KBA_ERR_BAD_ARG; }
+    for (int g = 0; g < w->n_gp; ++g)
+        if (w->gp_lm[g] < 0 || w->gp_lm[g] >= w->n_lm || w->gp_kf[g] < 0 || w->gp_kf[g] >= w->n_kf) { why = "ground-plane index out of range"; return KBA_ERR_BAD_ARG; }
+    if (w->speed_weight > 0 && (w->speed_kf < 0 || w->speed_kf >= w->n_kf || !(w->speed_dt > 0))) { why = "speed prior: keyframe out of range or dt <= 0"; return KBA_ERR_BAD_ARG; }
     if (w->n_lm > 0 && w->lm_obs_ptr[w->n_lm] != w->n_obs) { why = "lm_obs_ptr[n_lm] != n_obs"; return KBA_ERR_BAD_ARG; }
     for (int o = 0; o < w->n_obs; ++o) {
         if (w->obs_kf[o] < 0 || w->obs_kf[o] >= w->n_kf) { why = "obs_kf out of range"; return KBA_ERR_BAD_ARG; }
@@ -187,6 +193,20 @@ static void fill_window(kba_batch* b, int wi, const kba_window* w) {
             b->pm_cam.h[e] = b->obs_cam.h[src];
             b->pm_u.h[e] = b->obs_u.h[src]; b->pm_v.h[e] = b->obs_v.h[src]; b->pm_d.h[e] = b->obs_d.h[src];
         }
+    // ground-plane residuals follow their landmark into the sorted order
+    std::vector<int> gp_kf_of_lm(nl, -1);
+    {
+        std::vector<int> inv(nl);
+        for (int jn = 0; jn < nl; ++jn) { inv[orig[jn]] = jn; b->gp_of_lm.h[d.lm_off + jn] = -1; }
+        for (int g = 0; g < w->n_gp; ++g) {
+            const int jn = inv[w->gp_lm[g]];
+            b->gp_lm.h[d.gp_off + g] = jn;
+            b->gp_kf.h[d.gp_off + g] = w->gp_kf[g];
+            b->gp_weight.h[d.gp_off + g] = w->gp_weight[g];
+            b->gp_of_lm.h[d.lm_off + jn] = g;
+            gp_kf_of_lm[jn] = w->gp_kf[g];
+        }
+    }
     for (int c = 0; c < d.n_chunks; ++c) {
         const int j0 = c * 32, j1 = std::min(nl, (c + 1) * 32);
         b->chunk_lm0.h[d.chunk_off + c] = j0;
@@ -196,6 +216,8 @@ static void fill_window(kba_batch* b, int wi, const kba_window* w) {
             const int k = b->obs_kf.h[(size_t)d.obs_off + o];
             k0 = std::min(k0, k); k1 = std::max(k1, k);
         }
+        for (int j = j0; j < j1; ++j)
+            if (gp_kf_of_lm[j] >= 0) { k0 = std::min(k0, gp_kf_of_lm[j]); k1 = std::max(k1, gp_kf_of_lm[j]); }
         b->chunk_k0.h[d.chunk_off + c] = k0;
         b->chunk_k1.h[d.chunk_off + c] = k1;
     }
@@ -282,33 +304,39 @@ int kba_batch_create(kba_handle* h, int32_t n_windows, const kba_window* w, kba_
     for (int i = 0; i < n_windows; ++i) {
         const int rc = validate_window(&w[i], why);
         if (rc != KBA_OK) return fail(rc, "window " + std::to_string(i) + ": " + why);
-        if (w[i].n_kf < 3) return fail(KBA_ERR_NOT_ENOUGH_KF, "window " + std::to_string(i) + ": fewer than 3 keyframes");
+        if (w[i].n_kf < 3 && !w[i].landmarks_fixed)  // solve() needs 3 keyframes (cpp:630); adjustPoseOnly() has one
+            return fail(KBA_ERR_NOT_ENOUGH_KF, "window " + std::to_string(i) + ": fewer than 3 keyframes");
     }
     kba_batch* b = new kba_batch();
     b->h = h;
     BatchDev& bd = b->bd;
     bd.n_win = n_windows;
     b->desc_h.resize(n_windows);
-    long long kf = 0, cam = 0, lm = 0, obs = 0, chunks = 0, soff = 0;
+    long long kf = 0, cam = 0, lm = 0, obs = 0, chunks = 0, soff = 0, gp = 0;
+    int max_rows = 0;
     int nr_cap_max = 64;
     for (int i = 0; i < n_windows; ++i) {
         WinDesc& d = b->desc_h[i];
         memset(&d, 0, sizeof d);
-        d.n_kf = w[i].n_kf; d.n_cam = w[i].n_cam; d.n_lm = w[i].n_lm; d.n_obs = w[i].n_obs; d.n_gp = 0;
-        d.kf_off = (int)kf; d.cam_off = (int)cam; d.lm_off = (int)lm; d.obs_off = (int)obs; d.gp_off = 0;
+        d.n_kf = w[i].n_kf; d.n_cam = w[i].n_cam; d.n_lm = w[i].n_lm; d.n_obs = w[i].n_obs; d.n_gp = w[i].n_gp;
+        d.kf_off = (int)kf; d.cam_off = (int)cam; d.lm_off = (int)lm; d.obs_off = (int)obs; d.gp_off = (int)gp;
         d.chunk_off = (int)chunks; d.n_chunks = (w[i].n_lm + 31) / 32;
         d.scale_kf0 = w[i].scale_kf0; d.scale_kf1 = w[i].scale_kf1;
         d.scale_weight = w[i].scale_weight; d.scale_value = w[i].scale_value;
-        d.nr_cap = ((6 * w[i].n_kf + 1 + 63) / 64) * 64;
+        const bool planes = w[i].n_gp > 0 || w[i].plane_reg_weight > 0;
+        const int rows = (planes ? 10 : 6) * w[i].n_kf + 1;
+        max_rows = std::max(max_rows, rows);
+        d.nr_cap = ((rows + 63) / 64) * 64;
+        d.plane_reg_weight = w[i].plane_reg_weight; d.plane_dist_fixed = w[i].plane_dist_fixed;
         d.s_off = soff;
         soff += (long long)d.nr_cap * d.nr_cap;
         nr_cap_max = std::max(nr_cap_max, d.nr_cap);
-        kf += w[i].n_kf; cam += w[i].n_cam; lm += w[i].n_lm; obs += w[i].n_obs; chunks += d.n_chunks;
+        kf += w[i].n_kf; cam += w[i].n_cam; lm += w[i].n_lm; obs += w[i].n_obs; chunks += d.n_chunks; gp += w[i].n_gp;
         bd.max_obs = std::max(bd.max_obs, w[i].n_obs); bd.max_lm = std::max(bd.max_lm, w[i].n_lm);
         bd.max_kf = std::max(bd.max_kf, w[i].n_kf);
     }
     if (obs > 2000000000LL) { delete b; return fail(KBA_ERR_CAPACITY, "batch exceeds 2^31 observations"); }
-    bd.tot_kf = kf; bd.tot_cam = cam; bd.tot_lm = lm; bd.tot_obs = obs; bd.tot_chunks = (int)chunks;
+    bd.tot_kf = kf; bd.tot_cam = cam; bd.tot_lm = lm; bd.tot_obs = obs; bd.tot_chunks = (int)chunks; bd.tot_gp = gp;
     bd.nr_cap_max = nr_cap_max;
     b->lc.nr_cap_max = nr_cap_max;
     // split the landmark chunks of each window over several CTAs when the batch alone cannot fill the GPU
@@ -317,7 +345,7 @@ int kba_batch_create(kba_handle* h, int32_t n_windows, const kba_window* w, kba_
         int max_chunks = 1;
         for (auto& d : b->desc_h) max_chunks = std::max(max_chunks, d.n_chunks);
         int p = (2 * h->sm_count + n_windows * pairs - 1) / (n_windows * pairs);
-        b->lc.small_syrk = (6 * bd.max_kf + 1 <= 184);
+        b->lc.small_syrk = (max_rows <= 184);
         if (b->lc.small_syrk) p = (h->sm_count + n_windows - 1) / n_windows;  // one CTA per SM, each owning all tiles
         bd.p_split = std::max(1, std::min(p, max_chunks));
     }
@@ -340,7 +368,10 @@ int kba_batch_create(kba_handle* h, int32_t n_windows, const kba_window* w, kba_
     for (int q = 0; q < 2; ++q) { bad |= b->pose_out[q].alloc(7 * kf, true); bad |= b->lm_out[q].alloc(3 * lm, true); }
     bad |= b->lm_active.alloc(lm, true); bad |= b->n_active.alloc(1, true); bad |= b->jac_obs.alloc(1, true);
     // device-only scratch
-    bad |= b->dev_alloc(&bd.plane[0], 4 * kf); bad |= b->dev_alloc(&bd.plane[1], 4 * kf);
+    bad |= b->plane_out[0].alloc(4 * kf, true); bad |= b->plane_out[1].alloc(4 * kf, true);
+    bad |= b->gp_lm.alloc(gp, true); bad |= b->gp_kf.alloc(gp, true); bad |= b->gp_weight.alloc(gp, true); bad |= b->gp_of_lm.alloc(lm, true);
+    bad |= b->dev_alloc(&bd.gp_lin, 14 * gp); bad |= b->dev_alloc(&bd.vgp, 30 * gp);
+    bad |= b->dev_alloc(&bd.gp_cost_x, n_windows); bad |= b->dev_alloc(&bd.gp_cost_c, n_windows);
     bad |= b->dev_alloc(&bd.off_pose, kf); bad |= b->dev_alloc(&bd.off_dir, kf); bad |= b->dev_alloc(&bd.off_dist, kf);
     bad |= b->dev_alloc(&bd.bkf, 27 * kf);
     bad |= b->dev_alloc(&bd.scale_f, (size_t)n_windows * nr_cap_max); bad |= b->dev_alloc(&bd.lambda_f, (size_t)n_windows * nr_cap_max);
@@ -368,6 +399,8 @@ int kba_batch_create(kba_handle* h, int32_t n_windows, const kba_window* w, kba_
     bd.kf_ptr = b->kf_ptr.d; bd.pm_lm = b->pm_lm.d; bd.pm_cam = b->pm_cam.d; bd.pm_u = b->pm_u.d; bd.pm_v = b->pm_v.d; bd.pm_d = b->pm_d.d;
     bd.chunk_lm0 = b->chunk_lm0.d; bd.chunk_lm1 = b->chunk_lm1.d; bd.chunk_k0 = b->chunk_k0.d; bd.chunk_k1 = b->chunk_k1.d;
     bd.lm_orig = b->lm_orig.d;
+    bd.plane[0] = b->plane_out[0].d; bd.plane[1] = b->plane_out[1].d;
+    bd.gp_lm = b->gp_lm.d; bd.gp_kf = b->gp_kf.d; bd.gp_weight = b->gp_weight.d; bd.gp_of_lm = b->gp_of_lm.d;
     bd.n_active = b->n_active.d;
     bd.jac_obs = b->jac_obs.d;
     CU(cudaMemset(bd.jac_obs, 0, sizeof(unsigned long long)));
@@ -388,6 +421,11 @@ int kba_batch_upload(kba_batch* b, int32_t n_windows, const kba_window* w) {
             return fail(KBA_ERR_BAD_ARG, "kba_batch_upload: window shapes differ from kba_batch_create");
         b->desc_h[i].scale_weight = w[i].scale_weight; b->desc_h[i].scale_value = w[i].scale_value;
         b->desc_h[i].scale_kf0 = w[i].scale_kf0; b->desc_h[i].scale_kf1 = w[i].scale_kf1;
+        b->desc_h[i].landmarks_fixed = w[i].landmarks_fixed;
+        b->desc_h[i].plane_reg_weight = w[i].plane_reg_weight; b->desc_h[i].plane_dist_fixed = w[i].plane_dist_fixed;
+        b->desc_h[i].speed_kf = w[i].speed_kf; b->desc_h[i].speed_weight = w[i].speed_weight; b->desc_h[i].speed_dt = w[i].speed_dt;
+        memcpy(b->desc_h[i].speed_v_before, w[i].speed_v_before, sizeof(double) * 3);
+        memcpy(b->desc_h[i].speed_T_origin_before, w[i].speed_T_origin_before, sizeof(double) * 7);
         b->desc.h[i] = b->desc_h[i];
         fill_window(b, i, &w[i]);
     }
@@ -399,6 +437,7 @@ int kba_batch_upload(kba_batch* b, int32_t n_windows, const kba_window* w) {
     CU(b->kf_ptr.upload(s)); CU(b->pm_lm.upload(s)); CU(b->pm_cam.upload(s)); CU(b->pm_u.upload(s)); CU(b->pm_v.upload(s)); CU(b->pm_d.upload(s));
     CU(b->chunk_lm0.upload(s)); CU(b->chunk_lm1.upload(s)); CU(b->chunk_k0.upload(s)); CU(b->chunk_k1.upload(s));
     CU(b->lm_orig.upload(s));
+    CU(b->gp_lm.upload(s)); CU(b->gp_kf.upload(s)); CU(b->gp_weight.upload(s)); CU(b->gp_of_lm.upload(s));
     const BatchDev& bd = b->bd;
     b->h2d_bytes = sizeof(WinDesc) * bd.n_win + (7 + 4) * 8 * bd.tot_kf + bd.tot_kf + kCamStride * 8 * bd.tot_cam +
                    (3 + 1) * 8 * bd.tot_lm + 4 * (bd.tot_lm + bd.n_win) + (3 * 4 + 3 * 4) * bd.tot_obs +
@@ -408,6 +447,7 @@ int kba_batch_upload(kba_batch* b, int32_t n_windows, const kba_window* w) {
 
 static SolveParams make_params(const kba_options* o) {
     SolveParams sp;
+    sp.gp_huber = o->gp_huber; sp.gp_quantile = o->gp_quantile;
     sp.depth_thres = o->depth_thres; sp.reprojection_thres = o->reprojection_thres;
     sp.depth_quantile = o->depth_quantile; sp.reprojection_quantile = o->reprojection_quantile;
     sp.function_tolerance = o->function_tolerance; sp.gradient_tolerance = o->gradient_tolerance;
@@ -479,6 +519,7 @@ int kba_batch_download(kba_batch* b, kba_result* res) {
     CU(b->state.download(s)); CU(b->log.download(s));
     CU(b->pose_out[0].download(s)); CU(b->pose_out[1].download(s));
     CU(b->lm_out[0].download(s)); CU(b->lm_out[1].download(s)); CU(b->lm_active.download(s));
+    CU(b->plane_out[0].download(s)); CU(b->plane_out[1].download(s));
     CU(cudaStreamSynchronize(s));
     const BatchDev& bd = b->bd;
     b->d2h_bytes = sizeof(WinState) * bd.n_win + 2 * (7 * 8 * bd.tot_kf + 3 * 8 * bd.tot_lm) + bd.tot_lm;
@@ -488,7 +529,7 @@ int kba_batch_download(kba_batch* b, kba_result* res) {
         kba_result& r = res[i];
         const int cur = st.cur;
         if (r.kf_pose) memcpy(r.kf_pose, b->pose_out[cur].h + 7 * (size_t)d.kf_off, sizeof(double) * 7 * d.n_kf);
-        if (r.kf_plane) memcpy(r.kf_plane, b->plane0.h + 4 * (size_t)d.kf_off, sizeof(double) * 4 * d.n_kf);
+        if (r.kf_plane) memcpy(r.kf_plane, b->plane_out[cur].h + 4 * (size_t)d.kf_off, sizeof(double) * 4 * d.n_kf);
         const int* orig = b->lm_orig.h + d.lm_off;
         if (r.lm_pos)
             for (int j = 0; j < d.n_lm; ++j) memcpy(r.lm_pos + 3 * (size_t)orig[j], b->lm_out[cur].h + 3 * (size_t)(d.lm_off + j), 3 * sizeof(double));

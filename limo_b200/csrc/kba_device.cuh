@@ -149,9 +149,19 @@ struct BatchDev {
     int tot_chunks;
     int* n_active;            // [1] windows still running (device counter)
     unsigned long long* jac_obs;  // [1] observations linearised by the residual/Jacobian kernel since the last reset
+    // ground-plane height residuals (one per ground landmark, attached to a keyframe by the host)
+    int* gp_lm;               // [tot_gp] window-local (sorted) landmark index
+    int* gp_kf;               // [tot_gp] keyframe index
+    double* gp_weight;        // [tot_gp] ScaledLoss weight
+    int* gp_of_lm;            // [tot_lm] window-local gp index of the landmark or -1
+    double* gp_lin;           // [14][tot_gp] robustified residual, J_f (pose 6, dir 3 local, dist 1), J_l (3)
+    double* vgp;              // [30][tot_gp] V rows of the gp residual: (J_f^T J_l) L^-T, 10 x 3
+    double* gp_cost_x;        // [n_win] robustified cost of the gp blocks at x / at the candidate (fixed-order sums)
+    double* gp_cost_c;
 };
 
 struct SolveParams {  // kba_options subset used on the device
+    double gp_huber, gp_quantile;
     double depth_thres, reprojection_thres, depth_quantile, reprojection_quantile;
     double function_tolerance, gradient_tolerance, parameter_tolerance;
     double initial_radius, max_radius, min_radius, min_relative_decrease, min_lm_diagonal, max_lm_diagonal;

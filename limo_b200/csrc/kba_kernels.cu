@@ -6,6 +6,7 @@
 // host launches a fixed sequence without synchronising per iteration.
 #include "kba_device.cuh"
 #include "kba_kernels.h"
+#include "kba_regularisers.cuh"
 
 #include <cfloat>
 #include <cmath>
@@ -21,10 +22,22 @@ __global__ void __launch_bounds__(256) k_solve_begin(BatchDev bd, SolveParams sp
     if (st.phase != PH_SOLVE_BEGIN) return;
     const WinDesc wd = bd.desc[w];
     __shared__ int s_has[kMaxKf];
-    __shared__ int s_cnt[2];
-    for (int k = threadIdx.x; k < wd.n_kf; k += blockDim.x) s_has[k] = 0;
-    if (threadIdx.x < 2) s_cnt[threadIdx.x] = 0;
+    __shared__ int s_plane[kMaxKf];  // keyframe's plane blocks are referenced by a ground-plane residual
+    __shared__ int s_cnt[3];
+    for (int k = threadIdx.x; k < wd.n_kf; k += blockDim.x) { s_has[k] = 0; s_plane[k] = 0; }
+    if (threadIdx.x < 3) s_cnt[threadIdx.x] = 0;
     __syncthreads();
+    {
+        int n_gp_act = 0;
+        for (int gi = threadIdx.x; gi < wd.n_gp; gi += blockDim.x) {
+            const size_t G = (size_t)wd.gp_off + gi;
+            if (!bd.lm_active[wd.lm_off + bd.gp_lm[G]]) continue;
+            s_has[bd.gp_kf[G]] = 1;
+            s_plane[bd.gp_kf[G]] = 1;
+            n_gp_act++;
+        }
+        atomicAdd(&s_cnt[2], n_gp_act);
+    }
     const int* lm_ptr = bd.lm_ptr + wd.lm_off + w;
     int n_lm_in = 0, n_blocks = 0;
     for (int j = threadIdx.x; j < wd.n_lm; j += blockDim.x) {
@@ -41,14 +54,23 @@ __global__ void __launch_bounds__(256) k_solve_begin(BatchDev bd, SolveParams sp
     __syncthreads();
     if (threadIdx.x == 0) {
         if (wd.scale_weight > 0) { s_has[wd.scale_kf0] = 1; s_has[wd.scale_kf1] = 1; }
-        int n = 0;
+        if (wd.speed_weight > 0) s_has[wd.speed_kf] = 1;
+        if (wd.landmarks_fixed) s_cnt[0] = 0;  // landmark blocks are constant: none is in the program
+        const bool chain = wd.plane_reg_weight > 0 && wd.n_kf > 1;  // adds pose, normal and distance blocks of every keyframe
+        int n = 0, n_reg = 0;
         for (int k = 0; k < wd.n_kf; ++k) {
-            const bool var = s_has[k] && !bd.kf_fixed[wd.kf_off + k];
+            const bool fixed = bd.kf_fixed[wd.kf_off + k];
+            const bool var = (s_has[k] || chain) && !fixed;
             bd.off_pose[wd.kf_off + k] = var ? n : -1;
             if (var) n += 6;
-            bd.off_dir[wd.kf_off + k] = -1;
-            bd.off_dist[wd.kf_off + k] = -1;
+            const bool pl = (s_plane[k] || chain) && !fixed;       // reference cpp:198-219: fixed keyframe -> plane constant
+            bd.off_dir[wd.kf_off + k] = pl ? n : -1;
+            if (pl) n += 3;
+            const bool pd = pl && !wd.plane_dist_fixed;            // reference cpp:722-728
+            bd.off_dist[wd.kf_off + k] = pd ? n : -1;
+            if (pd) n += 1;
         }
+        if (chain) n_reg = 3 * (wd.n_kf - 1) + wd.n_kf;
         st.n_f = n;
         st.nr = (n + 1 + 7) & ~7;
         st.radius = sp.initial_radius;
@@ -66,7 +88,7 @@ __global__ void __launch_bounds__(256) k_solve_begin(BatchDev bd, SolveParams sp
         s.initial_cost = s.final_cost = 0.0;
         s.num_iterations = 0; s.num_successful_steps = 0; s.termination = 1;
         s.num_landmarks = s_cnt[0];
-        s.num_residual_blocks = s_cnt[1] + (wd.scale_weight > 0 ? 1 : 0);
+        s.num_residual_blocks = s_cnt[1] + s_cnt[2] + n_reg + (wd.scale_weight > 0 ? 1 : 0) + (wd.speed_weight > 0 ? 1 : 0);
         st.phase = PH_ITERATE;
     }
     __syncthreads();
@@ -80,8 +102,10 @@ __global__ void __launch_bounds__(256) k_solve_begin(BatchDev bd, SolveParams sp
     for (int c = threadIdx.x; c < wd.n_chunks; c += blockDim.x) {
         int r0 = 1 << 30, r1 = -1;
         for (int k = bd.chunk_k0[wd.chunk_off + c]; k <= bd.chunk_k1[wd.chunk_off + c]; ++k) {
-            const int off = bd.off_pose[wd.kf_off + k];
+            const int off = bd.off_pose[wd.kf_off + k], od = bd.off_dir[wd.kf_off + k], oz = bd.off_dist[wd.kf_off + k];
             if (off >= 0) { r0 = min(r0, off); r1 = max(r1, off + 6); }
+            if (od >= 0) { r0 = min(r0, od); r1 = max(r1, od + 3); }
+            if (oz >= 0) { r0 = min(r0, oz); r1 = max(r1, oz + 1); }
         }
         bd.chunk_t0[wd.chunk_off + c] = (r1 < 0) ? 0 : r0 / 8;
         bd.chunk_t1[wd.chunk_off + c] = (r1 < 0) ? 0 : (r1 + 7) / 8;
@@ -158,6 +182,76 @@ template __global__ void k_eval_obs<true>(BatchDev, SolveParams);
 template __global__ void k_eval_obs<false>(BatchDev, SolveParams);
 
 // =====================================================================================================================
+// ground-plane height residuals r = n . (R p + t) + dist with ScaledLoss(HuberLoss(0.1), w) (reference
+// cost_functors_ceres.hpp:355-392, bundle_adjuster_keyframes.cpp:517-562).  One CTA per window (a few hundred blocks).
+//   kJac: robustified residual + J_f (pose 6 | plane normal 3, local | distance 1) + J_l (3) -> gp_lin, cost at x
+//   else: cost at the candidate
+// =====================================================================================================================
+template <bool kJac>
+__global__ void __launch_bounds__(256) k_gp_eval(BatchDev bd, SolveParams sp) {
+    const int w = blockIdx.x;
+    const WinState& st = bd.state[w];
+    if (st.phase != PH_ITERATE) return;
+    if (kJac && !st.need_linearize) return;
+    if (!kJac && st.solve_failed) return;
+    const WinDesc& wd = bd.desc[w];
+    if (wd.n_gp == 0) return;
+    __shared__ double s_red[8];
+    const int buf = kJac ? st.cur : 1 - st.cur;
+    const size_t TG = (size_t)bd.tot_gp;
+    double cost = 0.0;
+    for (int gi = threadIdx.x; gi < wd.n_gp; gi += blockDim.x) {
+        const size_t G = (size_t)wd.gp_off + gi;
+        const int L = wd.lm_off + bd.gp_lm[G];
+        if (!bd.lm_active[L]) continue;
+        const int k = bd.gp_kf[G];
+        const double* ps = bd.pose[buf] + 7 * (size_t)(wd.kf_off + k);
+        const double* pl = bd.plane[buf] + 4 * (size_t)(wd.kf_off + k);
+        const double* p = bd.lm[buf] + 3 * (size_t)L;
+        double R[9];
+        quat_to_rot<double>(ps, R);
+        const double a[3] = {R[0] * p[0] + R[1] * p[1] + R[2] * p[2], R[3] * p[0] + R[4] * p[1] + R[5] * p[2],
+                             R[6] * p[0] + R[7] * p[1] + R[8] * p[2]};
+        const double px[3] = {a[0] + ps[4], a[1] + ps[5], a[2] + ps[6]};
+        const double n[3] = {pl[0], pl[1], pl[2]};
+        const double r = n[0] * px[0] + n[1] * px[1] + n[2] * px[2] + pl[3];
+        const double s = r * r, ah = sp.gp_huber, wt = bd.gp_weight[G];
+        double rho, rho1;
+        if (s > ah * ah) { const double q = sqrt(s); rho = 2.0 * ah * q - ah * ah; rho1 = fmax(DBL_MIN, ah / q); }
+        else { rho = s; rho1 = 1.0; }
+        cost += 0.5 * wt * rho;
+        if (kJac) {
+            const double sq = sqrt(wt * rho1);
+            double* o = bd.gp_lin + G;
+            o[0] = sq * r;
+            o[1 * TG] = sq * -2.0 * (n[1] * a[2] - n[2] * a[1]);
+            o[2 * TG] = sq * -2.0 * (n[2] * a[0] - n[0] * a[2]);
+            o[3 * TG] = sq * -2.0 * (n[0] * a[1] - n[1] * a[0]);
+            o[4 * TG] = sq * n[0]; o[5 * TG] = sq * n[1]; o[6 * TG] = sq * n[2];
+            const double nn = n[0] * n[0] + n[1] * n[1] + n[2] * n[2], inv = 1.0 / sqrt(nn);
+            const double npx = (n[0] * px[0] + n[1] * px[1] + n[2] * px[2]) / nn;
+            o[7 * TG] = sq * (px[0] - n[0] * npx) * inv;
+            o[8 * TG] = sq * (px[1] - n[1] * npx) * inv;
+            o[9 * TG] = sq * (px[2] - n[2] * npx) * inv;
+            o[10 * TG] = sq;
+            o[11 * TG] = sq * (n[0] * R[0] + n[1] * R[3] + n[2] * R[6]);
+            o[12 * TG] = sq * (n[0] * R[1] + n[1] * R[4] + n[2] * R[7]);
+            o[13 * TG] = sq * (n[0] * R[2] + n[1] * R[5] + n[2] * R[8]);
+        }
+    }
+    cost = warp_sum(cost);
+    if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = cost;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double s = 0.0;
+        for (int q = 0; q < 8; ++q) s += s_red[q];
+        (kJac ? bd.gp_cost_x : bd.gp_cost_c)[w] = s;
+    }
+}
+template __global__ void k_gp_eval<true>(BatchDev, SolveParams);
+template __global__ void k_gp_eval<false>(BatchDev, SolveParams);
+
+// =====================================================================================================================
 // pose-side Gauss-Newton blocks: one CTA per (keyframe, window) walks the keyframe-major copy of the observations,
 // re-evaluates the Jacobian rows (cheaper than gathering the materialised J_pose across sectors) and reduces
 // B_k = sum J_p^T J_p (21 unique) and g_k = sum J_p^T r (6) with a fixed-shape tree -> deterministic, no atomics.
@@ -230,6 +324,7 @@ __global__ void __launch_bounds__(256) k_landmark_prep(BatchDev bd, SolveParams 
     WinState& st = bd.state[w];
     if (st.phase != PH_ITERATE) return;
     const WinDesc& wd = bd.desc[w];
+    if (wd.landmarks_fixed) return;
     const int lane = threadIdx.x & 31;
     const int j = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (j >= wd.n_lm) return;
@@ -254,6 +349,19 @@ __global__ void __launch_bounds__(256) k_landmark_prep(BatchDev bd, SolveParams 
         c[5] += jl[2] * jl[2] + jl[5] * jl[5] + jl[8] * jl[8];
 #pragma unroll
         for (int a = 0; a < 3; ++a) g[a] += jl[a] * r[0] + jl[3 + a] * r[1] + jl[6 + a] * r[2];
+    }
+    // the landmark's ground-plane height residual (at most one) is one more row of its Jacobian
+    const int gl = (wd.n_gp > 0) ? bd.gp_of_lm[L] : -1;
+    const size_t TG = (size_t)bd.tot_gp, G = (size_t)wd.gp_off + (gl >= 0 ? gl : 0);
+    double gjl[3] = {0, 0, 0};
+    if (gl >= 0) {
+        gjl[0] = bd.gp_lin[11 * TG + G]; gjl[1] = bd.gp_lin[12 * TG + G]; gjl[2] = bd.gp_lin[13 * TG + G];
+        if (lane == 0) {
+            const double gr = bd.gp_lin[G];
+            c[0] += gjl[0] * gjl[0]; c[1] += gjl[0] * gjl[1]; c[2] += gjl[0] * gjl[2];
+            c[3] += gjl[1] * gjl[1]; c[4] += gjl[1] * gjl[2]; c[5] += gjl[2] * gjl[2];
+            g[0] += gjl[0] * gr; g[1] += gjl[1] * gr; g[2] += gjl[2] * gr;
+        }
     }
 #pragma unroll
     for (int q = 0; q < 6; ++q) c[q] = warp_sum(c[q]);
@@ -300,6 +408,13 @@ __global__ void __launch_bounds__(256) k_landmark_prep(BatchDev bd, SolveParams 
             if (st.iter0) bd.lm_scale[3 * (size_t)L + a] = sc[a];
         }
     }
+    if (gl >= 0 && lane < 10) {  // V rows of the gp block: E = J_f^T J_l is 10 x 3 (rank one), row `lane`
+        const double jf = bd.gp_lin[(1 + lane) * TG + G];
+        const double e0 = jf * gjl[0], e1 = jf * gjl[1], e2 = jf * gjl[2];
+        bd.vgp[(3 * lane + 0) * TG + G] = e0 * i00;
+        bd.vgp[(3 * lane + 1) * TG + G] = e0 * i10 + e1 * i11;
+        bd.vgp[(3 * lane + 2) * TG + G] = e0 * i20 + e1 * i21 + e2 * i22;
+    }
     // V_i = E_i L^-T with E_i = J_p^T J_l;  V[r][cc] = sum_m E[r][m] * Linv[cc][m]
     for (int o = o0 + lane; o < o1; o += 32) {
         if (bd.off_pose[wd.kf_off + bd.obs_kf[base + o]] < 0) continue;
@@ -330,6 +445,13 @@ constexpr int kLC = 32;            // landmarks per chunk
 constexpr int kKC = 3 * kLC;       // panel columns per chunk
 constexpr int kKS = kKC + 4;       // panel row stride in doubles (== 4 mod 16 -> conflict-free fragment loads)
 
+// reduced-system row of component r (0..5 pose, 6..8 plane normal, 9 plane distance) of keyframe k, -1 if constant
+__device__ __forceinline__ int gp_row(const BatchDev& bd, const WinDesc& wd, int k, int r) {
+    if (r < 6) { const int o = bd.off_pose[wd.kf_off + k]; return o < 0 ? -1 : o + r; }
+    if (r < 9) { const int o = bd.off_dir[wd.kf_off + k]; return o < 0 ? -1 : o + r - 6; }
+    return bd.off_dist[wd.kf_off + k];
+}
+
 __device__ __forceinline__ void dmma(double& c0, double& c1, double a, double b) {
     asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
                  : "+d"(c0), "+d"(c1)
@@ -341,6 +463,7 @@ __global__ void __launch_bounds__(256, 2) k_schur_syrk(BatchDev bd) {
     const WinState& st = bd.state[w];
     if (st.phase != PH_ITERATE || st.solve_failed) return;
     const WinDesc& wd = bd.desc[w];
+    if (wd.landmarks_fixed) return;
     // block pair (bi >= bj) from the linear index
     int bi = 0, rem = blockIdx.x;
     while (rem > bi) { rem -= bi + 1; ++bi; }
@@ -390,6 +513,20 @@ __global__ void __launch_bounds__(256, 2) k_schur_syrk(BatchDev bd) {
             if (rhs_row >= ra0 && rhs_row < ra0 + 64) pa[(rhs_row - ra0) * kKS + idx] = v;
             if (!diag && rhs_row >= rb0 && rhs_row < rb0 + 64) pb[(rhs_row - rb0) * kKS + idx] = v;
         }
+        if (wd.n_gp > 0) {  // ground-plane rows are ADDED: the pose rows may coincide with an observation's rows
+            __syncthreads();
+            for (int idx = threadIdx.x; idx < (j1 - j0) * 30; idx += blockDim.x) {
+                const int jl = j0 + idx / 30, e = idx % 30;
+                const int gl = bd.gp_of_lm[wd.lm_off + jl];
+                if (gl < 0 || !bd.lm_active[wd.lm_off + jl]) continue;
+                const int row = gp_row(bd, wd, bd.gp_kf[wd.gp_off + gl], e / 3);
+                if (row < 0) continue;
+                const int col = 3 * (jl - j0) + e % 3;
+                const double v = bd.vgp[(size_t)e * bd.tot_gp + wd.gp_off + gl];
+                if (row >= ra0 && row < ra0 + 64) pa[(row - ra0) * kKS + col] += v;
+                if (!diag && row >= rb0 && row < rb0 + 64) pb[(row - rb0) * kKS + col] += v;
+            }
+        }
         __syncthreads();
         const double* arow = pa + (8 * warp + (lane >> 2)) * kKS + (lane & 3);
         const double* brow = pb + (lane >> 2) * kKS + (lane & 3);
@@ -431,6 +568,7 @@ __global__ void __launch_bounds__(512, 1) k_schur_syrk_small(BatchDev bd) {
     const WinState& st = bd.state[w];
     if (st.phase != PH_ITERATE || st.solve_failed) return;
     const WinDesc& wd = bd.desc[w];
+    if (wd.landmarks_fixed) return;
     extern __shared__ double panel[];  // [kSmallTiles*8][kKS]
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int nt = (st.n_f + 1 + 7) >> 3, trhs = st.n_f >> 3, rhs_row = st.n_f;
@@ -470,6 +608,17 @@ __global__ void __launch_bounds__(512, 1) k_schur_syrk_small(BatchDev bd) {
             const int jl = j0 + idx / 3;
             if (!bd.lm_active[wd.lm_off + jl] || lm_ptr[jl + 1] <= lm_ptr[jl]) continue;
             panel[rhs_row * kKS + idx] = bd.lm_z[3 * (size_t)(wd.lm_off + jl) + idx % 3];
+        }
+        if (wd.n_gp > 0) {  // ground-plane rows are ADDED: the pose rows may coincide with an observation's rows
+            __syncthreads();
+            for (int idx = threadIdx.x; idx < (j1 - j0) * 30; idx += blockDim.x) {
+                const int jl = j0 + idx / 30, e = idx % 30;
+                const int gl = bd.gp_of_lm[wd.lm_off + jl];
+                if (gl < 0 || !bd.lm_active[wd.lm_off + jl]) continue;
+                const int row = gp_row(bd, wd, bd.gp_kf[wd.gp_off + gl], e / 3);
+                if (row < 0) continue;
+                panel[row * kKS + 3 * (jl - j0) + e % 3] += bd.vgp[(size_t)e * bd.tot_gp + wd.gp_off + gl];
+            }
         }
         __syncthreads();
 #pragma unroll
@@ -539,6 +688,25 @@ __device__ void scale_regulariser(const double* p1, const double* p0, double s0,
     j0[2] = -2.0 * (ur[0] * t0[1] - ur[1] * t0[0]);
 }
 
+// SpeedRegularizationVector2 (reference cost_functors_ceres.hpp:300-353): r = (R t_ob + t) / dt - v_before on one pose.
+__device__ void speed_regulariser(const double* p, const WinDesc& wd, double r[3], double* J) {
+    double R[9];
+    quat_to_rot<double>(p, R);
+    const double* tob = wd.speed_T_origin_before + 4;
+    double a[3];
+    for (int i = 0; i < 3; ++i) a[i] = R[3 * i] * tob[0] + R[3 * i + 1] * tob[1] + R[3 * i + 2] * tob[2];
+    const double idt = 1.0 / wd.speed_dt;
+    for (int i = 0; i < 3; ++i) r[i] = (a[i] + p[4 + i]) * idt - wd.speed_v_before[i];
+    if (!J) return;
+    // d/d(delta_rot) = -2 [a]x / dt, d/d(delta_t) = I / dt
+    const double X[9] = {0, -a[2], a[1], a[2], 0, -a[0], -a[1], a[0], 0};
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) {
+            J[6 * i + j] = -2.0 * X[3 * i + j] * idt;
+            J[6 * i + 3 + j] = (i == j) ? idt : 0.0;
+        }
+}
+
 __global__ void __launch_bounds__(512, 1) k_reduced_solve(BatchDev bd, SolveParams sp) {
     const int w = blockIdx.x;
     WinState& st = bd.state[w];
@@ -580,7 +748,8 @@ __global__ void __launch_bounds__(512, 1) k_reduced_solve(BatchDev bd, SolvePara
             const int r = idx / ld, c = idx - r * ld;
             if (c > r || c >= n + 1) continue;
             double s = 0.0;
-            for (int p = 0; p < bd.p_split; ++p) s += sp0[p * pstride + (size_t)r * ld + c];
+            if (!wd.landmarks_fixed)  // motion-only problem: no landmark blocks were eliminated
+                for (int p = 0; p < bd.p_split; ++p) s += sp0[p * pstride + (size_t)r * ld + c];
             A[(size_t)r * ld + c] = -s;
         }
     }
@@ -602,6 +771,99 @@ __global__ void __launch_bounds__(512, 1) k_reduced_solve(BatchDev bd, SolvePara
         }
     }
     __syncthreads();
+    // ---- + ground-plane blocks: per keyframe a 10 x 10 (pose | normal | distance) Gauss-Newton block, one warp per keyframe
+    if (wd.n_gp > 0) {
+        const int lane = tid & 31, nwarp = nth >> 5;
+        const size_t TG = (size_t)bd.tot_gp;
+        for (int k = tid >> 5; k < wd.n_kf; k += nwarp) {
+            double acc[3] = {0.0, 0.0, 0.0};
+            int ea[3], eb[3];
+#pragma unroll
+            for (int s = 0; s < 3; ++s) {
+                const int e = lane + 32 * s;
+                int a = 0, b = 0;
+                if (e < 55) { while ((a + 1) * (a + 2) / 2 <= e) ++a; b = e - a * (a + 1) / 2; }
+                else if (e < 65) { a = e - 55; b = -1; }
+                else { a = -1; b = -1; }
+                ea[s] = a; eb[s] = b;
+            }
+            for (int gi = 0; gi < wd.n_gp; ++gi) {
+                const size_t G = (size_t)wd.gp_off + gi;
+                if (bd.gp_kf[G] != k || !bd.lm_active[wd.lm_off + bd.gp_lm[G]]) continue;
+#pragma unroll
+                for (int s = 0; s < 3; ++s) {
+                    if (ea[s] < 0) continue;
+                    const double va = bd.gp_lin[(1 + ea[s]) * TG + G];
+                    const double vb = (eb[s] >= 0) ? bd.gp_lin[(1 + eb[s]) * TG + G] : bd.gp_lin[G];
+                    acc[s] += va * vb;
+                }
+            }
+#pragma unroll
+            for (int s = 0; s < 3; ++s) {
+                if (ea[s] < 0) continue;
+                const int ra = gp_row(bd, wd, k, ea[s]);
+                if (ra < 0) continue;
+                if (eb[s] < 0) { s_g[ra] += acc[s]; continue; }
+                const int rb = gp_row(bd, wd, k, eb[s]);
+                if (rb < 0) continue;
+                A[(size_t)ra * ld + rb] += acc[s];
+                if (ea[s] == eb[s]) s_fdiag[ra] += acc[s];
+            }
+        }
+        __syncthreads();
+    }
+    // ---- ground-plane regularisation chain (reference cpp:769-818), warp 0 cooperatively ----
+    if (tid < 32 && wd.plane_reg_weight > 0 && wd.n_kf > 1) {
+        const int lane = tid;
+        const double wgt = wd.plane_reg_weight;
+        const double* P = bd.pose[st.cur];
+        const double* PL = bd.plane[st.cur];
+        for (int k0 = 0; k0 + 1 < wd.n_kf; ++k0) {
+            const int k1 = k0 + 1;
+            const double* n0 = PL + 4 * (size_t)(wd.kf_off + k0), *n1 = PL + 4 * (size_t)(wd.kf_off + k1);
+            {   // VectorDifferenceRegularization(dir1, dir0), weight 3w
+                const double sq = sqrt(3.0 * wgt);
+                double P1[9], P0[9], J[18], r[3];
+                dir_plus_jacobian(n1, P1);
+                dir_plus_jacobian(n0, P0);
+                for (int i = 0; i < 3; ++i) {
+                    r[i] = sq * (n1[i] - n0[i]);
+                    for (int c = 0; c < 3; ++c) { J[6 * i + c] = sq * P1[3 * i + c]; J[6 * i + 3 + c] = -sq * P0[3 * i + c]; }
+                }
+                const int off[2] = {bd.off_dir[wd.kf_off + k1], bd.off_dir[wd.kf_off + k0]}, sz[2] = {3, 3};
+                warp_add_block(A, ld, s_fdiag, s_g, 3, r, 2, off, sz, J, lane);
+            }
+            {   // GroundPlaneDistanceRegularization(dist1, dist0), weight w
+                const double sq = sqrt(wgt);
+                const double r[1] = {sq * (n1[3] - n0[3])}, J[2] = {sq, -sq};
+                const int off[2] = {bd.off_dist[wd.kf_off + k1], bd.off_dist[wd.kf_off + k0]}, sz[2] = {1, 1};
+                warp_add_block(A, ld, s_fdiag, s_g, 1, r, 2, off, sz, J, lane);
+            }
+            {   // GroundPlaneMotionRegularization(pose0, pose1, dir0), weight 2w
+                const double sq = sqrt(2.0 * wgt);
+                double j0[6], j1[6], jd[3], J[15];
+                const double rm = plane_motion(P + 7 * (size_t)(wd.kf_off + k0), P + 7 * (size_t)(wd.kf_off + k1), n0, j0, j1, jd);
+                for (int c = 0; c < 6; ++c) { J[c] = sq * j0[c]; J[6 + c] = sq * j1[c]; }
+                for (int c = 0; c < 3; ++c) J[12 + c] = sq * jd[c];
+                const double r[1] = {sq * rm};
+                const int off[3] = {bd.off_pose[wd.kf_off + k0], bd.off_pose[wd.kf_off + k1], bd.off_dir[wd.kf_off + k0]};
+                const int sz[3] = {6, 6, 3};
+                warp_add_block(A, ld, s_fdiag, s_g, 1, r, 3, off, sz, J, lane);
+            }
+        }
+        for (int k = 0; k < wd.n_kf; ++k) {  // VectorDifferenceRegularization2((0,0,1)), weight w
+            const double* n = PL + 4 * (size_t)(wd.kf_off + k);
+            const double sq = sqrt(wgt);
+            double Pn[9], J[9], r[3] = {sq * (0.0 - n[0]), sq * (0.0 - n[1]), sq * (1.0 - n[2])};
+            dir_plus_jacobian(n, Pn);
+            for (int i = 0; i < 9; ++i) J[i] = -sq * Pn[i];
+            const int off[1] = {bd.off_dir[wd.kf_off + k]}, sz[1] = {3};
+            warp_add_block(A, ld, s_fdiag, s_g, 3, r, 1, off, sz, J, lane);
+        }
+        if (lane == 0 && st.need_linearize) st.x_cost += plane_chain_cost(wd, P, PL);
+    }
+    if (tid == 0 && wd.n_gp > 0 && st.need_linearize) st.x_cost += bd.gp_cost_x[w];
+    __syncthreads();
     // ---- regularisers (thread 0; a handful of residuals) ----
     if (tid == 0 && wd.scale_weight > 0) {
         const double* P = bd.pose[st.cur];
@@ -620,6 +882,21 @@ __global__ void __launch_bounds__(512, 1) k_reduced_solve(BatchDev bd, SolvePara
                 if (cols[b] <= cols[a]) A[(size_t)cols[a] * ld + cols[b]] += J[a] * J[b];
             s_fdiag[cols[a]] += J[a] * J[a];
             s_g[cols[a]] += J[a] * rr;
+        }
+    }
+    if (tid == 0 && wd.speed_weight > 0) {  // SpeedRegularizationVector2 of adjustPoseOnly (reference cpp:835-853)
+        double r[3], J[18];
+        speed_regulariser(bd.pose[st.cur] + 7 * (size_t)(wd.kf_off + wd.speed_kf), wd, r, J);
+        if (st.need_linearize) st.x_cost += 0.5 * wd.speed_weight * (r[0] * r[0] + r[1] * r[1] + r[2] * r[2]);
+        const int o = bd.off_pose[wd.kf_off + wd.speed_kf];
+        if (o >= 0) {
+            const double wgt = wd.speed_weight;  // rho' = w: J^T J and J^T r scale by w
+            for (int a = 0; a < 6; ++a) {
+                for (int b = 0; b <= a; ++b)
+                    A[(size_t)(o + a) * ld + o + b] += wgt * (J[a] * J[b] + J[6 + a] * J[6 + b] + J[12 + a] * J[12 + b]);
+                s_fdiag[o + a] += wgt * (J[a] * J[a] + J[6 + a] * J[6 + a] + J[12 + a] * J[12 + a]);
+                s_g[o + a] += wgt * (J[a] * r[0] + J[6 + a] * r[1] + J[12 + a] * r[2]);
+            }
         }
     }
     __syncthreads();
@@ -744,6 +1021,28 @@ __global__ void __launch_bounds__(512, 1) k_reduced_solve(BatchDev bd, SolvePara
         pose_plus(p, gneg, out);
         for (int i = 0; i < 7; ++i) gmax = fmax(gmax, fabs(out[i] - p[i]));
     }
+    // plane blocks: normal through FixScaleVectorPlus, distance Euclidean; constant ones are copied
+    for (int k = tid; k < wd.n_kf; k += nth) {
+        const double* pl = bd.plane[st.cur] + 4 * (size_t)(wd.kf_off + k);
+        double* ql = bd.plane[1 - st.cur] + 4 * (size_t)(wd.kf_off + k);
+        const int od = bd.off_dir[wd.kf_off + k], oz = bd.off_dist[wd.kf_off + k];
+        if (od < 0) { ql[0] = pl[0]; ql[1] = pl[1]; ql[2] = pl[2]; }
+        else {
+            double d[3], gneg[3], out[3];
+            for (int i = 0; i < 3; ++i) { d[i] = -s_y[od + i]; gneg[i] = -s_g[od + i]; }
+            dir_plus(pl, d, out);
+            for (int i = 0; i < 3; ++i) { ql[i] = out[i]; const double e = out[i] - pl[i]; step_sq += e * e; xn_sq += pl[i] * pl[i]; }
+            dir_plus(pl, gneg, out);
+            for (int i = 0; i < 3; ++i) gmax = fmax(gmax, fabs(out[i] - pl[i]));
+        }
+        if (oz < 0) ql[3] = pl[3];
+        else {
+            const double d = -s_y[oz];
+            ql[3] = pl[3] + d;
+            step_sq += d * d; xn_sq += pl[3] * pl[3];
+            gmax = fmax(gmax, fabs(s_g[oz]));
+        }
+    }
     model = warp_sum(model); step_sq = warp_sum(step_sq); xn_sq = warp_sum(xn_sq); gmax = warp_max(gmax);
     if (bad) s_fail = 1;
     if ((tid & 31) == 0) { s_red[tid >> 5][0] = model; s_red[tid >> 5][1] = step_sq; s_red[tid >> 5][2] = xn_sq; s_red[tid >> 5][3] = gmax; }
@@ -774,7 +1073,7 @@ __global__ void __launch_bounds__(256) k_backsub(BatchDev bd) {
         double* pn = bd.lm[1 - st.cur] + 3 * (size_t)L;
         const int* lm_ptr = bd.lm_ptr + wd.lm_off + w;
         const int o0 = lm_ptr[j], o1 = lm_ptr[j + 1];
-        const bool in = bd.lm_active[L] && o1 > o0;
+        const bool in = bd.lm_active[L] && o1 > o0 && !wd.landmarks_fixed;
         if (!in || st.solve_failed) {
             if (lane < 3) pn[lane] = pc[lane];
         } else {
@@ -789,6 +1088,15 @@ __global__ void __launch_bounds__(256) k_backsub(BatchDev bd) {
                     const double d = delta_f[off + r];
 #pragma unroll
                     for (int c = 0; c < 3; ++c) t[c] += bd.vobs[(3 * r + c) * T + base + o] * d;
+                }
+            }
+            const int gl = (wd.n_gp > 0) ? bd.gp_of_lm[L] : -1;
+            if (gl >= 0 && lane < 10) {  // the landmark's ground-plane block: row `lane` of its 10 x 3 V
+                const int row = gp_row(bd, wd, bd.gp_kf[wd.gp_off + gl], lane);
+                if (row >= 0) {
+                    const double d = delta_f[row];
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) t[c] += bd.vgp[(size_t)(3 * lane + c) * bd.tot_gp + wd.gp_off + gl] * d;
                 }
             }
 #pragma unroll
@@ -916,6 +1224,13 @@ __global__ void __launch_bounds__(128) k_lm_update(BatchDev bd, SolveParams sp) 
                           wd.scale_value, r, nullptr, nullptr);
         cand += 0.5 * wd.scale_weight * r * r;
     }
+    if (wd.speed_weight > 0) {
+        double r[3];
+        speed_regulariser(bd.pose[1 - st.cur] + 7 * (size_t)(wd.kf_off + wd.speed_kf), wd, r, nullptr);
+        cand += 0.5 * wd.speed_weight * (r[0] * r[0] + r[1] * r[1] + r[2] * r[2]);
+    }
+    if (wd.n_gp > 0) cand += bd.gp_cost_c[w];
+    if (wd.plane_reg_weight > 0 && wd.n_kf > 1) cand += plane_chain_cost(wd, bd.pose[1 - st.cur], bd.plane[1 - st.cur]);
     if (cand_eval_failed) cand = DBL_MAX;  // "Step failed to evaluate": infinite cost -> rejected
     const double step_norm = sqrt(st.f_step_sq + e_step);
     if (step_norm <= sp.parameter_tolerance * (st.x_norm + sp.parameter_tolerance)) {
@@ -984,7 +1299,18 @@ __global__ void __launch_bounds__(256) k_trim_eval(BatchDev bd, SolveParams sp) 
     if (lane == 0) {
         bd.trim_val[0 * (size_t)bd.tot_lm + L] = m_d;
         bd.trim_val[1 * (size_t)bd.tot_lm + L] = m_r;
-        bd.trim_val[2 * (size_t)bd.tot_lm + L] = -1.0;
+        double m_g = -1.0;  // ground-plane group: |n . (R p + t) + dist| of the landmark's gp block
+        const int gl = (wd.n_gp > 0 && bd.lm_active[L]) ? bd.gp_of_lm[L] : -1;
+        if (gl >= 0) {
+            const int k = bd.gp_kf[wd.gp_off + gl];
+            const double* ps = s_pose + kPoseStride * k;
+            const double* pl = bd.plane[st.cur] + 4 * (size_t)(wd.kf_off + k);
+            const double* lm = bd.lm[st.cur] + 3 * (size_t)L;
+            double px[3];
+            for (int i = 0; i < 3; ++i) px[i] = ps[3 * i] * lm[0] + ps[3 * i + 1] * lm[1] + ps[3 * i + 2] * lm[2] + ps[9 + i];
+            m_g = fabs(pl[0] * px[0] + pl[1] * px[1] + pl[2] * px[2] + pl[3]);
+        }
+        bd.trim_val[2 * (size_t)bd.tot_lm + L] = m_g;
     }
 }
 
@@ -995,7 +1321,7 @@ __global__ void __launch_bounds__(512) k_trim_select(BatchDev bd, SolveParams sp
     if (st.phase != PH_TRIM) return;
     const WinDesc& wd = bd.desc[w];
     __shared__ int s_n;
-    const double quant[3] = {sp.depth_quantile, sp.reprojection_quantile, 1.0};
+    const double quant[3] = {sp.depth_quantile, sp.reprojection_quantile, sp.gp_quantile};
     for (int j = threadIdx.x; j < wd.n_lm; j += blockDim.x) bd.trim_reject[wd.lm_off + j] = 0;
     for (int g = 0; g < 3; ++g) {
         const double* v = bd.trim_val + g * (size_t)bd.tot_lm + wd.lm_off;
@@ -1051,6 +1377,11 @@ __global__ void k_reset_state(BatchDev bd, int rounds_total_override, int min_la
         bd.pose[0][(size_t)wd.kf_off * 7 + i] = v;
         bd.pose[1][(size_t)wd.kf_off * 7 + i] = v;
     }
+    for (int i = threadIdx.x; i < wd.n_kf * 4; i += blockDim.x) {
+        const double v = bd.plane0[(size_t)wd.kf_off * 4 + i];
+        bd.plane[0][(size_t)wd.kf_off * 4 + i] = v;
+        bd.plane[1][(size_t)wd.kf_off * 4 + i] = v;
+    }
     for (int i = threadIdx.x; i < wd.n_lm * 3; i += blockDim.x) {
         const double v = bd.lm0[(size_t)wd.lm_off * 3 + i];
         bd.lm[0][(size_t)wd.lm_off * 3 + i] = v;
@@ -1099,6 +1430,7 @@ void launch_pass(const BatchDev& bd, const SolveParams& sp, const LaunchCfg& lc,
     if (timed) cudaEventRecord(lc.ev_pool[(*lc.ev_used)++], s);
     k_eval_obs<true><<<g_obs, 256, 0, s>>>(bd, sp);
     if (timed) cudaEventRecord(lc.ev_pool[(*lc.ev_used)++], s);
+    if (bd.tot_gp > 0) k_gp_eval<true><<<B, 256, 0, s>>>(bd, sp);
     k_pose_hessian<<<dim3(bd.max_kf, B), 256, 0, s>>>(bd, sp);
     k_landmark_prep<<<g_lm, 256, 0, s>>>(bd, sp);
     if (lc.small_syrk) {
@@ -1110,6 +1442,7 @@ void launch_pass(const BatchDev& bd, const SolveParams& sp, const LaunchCfg& lc,
     k_reduced_solve<<<B, 512, solve_smem(lc.nr_cap_max), s>>>(bd, sp);
     k_backsub<<<g_lm, 256, 0, s>>>(bd);
     k_eval_obs<false><<<g_obs, 256, 0, s>>>(bd, sp);
+    if (bd.tot_gp > 0) k_gp_eval<false><<<B, 256, 0, s>>>(bd, sp);
     k_lm_update<<<(B + 127) / 128, 128, 0, s>>>(bd, sp);
     k_trim_eval<<<g_lm, 256, 0, s>>>(bd, sp);
     k_trim_select<<<B, 512, 0, s>>>(bd, sp);

@@ -97,6 +97,68 @@ def test_config2_solve_matches_oracle(handle, oracle):
     _compare_solves(rg, rc, win, "config2")
 
 
+@pytest.mark.parametrize("shape", [dict(n_kf=8, n_lm=300, n_obs=1800, gp_frac=0.2), dict(n_kf=14, n_lm=500, n_obs=4500),
+                                   dict()])
+def test_config3_ground_plane_matches_oracle(handle, oracle, shape):
+    """BASELINE config 3 in FP64: ground-plane height residuals (Huber), plane normal / distance blocks with the
+    FixScaleVectorPlus parameterisation, the regularisation chain (cpp:769-818) and trimming, GPU vs oracle"""
+    win = synth.make_window(3, seed=41, **shape)
+    assert win.n_gp > 0 and win.plane_reg_weight == 10.0
+    rg = handle.solve_window(win)
+    rc = oracle.solve_window(win, num_threads=0 if not shape else 1)
+    _compare_solves(rg, rc, win, "config3 %s" % shape)
+    assert np.abs(rg.kf_plane - rc.kf_plane).max() <= 1e-7
+    assert np.allclose(np.linalg.norm(rg.kf_plane[:, :3], axis=1), 1.0, atol=1e-12)  # normals stay on the sphere
+
+
+def _motion_only_window(seed, with_prior):
+    """one frame of a config-2 scene against fixed landmarks = the problem adjustPoseOnly() builds (cpp:820-888)"""
+    from limo_b200.capi_types import Window
+    win, truth = synth.make_window(2, n_kf=12, n_lm=600, n_obs=5000, seed=seed, return_truth=True)
+    k = win.n_kf - 1
+    sel = win.obs_kf == k
+    lm_of_obs = np.repeat(np.arange(win.n_lm), np.diff(win.lm_obs_ptr))
+    lms = lm_of_obs[sel]
+    args = dict(kf_pose=win.kf_pose[k:k + 1], kf_fixed=[0], cam_intr=win.cam_intr, cam_pose=win.cam_pose,
+                lm_pos=truth["lm_pos"][lms], lm_weight=np.ones(len(lms)), lm_obs_ptr=np.arange(len(lms) + 1),
+                obs_kf=np.zeros(len(lms), dtype=np.int32), obs_u=win.obs_u[sel], obs_v=win.obs_v[sel],
+                obs_d=win.obs_d[sel], landmarks_fixed=True)
+    if with_prior:
+        Tb, Tb2 = g.pose_to_iso(truth["kf_pose"][k - 1]), g.pose_to_iso(truth["kf_pose"][k - 2])
+        args.update(speed_kf=0, speed_weight=0.7, speed_dt=0.1, speed_v_before=(Tb @ g.iso_inv(Tb2))[:3, 3] / 0.1,
+                    speed_T_origin_before=g.iso_to_pose(g.iso_inv(Tb)))
+    return Window(**args), truth["kf_pose"][k]
+
+
+@pytest.mark.parametrize("with_prior", [False, True])
+def test_motion_only_matches_oracle(handle, oracle, with_prior):
+    """adjustPoseOnly(): landmarks constant, one free pose, optional SpeedRegularizationVector2 prior, trimming rounds"""
+    win, pose_true = _motion_only_window(31, with_prior)
+    opt = handle.default_options()
+    opt.min_landmarks_for_trimming = 30
+    rg = handle.solve_window(win, opt)
+    rc = oracle.solve_window(win, opt)
+    _compare_solves(rg, rc, win, "motion only prior=%s" % with_prior)
+    assert np.array_equal(rg.lm_pos[:win.n_lm], win.lm_pos)  # constant blocks stay untouched
+    if not with_prior:
+        assert np.linalg.norm(rg.kf_pose[0, 4:] - pose_true[4:]) < 0.05
+
+
+def test_reference_adjust_motion_only_on_gpu(handle, oracle):
+    """BundleAdjusterKeyframes.adjustMotionOnly (reference test :1340-1344) through the CUDA path"""
+    from limo_b200.adjuster import Keyframe
+    out = []
+    for backend in (handle, oracle.OracleBackend()):
+        b, poses_gt, noisy, lms, ts, cameras, l2c = rs.build_adjuster(
+            backend, (0, 0, 0), (0, 0, 0, 0), [np.eye(4)], with_depth=True, motion_only=True)
+        kf = Keyframe(4, ts, b.keyframes_[0].cameras_[0], noisy[4])
+        b.landmark_selector_.select(b.getActiveLandmarkConstPtrs(), b.getActiveKeyframeConstPtrs())
+        b.adjustPoseOnly(kf)
+        assert g.is_approx(kf.getEigenPose(), poses_gt[4], 0.5)
+        out.append((b.last_result, b.last_window))
+    _compare_solves(out[0][0], out[1][0], out[0][1], "adjustMotionOnly")
+
+
 def test_batch_equals_single(handle):
     """a batch of different windows gives bit-identical results to solving them one by one (deterministic reductions)"""
     wins = [synth.make_window(1, seed=s) for s in (21, 22, 23)] + [synth.make_window(2, n_kf=10, n_lm=300, n_obs=2500, seed=5)]
