@@ -1,0 +1,3 @@
+// forwarding header: the facade keeps the reference include paths (keyframe_bundle_adjustment/landmark_selector.hpp)
+#pragma once
+#include "bundle_adjuster_keyframes.hpp"

@@ -1,0 +1,469 @@
+// bundle_adjuster_keyframes.cpp -- the replacement translation unit for limo's
+// keyframe_bundle_adjustment/src/{bundle_adjuster_keyframes,keyframe,definitions,landmark_selection_scheme_cheirality}.cpp:
+// window bookkeeping on the host exactly as the reference does it, the solve through the C ABI (kba_b200.h).
+#include "keyframe_bundle_adjustment/bundle_adjuster_keyframes.hpp"
+
+#include <algorithm>
+#include <cmath>
+#include <iterator>
+#include <sstream>
+#include <stdexcept>
+
+#include "kba_b200.h"
+
+namespace keyframe_bundle_adjustment {
+
+// ---- definitions.cpp ---------------------------------------------------------------------------------------------------
+Pose convert(EigenPose p) {
+    Eigen::Quaterniond q(p.rotation());
+    return Pose{{q.w(), q.x(), q.y(), q.z(), p.translation()[0], p.translation()[1], p.translation()[2]}};
+}
+EigenPose convert(const Pose& pose) {
+    EigenPose p = EigenPose::Identity();
+    p.translate(Eigen::Vector3d(pose[4], pose[5], pose[6]));
+    p.rotate(Eigen::Quaterniond(pose[0], pose[1], pose[2], pose[3]));
+    return p;
+}
+TimestampSec convert(const TimestampNSec& ts) { return static_cast<TimestampSec>(ts * 1e-09); }
+TimestampNSec convert(const TimestampSec& ts) { return static_cast<TimestampNSec>(ts * 1e09); }
+double calcQuaternionDiff(const Pose& p0, const Pose& p1) {
+    Eigen::Quaterniond q0(p0[0], p0[1], p0[2], p0[3]), q1(p1[0], p1[1], p1[2], p1[3]);
+    return Eigen::AngleAxisd(q1.inverse() * q0).angle();
+}
+
+Camera::Camera(double f, const Eigen::Vector2d& pp, const EigenPose& pose_cam_veh) : focal_length(f), principal_point(pp) {
+    pose_camera_vehicle = convert(pose_cam_veh);
+    intrin_inv = getIntrinsicMatrix().inverse();
+}
+Eigen::Matrix3d Camera::getIntrinsicMatrix() const {
+    Eigen::Matrix3d K;
+    K(0, 0) = focal_length; K(0, 2) = principal_point[0]; K(1, 1) = focal_length; K(1, 2) = principal_point[1]; K(2, 2) = 1.;
+    return K;
+}
+EigenPose Camera::getEigenPose() const { return convert(pose_camera_vehicle); }
+
+// ---- keyframe.cpp -------------------------------------------------------------------------------------------------------
+Keyframe::Keyframe(TimestampNSec timestamp, const Tracklets& tracklets, std::map<CameraId, Camera::Ptr> cameras,
+                   std::map<LandmarkId, CameraIds> landmark_to_cameras, EigenPose p, FixationStatus fix_stat,
+                   Plane ground_plane)
+        : timestamp_(timestamp), cameras_(cameras), fixation_status_(fix_stat), local_ground_plane_(ground_plane),
+          is_active_(true) {
+    assignMeasurements(tracklets, landmark_to_cameras);
+    assignPose(p);
+}
+Keyframe::Keyframe(TimestampNSec timestamp, const Tracklets& tracklets, Camera::Ptr camera, EigenPose p,
+                   FixationStatus fix_stat, Plane ground_plane)
+        : timestamp_(timestamp), fixation_status_(fix_stat), local_ground_plane_(ground_plane), is_active_(true) {
+    cameras_[0] = camera;
+    assignMeasurements(tracklets, CameraId(0));
+    assignPose(p);
+}
+void Keyframe::assignMeasurements(const Tracklets& tracklets, const std::map<LandmarkId, CameraIds>& lookup) {
+    std::map<CameraId, Tracklets> out;
+    for (const auto& track : tracklets.tracks)
+        for (const auto& cam_id : lookup.at(track.id)) {
+            out[cam_id].stamps = tracklets.stamps;
+            out[cam_id].tracks.push_back(track);
+        }
+    for (const auto& el : out) assignMeasurements(el.second, el.first);
+}
+void Keyframe::assignMeasurements(const Tracklets& tracklets, const CameraId& cam_id) {
+    auto iter = std::find(tracklets.stamps.begin(), tracklets.stamps.end(), this->timestamp_);
+    const int index = int(std::distance(tracklets.stamps.begin(), iter));
+    for (const auto& track : tracklets.tracks)
+        if (index < int(track.feature_points.size())) measurements_[track.id][cam_id] = track.feature_points[index];
+}
+std::map<CameraId, Measurement> Keyframe::getMeasurements(LandmarkId lm_id) const {
+    std::map<CameraId, Measurement> out;
+    for (const auto& cam : cameras_)
+        if (hasMeasurement(lm_id, cam.first)) out[cam.first] = getMeasurement(lm_id, cam.first);
+    return out;
+}
+bool Keyframe::hasMeasurement(const LandmarkId& lm_id, const CameraId& cam_id) const {
+    auto it = measurements_.find(lm_id);
+    return it != measurements_.cend() && it->second.find(cam_id) != it->second.cend();
+}
+bool Keyframe::hasMeasurement(LandmarkId lm_id) const {
+    for (const auto& cam : cameras_)
+        if (hasMeasurement(lm_id, cam.first)) return true;
+    return false;
+}
+std::map<CameraId, Eigen::Vector3d> Keyframe::getProjectedLandmarkPosition(
+    const std::pair<LandmarkId, Landmark::ConstPtr>& id_lm) const {
+    std::map<CameraId, Eigen::Vector3d> out;
+    auto it = measurements_.find(id_lm.first);
+    if (it == measurements_.cend()) return out;
+    const Eigen::Vector3d p_vehicle = getEigenPose() * Eigen::Vector3d(id_lm.second->pos.data());
+    for (const auto& cam_meas : it->second) out[cam_meas.first] = cameras_.at(cam_meas.first)->getEigenPose() * p_vehicle;
+    return out;
+}
+
+// ---- landmark selection ---------------------------------------------------------------------------------------------------
+std::set<LandmarkId> LandmarkRejectionSchemeCheirality::getSelection(const LandmarkMap& landmarks,
+                                                                     const KeyframeMap& keyframes) const {
+    std::set<LandmarkId> out;
+    for (const auto& lm_el : landmarks) {
+        bool ok = true;
+        for (const auto& id_kf : keyframes) {
+            if (!id_kf.second->is_active_) continue;
+            for (const auto& cam_lm : id_kf.second->getProjectedLandmarkPosition(lm_el))
+                if (cam_lm.second.z() < 0.) { ok = false; break; }
+            if (!ok) break;
+        }
+        if (ok) out.insert(lm_el.first);
+    }
+    return out;
+}
+
+std::set<LandmarkId> LandmarkSelector::select(const std::map<LandmarkId, Landmark::ConstPtr>& landmarks,
+                                              const std::map<KeyframeId, Keyframe::ConstPtr>& kfs) {
+    std::map<LandmarkId, Landmark::ConstPtr> non_rejected = landmarks;  // landmark_selector.hpp:118-253
+    for (const auto& id : outlier_ids_) non_rejected.erase(id);
+    auto add_to_map = [&](const std::map<LandmarkId, Landmark::ConstPtr>& src, const std::set<LandmarkId>& sel,
+                          std::map<LandmarkId, Landmark::ConstPtr>& dst) {
+        for (const auto& id : sel) { auto it = src.find(id); if (it != src.cend()) dst[id] = it->second; }
+    };
+    for (const auto& scheme : rejection_schemes_) {
+        auto cur = scheme->getSelection(non_rejected, kfs);
+        non_rejected.clear();
+        add_to_map(landmarks, cur, non_rejected);
+    }
+    std::map<LandmarkId, Landmark::ConstPtr> selected;
+    for (const auto& scheme : selection_schemes_) add_to_map(non_rejected, scheme->getSelection(non_rejected, kfs), selected);
+    std::map<LandmarkId, Landmark::ConstPtr> sparsified = non_rejected;
+    for (const auto& scheme : sparsification_schemes_) {
+        auto cur = scheme->getSelection(sparsified, kfs);
+        sparsified.clear();
+        add_to_map(non_rejected, cur, sparsified);
+    }
+    for (const auto& el : selected) sparsified[el.first] = el.second;
+    std::set<LandmarkId> selection;
+    for (const auto& el : sparsified) selection.insert(el.first);
+    TimestampNSec cur_ts = 0;
+    for (const auto& kf : kfs) cur_ts = std::max(cur_ts, kf.second->timestamp_);
+    for (const auto& lm : landmarks)
+        if (!selection.count(lm.first)) { unselected_lms_[lm.first] += 1; last_time_seen_[lm.first] = cur_ts; }
+    const TimestampNSec ten = convert(TimestampSec(10.));
+    const TimestampNSec oldest = cur_ts > ten ? cur_ts - ten : 0;
+    for (auto it = last_time_seen_.begin(); it != last_time_seen_.end();) {
+        if (it->second < oldest) { unselected_lms_.erase(it->first); it = last_time_seen_.erase(it); }
+        else ++it;
+    }
+    last_selected_lms_ = selection;
+    return selection;
+}
+
+// ---- triangulation ---------------------------------------------------------------------------------------------------------
+Eigen::Vector3d triangulate_rays(const std::vector<std::pair<EigenPose, Eigen::Vector3d>>& poses_rays) {
+    Eigen::Matrix3d sum = Eigen::Matrix3d::Zero();
+    Eigen::Vector3d rhs;
+    for (const auto& p_r : poses_rays) {
+        const Eigen::Vector3d r = p_r.first.rotation() * p_r.second;
+        const Eigen::Matrix3d cur = Eigen::Matrix3d::Identity() - Eigen::outer(r, r);
+        sum += cur;
+        rhs += cur * p_r.first.translation();
+    }
+    return sum.inverse() * rhs;  // the reference solves with a Jacobi SVD; identical for >= 2 non-parallel rays
+}
+
+// ---- exceptions --------------------------------------------------------------------------------------------------------------
+BundleAdjusterKeyframes::NotEnoughKeyframesException::NotEnoughKeyframesException(size_t is, size_t should)
+        : num_is(is), num_should_be(should) {
+    std::stringstream ss;
+    ss << "Not enough keyframes available in bundle_adjuster_keyframes. Should be " << num_should_be << " is " << num_is;
+    msg = ss.str();
+}
+BundleAdjusterKeyframes::KeyframeNotFoundException::KeyframeNotFoundException(TimestampNSec timestamp) : ts_(timestamp) {
+    std::stringstream ss;
+    ss << "keyframe corresponding to timestamp " << ts_ << " nano seconds not found";
+    msg = ss.str();
+}
+
+// ---- the adjuster ------------------------------------------------------------------------------------------------------------
+BundleAdjusterKeyframes::BundleAdjusterKeyframes() : solver_time_sec(0.2) {
+    landmark_selector_ = std::make_unique<LandmarkSelector>();
+    landmark_selector_->addScheme(LandmarkRejectionSchemeCheirality::create());  // cpp:116-118
+}
+BundleAdjusterKeyframes::~BundleAdjusterKeyframes() { if (handle_) kba_destroy(handle_); }
+
+void BundleAdjusterKeyframes::push(const std::vector<Keyframe>& kfs) { for (const auto& kf : kfs) push(kf); }
+
+void BundleAdjusterKeyframes::push(const Keyframe& kf) {  // cpp:289-329
+    keyframes_[kf.timestamp_] = std::make_shared<Keyframe>(kf);
+    active_keyframe_ids_.insert(kf.timestamp_);
+    for (const auto& m : kf.measurements_) {
+        if (landmarks_.find(m.first) == landmarks_.cend()) {
+            bool has_depth = false;
+            for (const auto& cam_meas : m.second) if (cam_meas.second.d >= 0) has_depth = true;  // containsDepth, cpp:37-48
+            v3 p;
+            const bool success = has_depth ? calculateLandmark(kf, m.first, p) : calculateLandmark(m.first, p);
+            if (!success) continue;
+            landmarks_.insert(std::make_pair(m.first, std::make_shared<Landmark>(p, has_depth)));
+        }
+        active_landmark_ids_.insert(m.first);
+    }
+}
+
+bool BundleAdjusterKeyframes::calculateLandmark(const Keyframe& kf, const LandmarkId& lId, v3& posAbs) {  // cpp:332-355
+    for (const auto& m : kf.measurements_.at(lId)) {
+        if (m.second.d < 0) continue;
+        const auto cam = kf.cameras_.at(m.first);
+        const double z = static_cast<double>(m.second.d);
+        const double x = (static_cast<double>(m.second.u) - cam->principal_point[0]) * z / cam->focal_length;
+        const double y = (static_cast<double>(m.second.v) - cam->principal_point[1]) * z / cam->focal_length;
+        posAbs = (cam->getEigenPose() * kf.getEigenPose()).inverse() * v3(x, y, z);
+        return true;
+    }
+    return false;
+}
+
+bool BundleAdjusterKeyframes::calculateLandmark(const LandmarkId& lId, v3& posAbs) {  // cpp:125-159, 358-382
+    std::vector<std::pair<EigenPose, v3>> poses_rays;
+    for (const auto& id : active_keyframe_ids_) {
+        const Keyframe& kf = *keyframes_.at(id);
+        for (const auto& id_cam : kf.cameras_) {
+            if (!kf.hasMeasurement(lId, id_cam.first)) continue;
+            const Measurement& m = kf.getMeasurement(lId, id_cam.first);
+            const v3 ray = (id_cam.second->intrin_inv * v3(static_cast<double>(m.u), static_cast<double>(m.v), 1.)).normalized();
+            poses_rays.emplace_back((id_cam.second->getEigenPose() * kf.getEigenPose()).inverse(), ray);
+        }
+    }
+    if (poses_rays.size() < 2) return false;
+    posAbs = triangulate_rays(poses_rays);
+    return true;
+}
+
+void BundleAdjusterKeyframes::updateLabels(const Tracklets& t, double shrubbery_weight) {  // cpp:388-431
+    std::set<LandmarkId> outlier_ids;
+    for (const auto& id : landmark_selector_->getOutliers())
+        if (active_landmark_ids_.count(id)) outlier_ids.insert(id);
+    for (const auto& track : t.tracks)
+        if (track.is_outlier || labels_["outliers"].count(track.label)) outlier_ids.insert(track.id);
+    landmark_selector_->clearOutliers();
+    landmark_selector_->setOutlier(outlier_ids);
+    for (const auto& track : t.tracks) {
+        if (!active_landmark_ids_.count(track.id)) continue;
+        if (labels_["shrubbery"].count(track.label)) landmarks_.at(track.id)->weight = shrubbery_weight;
+        landmarks_.at(track.id)->is_ground_plane = labels_["ground"].count(track.label) > 0;
+    }
+}
+
+std::map<LandmarkId, Landmark::ConstPtr> BundleAdjusterKeyframes::filterLandmarksById(const std::set<LandmarkId>& ids) const {
+    std::map<LandmarkId, Landmark::ConstPtr> out;
+    for (const auto& id : ids) { auto it = landmarks_.find(id); if (it != landmarks_.cend()) out[id] = it->second; }
+    return out;
+}
+std::map<LandmarkId, Landmark::ConstPtr> BundleAdjusterKeyframes::getActiveLandmarkConstPtrs() const { return filterLandmarksById(active_landmark_ids_); }
+std::map<LandmarkId, Landmark::ConstPtr> BundleAdjusterKeyframes::getSelectedLandmarkConstPtrs() const { return filterLandmarksById(selected_landmark_ids_); }
+std::map<KeyframeId, Keyframe::Ptr> BundleAdjusterKeyframes::getActiveKeyframePtrs() const {
+    std::map<KeyframeId, Keyframe::Ptr> out;
+    for (const auto& id : active_keyframe_ids_) out[id] = keyframes_.at(id);
+    return out;
+}
+std::map<KeyframeId, Keyframe::ConstPtr> BundleAdjusterKeyframes::getActiveKeyframeConstPtrs() const {
+    std::map<KeyframeId, Keyframe::ConstPtr> out;
+    for (const auto& id : active_keyframe_ids_) out[id] = keyframes_.at(id);
+    return out;
+}
+std::vector<std::pair<KeyframeId, Keyframe::Ptr>> BundleAdjusterKeyframes::getSortedIdsWithActiveKeyframePtrs() const {
+    std::vector<std::pair<KeyframeId, Keyframe::Ptr>> v;
+    for (const auto& kf : getActiveKeyframePtrs()) v.push_back(kf);
+    std::sort(v.begin(), v.end(), [](const auto& a, const auto& b) { return *(a.second) < *(b.second); });
+    return v;
+}
+std::vector<Keyframe::Ptr> BundleAdjusterKeyframes::getSortedActiveKeyframePtrs() const {
+    std::vector<Keyframe::Ptr> out;
+    for (const auto& el : getSortedIdsWithActiveKeyframePtrs()) out.push_back(el.second);
+    return out;
+}
+
+const Keyframe& BundleAdjusterKeyframes::getKeyframe(TimestampSec timestamp) const {  // cpp:989-1021
+    if (keyframes_.size() == 0) throw NotEnoughKeyframesException(keyframes_.size(), 1);
+    if (timestamp < 0.) {
+        auto it = std::max_element(active_keyframe_ids_.cbegin(), active_keyframe_ids_.cend(), [&](const auto& a, const auto& b) {
+            return keyframes_.at(a)->timestamp_ < keyframes_.at(b)->timestamp_;
+        });
+        return *keyframes_.at(*it);
+    }
+    const TimestampNSec ts_nsec = convert(timestamp);
+    for (const auto& kf : keyframes_)
+        if (kf.second->timestamp_ == ts_nsec) return *kf.second;
+    throw KeyframeNotFoundException(ts_nsec);
+}
+
+void BundleAdjusterKeyframes::deactivateKeyframes(int min_num_connecting_landmarks, int min_size_optimization_window,
+                                                  int max_size_optimization_window) {  // cpp:907-987
+    auto sorted = getSortedIdsWithActiveKeyframePtrs();
+    auto newest = sorted.back().second;
+    int n = 0;
+    for (auto it = sorted.crbegin(); it != sorted.crend(); ++it, ++n) {
+        auto& cur = *it->second;
+        if (n > max_size_optimization_window - 1) cur.is_active_ = false;
+        else if (n < min_size_optimization_window - 1) cur.is_active_ = true;
+        else {
+            int common = 0;
+            for (const auto& m : cur.measurements_) common += newest->measurements_.count(m.first) ? 1 : 0;
+            cur.is_active_ = common > min_num_connecting_landmarks;
+        }
+        if (!cur.is_active_) active_keyframe_ids_.erase(it->first);
+    }
+    std::set<LandmarkId> new_active;
+    for (const auto& id : active_keyframe_ids_)
+        for (const auto& m : keyframes_.at(id)->measurements_)
+            if (active_landmark_ids_.count(m.first)) new_active.insert(m.first);
+    active_landmark_ids_ = new_active;
+    auto rest = getSortedIdsWithActiveKeyframePtrs();
+    rest[0].second->fixation_status_ = Keyframe::FixationStatus::Pose;
+    rest[1].second->fixation_status_ = Keyframe::FixationStatus::Scale;
+}
+
+// Pack -> kba_solve_window -> scatter.  Replaces addActiveKeyframesToProblem / addKeyframeToProblem (cpp:498-627),
+// addGroundPlaneResiduals (:517-562), the scale / plane regulariser set-up (:703-728, 769-818, 890-904) and
+// robust_optimization::solveTrimmed (:765, :886).
+std::string BundleAdjusterKeyframes::runWindow(const std::vector<Keyframe*>& kfs, const std::vector<LandmarkId>& lm_ids,
+                                               bool motion_only, Keyframe* speed_kf) {
+    if (!handle_) {
+        if (kba_create(&handle_, 0) != KBA_OK) throw std::runtime_error(std::string("kba_b200: ") + kba_last_error());
+    }
+    std::vector<double> kf_pose, kf_plane, cam_intr, cam_pose, lm_pos, lm_weight, gp_weight;
+    std::vector<uint8_t> kf_fixed;
+    std::vector<int32_t> lm_obs_ptr{0}, obs_kf, obs_cam, gp_lm, gp_kf;
+    std::vector<float> obs_u, obs_v, obs_d;
+    std::map<const Camera*, int> cam_index;
+    for (const Keyframe* kf : kfs) {
+        kf_pose.insert(kf_pose.end(), kf->pose_.begin(), kf->pose_.end());
+        kf_fixed.push_back(!motion_only && kf->fixation_status_ == Keyframe::FixationStatus::Pose);  // cpp:198-219
+        kf_plane.insert(kf_plane.end(), kf->local_ground_plane_.direction.begin(), kf->local_ground_plane_.direction.end());
+        kf_plane.push_back(kf->local_ground_plane_.distance);
+        for (const auto& c : kf->cameras_)
+            if (cam_index.emplace(c.second.get(), int(cam_index.size())).second) {
+                cam_intr.insert(cam_intr.end(), {c.second->focal_length, c.second->principal_point[0], c.second->principal_point[1]});
+                cam_pose.insert(cam_pose.end(), c.second->pose_camera_vehicle.begin(), c.second->pose_camera_vehicle.end());
+            }
+    }
+    int n_depth = 0;
+    for (const auto lm_id : lm_ids) {
+        const Landmark& lm = *landmarks_.at(lm_id);
+        lm_pos.insert(lm_pos.end(), lm.pos.begin(), lm.pos.end());
+        lm_weight.push_back(lm.weight);
+        for (size_t k = 0; k < kfs.size(); ++k) {
+            auto it = kfs[k]->measurements_.find(lm_id);
+            if (it == kfs[k]->measurements_.end()) continue;
+            for (const auto& cm : it->second) {
+                obs_kf.push_back(int32_t(k));
+                obs_cam.push_back(cam_index.at(kfs[k]->cameras_.at(cm.first).get()));
+                obs_u.push_back(cm.second.u); obs_v.push_back(cm.second.v); obs_d.push_back(cm.second.d);
+                n_depth += cm.second.d > 0.0f;
+            }
+        }
+        lm_obs_ptr.push_back(int32_t(obs_kf.size()));
+    }
+    kba_window w{};
+    if (!motion_only) {
+        for (size_t j = 0; j < lm_ids.size(); ++j) {  // addGroundPlaneResiduals(10.), cpp:517-562
+            const Landmark& lm = *landmarks_.at(lm_ids[j]);
+            if (!lm.is_ground_plane) continue;
+            double min_dist = std::numeric_limits<double>::max();
+            int best = -1;
+            for (size_t k = 0; k < kfs.size(); ++k) {
+                if (kfs[k]->local_ground_plane_.distance < -10.) continue;
+                const double dist = (kfs[k]->getEigenPose() * v3(lm.pos.data())).norm();
+                if (dist < min_dist) { min_dist = dist; best = int(k); }
+            }
+            if (best < 0 || !(min_dist < 25.)) continue;
+            gp_lm.push_back(int32_t(j)); gp_kf.push_back(best); gp_weight.push_back(10. * (1. - min_dist / 25.));
+        }
+        const int n_gp = int(gp_lm.size());
+        double scale_weight = 0.;  // cpp:703-716
+        if (n_depth > 10 || n_gp > 10) { if (n_gp < 30) scale_weight = 1000. / (double(n_depth) + double(n_gp)); }
+        else scale_weight = 1000.;
+        if (scale_weight > 0 && kfs.size() > 1) {
+            w.scale_kf0 = 0; w.scale_kf1 = 1; w.scale_weight = scale_weight;
+            w.scale_value = (kfs[1]->getEigenPose() * kfs[0]->getEigenPose().inverse()).translation().norm();
+        }
+        if (n_gp > 0) w.plane_reg_weight = 10.;  // cpp:717-719
+        w.plane_dist_fixed = n_depth < 10;       // cpp:722-728
+    } else if (speed_kf && active_keyframe_ids_.size() > 2) {  // cpp:835-853
+        auto sorted = getSortedActiveKeyframePtrs();
+        const Keyframe& b0 = *sorted[sorted.size() - 1];
+        const Keyframe& b1 = *sorted[sorted.size() - 2];
+        const double rot_diff = calcQuaternionDiff(b0.pose_, b1.pose_);
+        if (rot_diff < 0.03) {
+            const double dt_cur = convert(speed_kf->timestamp_) - convert(b0.timestamp_);
+            const double dt_before = convert(b0.timestamp_) - convert(b1.timestamp_);
+            if (dt_cur <= 0. || dt_before <= 0.) throw std::runtime_error("In PoseRegularizationSpeed: invalid timestamps");
+            const v3 v_before = (b0.getEigenPose() * b1.getEigenPose().inverse()).translation() / dt_before;
+            const Pose T_ob = convert(b0.getEigenPose().inverse());
+            w.speed_kf = 0; w.speed_weight = 1. * (1 - rot_diff / 0.03); w.speed_dt = dt_cur;
+            for (int i = 0; i < 3; ++i) w.speed_v_before[i] = v_before[i];
+            for (int i = 0; i < 7; ++i) w.speed_T_origin_before[i] = T_ob[i];
+        }
+    }
+    w.landmarks_fixed = motion_only;
+    w.n_kf = int(kfs.size()); w.n_cam = int(cam_index.size()); w.n_lm = int(lm_ids.size()); w.n_obs = int(obs_kf.size());
+    w.n_gp = int(gp_lm.size());
+    w.kf_pose = kf_pose.data(); w.kf_fixed = kf_fixed.data(); w.kf_plane = kf_plane.data();
+    w.cam_intr = cam_intr.data(); w.cam_pose = cam_pose.data();
+    w.lm_pos = lm_pos.data(); w.lm_weight = lm_weight.data(); w.lm_obs_ptr = lm_obs_ptr.data();
+    w.obs_kf = obs_kf.data(); w.obs_cam = obs_cam.data(); w.obs_u = obs_u.data(); w.obs_v = obs_v.data(); w.obs_d = obs_d.data();
+    w.gp_lm = gp_lm.data(); w.gp_kf = gp_kf.data(); w.gp_weight = gp_weight.data();
+
+    kba_options opt;
+    kba_default_options(&opt);
+    opt.depth_thres = outlier_rejection_options_.depth_thres;
+    opt.reprojection_thres = outlier_rejection_options_.reprojection_thres;
+    opt.depth_quantile = outlier_rejection_options_.depth_quantile;
+    opt.reprojection_quantile = outlier_rejection_options_.reprojection_quantile;
+    opt.num_rounds_option = outlier_rejection_options_.num_iterations;
+    opt.solver_time_sec = solver_time_sec;
+    if (motion_only) {  // cpp:864-869
+        opt.min_landmarks_for_trimming = 30;
+        opt.num_trim_rounds = selected_landmark_ids_.size() > 30 ? outlier_rejection_options_.num_iterations : 0;
+    }
+    std::vector<double> out_pose(kf_pose.size()), out_plane(kf_plane.size()), out_lm(lm_pos.size() + 3);
+    kba_result r{};
+    r.kf_pose = out_pose.data(); r.kf_plane = out_plane.data(); r.lm_pos = out_lm.data();
+    if (kba_solve_window(handle_, &w, &opt, &r) != KBA_OK) throw std::runtime_error(std::string("kba_b200: ") + kba_last_error());
+
+    for (size_t k = 0; k < kfs.size(); ++k) {  // the reference optimises in place (cpp:554-557, 592-593)
+        std::copy_n(out_pose.begin() + 7 * k, 7, kfs[k]->pose_.begin());
+        if (!motion_only && w.n_gp > 0) {
+            std::copy_n(out_plane.begin() + 4 * k, 3, kfs[k]->local_ground_plane_.direction.begin());
+            kfs[k]->local_ground_plane_.distance = out_plane[4 * k + 3];
+        }
+    }
+    if (!motion_only)
+        for (size_t j = 0; j < lm_ids.size(); ++j) std::copy_n(out_lm.begin() + 3 * j, 3, landmarks_.at(lm_ids[j])->pos.begin());
+
+    static const char* term[] = {"CONVERGENCE", "NO_CONVERGENCE", "FAILURE"};
+    std::stringstream ss;  // stands in for robust_optimization::Summary::FullReport (robust_solving.hpp:54-59)
+    ss << "Merged summaries:\n";
+    for (int i = 0; i < r.num_solves; ++i) {
+        const kba_solve_summary& s = r.solves[i];
+        ss << "--------------------------------------------------\nIteration No." << i << "\n"
+           << "Residual blocks " << s.num_residual_blocks << ", landmarks " << s.num_landmarks << "; initial cost "
+           << s.initial_cost << ", final cost " << s.final_cost << ", iterations " << s.num_iterations << " (successful "
+           << s.num_successful_steps << "), termination " << term[s.termination < 3 ? s.termination : 2] << "\n";
+    }
+    ss << "\nDuration solveTrimmed=" << r.time_sec << " sec\n";
+    return ss.str();
+}
+
+std::string BundleAdjusterKeyframes::solve() {  // cpp:629-767
+    if (keyframes_.size() < 3) throw NotEnoughKeyframesException(keyframes_.size(), 3);
+    selected_landmark_ids_ = landmark_selector_->select(getActiveLandmarkConstPtrs(), getActiveKeyframeConstPtrs());
+    std::vector<Keyframe*> kfs;
+    for (const auto& id : active_keyframe_ids_) kfs.push_back(keyframes_.at(id).get());
+    std::vector<LandmarkId> lm_ids(selected_landmark_ids_.begin(), selected_landmark_ids_.end());
+    return runWindow(kfs, lm_ids, false, nullptr);
+}
+
+std::string BundleAdjusterKeyframes::adjustPoseOnly(Keyframe& kf) {  // cpp:820-888
+    selected_landmark_ids_ = landmark_selector_->getLastSelection();
+    std::vector<LandmarkId> lm_ids;
+    for (const auto& m : kf.measurements_)
+        if (selected_landmark_ids_.count(m.first)) lm_ids.push_back(m.first);  // landmarks_.at() would throw like the reference
+    return runWindow({&kf}, lm_ids, true, &kf);
+}
+
+}  // namespace keyframe_bundle_adjustment

@@ -1,0 +1,168 @@
+// Restatement of the reference's gtest cases for the facade (keyframe_bundle_adjustment/test/keyframe_bundle_adjustment.cpp),
+// driven through the C++ drop-in API.  `test_facade cpu` runs the cases that need no GPU; `test_facade gpu` adds the solves.
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <tuple>
+
+#include "keyframe_bundle_adjustment/bundle_adjuster_keyframes.hpp"
+
+using namespace keyframe_bundle_adjustment;
+static int g_fail = 0;
+#define CHECK(c) do { if (!(c)) { std::printf("CHECK FAILED %s:%d: %s\n", __FILE__, __LINE__, #c); ++g_fail; } } while (0)
+
+// deterministic draws of the reference's add_noise helpers (:180-216), libstdc++ default_random_engine
+static const double kNoiseAngle5deg = -0.01064352254023776;
+static const double kNoiseVec3[3] = {-0.024393156828319384, 0.068428994379655481, 0.0033269476420492391};
+static const double kNoisePix15[2] = {-0.18294867621239536, 1.0264349156948323};
+
+static std::vector<Eigen::Isometry3d> getPoses(double na, std::tuple<double, double, double> nt) {  // :232-249
+    const Eigen::Vector3d z(0., 0., 1.);
+    auto nv = [&](Eigen::Vector3d v) {
+        if (std::get<0>(nt) != 0. || std::get<1>(nt) != 0. || std::get<2>(nt) != 0.) {
+            v[0] += kNoiseVec3[0] * std::get<0>(nt) / 0.2; v[1] += kNoiseVec3[1] * std::get<1>(nt) / 0.1; v[2] += kNoiseVec3[2] * std::get<2>(nt) / 0.1;
+        }
+        return v;
+    };
+    const double da = na == 0. ? 0. : kNoiseAngle5deg * na / (5. * M_PI / 180.);
+    std::vector<Eigen::Isometry3d> P(5);
+    P[0] = Eigen::Isometry3d::Identity();
+    P[1] = P[0]; P[1].translate(Eigen::Vector3d(-1.5, 0., -2.)); P[1].rotate(Eigen::AngleAxisd(-0.05, z));
+    P[2] = P[1]; P[2].translate(nv(Eigen::Vector3d(-2.0, 0., 0.))); P[2].rotate(Eigen::AngleAxisd(-0.05 + da, z));
+    P[3] = P[2]; P[3].translate(nv(Eigen::Vector3d(-1.5, -0.1, 0.)));
+    P[4] = P[3]; P[4].translate(nv(Eigen::Vector3d(-2.9, -0., 0.)));
+    return P;
+}
+
+static Eigen::Isometry3d monoExtrinsics() {  // :808-814
+    Eigen::Isometry3d p = Eigen::Isometry3d::Identity();
+    p.rotate(Eigen::AngleAxisd(M_PI / 2., Eigen::Vector3d(1., 0., 0.)));
+    p.rotate(Eigen::AngleAxisd(M_PI / 2., Eigen::Vector3d(0., 0., 1.)));
+    p.translate(Eigen::Vector3d(-1.5, 0.2, -1.35));
+    return p.inverse();
+}
+
+struct Scene {
+    std::unique_ptr<BundleAdjusterKeyframes> b;
+    std::vector<Eigen::Isometry3d> gt, noisy;
+    std::vector<Eigen::Vector3d> lms;
+    Tracklets ts;
+    std::map<CameraId, Camera::Ptr> cams;
+    std::map<LandmarkId, CameraIds> l2c;
+};
+
+static Scene build(std::tuple<double, double> noise_px, std::tuple<double, double, double, double> noise_pose,
+                   std::vector<Eigen::Isometry3d> extr, bool depth, bool motion_only = false) {
+    Scene s;
+    s.gt = getPoses(0., std::make_tuple(0., 0., 0.));
+    s.noisy = getPoses(std::get<0>(noise_pose), std::make_tuple(std::get<1>(noise_pose), std::get<2>(noise_pose), std::get<3>(noise_pose)));
+    for (size_t i = 2; i < s.noisy.size(); ++i) s.noisy[i].translation().normalize();  // :446-449
+    if (depth) s.lms = {{10., 3., 5.5}, {11., 1., 6.5}, {14., -5., 6.}, {9., 1., 5.}, {16., -1., 4.}};
+    else s.lms = {{10., 0.5, 5.5}, {11., 1., 6.5}, {14., -5., 6.}, {9., 1., 5.}, {16., -1., 4.}};
+    for (size_t i = 0; i < extr.size(); ++i) s.cams[i] = std::make_shared<Camera>(600., Eigen::Vector2d(200., 100.), extr[i]);
+    for (size_t i = 0; i < s.lms.size(); ++i) s.l2c[i] = CameraIds{i % extr.size()};
+    s.ts.stamps = {0, 1, 2, 3, 4};
+    s.ts.tracks.resize(s.lms.size());
+    const bool px_noise = std::get<0>(noise_px) != 0.;
+    for (size_t i = 0; i < s.lms.size(); ++i) s.ts.tracks[i].id = i;
+    for (const auto& pose : s.gt)
+        for (size_t i = 0; i < s.lms.size(); ++i) {
+            const auto& cam = s.cams.at(s.l2c[i][0]);
+            const Eigen::Vector3d lm_cam = (cam->getEigenPose() * pose) * s.lms[i];
+            Eigen::Vector3d proj = cam->getIntrinsicMatrix() * lm_cam;
+            proj /= proj[2];
+            const double u = proj[0] + (px_noise ? kNoisePix15[0] * std::get<0>(noise_px) / 1.5 : 0.);
+            const double v = proj[1] + (px_noise ? kNoisePix15[1] * std::get<1>(noise_px) / 1.5 : 0.);
+            s.ts.tracks[i].feature_points.push_back(depth ? FeaturePoint(float(u), float(v), float(lm_cam[2])) : FeaturePoint(float(u), float(v)));
+        }
+    s.b.reset(new BundleAdjusterKeyframes());
+    s.b->set_solver_time(20.);
+    const int max_ind = depth ? 4 : 5;
+    if (motion_only) for (int i = 0; i < max_ind; ++i) s.noisy[i] = s.gt[i];
+    const Keyframe::FixationStatus fix[5] = {Keyframe::FixationStatus::Pose, Keyframe::FixationStatus::Scale, Keyframe::FixationStatus::None,
+                                             Keyframe::FixationStatus::None, Keyframe::FixationStatus::None};
+    for (int i = 0; i < max_ind; ++i) {
+        if (extr.size() == 1) s.b->push(Keyframe(i, s.ts, s.cams[0], s.noisy[i], fix[i]));
+        else s.b->push(Keyframe(i, s.ts, s.cams, s.l2c, s.noisy[i], fix[i]));
+    }
+    return s;
+}
+
+static void test_triangulator() {  // Triangulator.process :51-74
+    const Eigen::Vector3d p(1., 1., 3.);
+    Eigen::Isometry3d t = Eigen::Isometry3d::Identity();
+    t.translation() = Eigen::Vector3d(1., -1., 0.);
+    const Eigen::Vector3d v1 = p / p.norm(), v2 = (t.inverse() * p).normalized();
+    const Eigen::Vector3d out = triangulate_rays({{Eigen::Isometry3d::Identity(), v1}, {t, v2}});
+    CHECK((out - p).norm() < 1e-5);
+}
+
+static void test_landmark_creation() {  // LandmarkCreator.CreateWithDepth :1149-1210 and the triangulated variant :472-476
+    for (bool depth : {true, false}) {
+        Scene s = build(std::make_tuple(0., 0.), std::make_tuple(0., 0., 0., 0.), {depth ? Eigen::Isometry3d::Identity() : monoExtrinsics()}, depth);
+        CHECK(s.b->landmarks_.size() == s.lms.size());
+        for (size_t i = 0; i < s.lms.size(); ++i) {
+            const Eigen::Vector3d rec(s.b->landmarks_.at(i)->pos.data());
+            CHECK((s.lms[i] - rec).norm() < (depth ? 1e-2 : 1e-1));
+            CHECK(s.b->landmarks_.at(i)->has_measured_depth == depth);
+        }
+    }
+}
+
+static void test_bookkeeping() {  // deactivateKeyframes :744-805, NotEnoughKeyframesException cpp:630
+    Scene s = build(std::make_tuple(0., 0.), std::make_tuple(0., 0., 0., 0.), {monoExtrinsics()}, false);
+    CHECK(s.b->active_keyframe_ids_.size() == 5);
+    s.b->deactivateKeyframes(3, 2, 3);
+    CHECK(s.b->active_keyframe_ids_.size() == 3);
+    auto sorted = s.b->getSortedActiveKeyframePtrs();
+    CHECK(sorted[0]->fixation_status_ == Keyframe::FixationStatus::Pose);
+    CHECK(sorted[1]->fixation_status_ == Keyframe::FixationStatus::Scale);
+    CHECK(s.b->getKeyframe().timestamp_ == 4);
+    BundleAdjusterKeyframes empty;
+    bool thrown = false;
+    try { empty.solve(); } catch (const BundleAdjusterKeyframes::NotEnoughKeyframesException& e) { thrown = std::string(e.what()).find("Should be 3 is 0") != std::string::npos; }
+    CHECK(thrown);
+    auto sel = s.b->landmark_selector_->select(s.b->getActiveLandmarkConstPtrs(), s.b->getActiveKeyframeConstPtrs());
+    CHECK(sel.size() == 5);
+}
+
+static void test_solve(bool depth) {  // KeyFrameBundleAdjustment.solve :807-858, solve_depth :1090-1145
+    const std::tuple<double, double, double, double> pose_noise[3] = {std::make_tuple(0., 0., 0., 0.), std::make_tuple(5. * M_PI / 180., 0.2, 0.1, 0.1),
+                                                                      std::make_tuple(5. * M_PI / 180., 0.2, 0.1, 0.1)};
+    const std::tuple<double, double> px_noise[3] = {std::make_tuple(0., 0.), std::make_tuple(0., 0.), std::make_tuple(1.5, 1.5)};
+    const double thres[3] = {1e-3, 1e-3, 1e-2};
+    Eigen::Isometry3d p2 = monoExtrinsics();
+    p2.translate(Eigen::Vector3d(0., -0.5, 0.));
+    p2.rotate(Eigen::AngleAxisd(M_PI / 18., Eigen::Vector3d(0., 1., 0.)));
+    p2.rotate(Eigen::AngleAxisd(M_PI / 18., Eigen::Vector3d(1., 0., 0.)));
+    for (int rig = 0; rig < 2; ++rig)
+        for (int c = 0; c < 3; ++c) {
+            std::vector<Eigen::Isometry3d> extr;
+            if (rig == 0) extr = {depth ? Eigen::Isometry3d::Identity() : monoExtrinsics()};
+            else extr = {monoExtrinsics(), p2};
+            Scene s = build(px_noise[c], pose_noise[c], extr, depth);
+            const std::string summary = s.b->solve();
+            CHECK(summary.find("Merged summaries") != std::string::npos);
+            size_t i = 0;
+            for (const auto& kf : s.b->keyframes_) { CHECK(kf.second->getEigenPose().isApprox(s.gt[i], thres[c])); ++i; }
+        }
+}
+
+static void test_motion_only() {  // BundleAdjusterKeyframes.adjustMotionOnly :1340-1344
+    Scene s = build(std::make_tuple(0., 0.), std::make_tuple(0., 0., 0., 0.), {Eigen::Isometry3d::Identity()}, true, true);
+    Keyframe kf(4, s.ts, s.cams[0], s.noisy[4]);
+    s.b->landmark_selector_->select(s.b->getActiveLandmarkConstPtrs(), s.b->getActiveKeyframeConstPtrs());
+    s.b->adjustPoseOnly(kf);
+    CHECK(kf.getEigenPose().isApprox(s.gt[4], 0.5));
+}
+
+int main(int argc, char** argv) {
+    const bool gpu = argc > 1 && std::strcmp(argv[1], "gpu") == 0;
+    test_triangulator();
+    test_landmark_creation();
+    test_bookkeeping();
+    if (gpu) { test_solve(false); test_solve(true); test_motion_only(); }
+    std::printf("%s: %d failed checks\n", gpu ? "gpu" : "cpu", g_fail);
+    return g_fail ? 1 : 0;
+}
