@@ -236,6 +236,32 @@ typedef struct kba_counters {
 int kba_get_counters(kba_handle* h, kba_counters* out, int reset);
 int kba_enable_kernel_timing(kba_handle* h, int on);
 
+/* ---- lidar depth extraction (BASELINE config 4) --------------------------------------------------------------------
+ * Replaces the un-vendored mono_lidar_depth::DepthEstimator call the limo front end makes per frame (install_repos.sh:9;
+ * in-tree only its parameter file demo_keyframe_bundle_adjustment_meta/res/mono_lidar_fusion_parameters.yaml, whose
+ * keys the fields below carry, defaults = the YAML values).  Per feature: lidar points projected into the pixel
+ * rectangle around it -> depth-histogram segmentation (nearest local maximum) -> plane through the largest triangle
+ * -> intersection with the view ray; -1 when any gate fails.  No reference code or tests exist for it:
+ * the CPU restatement in oracle/ follows this specification, parity is "unpinned". */
+typedef struct kba_lidar_options {
+    int32_t image_width, image_height;  /* 1242 x 375 */
+    double rect_width, rect_height;     /* pixelarea_search_witdh 6, pixelarea_search_height 9 (yaml:11-13) */
+    double rect_offset_x, rect_offset_y;/* yaml:15-18 */
+    double hist_bin_width;              /* histogram_segmentation_bin_witdh 0.3 m (yaml:58-61) */
+    int32_t hist_min_count;             /* histogram_segmentation_min_pointcount 1 (yaml:63) */
+    int32_t min_points;                 /* points needed for a plane: 3 */
+    double depth_min, depth_max;        /* treshold_depth_min/max 0 / 100 (yaml:97-104) */
+    double local_rel_tolerance;         /* treshold_depth_local_value 0.5, relative (yaml:106-114); < 0 disables */
+    double triangle_crossnorm_min;      /* triangleplanar_crossnorm_treshold 0.1 (yaml:172-175) */
+    double viewray_plane_min;           /* viewray_plane_orthoganality_treshold 0.1 (yaml:177-178) */
+} kba_lidar_options;
+void kba_lidar_default_options(kba_lidar_options* opt);
+/* cloud: n_points x point_stride floats, xyz first (KITTI .bin layout x,y,z,intensity: apps/main_program/utility.h:28-39);
+ * T_cam_lidar: 7-vector camera <- lidar; intr: f, cx, cy; features: n_features x 2 floats (u, v); depth_out: n_features floats. */
+int kba_lidar_depth(kba_handle* h, const float* cloud, int32_t n_points, int32_t point_stride, const double* T_cam_lidar,
+                    const double* intr, const float* features_uv, int32_t n_features, const kba_lidar_options* opt,
+                    float* depth_out, float* device_ms);
+
 #ifdef __cplusplus
 }
 #endif

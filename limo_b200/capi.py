@@ -8,7 +8,7 @@ import os
 
 import numpy as np
 
-from .capi_types import (KbaCounters, KbaEvalOut, KbaOptions, KbaResult, KbaWindow, Result, c_double_p, c_int32_p)
+from .capi_types import (KbaCounters, KbaEvalOut, KbaLidarOptions, KbaOptions, KbaResult, KbaWindow, Result, c_double_p, c_int32_p)
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libkba_b200.so")
@@ -17,7 +17,7 @@ _lib = None
 SYMBOLS = ["kba_version", "kba_last_error", "kba_default_options", "kba_create", "kba_destroy", "kba_set_stream",
            "kba_solve_window", "kba_solve_batch", "kba_eval", "kba_batch_create", "kba_batch_upload",
            "kba_batch_solve", "kba_batch_download", "kba_batch_transfer_bytes", "kba_batch_jacobian_pass", "kba_batch_destroy",
-           "kba_get_counters", "kba_enable_kernel_timing"]
+           "kba_get_counters", "kba_enable_kernel_timing", "kba_lidar_default_options", "kba_lidar_depth"]
 
 
 class KbaError(RuntimeError):
@@ -52,6 +52,11 @@ def lib():
         L.kba_batch_destroy.restype = None
         L.kba_get_counters.argtypes = [vp, C.POINTER(KbaCounters), C.c_int]
         L.kba_enable_kernel_timing.argtypes = [vp, C.c_int]
+        L.kba_lidar_default_options.argtypes = [C.POINTER(KbaLidarOptions)]
+        L.kba_lidar_default_options.restype = None
+        fp = C.POINTER(C.c_float)
+        L.kba_lidar_depth.argtypes = [vp, fp, C.c_int32, C.c_int32, c_double_p, c_double_p, fp, C.c_int32,
+                                      C.POINTER(KbaLidarOptions), fp, fp]
         _lib = L
     return _lib
 
@@ -64,6 +69,12 @@ def _check(rc):
 def default_options():
     o = KbaOptions()
     lib().kba_default_options(C.byref(o))
+    return o
+
+
+def lidar_default_options():
+    o = KbaLidarOptions()
+    lib().kba_lidar_default_options(C.byref(o))
     return o
 
 
@@ -156,6 +167,20 @@ class Handle:
 
     def batch(self, windows):
         return Batch(self, windows)
+
+    def lidar_depth(self, cloud, T_cam_lidar, intr, features_uv, opt=None):
+        """cloud [n, stride>=3] float32, features_uv [m, 2] float32 -> (depth [m] float32 (-1 = none), device ms)"""
+        cloud = np.ascontiguousarray(cloud, dtype=np.float32)
+        feats = np.ascontiguousarray(features_uv, dtype=np.float32).reshape(-1, 2)
+        T = np.ascontiguousarray(T_cam_lidar, dtype=np.float64); K = np.ascontiguousarray(intr, dtype=np.float64)
+        out = np.zeros(max(len(feats), 1), dtype=np.float32)
+        ms = C.c_float()
+        fp = C.POINTER(C.c_float)
+        _check(lib().kba_lidar_depth(self._p, cloud.ctypes.data_as(fp), cloud.shape[0], cloud.shape[1],
+                                     T.ctypes.data_as(c_double_p), K.ctypes.data_as(c_double_p), feats.ctypes.data_as(fp),
+                                     len(feats), C.byref(opt or lidar_default_options()), out.ctypes.data_as(fp),
+                                     C.byref(ms)))
+        return out[:len(feats)], ms.value
 
     def counters(self, reset=False):
         c = KbaCounters()

@@ -92,6 +92,16 @@ class KbaCounters(C.Structure):
     ]
 
 
+class KbaLidarOptions(C.Structure):
+    _fields_ = [
+        ("image_width", C.c_int32), ("image_height", C.c_int32),
+        ("rect_width", C.c_double), ("rect_height", C.c_double), ("rect_offset_x", C.c_double), ("rect_offset_y", C.c_double),
+        ("hist_bin_width", C.c_double), ("hist_min_count", C.c_int32), ("min_points", C.c_int32),
+        ("depth_min", C.c_double), ("depth_max", C.c_double), ("local_rel_tolerance", C.c_double),
+        ("triangle_crossnorm_min", C.c_double), ("viewray_plane_min", C.c_double),
+    ]
+
+
 def _ptr(a, ctype):
     if a is None:
         return C.cast(None, C.POINTER(ctype))

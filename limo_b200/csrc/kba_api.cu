@@ -226,6 +226,13 @@ static void fill_window(kba_batch* b, int wi, const kba_window* w) {
 extern "C" {
 
 int kba_version(void) { return KBA_VERSION_MAJOR * 100 + KBA_VERSION_MINOR; }
+// helpers for the other translation units of the library (not part of the public header)
+int kba_internal_stream(kba_handle* h, cudaStream_t* s, int* device) {
+    if (!h) return fail(KBA_ERR_BAD_ARG, "null handle");
+    *s = h->stream; *device = h->device;
+    return KBA_OK;
+}
+int kba_internal_fail(int code, const char* msg) { return fail(code, msg ? msg : ""); }
 const char* kba_last_error(void) { return g_last_error.c_str(); }
 
 void kba_default_options(kba_options* o) {

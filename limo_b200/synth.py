@@ -233,3 +233,42 @@ def make_window(config=2, seed=None, n_kf=None, n_lm=None, n_obs=None, depth_fra
         truth = dict(kf_pose=np.stack([g.iso_to_pose(T) for T in T_true]), lm_pos=P_true, is_outlier=is_out, is_gp=is_gp)
         return win, truth
     return win
+
+
+# ---- lidar scene of BASELINE config 4 --------------------------------------------------------------------------
+def velo_to_cam():
+    """camera <- velodyne, KITTI nominal: camera z = velodyne x, camera x = -velodyne y, camera y = -velodyne z;
+    the camera sits 0.27 m ahead of and 0.08 m below the lidar."""
+    R = np.array([[0.0, -1.0, 0.0], [0.0, 0.0, -1.0], [1.0, 0.0, 0.0]])
+    return g.iso(R, [0.0, -0.08, -0.27])
+
+
+def make_lidar_scene(seed=0xBA5E0004, n_rings=64, n_azimuth=1875, n_features=2000, n_facades=20):
+    """64 rings x 1875 azimuth steps = 120k returns of a synthetic scene: ground plane z = -1.73 m (velodyne frame) plus
+    vertical planar facades 5..60 m away; xyz + intensity float32 (KITTI .bin layout); features at uniform random pixels."""
+    rng = np.random.Generator(np.random.MT19937(seed))
+    elev = np.deg2rad(np.linspace(2.0, -24.8, n_rings))
+    az = np.linspace(-np.pi, np.pi, n_azimuth, endpoint=False)
+    E, A = np.meshgrid(elev, az, indexing="ij")
+    d = np.stack([np.cos(E) * np.cos(A), np.cos(E) * np.sin(A), np.sin(E)], axis=-1).reshape(-1, 3)
+    rng_ = np.full(len(d), np.inf)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        lam = -1.73 / d[:, 2]
+    rng_ = np.where((d[:, 2] < 0) & (lam < 120.0), lam, rng_)
+    for _ in range(n_facades):  # vertical facade: plane n . p = dist, bounded patch
+        ang = rng.uniform(-np.pi, np.pi)
+        n = np.array([np.cos(ang), np.sin(ang), 0.0])
+        dist = rng.uniform(5.0, 60.0)
+        centre = n * dist
+        half_w, top = rng.uniform(2.0, 8.0), rng.uniform(1.0, 6.0)
+        with np.errstate(divide="ignore", invalid="ignore"):
+            lam = dist / (d @ n)
+        hit = d * lam[:, None]
+        tang = np.array([-n[1], n[0], 0.0])
+        ok = (lam > 0) & (np.abs((hit - centre) @ tang) < half_w) & (hit[:, 2] < top) & (hit[:, 2] > -1.73)
+        rng_ = np.where(ok & (lam < rng_), lam, rng_)
+    keep = np.isfinite(rng_)
+    pts = d[keep] * (rng_[keep] + rng.normal(0, 0.01, keep.sum()))[:, None]
+    cloud = np.concatenate([pts, rng.uniform(0, 1, (len(pts), 1))], axis=1).astype(np.float32)
+    feats = np.stack([rng.uniform(0, IMG_W, n_features), rng.uniform(0, IMG_H, n_features)], axis=1).astype(np.float32)
+    return cloud, g.iso_to_pose(velo_to_cam()), np.array([F, CX, CY]), feats

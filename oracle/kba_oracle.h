@@ -62,6 +62,11 @@ int kbo_trimmer_quantile(const double* values, int n, double quantile, unsigned 
 /* Triangulator::triangulate_rays (internal/triangulator.hpp:51-75): R_oc [n*9] row-major, t_oc [n*3], rays [n*3] (unit, camera frame). */
 void kbo_triangulate_rays(int n, const double* R_oc, const double* t_oc, const double* rays, double out[3]);
 
+/* lidar depth extraction per the parameter file's specification (lidar_oracle.c; parity unpinned, see there) */
+void kbo_lidar_default_options(kba_lidar_options* opt);
+int kbo_lidar_depth(const float* cloud, int n_points, int stride, const double* T_cam_lidar, const double* intr,
+                    const float* features_uv, int n_features, const kba_lidar_options* opt, float* depth_out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -9,7 +9,7 @@ import subprocess
 
 import numpy as np
 
-from limo_b200.capi_types import (KbaEvalOut, KbaOptions, KbaResult, KbaWindow, Result, c_double_p, c_int32_p)
+from limo_b200.capi_types import (KbaEvalOut, KbaLidarOptions, KbaOptions, KbaResult, KbaWindow, Result, c_double_p, c_int32_p)
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB_PATH = os.path.join(_HERE, "libkba_oracle.so")
@@ -46,6 +46,10 @@ def lib():
         _lib.kbo_trimmer_quantile.argtypes = [dp, C.c_int, C.c_double, C.POINTER(C.c_uint8)]
         _lib.kbo_trimmer_quantile.restype = C.c_int
         _lib.kbo_triangulate_rays.argtypes = [C.c_int, dp, dp, dp, dp]
+        fp = C.POINTER(C.c_float)
+        _lib.kbo_lidar_default_options.argtypes = [C.POINTER(KbaLidarOptions)]
+        _lib.kbo_lidar_depth.argtypes = [fp, C.c_int, C.c_int, dp, dp, fp, C.c_int, C.POINTER(KbaLidarOptions), fp]
+        _lib.kbo_lidar_depth.restype = C.c_int
     return _lib
 
 
@@ -161,6 +165,25 @@ def triangulate_rays(R_oc, t_oc, rays):
     out = np.zeros(3)
     lib().kbo_triangulate_rays(len(t.reshape(-1, 3)), Rp, tp, rp, out.ctypes.data_as(c_double_p))
     return out
+
+
+def lidar_default_options():
+    o = KbaLidarOptions()
+    lib().kbo_lidar_default_options(C.byref(o))
+    return o
+
+
+def lidar_depth(cloud, T_cam_lidar, intr, features_uv, opt=None):
+    cloud = np.ascontiguousarray(cloud, dtype=np.float32)
+    feats = np.ascontiguousarray(features_uv, dtype=np.float32).reshape(-1, 2)
+    T, Tp = _d(T_cam_lidar); K, Kp = _d(intr)
+    out = np.zeros(max(len(feats), 1), dtype=np.float32)
+    fp = C.POINTER(C.c_float)
+    rc = lib().kbo_lidar_depth(cloud.ctypes.data_as(fp), cloud.shape[0], cloud.shape[1], Tp, Kp, feats.ctypes.data_as(fp),
+                               len(feats), C.byref(opt or lidar_default_options()), out.ctypes.data_as(fp))
+    if rc != 0:
+        raise RuntimeError("kbo_lidar_depth failed: %d" % rc)
+    return out[:len(feats)]
 
 
 class OracleBackend:

@@ -31,14 +31,14 @@ def test_struct_sizes_match_header(tmp_path):
     """sizeof() of every POD struct as the C compiler sees it == size of the ctypes mirror"""
     from limo_b200 import capi_types as T
     prog = tmp_path / "sz.c"
-    prog.write_text('#include <stdio.h>\n#include "kba_b200.h"\nint main(){printf("%zu %zu %zu %zu %zu %zu %zu\\n",'
+    prog.write_text('#include <stdio.h>\n#include "kba_b200.h"\nint main(){printf("%zu %zu %zu %zu %zu %zu %zu %zu\\n",'
                     'sizeof(kba_window),sizeof(kba_options),sizeof(kba_iteration),sizeof(kba_solve_summary),'
-                    'sizeof(kba_result),sizeof(kba_eval_out),sizeof(kba_counters));return 0;}\n')
+                    'sizeof(kba_result),sizeof(kba_eval_out),sizeof(kba_counters),sizeof(kba_lidar_options));return 0;}\n')
     exe = tmp_path / "sz"
     subprocess.check_call(["/usr/bin/gcc", "-I", os.path.join(ROOT, "include"), str(prog), "-o", str(exe)])
     sizes = [int(x) for x in subprocess.check_output([str(exe)]).split()]
     mirror = [C.sizeof(t) for t in (T.KbaWindow, T.KbaOptions, T.KbaIteration, T.KbaSolveSummary, T.KbaResult,
-                                    T.KbaEvalOut, T.KbaCounters)]
+                                    T.KbaEvalOut, T.KbaCounters, T.KbaLidarOptions)]
     assert sizes == mirror
 
 
