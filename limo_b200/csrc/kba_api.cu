@@ -69,6 +69,7 @@ struct kba_batch {
     Staged<double> pose0, plane0, cam, lm0, lm_weight;
     Staged<uint8_t> kf_fixed;
     Staged<int> lm_ptr, obs_kf, obs_cam, obs_lm, kf_ptr, pm_lm, pm_cam, chunk_lm0, chunk_lm1, chunk_k0, chunk_k1, lm_orig, obs_orig;
+    Staged<int> obs_rank;
     Staged<float> obs_u, obs_v, obs_d, pm_u, pm_v, pm_d;
     // outputs
     Staged<WinState> state;
@@ -97,7 +98,7 @@ struct kba_batch {
         desc.release(); pose0.release(); plane0.release(); cam.release(); lm0.release(); lm_weight.release();
         kf_fixed.release(); lm_ptr.release(); obs_kf.release(); obs_cam.release(); obs_lm.release(); kf_ptr.release();
         pm_lm.release(); pm_cam.release(); chunk_lm0.release(); chunk_lm1.release(); chunk_k0.release(); chunk_k1.release();
-        lm_orig.release(); obs_orig.release(); obs_u.release(); obs_v.release();
+        lm_orig.release(); obs_orig.release(); obs_rank.release(); obs_u.release(); obs_v.release();
         obs_d.release(); pm_u.release(); pm_v.release(); pm_d.release(); state.release(); log.release();
         pose_out[0].release(); pose_out[1].release(); lm_out[0].release(); lm_out[1].release(); lm_active.release();
         n_active.release(); jac_obs.release(); plane_out[0].release(); plane_out[1].release();
@@ -165,7 +166,7 @@ static void fill_window(kba_batch* b, int wi, const kba_window* w) {
     int* lp = b->lm_ptr.h + d.lm_off + wi;
     int* kp = b->kf_ptr.h + d.kf_off + wi;
     std::fill(kp, kp + w->n_kf + 1, 0);
-    int pos = 0;
+    int pos = 0, max_rank = 0;
     lp[0] = 0;
     for (int jn = 0; jn < nl; ++jn) {
         const int jo = orig[jn];
@@ -178,10 +179,16 @@ static void fill_window(kba_batch* b, int wi, const kba_window* w) {
             b->obs_lm.h[e] = jn;
             b->obs_u.h[e] = w->obs_u[o]; b->obs_v.h[e] = w->obs_v[o]; b->obs_d.h[e] = w->obs_d[o];
             b->obs_orig.h[e] = o;
+            // rank among the observations of this landmark in the same keyframe (multi-camera rigs)
+            const int rank = (o > w->lm_obs_ptr[jo] && w->obs_kf[o - 1] == w->obs_kf[o]) ? b->obs_rank.h[e - 1] + 1 : 0;
+            b->obs_rank.h[e] = rank;
+            max_rank = std::max(max_rank, rank);
             kp[w->obs_kf[o] + 1]++;
         }
         lp[jn + 1] = pos;
     }
+    b->desc_h[wi].max_rank = max_rank;
+    b->desc.h[wi].max_rank = max_rank;
     // keyframe-major copy (counting sort, stable -> deterministic reduction order)
     for (int k = 0; k < w->n_kf; ++k) kp[k + 1] += kp[k];
     std::vector<int> cur(kp, kp + w->n_kf);
@@ -369,7 +376,16 @@ int kba_batch_create(kba_handle* h, int32_t n_windows, const kba_window* w, kba_
     bad |= b->pm_u.alloc(obs, true); bad |= b->pm_v.alloc(obs, true); bad |= b->pm_d.alloc(obs, true);
     bad |= b->chunk_lm0.alloc(chunks, true); bad |= b->chunk_lm1.alloc(chunks, true);
     bad |= b->chunk_k0.alloc(chunks, true); bad |= b->chunk_k1.alloc(chunks, true);
-    bad |= b->lm_orig.alloc(lm, true); bad |= b->obs_orig.alloc(obs, true);
+    bad |= b->lm_orig.alloc(lm, true); bad |= b->obs_orig.alloc(obs, true); bad |= b->obs_rank.alloc(obs, true);
+    {   // dense V panels of the TMA-fed Schur kernel: worst case 96 columns x 196 rows per chunk
+        long long cap = 0;
+        for (auto& d : b->desc_h) cap = std::max<long long>(cap, (long long)d.n_chunks * 96 * 196);
+        bd.use_panel = b->lc.small_syrk ? 1 : 0;
+        bd.panel_cap = bd.use_panel ? cap : 0;
+        for (int i = 0; i < n_windows; ++i) b->desc_h[i].panel_off = (long long)i * bd.panel_cap;
+        bad |= b->dev_alloc(&bd.vpanel, (size_t)n_windows * bd.panel_cap);
+        bad |= b->dev_alloc(&bd.chunk_poff, chunks); bad |= b->dev_alloc(&bd.chunk_rs, chunks);
+    }
     bad |= b->dev_alloc(&bd.chunk_t0, chunks); bad |= b->dev_alloc(&bd.chunk_t1, chunks); bad |= b->dev_alloc(&bd.obs_row, obs);
     bad |= b->state.alloc(n_windows, true); bad |= b->log.alloc((size_t)n_windows * kIterLogCap, true);
     for (int q = 0; q < 2; ++q) { bad |= b->pose_out[q].alloc(7 * kf, true); bad |= b->lm_out[q].alloc(3 * lm, true); }
@@ -406,6 +422,7 @@ int kba_batch_create(kba_handle* h, int32_t n_windows, const kba_window* w, kba_
     bd.kf_ptr = b->kf_ptr.d; bd.pm_lm = b->pm_lm.d; bd.pm_cam = b->pm_cam.d; bd.pm_u = b->pm_u.d; bd.pm_v = b->pm_v.d; bd.pm_d = b->pm_d.d;
     bd.chunk_lm0 = b->chunk_lm0.d; bd.chunk_lm1 = b->chunk_lm1.d; bd.chunk_k0 = b->chunk_k0.d; bd.chunk_k1 = b->chunk_k1.d;
     bd.lm_orig = b->lm_orig.d;
+    bd.obs_rank = b->obs_rank.d;
     bd.plane[0] = b->plane_out[0].d; bd.plane[1] = b->plane_out[1].d;
     bd.gp_lm = b->gp_lm.d; bd.gp_kf = b->gp_kf.d; bd.gp_weight = b->gp_weight.d; bd.gp_of_lm = b->gp_of_lm.d;
     bd.n_active = b->n_active.d;
@@ -443,7 +460,7 @@ int kba_batch_upload(kba_batch* b, int32_t n_windows, const kba_window* w) {
     CU(b->obs_u.upload(s)); CU(b->obs_v.upload(s)); CU(b->obs_d.upload(s));
     CU(b->kf_ptr.upload(s)); CU(b->pm_lm.upload(s)); CU(b->pm_cam.upload(s)); CU(b->pm_u.upload(s)); CU(b->pm_v.upload(s)); CU(b->pm_d.upload(s));
     CU(b->chunk_lm0.upload(s)); CU(b->chunk_lm1.upload(s)); CU(b->chunk_k0.upload(s)); CU(b->chunk_k1.upload(s));
-    CU(b->lm_orig.upload(s));
+    CU(b->lm_orig.upload(s)); CU(b->obs_rank.upload(s));
     CU(b->gp_lm.upload(s)); CU(b->gp_kf.upload(s)); CU(b->gp_weight.upload(s)); CU(b->gp_of_lm.upload(s));
     const BatchDev& bd = b->bd;
     b->h2d_bytes = sizeof(WinDesc) * bd.n_win + (7 + 4) * 8 * bd.tot_kf + bd.tot_kf + kCamStride * 8 * bd.tot_cam +

@@ -29,7 +29,9 @@ struct WinDesc {
     double speed_v_before[3];
     double speed_T_origin_before[7];
     long long s_off;                                // offset (doubles) of this window's reduced-system storage
-    int nr_cap, pad1;                               // allocated panel rows (multiple of 64)
+    int nr_cap;                                     // allocated rows of the reduced system (multiple of 64)
+    int max_rank;                                   // > 0: some landmark is seen by several cameras in one keyframe
+    long long panel_off;                            // offset (doubles) of this window's dense V panel storage
 };
 
 // ---- per-window solver state (device resident, mutated by the kernels) ----------------------------------------------
@@ -112,6 +114,7 @@ struct BatchDev {
     int* obs_kf;              // [tot_obs]
     int* obs_cam;
     int* obs_lm;              // window-local landmark index
+    int* obs_rank;            // [tot_obs] 0, or k for the k-th further observation of the same (landmark, keyframe)
     float* obs_u, *obs_v, *obs_d;
     // observations, keyframe-major copy (built on device at upload)
     int* kf_ptr;              // [tot_kf + n_win]
@@ -122,7 +125,14 @@ struct BatchDev {
     double* res;              // [3][tot_obs]  robustified residual rows (u, v, depth)
     double* jp;               // [18][tot_obs] 3x6 d r~ / d (rot, trans)
     double* jl;               // [9][tot_obs]  3x3 d r~ / d landmark
-    double* vobs;             // [18][tot_obs] V_i = (J_p^T J_l) L^-T, 6x3
+    double* vobs;             // [18][tot_obs] V_i = (J_p^T J_l) L^-T, 6x3 (generic Schur kernel)
+    // dense per-chunk V panels for the TMA-fed Schur kernel: chunk c of window w occupies 96 columns x chunk_rs[c] rows,
+    // column-major ([col][row]), at vpanel + desc.panel_off + chunk_poff[c]; rows = the chunk's 8-row tile range (+ rhs tile)
+    double* vpanel;
+    long long panel_cap;      // doubles reserved per window
+    int* chunk_poff;          // [tot_chunks] offset (doubles) inside the window's panel storage
+    int* chunk_rs;            // [tot_chunks] row stride (== 4 mod 16, 0 for chunks without free keyframes)
+    int use_panel;            // 1: V lives in vpanel (register-resident Schur kernel), 0: in vobs
     // reductions
     double* cost_part_x;      // [n_win][cost_parts] cost partials of the linearisation at x
     double* cost_part_c;      // [n_win][cost_parts] cost partials at the candidate

@@ -110,6 +110,35 @@ __global__ void __launch_bounds__(256) k_solve_begin(BatchDev bd, SolveParams sp
         bd.chunk_t0[wd.chunk_off + c] = (r1 < 0) ? 0 : r0 / 8;
         bd.chunk_t1[wd.chunk_off + c] = (r1 < 0) ? 0 : (r1 + 7) / 8;
     }
+    if (bd.use_panel) {  // layout of the dense V panels: per chunk 96 columns x rs rows (rs == 4 mod 16), column-major
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            const int trhs = st.n_f >> 3;
+            int poff = 0;
+            for (int c = 0; c < wd.n_chunks; ++c) {
+                const int t0 = bd.chunk_t0[wd.chunk_off + c], t1 = bd.chunk_t1[wd.chunk_off + c];
+                int rs = 0;
+                if (t1 > t0) {
+                    const int rows = 8 * (t1 - t0) + ((trhs >= t0 && trhs < t1) ? 0 : 8);
+                    rs = ((rows - 4 + 15) / 16) * 16 + 4;
+                }
+                bd.chunk_rs[wd.chunk_off + c] = rs;
+                bd.chunk_poff[wd.chunk_off + c] = poff;
+                poff += 96 * rs;
+            }
+        }
+    }
+}
+
+// zero the dense V panels of windows that are about to start a solve (the sparsity pattern is fixed within a solve:
+// k_landmark_prep overwrites every structurally non-zero entry in each pass)
+__global__ void __launch_bounds__(256) k_panel_zero(BatchDev bd) {
+    const int w = blockIdx.y;
+    if (bd.state[w].phase != PH_SOLVE_BEGIN || bd.desc[w].landmarks_fixed) return;
+    double2* p = reinterpret_cast<double2*>(bd.vpanel + bd.desc[w].panel_off);
+    const long long n2 = bd.panel_cap / 2;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n2; i += (long long)gridDim.x * blockDim.x)
+        p[i] = make_double2(0.0, 0.0);
 }
 
 // =====================================================================================================================
@@ -319,6 +348,8 @@ __global__ void __launch_bounds__(256) k_pose_hessian(BatchDev bd, SolveParams s
 // landmark preparation: one warp per landmark.  C_j = sum J_l^T J_l, g_j = sum J_l^T r (warp-shuffle tree), Jacobi-scaled
 // LM damping, 3x3 Cholesky, then per observation V_i = (J_p^T J_l) L^-T (6x3) for the Schur kernel and the back-substitution.
 // =====================================================================================================================
+__device__ __forceinline__ int gp_row(const BatchDev& bd, const WinDesc& wd, int k, int r);
+
 __global__ void __launch_bounds__(256) k_landmark_prep(BatchDev bd, SolveParams sp) {
     const int w = blockIdx.y;
     WinState& st = bd.state[w];
@@ -416,21 +447,60 @@ __global__ void __launch_bounds__(256) k_landmark_prep(BatchDev bd, SolveParams 
         bd.vgp[(3 * lane + 2) * TG + G] = e0 * i20 + e1 * i21 + e2 * i22;
     }
     // V_i = E_i L^-T with E_i = J_p^T J_l;  V[r][cc] = sum_m E[r][m] * Linv[cc][m]
-    for (int o = o0 + lane; o < o1; o += 32) {
-        if (bd.off_pose[wd.kf_off + bd.obs_kf[base + o]] < 0) continue;
-        double jl[9], jp[18];
+    // panel mode: written straight into the chunk's dense column-major panel (what the Schur kernel bulk-loads)
+    double* pcol = nullptr;  // column 3 * (j % 32) of the chunk panel, row 0 = first row of the chunk's tile range
+    int prs = 0, prow0 = 0;
+    if (bd.use_panel) {
+        const int ch = wd.chunk_off + (j >> 5);
+        prs = bd.chunk_rs[ch];
+        prow0 = 8 * bd.chunk_t0[ch];
+        pcol = bd.vpanel + wd.panel_off + bd.chunk_poff[ch] + (size_t)(3 * (j & 31)) * prs;
+        if (lane == 0 && prs > 0) {  // right-hand-side row z_j
+            const int t0 = bd.chunk_t0[ch], t1 = bd.chunk_t1[ch], trhs = st.n_f >> 3;
+            const int rl = (trhs >= t0 && trhs < t1) ? st.n_f - prow0 : 8 * (t1 - t0) + (st.n_f - 8 * trhs);
+            pcol[rl] = z0; pcol[prs + rl] = z1; pcol[2 * prs + rl] = z2;
+        }
+    }
+    // obs_rank > 0: a further observation of the same (landmark, keyframe) by another camera of the rig; its block is
+    // ADDED to the rows the rank-0 observation wrote, one rank per round so that no two lanes touch the same entry.
+    for (int round = 0; round <= wd.max_rank; ++round) {
+        for (int o = o0 + lane; o < o1; o += 32) {
+            const int row0 = bd.off_pose[wd.kf_off + bd.obs_kf[base + o]];
+            if (row0 < 0 || bd.obs_rank[base + o] != round) continue;
+            double jl[9], jp[18];
 #pragma unroll
-        for (int q = 0; q < 9; ++q) jl[q] = bd.jl[q * T + base + o];
+            for (int q = 0; q < 9; ++q) jl[q] = bd.jl[q * T + base + o];
 #pragma unroll
-        for (int q = 0; q < 18; ++q) jp[q] = bd.jp[q * T + base + o];
+            for (int q = 0; q < 18; ++q) jp[q] = bd.jp[q * T + base + o];
 #pragma unroll
-        for (int r = 0; r < 6; ++r) {
-            const double e0 = jp[r] * jl[0] + jp[6 + r] * jl[3] + jp[12 + r] * jl[6];
-            const double e1 = jp[r] * jl[1] + jp[6 + r] * jl[4] + jp[12 + r] * jl[7];
-            const double e2 = jp[r] * jl[2] + jp[6 + r] * jl[5] + jp[12 + r] * jl[8];
-            bd.vobs[(3 * r + 0) * T + base + o] = e0 * i00;
-            bd.vobs[(3 * r + 1) * T + base + o] = e0 * i10 + e1 * i11;
-            bd.vobs[(3 * r + 2) * T + base + o] = e0 * i20 + e1 * i21 + e2 * i22;
+            for (int r = 0; r < 6; ++r) {
+                const double e0 = jp[r] * jl[0] + jp[6 + r] * jl[3] + jp[12 + r] * jl[6];
+                const double e1 = jp[r] * jl[1] + jp[6 + r] * jl[4] + jp[12 + r] * jl[7];
+                const double e2 = jp[r] * jl[2] + jp[6 + r] * jl[5] + jp[12 + r] * jl[8];
+                const double v0 = e0 * i00, v1 = e0 * i10 + e1 * i11, v2 = e0 * i20 + e1 * i21 + e2 * i22;
+                if (bd.use_panel) {
+                    double* q = pcol + (row0 - prow0 + r);
+                    if (round == 0) { q[0] = v0; q[prs] = v1; q[2 * prs] = v2; }
+                    else { q[0] += v0; q[prs] += v1; q[2 * prs] += v2; }
+                } else {
+                    bd.vobs[(3 * r + 0) * T + base + o] = v0;
+                    bd.vobs[(3 * r + 1) * T + base + o] = v1;
+                    bd.vobs[(3 * r + 2) * T + base + o] = v2;
+                }
+            }
+        }
+        if (wd.max_rank > 0) __syncwarp();
+    }
+    if (bd.use_panel && gl >= 0) {  // ground-plane rows are added on top (its pose rows may coincide with an observation's)
+        __syncwarp();
+        if (lane < 10) {
+            const int row = gp_row(bd, wd, bd.gp_kf[G], lane);
+            if (row >= 0) {
+                double* q = pcol + (row - prow0);
+                q[0] += bd.vgp[(3 * lane + 0) * TG + G];
+                q[prs] += bd.vgp[(3 * lane + 1) * TG + G];
+                q[2 * prs] += bd.vgp[(3 * lane + 2) * TG + G];
+            }
         }
     }
 }
@@ -493,17 +563,20 @@ __global__ void __launch_bounds__(256, 2) k_schur_syrk(BatchDev bd) {
         __syncthreads();
         // scatter V_i (6x3) into the panel(s)
         const int nobs = o1 - o0;
-        for (int idx = threadIdx.x; idx < nobs * 18; idx += blockDim.x) {
-            const int e = idx / nobs, oo = idx - e * nobs;
-            const size_t o = base + o0 + oo;
-            const int jl = bd.obs_lm[o];
-            if (!bd.lm_active[wd.lm_off + jl]) continue;
-            const int off = bd.off_pose[wd.kf_off + bd.obs_kf[o]];
-            if (off < 0) continue;
-            const int row = off + e / 3, col = 3 * (jl - j0) + e % 3;
-            const double v = bd.vobs[e * T + o];
-            if (row >= ra0 && row < ra0 + 64) pa[(row - ra0) * kKS + col] = v;
-            if (!diag && row >= rb0 && row < rb0 + 64) pb[(row - rb0) * kKS + col] = v;
+        for (int round = 0; round <= wd.max_rank; ++round) {  // rank > 0: second camera of the rig on the same rows -> add
+            if (round > 0) __syncthreads();
+            for (int idx = threadIdx.x; idx < nobs * 18; idx += blockDim.x) {
+                const int e = idx / nobs, oo = idx - e * nobs;
+                const size_t o = base + o0 + oo;
+                const int jl = bd.obs_lm[o];
+                if (!bd.lm_active[wd.lm_off + jl] || bd.obs_rank[o] != round) continue;
+                const int off = bd.off_pose[wd.kf_off + bd.obs_kf[o]];
+                if (off < 0) continue;
+                const int row = off + e / 3, col = 3 * (jl - j0) + e % 3;
+                const double v = bd.vobs[e * T + o];
+                if (row >= ra0 && row < ra0 + 64) pa[(row - ra0) * kKS + col] += v;
+                if (!diag && row >= rb0 && row < rb0 + 64) pb[(row - rb0) * kKS + col] += v;
+            }
         }
         // rhs row: z_j
         for (int idx = threadIdx.x; idx < (j1 - j0) * 3; idx += blockDim.x) {
@@ -636,6 +709,122 @@ __global__ void __launch_bounds__(512, 1) k_schur_syrk_small(BatchDev bd) {
 #pragma unroll 8
             for (int kk = 0; kk < kKC; kk += 4) dmma(acc[s][0], acc[s][1], arow[kk], brow[kk]);
         }
+    }
+    double* out = bd.sred + wd.s_off * (size_t)bd.p_split + (size_t)blockIdx.x * wd.nr_cap * wd.nr_cap;
+#pragma unroll
+    for (int s = 0; s < kSmallSlots; ++s) {
+        const int t = s * 16 + warp;
+        int i = (int)((sqrtf(8.0f * (float)t + 1.0f) - 1.0f) * 0.5f);
+        while ((i + 1) * (i + 2) / 2 <= t) ++i;
+        while (i * (i + 1) / 2 > t) --i;
+        const int j = t - i * (i + 1) / 2;
+        if (i >= nt) continue;
+        double* o = out + (size_t)(8 * i + fr) * wd.nr_cap + 8 * j + 2 * fc;
+        o[0] = acc[s][0];
+        o[1] = acc[s][1];
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// TMA-fed variant of the register-resident kernel: k_landmark_prep has already laid V out as dense column-major chunk
+// panels in global memory (zeros included), so a panel half (48 columns x rs rows, <= 75 KB) arrives with ONE
+// cp.async.bulk into a 2-stage shared-memory ring while the tensor-core loop works on the other stage: no scatter, no
+// zero fill, no index loads in this kernel.  rs == 4 (mod 16) keeps the m8n8k4 fragment loads bank-conflict free.
+// ---------------------------------------------------------------------------------------------------------------------
+constexpr int kHalfCols = 48;
+constexpr int kStageDoubles = kHalfCols * 196;  // 184 rows -> rs = 196
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_load_1d(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t done = 0;
+    while (!done)
+        asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
+                     : "=r"(done)
+                     : "r"(smem_u32(bar)), "r"(parity)
+                     : "memory");
+}
+
+__global__ void __launch_bounds__(512, 1) k_schur_syrk_tma(BatchDev bd) {
+    const int w = blockIdx.y;
+    const WinState& st = bd.state[w];
+    if (st.phase != PH_ITERATE || st.solve_failed) return;
+    const WinDesc& wd = bd.desc[w];
+    if (wd.landmarks_fixed) return;
+    extern __shared__ __align__(128) double stage[];  // [2][kStageDoubles]
+    __shared__ __align__(8) uint64_t full[2];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int nt = (st.n_f + 1 + 7) >> 3, trhs = st.n_f >> 3;
+    if (tid == 0) {
+        mbar_init(&full[0], 1);
+        mbar_init(&full[1], 1);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    __syncthreads();
+    double acc[kSmallSlots][2];
+#pragma unroll
+    for (int s = 0; s < kSmallSlots; ++s) acc[s][0] = acc[s][1] = 0.0;
+    const int per = (wd.n_chunks + bd.p_split - 1) / bd.p_split;
+    const int ch0 = blockIdx.x * per, ch1 = min(wd.n_chunks, ch0 + per);
+    const int* crs = bd.chunk_rs + wd.chunk_off;
+    const double* pbase = bd.vpanel + wd.panel_off;
+    const int fr = lane >> 2, fc = lane & 3;
+    int ic = ch0, ih = 0, slot_i = 0;  // issue cursor (chunk, half, stage)
+    while (ic < ch1 && crs[ic] == 0) ++ic;
+    int cc = ic, chh = 0, slot_c = 0;  // consume cursor
+    uint32_t ph0 = 0, ph1 = 0;
+    auto issue = [&]() {
+        if (ic >= ch1) return;
+        if (tid == 0) {
+            const int rs = crs[ic];
+            const uint32_t bytes = (uint32_t)(kHalfCols * rs * sizeof(double));
+            mbar_expect_tx(&full[slot_i], bytes);
+            tma_load_1d(stage + (size_t)slot_i * kStageDoubles,
+                        pbase + bd.chunk_poff[wd.chunk_off + ic] + (size_t)ih * kHalfCols * rs, bytes, &full[slot_i]);
+        }
+        slot_i ^= 1;
+        if (ih == 0) ih = 1;
+        else { ih = 0; ++ic; while (ic < ch1 && crs[ic] == 0) ++ic; }
+    };
+    issue();
+    while (cc < ch1) {
+        issue();  // the other stage was released by the __syncthreads that ended the previous iteration
+        if (slot_c == 0) { mbar_wait(&full[0], ph0); ph0 ^= 1; } else { mbar_wait(&full[1], ph1); ph1 ^= 1; }
+        const int rs = crs[cc];
+        const int t0 = bd.chunk_t0[wd.chunk_off + cc], t1 = bd.chunk_t1[wd.chunk_off + cc];
+        const bool rhs_in = trhs >= t0 && trhs < t1;
+        const double* sb = stage + (size_t)slot_c * kStageDoubles + (size_t)fc * rs + fr;
+#pragma unroll
+        for (int s = 0; s < kSmallSlots; ++s) {
+            const int t = s * 16 + warp;
+            int i = (int)((sqrtf(8.0f * (float)t + 1.0f) - 1.0f) * 0.5f);
+            while ((i + 1) * (i + 2) / 2 <= t) ++i;
+            while (i * (i + 1) / 2 > t) --i;
+            const int j = t - i * (i + 1) / 2;
+            if (i >= nt) continue;
+            const bool ai = (i >= t0 && i < t1) || i == trhs, aj = (j >= t0 && j < t1) || j == trhs;
+            if (!(ai && aj)) continue;
+            const int ri = (i == trhs && !rhs_in) ? 8 * (t1 - t0) : 8 * (i - t0);
+            const int rj = (j == trhs && !rhs_in) ? 8 * (t1 - t0) : 8 * (j - t0);
+            const double* pa = sb + ri;
+            const double* pb = sb + rj;
+#pragma unroll 4
+            for (int kk = 0; kk < kHalfCols; kk += 4) dmma(acc[s][0], acc[s][1], pa[(size_t)kk * rs], pb[(size_t)kk * rs]);
+        }
+        __syncthreads();
+        slot_c ^= 1;
+        if (chh == 0) chh = 1;
+        else { chh = 0; ++cc; while (cc < ch1 && crs[cc] == 0) ++cc; }
     }
     double* out = bd.sred + wd.s_off * (size_t)bd.p_split + (size_t)blockIdx.x * wd.nr_cap * wd.nr_cap;
 #pragma unroll
@@ -1080,18 +1269,43 @@ __global__ void __launch_bounds__(256) k_backsub(BatchDev bd) {
             const size_t T = (size_t)bd.tot_obs, base = (size_t)wd.obs_off;
             const double* delta_f = bd.delta_f + (size_t)w * bd.nr_cap_max;
             double t[3] = {0, 0, 0};
+            const double* pcol = nullptr;
+            int prs = 0, prow0 = 0;
+            if (bd.use_panel) {
+                const int ch = wd.chunk_off + (j >> 5);
+                prs = bd.chunk_rs[ch];
+                prow0 = 8 * bd.chunk_t0[ch];
+                pcol = bd.vpanel + wd.panel_off + bd.chunk_poff[ch] + (size_t)(3 * (j & 31)) * prs;
+            }
             for (int o = o0 + lane; o < o1; o += 32) {
                 const int off = bd.off_pose[wd.kf_off + bd.obs_kf[base + o]];
                 if (off < 0) continue;
+                if (bd.use_panel) {  // the panel rows hold the sum over the rig's cameras: read them once (rank 0)
+                    if (bd.obs_rank[base + o] != 0) continue;
+                    const double* q = pcol + (off - prow0);
 #pragma unroll
-                for (int r = 0; r < 6; ++r) {
-                    const double d = delta_f[off + r];
+                    for (int r = 0; r < 6; ++r) {
+                        const double d = delta_f[off + r];
+                        t[0] += q[r] * d; t[1] += q[prs + r] * d; t[2] += q[2 * prs + r] * d;
+                    }
+                } else {
 #pragma unroll
-                    for (int c = 0; c < 3; ++c) t[c] += bd.vobs[(3 * r + c) * T + base + o] * d;
+                    for (int r = 0; r < 6; ++r) {
+                        const double d = delta_f[off + r];
+#pragma unroll
+                        for (int c = 0; c < 3; ++c) t[c] += bd.vobs[(3 * r + c) * T + base + o] * d;
+                    }
                 }
             }
             const int gl = (wd.n_gp > 0) ? bd.gp_of_lm[L] : -1;
-            if (gl >= 0 && lane < 10) {  // the landmark's ground-plane block: row `lane` of its 10 x 3 V
+            bool gp_pose_in_panel = false;  // panel mode: the gp block's pose rows were added onto an observation's rows
+            if (gl >= 0 && bd.use_panel) {
+                const int gk = bd.gp_kf[wd.gp_off + gl];
+                bool mine = false;
+                for (int o = o0 + lane; o < o1; o += 32) mine |= (bd.obs_kf[base + o] == gk);
+                gp_pose_in_panel = __any_sync(0xffffffffu, mine);
+            }
+            if (gl >= 0 && lane < 10 && !(gp_pose_in_panel && lane < 6)) {  // row `lane` of the gp block's 10 x 3 V
                 const int row = gp_row(bd, wd, bd.gp_kf[wd.gp_off + gl], lane);
                 if (row >= 0) {
                     const double d = delta_f[row];
@@ -1407,12 +1621,15 @@ __global__ void k_reset_state(BatchDev bd, int rounds_total_override, int min_la
 // =====================================================================================================================
 static inline size_t schur_smem() { return (size_t)2 * 64 * kKS * sizeof(double); }
 static inline size_t schur_small_smem() { return (size_t)kSmallTiles * 8 * kKS * sizeof(double); }
+static inline size_t schur_tma_smem() { return (size_t)2 * kStageDoubles * sizeof(double); }
 static inline size_t solve_smem(int ld) { return ((size_t)4 * ld + kNB * (kNB + 1) + (size_t)ld * (kNB + 1)) * sizeof(double); }
 
 cudaError_t configure_kernels(int nr_cap_max) {
     cudaError_t e = cudaFuncSetAttribute(k_schur_syrk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)schur_smem());
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(k_schur_syrk_small, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)schur_small_smem());
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(k_schur_syrk_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)schur_tma_smem());
     if (e != cudaSuccess) return e;
     return cudaFuncSetAttribute(k_reduced_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)solve_smem(nr_cap_max));
 }
@@ -1425,6 +1642,7 @@ void launch_pass(const BatchDev& bd, const SolveParams& sp, const LaunchCfg& lc,
     const int B = bd.n_win;
     const dim3 g_obs((bd.max_obs + 255) / 256, B);
     const dim3 g_lm((bd.max_lm + 7) / 8, B);
+    if (bd.use_panel) k_panel_zero<<<dim3(64, B), 256, 0, s>>>(bd);
     k_solve_begin<<<B, 256, 0, s>>>(bd, sp);
     const bool timed = lc.time_jacobian && lc.ev_pool && *lc.ev_used + 2 <= lc.ev_cap;
     if (timed) cudaEventRecord(lc.ev_pool[(*lc.ev_used)++], s);
@@ -1433,7 +1651,9 @@ void launch_pass(const BatchDev& bd, const SolveParams& sp, const LaunchCfg& lc,
     if (bd.tot_gp > 0) k_gp_eval<true><<<B, 256, 0, s>>>(bd, sp);
     k_pose_hessian<<<dim3(bd.max_kf, B), 256, 0, s>>>(bd, sp);
     k_landmark_prep<<<g_lm, 256, 0, s>>>(bd, sp);
-    if (lc.small_syrk) {
+    if (lc.small_syrk && bd.use_panel) {
+        k_schur_syrk_tma<<<dim3(bd.p_split, B), 512, schur_tma_smem(), s>>>(bd);
+    } else if (lc.small_syrk) {
         k_schur_syrk_small<<<dim3(bd.p_split, B), 512, schur_small_smem(), s>>>(bd);
     } else {
         const int nb = lc.nr_cap_max / 64;

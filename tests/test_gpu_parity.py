@@ -113,6 +113,34 @@ def test_config3_ground_plane_matches_oracle(handle, oracle, shape):
     assert np.allclose(np.linalg.norm(rg.kf_plane[:, :3], axis=1), 1.0, atol=1e-12)  # normals stay on the sphere
 
 
+def test_stereo_rig_same_landmark_in_both_cameras(handle, oracle):
+    """a landmark observed by BOTH cameras of the rig in the same keyframe: two residual blocks share the pose and the
+    landmark block, their Schur contributions must be summed (oracle: segments keyed by parameter block)"""
+    from limo_b200.capi_types import Window
+    win, truth = synth.make_window(2, n_kf=8, n_lm=250, n_obs=1500, seed=77, return_truth=True)
+    T0 = g.pose_to_iso(win.cam_pose[0])
+    T1 = g.iso(t=[-0.54, 0.0, 0.0]) @ T0   # second camera 0.54 m to the right of the first (KITTI stereo baseline)
+    rng = np.random.default_rng(5)
+    lm_of_obs = np.repeat(np.arange(win.n_lm), np.diff(win.lm_obs_ptr))
+    okf, ocam, ou, ov, od, ptr = [], [], [], [], [], [0]
+    for j in range(win.n_lm):
+        for o in range(win.lm_obs_ptr[j], win.lm_obs_ptr[j + 1]):
+            k = win.obs_kf[o]
+            okf.append(k); ocam.append(0); ou.append(win.obs_u[o]); ov.append(win.obs_v[o]); od.append(win.obs_d[o])
+            pc = g.apply(T1 @ g.pose_to_iso(truth["kf_pose"][k]), truth["lm_pos"][j])
+            if pc[2] > 0.5 and j % 3 != 0:  # two thirds of the landmarks are also seen by camera 1
+                okf.append(k); ocam.append(1)
+                ou.append(synth.F * pc[0] / pc[2] + synth.CX + rng.normal(0, 0.5))
+                ov.append(synth.F * pc[1] / pc[2] + synth.CY + rng.normal(0, 0.5)); od.append(-1.0)
+        ptr.append(len(okf))
+    w2 = Window(kf_pose=win.kf_pose, kf_fixed=win.kf_fixed, cam_intr=[win.cam_intr[0]] * 2,
+                cam_pose=[win.cam_pose[0], g.iso_to_pose(T1)], lm_pos=win.lm_pos, lm_weight=win.lm_weight, lm_obs_ptr=ptr,
+                obs_kf=okf, obs_cam=ocam, obs_u=ou, obs_v=ov, obs_d=od, scale_kf0=0, scale_kf1=1,
+                scale_weight=win.scale_weight, scale_value=win.scale_value)
+    assert w2.n_obs > win.n_obs
+    _compare_solves(handle.solve_window(w2), oracle.solve_window(w2), w2, "stereo duplicates")
+
+
 def _motion_only_window(seed, with_prior):
     """one frame of a config-2 scene against fixed landmarks = the problem adjustPoseOnly() builds (cpp:820-888)"""
     from limo_b200.capi_types import Window
