@@ -75,7 +75,7 @@ struct kba_batch {
     Staged<WinState> state;
     Staged<IterRecord> log;
     Staged<double> pose_out[2], lm_out[2], plane_out[2];
-    Staged<int> gp_lm, gp_kf, gp_of_lm;
+    Staged<int> gp_lm, gp_kf, gp_of_lm, gp_shared;
     Staged<double> gp_weight;
     Staged<uint8_t> lm_active;
     Staged<int> n_active;
@@ -102,7 +102,7 @@ struct kba_batch {
         obs_d.release(); pm_u.release(); pm_v.release(); pm_d.release(); state.release(); log.release();
         pose_out[0].release(); pose_out[1].release(); lm_out[0].release(); lm_out[1].release(); lm_active.release();
         n_active.release(); jac_obs.release(); plane_out[0].release(); plane_out[1].release();
-        gp_lm.release(); gp_kf.release(); gp_of_lm.release(); gp_weight.release();
+        gp_lm.release(); gp_kf.release(); gp_of_lm.release(); gp_weight.release(); gp_shared.release();
         for (void* p : scratch) cudaFree(p);
         scratch.clear();
         if (ev_a) cudaEventDestroy(ev_a);
@@ -188,6 +188,7 @@ static void fill_window(kba_batch* b, int wi, const kba_window* w) {
         lp[jn + 1] = pos;
     }
     b->desc_h[wi].max_rank = max_rank;
+    b->lc.max_rank = std::max(b->lc.max_rank, max_rank);
     b->desc.h[wi].max_rank = max_rank;
     // keyframe-major copy (counting sort, stable -> deterministic reduction order)
     for (int k = 0; k < w->n_kf; ++k) kp[k + 1] += kp[k];
@@ -212,6 +213,9 @@ static void fill_window(kba_batch* b, int wi, const kba_window* w) {
             b->gp_weight.h[d.gp_off + g] = w->gp_weight[g];
             b->gp_of_lm.h[d.lm_off + jn] = g;
             gp_kf_of_lm[jn] = w->gp_kf[g];
+            int shared = 0;
+            for (int o = lp[jn]; o < lp[jn + 1]; ++o) shared |= (b->obs_kf.h[(size_t)d.obs_off + o] == w->gp_kf[g]);
+            b->gp_shared.h[d.gp_off + g] = shared;
         }
     }
     for (int c = 0; c < d.n_chunks; ++c) {
@@ -347,7 +351,7 @@ int kba_batch_create(kba_handle* h, int32_t n_windows, const kba_window* w, kba_
         nr_cap_max = std::max(nr_cap_max, d.nr_cap);
         kf += w[i].n_kf; cam += w[i].n_cam; lm += w[i].n_lm; obs += w[i].n_obs; chunks += d.n_chunks; gp += w[i].n_gp;
         bd.max_obs = std::max(bd.max_obs, w[i].n_obs); bd.max_lm = std::max(bd.max_lm, w[i].n_lm);
-        bd.max_kf = std::max(bd.max_kf, w[i].n_kf);
+        bd.max_kf = std::max(bd.max_kf, w[i].n_kf); bd.max_gp = std::max(bd.max_gp, w[i].n_gp);
     }
     if (obs > 2000000000LL) { delete b; return fail(KBA_ERR_CAPACITY, "batch exceeds 2^31 observations"); }
     bd.tot_kf = kf; bd.tot_cam = cam; bd.tot_lm = lm; bd.tot_obs = obs; bd.tot_chunks = (int)chunks; bd.tot_gp = gp;
@@ -392,7 +396,7 @@ int kba_batch_create(kba_handle* h, int32_t n_windows, const kba_window* w, kba_
     bad |= b->lm_active.alloc(lm, true); bad |= b->n_active.alloc(1, true); bad |= b->jac_obs.alloc(1, true);
     // device-only scratch
     bad |= b->plane_out[0].alloc(4 * kf, true); bad |= b->plane_out[1].alloc(4 * kf, true);
-    bad |= b->gp_lm.alloc(gp, true); bad |= b->gp_kf.alloc(gp, true); bad |= b->gp_weight.alloc(gp, true); bad |= b->gp_of_lm.alloc(lm, true);
+    bad |= b->gp_lm.alloc(gp, true); bad |= b->gp_kf.alloc(gp, true); bad |= b->gp_weight.alloc(gp, true); bad |= b->gp_of_lm.alloc(lm, true); bad |= b->gp_shared.alloc(gp, true);
     bad |= b->dev_alloc(&bd.gp_lin, 14 * gp); bad |= b->dev_alloc(&bd.vgp, 30 * gp);
     bad |= b->dev_alloc(&bd.gp_cost_x, n_windows); bad |= b->dev_alloc(&bd.gp_cost_c, n_windows);
     bad |= b->dev_alloc(&bd.off_pose, kf); bad |= b->dev_alloc(&bd.off_dir, kf); bad |= b->dev_alloc(&bd.off_dist, kf);
@@ -424,7 +428,7 @@ int kba_batch_create(kba_handle* h, int32_t n_windows, const kba_window* w, kba_
     bd.lm_orig = b->lm_orig.d;
     bd.obs_rank = b->obs_rank.d;
     bd.plane[0] = b->plane_out[0].d; bd.plane[1] = b->plane_out[1].d;
-    bd.gp_lm = b->gp_lm.d; bd.gp_kf = b->gp_kf.d; bd.gp_weight = b->gp_weight.d; bd.gp_of_lm = b->gp_of_lm.d;
+    bd.gp_lm = b->gp_lm.d; bd.gp_kf = b->gp_kf.d; bd.gp_weight = b->gp_weight.d; bd.gp_of_lm = b->gp_of_lm.d; bd.gp_shared = b->gp_shared.d;
     bd.n_active = b->n_active.d;
     bd.jac_obs = b->jac_obs.d;
     CU(cudaMemset(bd.jac_obs, 0, sizeof(unsigned long long)));
@@ -461,7 +465,7 @@ int kba_batch_upload(kba_batch* b, int32_t n_windows, const kba_window* w) {
     CU(b->kf_ptr.upload(s)); CU(b->pm_lm.upload(s)); CU(b->pm_cam.upload(s)); CU(b->pm_u.upload(s)); CU(b->pm_v.upload(s)); CU(b->pm_d.upload(s));
     CU(b->chunk_lm0.upload(s)); CU(b->chunk_lm1.upload(s)); CU(b->chunk_k0.upload(s)); CU(b->chunk_k1.upload(s));
     CU(b->lm_orig.upload(s)); CU(b->obs_rank.upload(s));
-    CU(b->gp_lm.upload(s)); CU(b->gp_kf.upload(s)); CU(b->gp_weight.upload(s)); CU(b->gp_of_lm.upload(s));
+    CU(b->gp_lm.upload(s)); CU(b->gp_kf.upload(s)); CU(b->gp_weight.upload(s)); CU(b->gp_of_lm.upload(s)); CU(b->gp_shared.upload(s));
     const BatchDev& bd = b->bd;
     b->h2d_bytes = sizeof(WinDesc) * bd.n_win + (7 + 4) * 8 * bd.tot_kf + bd.tot_kf + kCamStride * 8 * bd.tot_cam +
                    (3 + 1) * 8 * bd.tot_lm + 4 * (bd.tot_lm + bd.n_win) + (3 * 4 + 3 * 4) * bd.tot_obs +

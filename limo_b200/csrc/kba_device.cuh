@@ -164,6 +164,7 @@ struct BatchDev {
     int* gp_kf;               // [tot_gp] keyframe index
     double* gp_weight;        // [tot_gp] ScaledLoss weight
     int* gp_of_lm;            // [tot_lm] window-local gp index of the landmark or -1
+    int* gp_shared;           // [tot_gp] 1: the landmark is also observed from the gp keyframe (same pose rows)
     double* gp_lin;           // [14][tot_gp] robustified residual, J_f (pose 6, dir 3 local, dist 1), J_l (3)
     double* vgp;              // [30][tot_gp] V rows of the gp residual: (J_f^T J_l) L^-T, 10 x 3
     double* gp_cost_x;        // [n_win] robustified cost of the gp blocks at x / at the candidate (fixed-order sums)

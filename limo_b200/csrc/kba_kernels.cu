@@ -7,6 +7,7 @@
 #include "kba_device.cuh"
 #include "kba_kernels.h"
 #include "kba_regularisers.cuh"
+#include "kba_prep.cuh"
 
 #include <cfloat>
 #include <cmath>
@@ -341,167 +342,6 @@ __global__ void __launch_bounds__(256) k_pose_hessian(BatchDev bd, SolveParams s
         double s = 0.0;
         for (int q = 0; q < 8; ++q) s += s_red[q][threadIdx.x];
         bd.bkf[(size_t)(wd.kf_off + k) * 27 + threadIdx.x] = s;
-    }
-}
-
-// =====================================================================================================================
-// landmark preparation: one warp per landmark.  C_j = sum J_l^T J_l, g_j = sum J_l^T r (warp-shuffle tree), Jacobi-scaled
-// LM damping, 3x3 Cholesky, then per observation V_i = (J_p^T J_l) L^-T (6x3) for the Schur kernel and the back-substitution.
-// =====================================================================================================================
-__device__ __forceinline__ int gp_row(const BatchDev& bd, const WinDesc& wd, int k, int r);
-
-__global__ void __launch_bounds__(256) k_landmark_prep(BatchDev bd, SolveParams sp) {
-    const int w = blockIdx.y;
-    WinState& st = bd.state[w];
-    if (st.phase != PH_ITERATE) return;
-    const WinDesc& wd = bd.desc[w];
-    if (wd.landmarks_fixed) return;
-    const int lane = threadIdx.x & 31;
-    const int j = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (j >= wd.n_lm) return;
-    const int L = wd.lm_off + j;
-    if (!bd.lm_active[L]) return;
-    const int* lm_ptr = bd.lm_ptr + wd.lm_off + w;
-    const int o0 = lm_ptr[j], o1 = lm_ptr[j + 1];
-    if (o1 <= o0) return;
-    const size_t T = (size_t)bd.tot_obs, base = (size_t)wd.obs_off;
-    double c[6] = {0, 0, 0, 0, 0, 0}, g[3] = {0, 0, 0};
-    for (int o = o0 + lane; o < o1; o += 32) {
-        double jl[9], r[3];
-#pragma unroll
-        for (int q = 0; q < 9; ++q) jl[q] = bd.jl[q * T + base + o];
-#pragma unroll
-        for (int q = 0; q < 3; ++q) r[q] = bd.res[q * T + base + o];
-        c[0] += jl[0] * jl[0] + jl[3] * jl[3] + jl[6] * jl[6];
-        c[1] += jl[0] * jl[1] + jl[3] * jl[4] + jl[6] * jl[7];
-        c[2] += jl[0] * jl[2] + jl[3] * jl[5] + jl[6] * jl[8];
-        c[3] += jl[1] * jl[1] + jl[4] * jl[4] + jl[7] * jl[7];
-        c[4] += jl[1] * jl[2] + jl[4] * jl[5] + jl[7] * jl[8];
-        c[5] += jl[2] * jl[2] + jl[5] * jl[5] + jl[8] * jl[8];
-#pragma unroll
-        for (int a = 0; a < 3; ++a) g[a] += jl[a] * r[0] + jl[3 + a] * r[1] + jl[6 + a] * r[2];
-    }
-    // the landmark's ground-plane height residual (at most one) is one more row of its Jacobian
-    const int gl = (wd.n_gp > 0) ? bd.gp_of_lm[L] : -1;
-    const size_t TG = (size_t)bd.tot_gp, G = (size_t)wd.gp_off + (gl >= 0 ? gl : 0);
-    double gjl[3] = {0, 0, 0};
-    if (gl >= 0) {
-        gjl[0] = bd.gp_lin[11 * TG + G]; gjl[1] = bd.gp_lin[12 * TG + G]; gjl[2] = bd.gp_lin[13 * TG + G];
-        if (lane == 0) {
-            const double gr = bd.gp_lin[G];
-            c[0] += gjl[0] * gjl[0]; c[1] += gjl[0] * gjl[1]; c[2] += gjl[0] * gjl[2];
-            c[3] += gjl[1] * gjl[1]; c[4] += gjl[1] * gjl[2]; c[5] += gjl[2] * gjl[2];
-            g[0] += gjl[0] * gr; g[1] += gjl[1] * gr; g[2] += gjl[2] * gr;
-        }
-    }
-#pragma unroll
-    for (int q = 0; q < 6; ++q) c[q] = warp_sum(c[q]);
-#pragma unroll
-    for (int q = 0; q < 3; ++q) g[q] = warp_sum(g[q]);
-    // Jacobi scaling (fixed at iteration zero of the solve) and LM damping of the three landmark columns
-    const double cd[3] = {c[0], c[3], c[5]};
-    double sc[3], lam[3];
-#pragma unroll
-    for (int a = 0; a < 3; ++a) {
-        if (st.iter0) sc[a] = 1.0 / (1.0 + sqrt(cd[a]));
-        else sc[a] = bd.lm_scale[3 * (size_t)L + a];
-        const double s2 = sc[a] * sc[a];
-        lam[a] = fmin(fmax(cd[a] * s2, sp.min_lm_diagonal), sp.max_lm_diagonal) / (st.radius * s2);
-    }
-    // Cholesky of C + diag(lam):  [l00; l10 l11; l20 l21 l22]
-    const double a00 = c[0] + lam[0], a11 = c[3] + lam[1], a22 = c[5] + lam[2];
-    const double l00 = sqrt(a00);
-    const double l10 = c[1] / l00, l20 = c[2] / l00;
-    const double d11 = a11 - l10 * l10;
-    const double l11 = sqrt(d11);
-    const double l21 = (c[4] - l20 * l10) / l11;
-    const double d22 = a22 - l20 * l20 - l21 * l21;
-    const double l22 = sqrt(d22);
-    if (!(a00 > 0.0) || !(d11 > 0.0) || !(d22 > 0.0)) {
-        if (lane == 0) st.solve_failed = 1;
-        return;
-    }
-    // inverse of L (lower): i00; i10 i11; i20 i21 i22
-    const double i00 = 1.0 / l00, i11 = 1.0 / l11, i22 = 1.0 / l22;
-    const double i10 = -l10 * i00 * i11;
-    const double i21 = -l21 * i11 * i22;
-    const double i20 = -(l20 * i00 + l21 * i10) * i22;
-    const double z0 = i00 * g[0], z1 = i10 * g[0] + i11 * g[1], z2 = i20 * g[0] + i21 * g[1] + i22 * g[2];
-    if (lane == 0) {
-        double* li = bd.lm_linv + 6 * (size_t)L;
-        li[0] = i00; li[1] = i10; li[2] = i11; li[3] = i20; li[4] = i21; li[5] = i22;
-        double* zz = bd.lm_z + 3 * (size_t)L;
-        zz[0] = z0; zz[1] = z1; zz[2] = z2;
-#pragma unroll
-        for (int a = 0; a < 3; ++a) {
-            bd.lm_g[3 * (size_t)L + a] = g[a];
-            bd.lm_lambda[3 * (size_t)L + a] = lam[a];
-            if (st.iter0) bd.lm_scale[3 * (size_t)L + a] = sc[a];
-        }
-    }
-    if (gl >= 0 && lane < 10) {  // V rows of the gp block: E = J_f^T J_l is 10 x 3 (rank one), row `lane`
-        const double jf = bd.gp_lin[(1 + lane) * TG + G];
-        const double e0 = jf * gjl[0], e1 = jf * gjl[1], e2 = jf * gjl[2];
-        bd.vgp[(3 * lane + 0) * TG + G] = e0 * i00;
-        bd.vgp[(3 * lane + 1) * TG + G] = e0 * i10 + e1 * i11;
-        bd.vgp[(3 * lane + 2) * TG + G] = e0 * i20 + e1 * i21 + e2 * i22;
-    }
-    // V_i = E_i L^-T with E_i = J_p^T J_l;  V[r][cc] = sum_m E[r][m] * Linv[cc][m]
-    // panel mode: written straight into the chunk's dense column-major panel (what the Schur kernel bulk-loads)
-    double* pcol = nullptr;  // column 3 * (j % 32) of the chunk panel, row 0 = first row of the chunk's tile range
-    int prs = 0, prow0 = 0;
-    if (bd.use_panel) {
-        const int ch = wd.chunk_off + (j >> 5);
-        prs = bd.chunk_rs[ch];
-        prow0 = 8 * bd.chunk_t0[ch];
-        pcol = bd.vpanel + wd.panel_off + bd.chunk_poff[ch] + (size_t)(3 * (j & 31)) * prs;
-        if (lane == 0 && prs > 0) {  // right-hand-side row z_j
-            const int t0 = bd.chunk_t0[ch], t1 = bd.chunk_t1[ch], trhs = st.n_f >> 3;
-            const int rl = (trhs >= t0 && trhs < t1) ? st.n_f - prow0 : 8 * (t1 - t0) + (st.n_f - 8 * trhs);
-            pcol[rl] = z0; pcol[prs + rl] = z1; pcol[2 * prs + rl] = z2;
-        }
-    }
-    // obs_rank > 0: a further observation of the same (landmark, keyframe) by another camera of the rig; its block is
-    // ADDED to the rows the rank-0 observation wrote, one rank per round so that no two lanes touch the same entry.
-    for (int round = 0; round <= wd.max_rank; ++round) {
-        for (int o = o0 + lane; o < o1; o += 32) {
-            const int row0 = bd.off_pose[wd.kf_off + bd.obs_kf[base + o]];
-            if (row0 < 0 || bd.obs_rank[base + o] != round) continue;
-            double jl[9], jp[18];
-#pragma unroll
-            for (int q = 0; q < 9; ++q) jl[q] = bd.jl[q * T + base + o];
-#pragma unroll
-            for (int q = 0; q < 18; ++q) jp[q] = bd.jp[q * T + base + o];
-#pragma unroll
-            for (int r = 0; r < 6; ++r) {
-                const double e0 = jp[r] * jl[0] + jp[6 + r] * jl[3] + jp[12 + r] * jl[6];
-                const double e1 = jp[r] * jl[1] + jp[6 + r] * jl[4] + jp[12 + r] * jl[7];
-                const double e2 = jp[r] * jl[2] + jp[6 + r] * jl[5] + jp[12 + r] * jl[8];
-                const double v0 = e0 * i00, v1 = e0 * i10 + e1 * i11, v2 = e0 * i20 + e1 * i21 + e2 * i22;
-                if (bd.use_panel) {
-                    double* q = pcol + (row0 - prow0 + r);
-                    if (round == 0) { q[0] = v0; q[prs] = v1; q[2 * prs] = v2; }
-                    else { q[0] += v0; q[prs] += v1; q[2 * prs] += v2; }
-                } else {
-                    bd.vobs[(3 * r + 0) * T + base + o] = v0;
-                    bd.vobs[(3 * r + 1) * T + base + o] = v1;
-                    bd.vobs[(3 * r + 2) * T + base + o] = v2;
-                }
-            }
-        }
-        if (wd.max_rank > 0) __syncwarp();
-    }
-    if (bd.use_panel && gl >= 0) {  // ground-plane rows are added on top (its pose rows may coincide with an observation's)
-        __syncwarp();
-        if (lane < 10) {
-            const int row = gp_row(bd, wd, bd.gp_kf[G], lane);
-            if (row >= 0) {
-                double* q = pcol + (row - prow0);
-                q[0] += bd.vgp[(3 * lane + 0) * TG + G];
-                q[prs] += bd.vgp[(3 * lane + 1) * TG + G];
-                q[2 * prs] += bd.vgp[(3 * lane + 2) * TG + G];
-            }
-        }
     }
 }
 
@@ -1650,7 +1490,9 @@ void launch_pass(const BatchDev& bd, const SolveParams& sp, const LaunchCfg& lc,
     if (timed) cudaEventRecord(lc.ev_pool[(*lc.ev_used)++], s);
     if (bd.tot_gp > 0) k_gp_eval<true><<<B, 256, 0, s>>>(bd, sp);
     k_pose_hessian<<<dim3(bd.max_kf, B), 256, 0, s>>>(bd, sp);
-    k_landmark_prep<<<g_lm, 256, 0, s>>>(bd, sp);
+    k_landmark_reduce<<<dim3((bd.max_lm + 15) / 16, B), 256, 0, s>>>(bd, sp);
+    for (int round = 0; round <= lc.max_rank; ++round) k_obs_v<<<g_obs, 256, 0, s>>>(bd, round);
+    if (bd.tot_gp > 0 && bd.use_panel) k_gp_panel<<<dim3((bd.max_gp * 10 + 255) / 256, B), 256, 0, s>>>(bd);
     if (lc.small_syrk && bd.use_panel) {
         k_schur_syrk_tma<<<dim3(bd.p_split, B), 512, schur_tma_smem(), s>>>(bd);
     } else if (lc.small_syrk) {

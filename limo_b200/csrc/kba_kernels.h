@@ -16,6 +16,7 @@ struct Counters {
 
 struct LaunchCfg {
     int nr_cap_max = 64;
+    int max_rank = 0;         // largest observation rank in the batch (multi-camera rigs)
     bool small_syrk = false;  // every window has <= 184 reduced rows: register-resident Schur kernel
     int rounds_override = -1, min_landmarks_for_trimming = 100, num_rounds_option = 1;
     bool time_jacobian = false;
