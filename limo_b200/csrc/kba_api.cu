@@ -368,7 +368,7 @@ int kba_batch_create(kba_handle* h, int32_t n_windows, const kba_window* w, kba_
         bd.p_split = std::max(1, std::min(p, max_chunks));
     }
     bd.cost_parts = (bd.max_obs + 255) / 256;
-    bd.bs_parts = (bd.max_lm + 7) / 8;
+    bd.bs_parts = (bd.max_lm + 15) / 16;
     int bad = 0;
     bad |= b->desc.alloc(n_windows, true);
     bad |= b->pose0.alloc(7 * kf, true); bad |= b->plane0.alloc(4 * kf, true); bad |= b->kf_fixed.alloc(kf, true);

@@ -286,7 +286,7 @@ template __global__ void k_gp_eval<false>(BatchDev, SolveParams);
 // re-evaluates the Jacobian rows (cheaper than gathering the materialised J_pose across sectors) and reduces
 // B_k = sum J_p^T J_p (21 unique) and g_k = sum J_p^T r (6) with a fixed-shape tree -> deterministic, no atomics.
 // =====================================================================================================================
-__global__ void __launch_bounds__(256) k_pose_hessian(BatchDev bd, SolveParams sp) {
+__global__ void __launch_bounds__(256, 2) k_pose_hessian(BatchDev bd, SolveParams sp) {
     const int w = blockIdx.y, k = blockIdx.x;
     const WinState& st = bd.state[w];
     if (st.phase != PH_ITERATE || !st.need_linearize) return;
@@ -595,6 +595,8 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
                      : "memory");
 }
 
+constexpr int kBlockSlots = 5;  // ceil(12*13/2 / 16) 16x16 blocks per warp for up to 184 reduced rows
+
 __global__ void __launch_bounds__(512, 1) k_schur_syrk_tma(BatchDev bd) {
     const int w = blockIdx.y;
     const WinState& st = bd.state[w];
@@ -611,9 +613,14 @@ __global__ void __launch_bounds__(512, 1) k_schur_syrk_tma(BatchDev bd) {
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
     __syncthreads();
-    double acc[kSmallSlots][2];
+    // each warp owns kBlockSlots 16x16 blocks (2x2 m8n8k4 tiles) of the lower triangle: two A and two B fragments feed
+    // four DMMAs, i.e. one shared-memory load per DMMA instead of two
+    double acc[kBlockSlots][4][2];
 #pragma unroll
-    for (int s = 0; s < kSmallSlots; ++s) acc[s][0] = acc[s][1] = 0.0;
+    for (int s = 0; s < kBlockSlots; ++s)
+#pragma unroll
+        for (int q = 0; q < 4; ++q) acc[s][q][0] = acc[s][q][1] = 0.0;
+    const int nb2 = (nt + 1) >> 1;
     const int per = (wd.n_chunks + bd.p_split - 1) / bd.p_split;
     const int ch0 = blockIdx.x * per, ch1 = min(wd.n_chunks, ch0 + per);
     const int* crs = bd.chunk_rs + wd.chunk_off;
@@ -642,24 +649,53 @@ __global__ void __launch_bounds__(512, 1) k_schur_syrk_tma(BatchDev bd) {
         if (slot_c == 0) { mbar_wait(&full[0], ph0); ph0 ^= 1; } else { mbar_wait(&full[1], ph1); ph1 ^= 1; }
         const int rs = crs[cc];
         const int t0 = bd.chunk_t0[wd.chunk_off + cc], t1 = bd.chunk_t1[wd.chunk_off + cc];
-        const bool rhs_in = trhs >= t0 && trhs < t1;
         const double* sb = stage + (size_t)slot_c * kStageDoubles + (size_t)fc * rs + fr;
+        auto tile_row = [&](int i) -> int {  // panel row of tile i in this chunk, -1 if the chunk has no such rows
+            if (i >= t0 && i < t1) return 8 * (i - t0);
+            if (i == trhs) return 8 * (t1 - t0);
+            return -1;
+        };
 #pragma unroll
-        for (int s = 0; s < kSmallSlots; ++s) {
+        for (int s = 0; s < kBlockSlots; ++s) {
             const int t = s * 16 + warp;
-            int i = (int)((sqrtf(8.0f * (float)t + 1.0f) - 1.0f) * 0.5f);
-            while ((i + 1) * (i + 2) / 2 <= t) ++i;
-            while (i * (i + 1) / 2 > t) --i;
-            const int j = t - i * (i + 1) / 2;
-            if (i >= nt) continue;
-            const bool ai = (i >= t0 && i < t1) || i == trhs, aj = (j >= t0 && j < t1) || j == trhs;
-            if (!(ai && aj)) continue;
-            const int ri = (i == trhs && !rhs_in) ? 8 * (t1 - t0) : 8 * (i - t0);
-            const int rj = (j == trhs && !rhs_in) ? 8 * (t1 - t0) : 8 * (j - t0);
-            const double* pa = sb + ri;
-            const double* pb = sb + rj;
+            int bi = (int)((sqrtf(8.0f * (float)t + 1.0f) - 1.0f) * 0.5f);
+            while ((bi + 1) * (bi + 2) / 2 <= t) ++bi;
+            while (bi * (bi + 1) / 2 > t) --bi;
+            const int bj = t - bi * (bi + 1) / 2;
+            if (bi >= nb2) continue;
+            const int ri0 = tile_row(2 * bi), ri1 = tile_row(2 * bi + 1), rj0 = tile_row(2 * bj), rj1 = tile_row(2 * bj + 1);
+            if ((ri0 < 0 && ri1 < 0) || (rj0 < 0 && rj1 < 0)) continue;
+            const double* pa0 = sb + max(ri0, 0);
+            const double* pa1 = sb + max(ri1, 0);
+            const double* pb0 = sb + max(rj0, 0);
+            const double* pb1 = sb + max(rj1, 0);
+            const double mi0 = ri0 < 0 ? 0.0 : 1.0, mi1 = ri1 < 0 ? 0.0 : 1.0;
+            const bool diag = bi == bj;
+            if (ri0 >= 0 && ri1 >= 0 && rj0 >= 0 && rj1 >= 0) {
 #pragma unroll 4
-            for (int kk = 0; kk < kHalfCols; kk += 4) dmma(acc[s][0], acc[s][1], pa[(size_t)kk * rs], pb[(size_t)kk * rs]);
+                for (int kk = 0; kk < kHalfCols; kk += 4) {
+                    const size_t o = (size_t)kk * rs;
+                    const double a0 = pa0[o], a1 = pa1[o], b0 = pb0[o], b1 = pb1[o];
+                    dmma(acc[s][0][0], acc[s][0][1], a0, b0);
+                    if (!diag) dmma(acc[s][1][0], acc[s][1][1], a0, b1);
+                    dmma(acc[s][2][0], acc[s][2][1], a1, b0);
+                    dmma(acc[s][3][0], acc[s][3][1], a1, b1);
+                }
+            } else {  // a block on the edge of the chunk's keyframe range: zero the missing fragments
+#pragma unroll 2
+                for (int kk = 0; kk < kHalfCols; kk += 4) {
+                    const size_t o = (size_t)kk * rs;
+                    const double a0 = pa0[o] * mi0, a1 = pa1[o] * mi1, b0 = pb0[o], b1 = pb1[o];
+                    if (rj0 >= 0) {
+                        dmma(acc[s][0][0], acc[s][0][1], a0, b0);
+                        dmma(acc[s][2][0], acc[s][2][1], a1, b0);
+                    }
+                    if (rj1 >= 0) {
+                        if (!diag) dmma(acc[s][1][0], acc[s][1][1], a0, b1);
+                        dmma(acc[s][3][0], acc[s][3][1], a1, b1);
+                    }
+                }
+            }
         }
         __syncthreads();
         slot_c ^= 1;
@@ -668,16 +704,21 @@ __global__ void __launch_bounds__(512, 1) k_schur_syrk_tma(BatchDev bd) {
     }
     double* out = bd.sred + wd.s_off * (size_t)bd.p_split + (size_t)blockIdx.x * wd.nr_cap * wd.nr_cap;
 #pragma unroll
-    for (int s = 0; s < kSmallSlots; ++s) {
+    for (int s = 0; s < kBlockSlots; ++s) {
         const int t = s * 16 + warp;
-        int i = (int)((sqrtf(8.0f * (float)t + 1.0f) - 1.0f) * 0.5f);
-        while ((i + 1) * (i + 2) / 2 <= t) ++i;
-        while (i * (i + 1) / 2 > t) --i;
-        const int j = t - i * (i + 1) / 2;
-        if (i >= nt) continue;
-        double* o = out + (size_t)(8 * i + fr) * wd.nr_cap + 8 * j + 2 * fc;
-        o[0] = acc[s][0];
-        o[1] = acc[s][1];
+        int bi = (int)((sqrtf(8.0f * (float)t + 1.0f) - 1.0f) * 0.5f);
+        while ((bi + 1) * (bi + 2) / 2 <= t) ++bi;
+        while (bi * (bi + 1) / 2 > t) --bi;
+        const int bj = t - bi * (bi + 1) / 2;
+        if (bi >= nb2) continue;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int i = 2 * bi + (q >> 1), j = 2 * bj + (q & 1);
+            if (i >= nt || j > i) continue;
+            double* o = out + (size_t)(8 * i + fr) * wd.nr_cap + 8 * j + 2 * fc;
+            o[0] = acc[s][q][0];
+            o[1] = acc[s][q][1];
+        }
     }
 }
 
@@ -1088,73 +1129,77 @@ __global__ void __launch_bounds__(512, 1) k_reduced_solve(BatchDev bd, SolvePara
 // back-substitution: delta_p_j = -L^-T (z_j + sum_i V_i^T delta_f,i); candidate landmarks; deterministic partial sums
 // =====================================================================================================================
 __global__ void __launch_bounds__(256) k_backsub(BatchDev bd) {
+    // 16 lanes per landmark (tracks average ~13 observations); every shuffle sits outside the divergent parts
     const int w = blockIdx.y;
     const WinState& st = bd.state[w];
     if (st.phase != PH_ITERATE) return;
     const WinDesc& wd = bd.desc[w];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int j = blockIdx.x * 8 + warp;
-    __shared__ double s_red[8][4];
+    const int hl = threadIdx.x & 15, grp = threadIdx.x >> 4;
+    const int j = blockIdx.x * 16 + grp;
+    __shared__ double s_red[16][4];
     double model = 0.0, step_sq = 0.0, xn_sq = 0.0, gmax = 0.0;
-    if (j < wd.n_lm) {
-        const int L = wd.lm_off + j;
-        const double* pc = bd.lm[st.cur] + 3 * (size_t)L;
-        double* pn = bd.lm[1 - st.cur] + 3 * (size_t)L;
-        const int* lm_ptr = bd.lm_ptr + wd.lm_off + w;
-        const int o0 = lm_ptr[j], o1 = lm_ptr[j + 1];
-        const bool in = bd.lm_active[L] && o1 > o0 && !wd.landmarks_fixed;
-        if (!in || st.solve_failed) {
-            if (lane < 3) pn[lane] = pc[lane];
+    const bool have = j < wd.n_lm;
+    const int L = wd.lm_off + (have ? j : 0);
+    const double* pc = bd.lm[st.cur] + 3 * (size_t)L;
+    double* pn = bd.lm[1 - st.cur] + 3 * (size_t)L;
+    const int* lm_ptr = bd.lm_ptr + wd.lm_off + w;
+    const int o0 = have ? lm_ptr[j] : 0, o1 = have ? lm_ptr[j + 1] : 0;
+    const bool in = have && bd.lm_active[L] && o1 > o0 && !wd.landmarks_fixed && !st.solve_failed;
+    const size_t T = (size_t)bd.tot_obs, base = (size_t)wd.obs_off;
+    const double* delta_f = bd.delta_f + (size_t)w * bd.nr_cap_max;
+    double t[3] = {0, 0, 0};
+    const int gl = (in && wd.n_gp > 0) ? bd.gp_of_lm[L] : -1;
+    bool mine = false;  // panel mode: the gp block's pose rows were added onto one of this landmark's observation rows
+    if (in) {
+        const double* pcol = nullptr;
+        int prs = 0, prow0 = 0;
+        if (bd.use_panel) {
+            const int ch = wd.chunk_off + (j >> 5);
+            prs = bd.chunk_rs[ch];
+            prow0 = 8 * bd.chunk_t0[ch];
+            pcol = bd.vpanel + wd.panel_off + bd.chunk_poff[ch] + (size_t)(3 * (j & 31)) * prs;
+        }
+        const int gk = (gl >= 0 && bd.use_panel) ? bd.gp_kf[wd.gp_off + gl] : -1;
+        for (int o = o0 + hl; o < o1; o += 16) {
+            const int k = bd.obs_kf[base + o];
+            mine |= (k == gk);
+            const int off = bd.off_pose[wd.kf_off + k];
+            if (off < 0) continue;
+            if (bd.use_panel) {  // the panel rows hold the sum over the rig's cameras: read them once (rank 0)
+                if (bd.obs_rank[base + o] != 0) continue;
+                const double* q = pcol + (off - prow0);
+#pragma unroll
+                for (int r = 0; r < 6; ++r) {
+                    const double d = delta_f[off + r];
+                    t[0] += q[r] * d; t[1] += q[prs + r] * d; t[2] += q[2 * prs + r] * d;
+                }
+            } else {
+#pragma unroll
+                for (int r = 0; r < 6; ++r) {
+                    const double d = delta_f[off + r];
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) t[c] += bd.vobs[(3 * r + c) * T + base + o] * d;
+                }
+            }
+        }
+    }
+    const unsigned any = __ballot_sync(0xffffffffu, mine) & (0xffffu << (threadIdx.x & 16));
+    if (gl >= 0 && hl < 10 && !(any != 0u && hl < 6)) {  // row `hl` of the gp block's 10 x 3 V
+        const int row = gp_row(bd, wd, bd.gp_kf[wd.gp_off + gl], hl);
+        if (row >= 0) {
+            const double d = delta_f[row];
+#pragma unroll
+            for (int c = 0; c < 3; ++c) t[c] += bd.vgp[(size_t)(3 * hl + c) * bd.tot_gp + wd.gp_off + gl] * d;
+        }
+    }
+#pragma unroll
+    for (int c = 0; c < 3; ++c)
+#pragma unroll
+        for (int m = 8; m >= 1; m >>= 1) t[c] += __shfl_xor_sync(0xffffffffu, t[c], m);
+    if (have && hl == 0) {
+        if (!in) {
+            pn[0] = pc[0]; pn[1] = pc[1]; pn[2] = pc[2];
         } else {
-            const size_t T = (size_t)bd.tot_obs, base = (size_t)wd.obs_off;
-            const double* delta_f = bd.delta_f + (size_t)w * bd.nr_cap_max;
-            double t[3] = {0, 0, 0};
-            const double* pcol = nullptr;
-            int prs = 0, prow0 = 0;
-            if (bd.use_panel) {
-                const int ch = wd.chunk_off + (j >> 5);
-                prs = bd.chunk_rs[ch];
-                prow0 = 8 * bd.chunk_t0[ch];
-                pcol = bd.vpanel + wd.panel_off + bd.chunk_poff[ch] + (size_t)(3 * (j & 31)) * prs;
-            }
-            for (int o = o0 + lane; o < o1; o += 32) {
-                const int off = bd.off_pose[wd.kf_off + bd.obs_kf[base + o]];
-                if (off < 0) continue;
-                if (bd.use_panel) {  // the panel rows hold the sum over the rig's cameras: read them once (rank 0)
-                    if (bd.obs_rank[base + o] != 0) continue;
-                    const double* q = pcol + (off - prow0);
-#pragma unroll
-                    for (int r = 0; r < 6; ++r) {
-                        const double d = delta_f[off + r];
-                        t[0] += q[r] * d; t[1] += q[prs + r] * d; t[2] += q[2 * prs + r] * d;
-                    }
-                } else {
-#pragma unroll
-                    for (int r = 0; r < 6; ++r) {
-                        const double d = delta_f[off + r];
-#pragma unroll
-                        for (int c = 0; c < 3; ++c) t[c] += bd.vobs[(3 * r + c) * T + base + o] * d;
-                    }
-                }
-            }
-            const int gl = (wd.n_gp > 0) ? bd.gp_of_lm[L] : -1;
-            bool gp_pose_in_panel = false;  // panel mode: the gp block's pose rows were added onto an observation's rows
-            if (gl >= 0 && bd.use_panel) {
-                const int gk = bd.gp_kf[wd.gp_off + gl];
-                bool mine = false;
-                for (int o = o0 + lane; o < o1; o += 32) mine |= (bd.obs_kf[base + o] == gk);
-                gp_pose_in_panel = __any_sync(0xffffffffu, mine);
-            }
-            if (gl >= 0 && lane < 10 && !(gp_pose_in_panel && lane < 6)) {  // row `lane` of the gp block's 10 x 3 V
-                const int row = gp_row(bd, wd, bd.gp_kf[wd.gp_off + gl], lane);
-                if (row >= 0) {
-                    const double d = delta_f[row];
-#pragma unroll
-                    for (int c = 0; c < 3; ++c) t[c] += bd.vgp[(size_t)(3 * lane + c) * bd.tot_gp + wd.gp_off + gl] * d;
-                }
-            }
-#pragma unroll
-            for (int c = 0; c < 3; ++c) t[c] = warp_sum(t[c]);
             const double* z = bd.lm_z + 3 * (size_t)L;
             const double* li = bd.lm_linv + 6 * (size_t)L;  // i00; i10 i11; i20 i21 i22
             const double t0 = t[0] + z[0], t1 = t[1] + z[1], t2 = t[2] + z[2];
@@ -1164,21 +1209,19 @@ __global__ void __launch_bounds__(256) k_backsub(BatchDev bd) {
             const double d2 = -(li[5] * t2);
             const double* g = bd.lm_g + 3 * (size_t)L;
             const double* lam = bd.lm_lambda + 3 * (size_t)L;
-            if (lane == 0) {
-                pn[0] = pc[0] + d0; pn[1] = pc[1] + d1; pn[2] = pc[2] + d2;
-                model = -(g[0] * d0 + g[1] * d1 + g[2] * d2) + lam[0] * d0 * d0 + lam[1] * d1 * d1 + lam[2] * d2 * d2;
-                step_sq = d0 * d0 + d1 * d1 + d2 * d2;
-                xn_sq = pc[0] * pc[0] + pc[1] * pc[1] + pc[2] * pc[2];
-                gmax = fmax(fabs(g[0]), fmax(fabs(g[1]), fabs(g[2])));
-                if (!isfinite(d0) || !isfinite(d1) || !isfinite(d2)) model = nan("");
-            }
+            pn[0] = pc[0] + d0; pn[1] = pc[1] + d1; pn[2] = pc[2] + d2;
+            model = -(g[0] * d0 + g[1] * d1 + g[2] * d2) + lam[0] * d0 * d0 + lam[1] * d1 * d1 + lam[2] * d2 * d2;
+            step_sq = d0 * d0 + d1 * d1 + d2 * d2;
+            xn_sq = pc[0] * pc[0] + pc[1] * pc[1] + pc[2] * pc[2];
+            gmax = fmax(fabs(g[0]), fmax(fabs(g[1]), fabs(g[2])));
+            if (!isfinite(d0) || !isfinite(d1) || !isfinite(d2)) model = nan("");
         }
     }
-    if (lane == 0) { s_red[warp][0] = model; s_red[warp][1] = step_sq; s_red[warp][2] = xn_sq; s_red[warp][3] = gmax; }
+    if (hl == 0) { s_red[grp][0] = model; s_red[grp][1] = step_sq; s_red[grp][2] = xn_sq; s_red[grp][3] = gmax; }
     __syncthreads();
     if (threadIdx.x == 0) {
         double a = 0, b = 0, c = 0, g = 0;
-        for (int q = 0; q < 8; ++q) { a += s_red[q][0]; b += s_red[q][1]; c += s_red[q][2]; g = fmax(g, s_red[q][3]); }
+        for (int q = 0; q < 16; ++q) { a += s_red[q][0]; b += s_red[q][1]; c += s_red[q][2]; g = fmax(g, s_red[q][3]); }
         double* out = bd.bs_part + ((size_t)w * bd.bs_parts + blockIdx.x) * 4;
         out[0] = a; out[1] = b; out[2] = c; out[3] = g;
     }
@@ -1212,12 +1255,23 @@ __device__ void solve_end(WinState& st, int termination) {
 }
 
 __global__ void __launch_bounds__(128) k_lm_update(BatchDev bd, SolveParams sp) {
-    const int w = blockIdx.x * blockDim.x + threadIdx.x;
+    // one warp per window: the lanes reduce the partial sums (fixed shape: strided partials, then a butterfly), lane 0
+    // then runs the controller
+    const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (w >= bd.n_win) return;
     WinState& st = bd.state[w];
     if (st.phase != PH_ITERATE) return;
     const WinDesc& wd = bd.desc[w];
     SolveSummary& sum = st.solves[st.solve_index];
+    double e_model = 0, e_step = 0, e_xn = 0, e_g = 0, cand_sum = 0;
+    for (int q = lane; q < (wd.n_lm + 15) / 16; q += 32) {
+        const double* p = bd.bs_part + ((size_t)w * bd.bs_parts + q) * 4;
+        e_model += p[0]; e_step += p[1]; e_xn += p[2]; e_g = fmax(e_g, p[3]);
+    }
+    for (int q = lane; q < bd.cost_parts; q += 32) cand_sum += bd.cost_part_c[(size_t)w * bd.cost_parts + q];
+    e_model = warp_sum(e_model); e_step = warp_sum(e_step); e_xn = warp_sum(e_xn); e_g = warp_max(e_g);
+    cand_sum = warp_sum(cand_sum);
+    if (lane != 0) return;
     if (st.solve_failed == 2) {  // evaluation failed at iteration zero
         sum.initial_cost = sum.final_cost = -1.0;
         st.solve_failed = 0; st.eval_failed = 0;
@@ -1226,12 +1280,6 @@ __global__ void __launch_bounds__(128) k_lm_update(BatchDev bd, SolveParams sp) 
     }
     const int cand_eval_failed = st.eval_failed;  // set by the candidate cost pass of THIS pass (|z| < 0.01)
     st.eval_failed = 0;
-    // reduce the landmark-side partials (fixed order)
-    double e_model = 0, e_step = 0, e_xn = 0, e_g = 0;
-    for (int q = 0; q < (wd.n_lm + 7) / 8; ++q) {
-        const double* p = bd.bs_part + ((size_t)w * bd.bs_parts + q) * 4;
-        e_model += p[0]; e_step += p[1]; e_xn += p[2]; e_g = fmax(e_g, p[3]);
-    }
     const bool step_ok = !st.solve_failed;
     if (st.need_linearize) {  // a fresh linearisation was evaluated in this pass
         if (step_ok || st.iter0) {
@@ -1269,8 +1317,7 @@ __global__ void __launch_bounds__(128) k_lm_update(BatchDev bd, SolveParams sp) 
     }
     st.num_invalid = 0;
     // ---- candidate cost ----
-    double cand = 0.0;
-    for (int q = 0; q < bd.cost_parts; ++q) cand += bd.cost_part_c[(size_t)w * bd.cost_parts + q];
+    double cand = cand_sum;
     if (wd.scale_weight > 0) {
         const double* P = bd.pose[1 - st.cur];
         double r;
@@ -1502,10 +1549,10 @@ void launch_pass(const BatchDev& bd, const SolveParams& sp, const LaunchCfg& lc,
         k_schur_syrk<<<dim3(nb * (nb + 1) / 2, bd.p_split, B), 256, schur_smem(), s>>>(bd);
     }
     k_reduced_solve<<<B, 512, solve_smem(lc.nr_cap_max), s>>>(bd, sp);
-    k_backsub<<<g_lm, 256, 0, s>>>(bd);
+    k_backsub<<<dim3((bd.max_lm + 15) / 16, B), 256, 0, s>>>(bd);
     k_eval_obs<false><<<g_obs, 256, 0, s>>>(bd, sp);
     if (bd.tot_gp > 0) k_gp_eval<false><<<B, 256, 0, s>>>(bd, sp);
-    k_lm_update<<<(B + 127) / 128, 128, 0, s>>>(bd, sp);
+    k_lm_update<<<(B * 32 + 127) / 128, 128, 0, s>>>(bd, sp);
     k_trim_eval<<<g_lm, 256, 0, s>>>(bd, sp);
     k_trim_select<<<B, 512, 0, s>>>(bd, sp);
     if (cnt) {

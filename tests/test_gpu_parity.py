@@ -24,12 +24,15 @@ def handle():
     h.close()
 
 
-def _compare_solves(res_gpu, res_cpu, win, label=""):
+def _compare_solves(res_gpu, res_cpu, win, label="", iter_slack=0):
     assert res_gpu.c.status == 0, label
     assert res_gpu.c.num_solves == res_cpu.c.num_solves, label
     for a, b in zip(res_gpu.solves, res_cpu.solves):
         assert a.termination == b.termination, (label, a.termination, b.termination)
-        assert a.num_iterations == b.num_iterations, (label, a.num_iterations, b.num_iterations)
+        # iter_slack: with the ground-plane blocks the late iterations run at trust-region radii ~1e15 where the reduced
+        # system is numerically singular; whether such a step is "invalid" (and retried at a smaller radius) is decided
+        # at rounding level, so the count of UNSUCCESSFUL iterations may differ by a few while the accepted steps agree
+        assert abs(a.num_iterations - b.num_iterations) <= iter_slack, (label, a.num_iterations, b.num_iterations)
         assert a.num_successful_steps == b.num_successful_steps, label
         assert a.num_landmarks == b.num_landmarks, label
         assert a.initial_cost == pytest.approx(b.initial_cost, rel=COST_REL_TOL), label
@@ -106,7 +109,7 @@ def test_config3_ground_plane_matches_oracle(handle, oracle, shape):
     assert win.n_gp > 0 and win.plane_reg_weight == 10.0
     rg = handle.solve_window(win)
     rc = oracle.solve_window(win, num_threads=8 if not shape else 1)
-    _compare_solves(rg, rc, win, "config3 %s" % shape)
+    _compare_solves(rg, rc, win, "config3 %s" % shape, iter_slack=3)
     # plane blocks are the flattest directions of the problem (a handful of ground points per keyframe): rounding
     # differences are amplified there first; poses and costs above are held to north_star's tolerances
     assert np.abs(rg.kf_plane - rc.kf_plane).max() <= 1e-3
