@@ -148,68 +148,104 @@ __global__ void __launch_bounds__(256) k_panel_zero(BatchDev bd) {
 //   kJac = false: cost only, at the candidate point
 // Algorithmic HBM bytes per observation (FP64, with depth row): 20 read + 240 written.
 // =====================================================================================================================
-template <bool kJac>
-__global__ void __launch_bounds__(256, 4) k_eval_obs(BatchDev bd, SolveParams sp) {
+template <bool kJac, int kPer, int kMinBlocks>
+__global__ void __launch_bounds__(256, kMinBlocks) k_eval_obs(BatchDev bd, SolveParams sp) {
+    // each thread handles kPer observations (256 apart); all of their index / measurement / landmark loads are issued
+    // before the pose staging barrier so the dependent-load chain (index -> landmark) overlaps the staging
     const int w = blockIdx.y;
     WinState& st = bd.state[w];
+    const WinDesc& wd = bd.desc[w];
+    const int n_obs = wd.n_obs, obs_off = wd.obs_off, lm_off = wd.lm_off;
     if (st.phase != PH_ITERATE) return;
     if (kJac && !st.need_linearize) return;
     if (!kJac && st.solve_failed) return;
-    const WinDesc& wd = bd.desc[w];
     __shared__ double s_pose[kMaxKf * kPoseStride];
     __shared__ double s_cam[kMaxCam * kCamStride];
     __shared__ double s_red[8];
     const int buf = kJac ? st.cur : 1 - st.cur;
+    int L[kPer], kc[kPer];
+    float u[kPer], v[kPer], d[kPer];
+#pragma unroll
+    for (int q = 0; q < kPer; ++q) {
+        const int i = (blockIdx.x * kPer + q) * 256 + threadIdx.x;
+        L[q] = -1;
+        if (i < n_obs) {
+            const size_t o = (size_t)obs_off + i;
+            L[q] = lm_off + bd.obs_lm[o];
+            kc[q] = bd.obs_kf[o] | (bd.obs_cam[o] << 16);
+            u[q] = bd.obs_u[o]; v[q] = bd.obs_v[o]; d[q] = bd.obs_d[o];
+        }
+    }
+    double p[kPer][3], wgt[kPer];
+#pragma unroll
+    for (int q = 0; q < kPer; ++q) {
+        if (L[q] >= 0 && !bd.lm_active[L[q]]) L[q] = -1;
+        if (L[q] >= 0) {
+            const double* lm = bd.lm[buf] + 3 * (size_t)L[q];
+            p[q][0] = lm[0]; p[q][1] = lm[1]; p[q][2] = lm[2];
+            wgt[q] = bd.lm_weight[L[q]];
+        }
+    }
     stage_window(wd, bd.pose[buf], bd.cam, s_pose, s_cam);
     __syncthreads();
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
     double cost = 0.0;
     int done = 0;
-    if (i < wd.n_obs) {
-        const size_t o = (size_t)wd.obs_off + i;
-        const int L = wd.lm_off + bd.obs_lm[o];
-        if (bd.lm_active[L]) {
-            const double* lm = bd.lm[buf] + 3 * (size_t)L;
-            const double p[3] = {lm[0], lm[1], lm[2]};
-            const int k = bd.obs_kf[o], c = bd.obs_cam[o];
-            double hr = 0.0;
-            bool ok;
-            if (kJac) {  // rows are stored to their SoA slots as they are formed
-                ok = eval_observation_store<double>(
-                    s_pose + kPoseStride * k, s_cam + kCamStride * c, p, (double)bd.obs_u[o], (double)bd.obs_v[o],
-                    (double)bd.obs_d[o], bd.lm_weight[L], sp.reprojection_thres * sp.reprojection_thres,
-                    sp.depth_thres * sp.depth_thres, bd.res + o, bd.jp + o, bd.jl + o, (size_t)bd.tot_obs,
-                    bd.off_pose[wd.kf_off + k] >= 0, hr);
-            } else {
-                double r[3], raw[2];
-                ok = eval_observation<double, false>(
-                    s_pose + kPoseStride * k, s_cam + kCamStride * c, p, (double)bd.obs_u[o], (double)bd.obs_v[o],
-                    (double)bd.obs_d[o], bd.lm_weight[L], sp.reprojection_thres * sp.reprojection_thres,
-                    sp.depth_thres * sp.depth_thres, r, nullptr, nullptr, hr, raw);
-            }
-            if (!ok) {
-                st.eval_failed = 1;  // benign race
-            } else {
-                cost = hr;
-                done = 1;
-            }
+#pragma unroll
+    for (int q = 0; q < kPer; ++q) {
+        if (L[q] < 0) continue;
+        const size_t o = (size_t)obs_off + (blockIdx.x * kPer + q) * 256 + threadIdx.x;
+        const int k = kc[q] & 0xffff, c = kc[q] >> 16;
+        double hr = 0.0;
+        bool ok;
+        if (kJac) {  // rows are stored to their SoA slots as they are formed
+            ok = eval_observation_store<double>(
+                s_pose + kPoseStride * k, s_cam + kCamStride * c, p[q], (double)u[q], (double)v[q], (double)d[q], wgt[q],
+                sp.reprojection_thres * sp.reprojection_thres, sp.depth_thres * sp.depth_thres, bd.res + o, bd.jp + o,
+                bd.jl + o, (size_t)bd.tot_obs, bd.off_pose[wd.kf_off + k] >= 0, hr);
+        } else {
+            double r[3], raw[2];
+            ok = eval_observation<double, false>(
+                s_pose + kPoseStride * k, s_cam + kCamStride * c, p[q], (double)u[q], (double)v[q], (double)d[q], wgt[q],
+                sp.reprojection_thres * sp.reprojection_thres, sp.depth_thres * sp.depth_thres, r, nullptr, nullptr, hr,
+                raw);
+        }
+        if (!ok) {
+            st.eval_failed = 1;  // benign race
+        } else {
+            cost += hr;
+            ++done;
         }
     }
     cost = warp_sum(cost);
     if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = cost;
     __syncthreads();
-    if (threadIdx.x == 0) {
+    if (threadIdx.x < kPer) {  // slot blockIdx.x * kPer carries the CTA's sum, its other slots are zero
         double s = 0.0;
-        for (int q = 0; q < 8; ++q) s += s_red[q];
-        (kJac ? bd.cost_part_x : bd.cost_part_c)[(size_t)w * bd.cost_parts + blockIdx.x] = s;
+        if (threadIdx.x == 0)
+            for (int q = 0; q < 8; ++q) s += s_red[q];
+        const int slot = blockIdx.x * kPer + threadIdx.x;
+        if (slot < bd.cost_parts) (kJac ? bd.cost_part_x : bd.cost_part_c)[(size_t)w * bd.cost_parts + slot] = s;
     }
     if (kJac) {  // observation count for the roofline report (one atomic per CTA)
-        const int cnt = __syncthreads_count(done);
+        const int cnt = __syncthreads_count(done) + (kPer > 1 ? __syncthreads_count(done > 1) : 0) +
+                        (kPer > 2 ? __syncthreads_count(done > 2) + __syncthreads_count(done > 3) : 0);
         if (threadIdx.x == 0 && cnt) atomicAdd(bd.jac_obs, (unsigned long long)cnt);
     }
 }
-template __global__ void k_eval_obs<true>(BatchDev, SolveParams);
-template __global__ void k_eval_obs<false>(BatchDev, SolveParams);
+
+template <bool kJac>
+static void launch_eval_obs(const BatchDev& bd, const SolveParams& sp, cudaStream_t s) {
+    const int per = kJac ? bd.eval_per_jac : bd.eval_per_cost;
+    const dim3 g((bd.max_obs + 256 * per - 1) / (256 * per), bd.n_win);
+    switch (per * 10 + (kJac ? bd.eval_min_blocks : 4)) {
+        case 13: k_eval_obs<kJac, 1, 3><<<g, 256, 0, s>>>(bd, sp); break;
+        case 23: k_eval_obs<kJac, 2, 3><<<g, 256, 0, s>>>(bd, sp); break;
+        case 24: k_eval_obs<kJac, 2, 4><<<g, 256, 0, s>>>(bd, sp); break;
+        case 44: k_eval_obs<kJac, 4, 4><<<g, 256, 0, s>>>(bd, sp); break;
+        case 43: k_eval_obs<kJac, 4, 3><<<g, 256, 0, s>>>(bd, sp); break;
+        default: k_eval_obs<kJac, 1, 4><<<g, 256, 0, s>>>(bd, sp); break;
+    }
+}
 
 // =====================================================================================================================
 // ground-plane height residuals r = n . (R p + t) + dist with ScaledLoss(HuberLoss(0.1), w) (reference
@@ -1533,7 +1569,7 @@ void launch_pass(const BatchDev& bd, const SolveParams& sp, const LaunchCfg& lc,
     k_solve_begin<<<B, 256, 0, s>>>(bd, sp);
     const bool timed = lc.time_jacobian && lc.ev_pool && *lc.ev_used + 2 <= lc.ev_cap;
     if (timed) cudaEventRecord(lc.ev_pool[(*lc.ev_used)++], s);
-    k_eval_obs<true><<<g_obs, 256, 0, s>>>(bd, sp);
+    launch_eval_obs<true>(bd, sp, s);
     if (timed) cudaEventRecord(lc.ev_pool[(*lc.ev_used)++], s);
     if (bd.tot_gp > 0) k_gp_eval<true><<<B, 256, 0, s>>>(bd, sp);
     k_pose_hessian<<<dim3(bd.max_kf, B), 256, 0, s>>>(bd, sp);
@@ -1550,7 +1586,7 @@ void launch_pass(const BatchDev& bd, const SolveParams& sp, const LaunchCfg& lc,
     }
     k_reduced_solve<<<B, 512, solve_smem(lc.nr_cap_max), s>>>(bd, sp);
     k_backsub<<<dim3((bd.max_lm + 15) / 16, B), 256, 0, s>>>(bd);
-    k_eval_obs<false><<<g_obs, 256, 0, s>>>(bd, sp);
+    launch_eval_obs<false>(bd, sp, s);
     if (bd.tot_gp > 0) k_gp_eval<false><<<B, 256, 0, s>>>(bd, sp);
     k_lm_update<<<(B * 32 + 127) / 128, 128, 0, s>>>(bd, sp);
     k_trim_eval<<<g_lm, 256, 0, s>>>(bd, sp);
@@ -1576,7 +1612,7 @@ __global__ void k_force_linearize(BatchDev bd) {
 }
 void launch_jacobian_only(const BatchDev& bd, const SolveParams& sp, cudaStream_t s) {
     const dim3 g_obs((bd.max_obs + 255) / 256, bd.n_win);
-    k_eval_obs<true><<<g_obs, 256, 0, s>>>(bd, sp);
+    launch_eval_obs<true>(bd, sp, s);
 }
 void launch_force_linearize(const BatchDev& bd, cudaStream_t s) {
     k_solve_begin<<<bd.n_win, 256, 0, s>>>(bd, SolveParams{});  // layout (off_pose) for the eval entry point
