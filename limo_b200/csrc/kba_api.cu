@@ -371,9 +371,9 @@ int kba_batch_create(kba_handle* h, int32_t n_windows, const kba_window* w, kba_
     bd.cost_parts = (bd.max_obs + 255) / 256;
     {  // tuning knobs of the residual/Jacobian kernel (defaults measured on B200)
         auto knob = [](const char* name, int dflt) { const char* e = std::getenv(name); return e ? std::atoi(e) : dflt; };
-        bd.eval_per_jac = knob("KBA_EVAL_PER_JAC", 2);
-        bd.eval_per_cost = knob("KBA_EVAL_PER_COST", 2);
-        bd.eval_min_blocks = knob("KBA_EVAL_MIN_BLOCKS", 3);
+        bd.eval_tiles_jac = std::max(1, knob("KBA_EVAL_TILES_JAC", 8));
+        bd.eval_tiles_cost = std::max(1, knob("KBA_EVAL_TILES_COST", 8));
+        bd.eval_min_blocks = knob("KBA_EVAL_MIN_BLOCKS", 2);
     }
     bd.bs_parts = (bd.max_lm + 15) / 16;
     int bad = 0;

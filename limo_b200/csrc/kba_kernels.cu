@@ -148,10 +148,11 @@ __global__ void __launch_bounds__(256) k_panel_zero(BatchDev bd) {
 //   kJac = false: cost only, at the candidate point
 // Algorithmic HBM bytes per observation (FP64, with depth row): 20 read + 240 written.
 // =====================================================================================================================
-template <bool kJac, int kPer, int kMinBlocks>
-__global__ void __launch_bounds__(256, kMinBlocks) k_eval_obs(BatchDev bd, SolveParams sp) {
-    // each thread handles kPer observations (256 apart); all of their index / measurement / landmark loads are issued
-    // before the pose staging barrier so the dependent-load chain (index -> landmark) overlaps the staging
+template <bool kJac, int kMinBlocks>
+__global__ void __launch_bounds__(256, kMinBlocks) k_eval_obs(BatchDev bd, SolveParams sp, int tiles) {
+    // A CTA walks `tiles` consecutive 256-observation tiles of one window with a two-deep software pipeline: while tile
+    // t is evaluated, the measurement / landmark loads of tile t+1 and the landmark-index load of tile t+2 are in
+    // flight, so the dependent chain index -> landmark is hidden; the keyframe poses are staged once per CTA.
     const int w = blockIdx.y;
     WinState& st = bd.state[w];
     const WinDesc& wd = bd.desc[w];
@@ -162,89 +163,101 @@ __global__ void __launch_bounds__(256, kMinBlocks) k_eval_obs(BatchDev bd, Solve
     __shared__ double s_pose[kMaxKf * kPoseStride];
     __shared__ double s_cam[kMaxCam * kCamStride];
     __shared__ double s_red[8];
+    __shared__ int s_cnt[8];
     const int buf = kJac ? st.cur : 1 - st.cur;
-    int L[kPer], kc[kPer];
-    float u[kPer], v[kPer], d[kPer];
-#pragma unroll
-    for (int q = 0; q < kPer; ++q) {
-        const int i = (blockIdx.x * kPer + q) * 256 + threadIdx.x;
-        L[q] = -1;
-        if (i < n_obs) {
-            const size_t o = (size_t)obs_off + i;
-            L[q] = lm_off + bd.obs_lm[o];
-            kc[q] = bd.obs_kf[o] | (bd.obs_cam[o] << 16);
-            u[q] = bd.obs_u[o]; v[q] = bd.obs_v[o]; d[q] = bd.obs_d[o];
-        }
-    }
-    double p[kPer][3], wgt[kPer];
-#pragma unroll
-    for (int q = 0; q < kPer; ++q) {
-        if (L[q] >= 0 && !bd.lm_active[L[q]]) L[q] = -1;
-        if (L[q] >= 0) {
-            const double* lm = bd.lm[buf] + 3 * (size_t)L[q];
-            p[q][0] = lm[0]; p[q][1] = lm[1]; p[q][2] = lm[2];
-            wgt[q] = bd.lm_weight[L[q]];
-        }
+    const double* __restrict__ lm_buf = bd.lm[buf];
+    const int i0 = blockIdx.x * tiles * 256 + threadIdx.x;
+    // stage A: landmark index of a tile; stage B: everything else the evaluation reads
+    int idx_b = (i0 < n_obs) ? bd.obs_lm[(size_t)obs_off + i0] : -1;                  // tile 0
+    int idx_a = (tiles > 1 && i0 + 256 < n_obs) ? bd.obs_lm[(size_t)obs_off + i0 + 256] : -1;  // tile 1
+    int L = -1, kc = 0;
+    float u = 0.f, v = 0.f, d = 0.f;
+    double p0 = 0, p1 = 0, p2 = 0, wgt = 0;
+    unsigned char act = 0;
+    if (idx_b >= 0) {
+        const size_t o = (size_t)obs_off + i0;
+        L = lm_off + idx_b;
+        kc = bd.obs_kf[o] | (bd.obs_cam[o] << 16);
+        u = bd.obs_u[o]; v = bd.obs_v[o]; d = bd.obs_d[o];
+        p0 = lm_buf[3 * (size_t)L]; p1 = lm_buf[3 * (size_t)L + 1]; p2 = lm_buf[3 * (size_t)L + 2];
+        wgt = bd.lm_weight[L];
+        act = bd.lm_active[L];
     }
     stage_window(wd, bd.pose[buf], bd.cam, s_pose, s_cam);
     __syncthreads();
     double cost = 0.0;
     int done = 0;
-#pragma unroll
-    for (int q = 0; q < kPer; ++q) {
-        if (L[q] < 0) continue;
-        const size_t o = (size_t)obs_off + (blockIdx.x * kPer + q) * 256 + threadIdx.x;
-        const int k = kc[q] & 0xffff, c = kc[q] >> 16;
-        double hr = 0.0;
-        bool ok;
-        if (kJac) {  // rows are stored to their SoA slots as they are formed
-            ok = eval_observation_store<double>(
-                s_pose + kPoseStride * k, s_cam + kCamStride * c, p[q], (double)u[q], (double)v[q], (double)d[q], wgt[q],
-                sp.reprojection_thres * sp.reprojection_thres, sp.depth_thres * sp.depth_thres, bd.res + o, bd.jp + o,
-                bd.jl + o, (size_t)bd.tot_obs, bd.off_pose[wd.kf_off + k] >= 0, hr);
-        } else {
-            double r[3], raw[2];
-            ok = eval_observation<double, false>(
-                s_pose + kPoseStride * k, s_cam + kCamStride * c, p[q], (double)u[q], (double)v[q], (double)d[q], wgt[q],
-                sp.reprojection_thres * sp.reprojection_thres, sp.depth_thres * sp.depth_thres, r, nullptr, nullptr, hr,
-                raw);
+#pragma unroll 1
+    for (int t = 0; t < tiles; ++t) {
+        // issue the next tile's loads (stage B of t+1, stage A of t+2) before touching this tile's values
+        const int i_n = i0 + (t + 1) * 256;
+        int Ln = -1, kcn = 0;
+        float un = 0.f, vn = 0.f, dn = 0.f;
+        double q0 = 0, q1 = 0, q2 = 0, wn = 0;
+        unsigned char actn = 0;
+        if (idx_a >= 0) {
+            const size_t o = (size_t)obs_off + i_n;
+            Ln = lm_off + idx_a;
+            kcn = bd.obs_kf[o] | (bd.obs_cam[o] << 16);
+            un = bd.obs_u[o]; vn = bd.obs_v[o]; dn = bd.obs_d[o];
+            q0 = lm_buf[3 * (size_t)Ln]; q1 = lm_buf[3 * (size_t)Ln + 1]; q2 = lm_buf[3 * (size_t)Ln + 2];
+            wn = bd.lm_weight[Ln];
+            actn = bd.lm_active[Ln];
         }
-        if (!ok) {
-            st.eval_failed = 1;  // benign race
-        } else {
-            cost += hr;
-            ++done;
+        idx_a = (t + 2 < tiles && i_n + 256 < n_obs) ? bd.obs_lm[(size_t)obs_off + i_n + 256] : -1;
+        if (L >= 0 && act) {
+            const size_t o = (size_t)obs_off + i0 + t * 256;
+            const int k = kc & 0xffff, c = kc >> 16;
+            const double p[3] = {p0, p1, p2};
+            double hr = 0.0;
+            bool ok;
+            if (kJac) {  // rows are stored to their SoA slots as they are formed
+                ok = eval_observation_store<double>(
+                    s_pose + kPoseStride * k, s_cam + kCamStride * c, p, (double)u, (double)v, (double)d, wgt,
+                    sp.reprojection_thres * sp.reprojection_thres, sp.depth_thres * sp.depth_thres, bd.res + o, bd.jp + o,
+                    bd.jl + o, (size_t)bd.tot_obs, bd.off_pose[wd.kf_off + k] >= 0, hr);
+            } else {
+                double r[3], raw[2];
+                ok = eval_observation<double, false>(
+                    s_pose + kPoseStride * k, s_cam + kCamStride * c, p, (double)u, (double)v, (double)d, wgt,
+                    sp.reprojection_thres * sp.reprojection_thres, sp.depth_thres * sp.depth_thres, r, nullptr, nullptr,
+                    hr, raw);
+            }
+            if (!ok) {
+                st.eval_failed = 1;  // benign race
+            } else {
+                cost += hr;
+                ++done;
+            }
         }
+        L = Ln; kc = kcn; u = un; v = vn; d = dn; p0 = q0; p1 = q1; p2 = q2; wgt = wn; act = actn;
     }
     cost = warp_sum(cost);
-    if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = cost;
+    if (kJac) done = __reduce_add_sync(0xffffffffu, done);
+    if ((threadIdx.x & 31) == 0) { s_red[threadIdx.x >> 5] = cost; s_cnt[threadIdx.x >> 5] = done; }
     __syncthreads();
-    if (threadIdx.x < kPer) {  // slot blockIdx.x * kPer carries the CTA's sum, its other slots are zero
+    if (threadIdx.x < tiles) {  // slot blockIdx.x * tiles carries the CTA's sum, its other slots are zero
         double s = 0.0;
         if (threadIdx.x == 0)
             for (int q = 0; q < 8; ++q) s += s_red[q];
-        const int slot = blockIdx.x * kPer + threadIdx.x;
+        const int slot = blockIdx.x * tiles + threadIdx.x;
         if (slot < bd.cost_parts) (kJac ? bd.cost_part_x : bd.cost_part_c)[(size_t)w * bd.cost_parts + slot] = s;
     }
-    if (kJac) {  // observation count for the roofline report (one atomic per CTA)
-        const int cnt = __syncthreads_count(done) + (kPer > 1 ? __syncthreads_count(done > 1) : 0) +
-                        (kPer > 2 ? __syncthreads_count(done > 2) + __syncthreads_count(done > 3) : 0);
-        if (threadIdx.x == 0 && cnt) atomicAdd(bd.jac_obs, (unsigned long long)cnt);
+    if (kJac && threadIdx.x == 0) {  // observation count for the roofline report (one atomic per CTA)
+        int cnt = 0;
+        for (int q = 0; q < 8; ++q) cnt += s_cnt[q];
+        if (cnt) atomicAdd(bd.jac_obs, (unsigned long long)cnt);
     }
 }
 
 template <bool kJac>
 static void launch_eval_obs(const BatchDev& bd, const SolveParams& sp, cudaStream_t s) {
-    const int per = kJac ? bd.eval_per_jac : bd.eval_per_cost;
-    const dim3 g((bd.max_obs + 256 * per - 1) / (256 * per), bd.n_win);
-    switch (per * 10 + (kJac ? bd.eval_min_blocks : 4)) {
-        case 13: k_eval_obs<kJac, 1, 3><<<g, 256, 0, s>>>(bd, sp); break;
-        case 23: k_eval_obs<kJac, 2, 3><<<g, 256, 0, s>>>(bd, sp); break;
-        case 24: k_eval_obs<kJac, 2, 4><<<g, 256, 0, s>>>(bd, sp); break;
-        case 44: k_eval_obs<kJac, 4, 4><<<g, 256, 0, s>>>(bd, sp); break;
-        case 43: k_eval_obs<kJac, 4, 3><<<g, 256, 0, s>>>(bd, sp); break;
-        default: k_eval_obs<kJac, 1, 4><<<g, 256, 0, s>>>(bd, sp); break;
-    }
+    const int tiles = kJac ? bd.eval_tiles_jac : bd.eval_tiles_cost;
+    const dim3 g((bd.max_obs + 256 * tiles - 1) / (256 * tiles), bd.n_win);
+    const int mb = kJac ? bd.eval_min_blocks : 4;
+    if (mb == 2) k_eval_obs<kJac, 2><<<g, 256, 0, s>>>(bd, sp, tiles);
+    else if (mb == 3) k_eval_obs<kJac, 3><<<g, 256, 0, s>>>(bd, sp, tiles);
+    else k_eval_obs<kJac, 4><<<g, 256, 0, s>>>(bd, sp, tiles);
 }
 
 // =====================================================================================================================
