@@ -24,6 +24,10 @@ import numpy as np  # noqa: E402
 
 METRIC = "BA windows/s (30 KF, 3k LM, 40k obs)"
 B_OBS_ALGORITHMIC = 259.0  # bytes per observation of the residual/Jacobian kernel, mono + depth FP64
+# dram__bytes_read.sum + dram__bytes_write.sum of one k_eval_obs<true> launch / its observations, from the ncu --set full
+# capture summarised in profiles/ (re-measured whenever the kernel changes)
+B_OBS_DRAM_MEASURED = 293.0
+TRAFFIC_SOURCE = "ncu --set full, profiles/r01_v5_ncu_summary.md: (0.214 GB read + 1.410 GB written) / 5.54 M observations"
 
 
 def usable_cores():
@@ -51,7 +55,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -143,10 +147,10 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--batch", type=int, default=128, help="windows per GPU per step")
+    ap.add_argument("--batch", type=int, default=148, help="windows per GPU per step (one per SM)")
     ap.add_argument("--distinct", type=int, default=16, help="distinct synthetic windows per GPU (tiled to --batch)")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--cpu-sample", type=int, default=2)
+    ap.add_argument("--cpu-sample", type=int, default=16, help="window solves timed for cpu_baseline (~0.7 s each)")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -197,7 +201,6 @@ def main():
     ev1.record(stream)
     barrier()
     ms = ev0.elapsed_time(ev1)
-    clocks = sampler.stop()
     cnt = h.counters(reset=True)
     h.enable_kernel_timing(False)
     results = batch.download()
@@ -211,13 +214,19 @@ def main():
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t_wall = time.perf_counter()
     e0.record(stream)
+    t_up = t_dn = 0.0
     for _ in range(args.steps):
-        batch.upload()
-        batch.solve(opt)
+        t0 = time.perf_counter()
+        batch.upload()       # host pack (threads) + async H2D
+        t1 = time.perf_counter()
+        batch.solve(opt)     # returns when every window is done
+        t2 = time.perf_counter()
         batch.download(results=results)
+        t_up += t1 - t0; t_dn += time.perf_counter() - t2
     e1.record(stream)
     barrier()
     ms_e2e = max(e0.elapsed_time(e1), 1e3 * (time.perf_counter() - t_wall))
+    clocks = sampler.stop()  # sampled over both timed regions
     h2d, d2h = batch.transfer_bytes()
 
     t = torch.tensor([ms, ms_e2e], dtype=torch.float64, device="cuda")
@@ -244,11 +253,15 @@ def main():
                                     % (args.batch * n_obs_win * 240 / 1e9),
                        "all_windows_converged": bool(ok)},
             "e2e": {"value": total_windows / (ms_e2e * 1e-3), "unit": "windows/s",
-                    "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
+                    "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                    "host_pack_upload_ms_per_step": 1e3 * t_up / args.steps,
+                    "download_ms_per_step": 1e3 * t_dn / args.steps},
             "gpu_launches": int(cnt.launches_total),
             "roofline": {"kernel": "k_eval_obs<true> (residual/Jacobian)", "bound": "hbm", "achieved": jac_gbs,
                          "peak": peak, "unit": "GB/s", "frac": (jac_gbs / peak) if jac_gbs else None,
-                         "peak_source": peak_src, "traffic": None,
+                         "peak_source": peak_src,
+                         "traffic": B_OBS_DRAM_MEASURED * cnt.jacobian_obs / max(cnt.launches_jacobian, 1),
+                         "traffic_unit": "bytes per launch", "traffic_source": TRAFFIC_SOURCE,
                          "algorithmic_bytes_per_obs": B_OBS_ALGORITHMIC,
                          "launch_ms_mean": cnt.ms_jacobian / max(cnt.launches_jacobian, 1),
                          "obs_per_launch_mean": cnt.jacobian_obs / max(cnt.launches_jacobian, 1)},

@@ -1,11 +1,13 @@
 // kba_api.cu -- host side of the C ABI declared in include/kba_b200.h: handle / batch lifetime, packing of caller
 // windows into the batch-flat device layout, the pass loop, result download.  No numerical work happens on the host.
 #include <algorithm>
+#include <atomic>
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include <cuda_runtime.h>
@@ -189,7 +191,6 @@ static void fill_window(kba_batch* b, int wi, const kba_window* w) {
         lp[jn + 1] = pos;
     }
     b->desc_h[wi].max_rank = max_rank;
-    b->lc.max_rank = std::max(b->lc.max_rank, max_rank);
     b->desc.h[wi].max_rank = max_rank;
     // keyframe-major copy (counting sort, stable -> deterministic reduction order)
     for (int k = 0; k < w->n_kf; ++k) kp[k + 1] += kp[k];
@@ -374,6 +375,7 @@ int kba_batch_create(kba_handle* h, int32_t n_windows, const kba_window* w, kba_
         bd.eval_tiles_jac = std::max(1, knob("KBA_EVAL_TILES_JAC", 8));
         bd.eval_tiles_cost = std::max(1, knob("KBA_EVAL_TILES_COST", 8));
         bd.eval_min_blocks = knob("KBA_EVAL_MIN_BLOCKS", 2);
+        bd.solve_row_major = knob("KBA_SOLVE_ROW_MAJOR", 0);
     }
     bd.bs_parts = (bd.max_lm + 15) / 16;
     int bad = 0;
@@ -454,6 +456,9 @@ int kba_batch_upload(kba_batch* b, int32_t n_windows, const kba_window* w) {
         const WinDesc& d = b->desc_h[i];
         if (w[i].n_kf != d.n_kf || w[i].n_lm != d.n_lm || w[i].n_obs != d.n_obs || w[i].n_cam != d.n_cam)
             return fail(KBA_ERR_BAD_ARG, "kba_batch_upload: window shapes differ from kba_batch_create");
+    }
+    // packing (landmark sort, observation permutation, keyframe-major copy) is independent per window: host threads
+    auto pack = [&](int i) {
         b->desc_h[i].scale_weight = w[i].scale_weight; b->desc_h[i].scale_value = w[i].scale_value;
         b->desc_h[i].scale_kf0 = w[i].scale_kf0; b->desc_h[i].scale_kf1 = w[i].scale_kf1;
         b->desc_h[i].landmarks_fixed = w[i].landmarks_fixed;
@@ -463,7 +468,22 @@ int kba_batch_upload(kba_batch* b, int32_t n_windows, const kba_window* w) {
         memcpy(b->desc_h[i].speed_T_origin_before, w[i].speed_T_origin_before, sizeof(double) * 7);
         b->desc.h[i] = b->desc_h[i];
         fill_window(b, i, &w[i]);
+    };
+    {
+        const char* e = std::getenv("KBA_HOST_THREADS");
+        int nt = e ? std::atoi(e) : (int)std::min(16u, std::max(1u, std::thread::hardware_concurrency()));
+        nt = std::max(1, std::min(nt, n_windows));
+        if (nt == 1) {
+            for (int i = 0; i < n_windows; ++i) pack(i);
+        } else {
+            std::atomic<int> next{0};
+            std::vector<std::thread> pool;
+            for (int t = 0; t < nt; ++t)
+                pool.emplace_back([&] { for (int i = next.fetch_add(1); i < n_windows; i = next.fetch_add(1)) pack(i); });
+            for (auto& th : pool) th.join();
+        }
     }
+    for (int i = 0; i < n_windows; ++i) b->lc.max_rank = std::max(b->lc.max_rank, b->desc_h[i].max_rank);
     cudaStream_t s = b->h->stream;
     CU(b->desc.upload(s)); CU(b->pose0.upload(s)); CU(b->plane0.upload(s)); CU(b->kf_fixed.upload(s)); CU(b->cam.upload(s));
     CU(b->lm0.upload(s)); CU(b->lm_weight.upload(s)); CU(b->lm_ptr.upload(s));

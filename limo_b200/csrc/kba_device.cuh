@@ -137,6 +137,7 @@ struct BatchDev {
     double* cost_part_x;      // [n_win][cost_parts] cost partials of the linearisation at x
     double* cost_part_c;      // [n_win][cost_parts] cost partials at the candidate
     int cost_parts;
+    int solve_row_major;      // debug knob: force the global-memory Cholesky even when the tiled one fits
     int eval_tiles_jac, eval_tiles_cost, eval_min_blocks;  // 256-observation tiles per CTA / CTAs per SM of k_eval_obs
     double* bs_part;          // [n_win][bs_parts][4]: model_e, step_sq, xnorm_sq, gmax_e
     int bs_parts;

@@ -10,7 +10,9 @@
 #include "kba_prep.cuh"
 
 #include <cfloat>
+#include <cstdio>
 #include <cmath>
+#include <type_traits>
 
 namespace kba {
 
@@ -516,107 +518,9 @@ __global__ void __launch_bounds__(256, 2) k_schur_syrk(BatchDev bd) {
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
-// Register-resident variant for reduced systems of up to 184 rows (<= 30 free keyframes): ONE CTA owns the whole lower
-// triangle of Sred as 8x8 accumulator tiles spread cyclically over 16 warps (<= 18 tiles = 36 FP64 registers per lane),
-// so the V panel of a chunk is scattered into shared memory once (not once per 64x64 block), and only the tiles inside
-// the chunk's row range [t0, t1) (+ the rhs tile row) are multiplied.  Landmarks are stored sorted by first keyframe,
-// which makes those ranges tight.  grid = (p_split, windows); each CTA handles a contiguous range of chunks.
-// ---------------------------------------------------------------------------------------------------------------------
-constexpr int kSmallTiles = 23;               // tile rows (184 rows)
-constexpr int kSmallSlots = 18;               // ceil(23*24/2 / 16)
-
-__global__ void __launch_bounds__(512, 1) k_schur_syrk_small(BatchDev bd) {
-    const int w = blockIdx.y;
-    const WinState& st = bd.state[w];
-    if (st.phase != PH_ITERATE || st.solve_failed) return;
-    const WinDesc& wd = bd.desc[w];
-    if (wd.landmarks_fixed) return;
-    extern __shared__ double panel[];  // [kSmallTiles*8][kKS]
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int nt = (st.n_f + 1 + 7) >> 3, trhs = st.n_f >> 3, rhs_row = st.n_f;
-    double acc[kSmallSlots][2];
-#pragma unroll
-    for (int s = 0; s < kSmallSlots; ++s) acc[s][0] = acc[s][1] = 0.0;
-    const int* lm_ptr = bd.lm_ptr + wd.lm_off + w;
-    const size_t T = (size_t)bd.tot_obs, base = (size_t)wd.obs_off;
-    const int per = (wd.n_chunks + bd.p_split - 1) / bd.p_split;
-    const int ch0 = blockIdx.x * per, ch1 = min(wd.n_chunks, ch0 + per);
-    const int fr = lane >> 2, fc = lane & 3;  // fragment row / k index of this lane
-    for (int ch = ch0; ch < ch1; ++ch) {
-        const int t0 = bd.chunk_t0[wd.chunk_off + ch], t1 = bd.chunk_t1[wd.chunk_off + ch];
-        if (t1 <= t0) continue;  // the chunk's landmarks are seen by constant keyframes only
-        const int j0 = bd.chunk_lm0[wd.chunk_off + ch], j1 = bd.chunk_lm1[wd.chunk_off + ch];
-        const int o0 = lm_ptr[j0], o1 = lm_ptr[j1];
-        __syncthreads();  // MMA of the previous chunk finished
-        {
-            double* z0 = panel + (size_t)8 * t0 * kKS;
-            const int nz = 8 * (t1 - t0) * kKS;
-            for (int i = threadIdx.x; i < nz; i += blockDim.x) z0[i] = 0.0;
-            if (trhs < t0 || trhs >= t1) {
-                double* z1 = panel + (size_t)8 * trhs * kKS;
-                for (int i = threadIdx.x; i < 8 * kKS; i += blockDim.x) z1[i] = 0.0;
-            }
-        }
-        __syncthreads();
-        const int nobs = o1 - o0;
-        for (int idx = threadIdx.x; idx < nobs * 18; idx += blockDim.x) {
-            const int e = idx / nobs, oo = idx - e * nobs;
-            const size_t o = base + o0 + oo;
-            const int row0 = bd.obs_row[o];
-            if (row0 < 0) continue;
-            panel[(row0 + e / 3) * kKS + 3 * (bd.obs_lm[o] - j0) + e % 3] = bd.vobs[e * T + o];
-        }
-        for (int idx = threadIdx.x; idx < (j1 - j0) * 3; idx += blockDim.x) {
-            const int jl = j0 + idx / 3;
-            if (!bd.lm_active[wd.lm_off + jl] || lm_ptr[jl + 1] <= lm_ptr[jl]) continue;
-            panel[rhs_row * kKS + idx] = bd.lm_z[3 * (size_t)(wd.lm_off + jl) + idx % 3];
-        }
-        if (wd.n_gp > 0) {  // ground-plane rows are ADDED: the pose rows may coincide with an observation's rows
-            __syncthreads();
-            for (int idx = threadIdx.x; idx < (j1 - j0) * 30; idx += blockDim.x) {
-                const int jl = j0 + idx / 30, e = idx % 30;
-                const int gl = bd.gp_of_lm[wd.lm_off + jl];
-                if (gl < 0 || !bd.lm_active[wd.lm_off + jl]) continue;
-                const int row = gp_row(bd, wd, bd.gp_kf[wd.gp_off + gl], e / 3);
-                if (row < 0) continue;
-                panel[row * kKS + 3 * (jl - j0) + e % 3] += bd.vgp[(size_t)e * bd.tot_gp + wd.gp_off + gl];
-            }
-        }
-        __syncthreads();
-#pragma unroll
-        for (int s = 0; s < kSmallSlots; ++s) {
-            const int t = s * 16 + warp;
-            int i = (int)((sqrtf(8.0f * (float)t + 1.0f) - 1.0f) * 0.5f);
-            while ((i + 1) * (i + 2) / 2 <= t) ++i;
-            while (i * (i + 1) / 2 > t) --i;
-            const int j = t - i * (i + 1) / 2;
-            if (i >= nt) continue;
-            const bool ai = (i >= t0 && i < t1) || i == trhs, aj = (j >= t0 && j < t1) || j == trhs;
-            if (!(ai && aj)) continue;
-            const double* arow = panel + (8 * i + fr) * kKS + fc;
-            const double* brow = panel + (8 * j + fr) * kKS + fc;
-#pragma unroll 8
-            for (int kk = 0; kk < kKC; kk += 4) dmma(acc[s][0], acc[s][1], arow[kk], brow[kk]);
-        }
-    }
-    double* out = bd.sred + wd.s_off * (size_t)bd.p_split + (size_t)blockIdx.x * wd.nr_cap * wd.nr_cap;
-#pragma unroll
-    for (int s = 0; s < kSmallSlots; ++s) {
-        const int t = s * 16 + warp;
-        int i = (int)((sqrtf(8.0f * (float)t + 1.0f) - 1.0f) * 0.5f);
-        while ((i + 1) * (i + 2) / 2 <= t) ++i;
-        while (i * (i + 1) / 2 > t) --i;
-        const int j = t - i * (i + 1) / 2;
-        if (i >= nt) continue;
-        double* o = out + (size_t)(8 * i + fr) * wd.nr_cap + 8 * j + 2 * fc;
-        o[0] = acc[s][0];
-        o[1] = acc[s][1];
-    }
-}
-
-// ---------------------------------------------------------------------------------------------------------------------
-// TMA-fed variant of the register-resident kernel: k_landmark_prep has already laid V out as dense column-major chunk
-// panels in global memory (zeros included), so a panel half (48 columns x rs rows, <= 75 KB) arrives with ONE
+// Register-resident, TMA-fed kernel for reduced systems of up to 184 rows (<= 30 free keyframes): ONE CTA owns the whole
+// lower triangle of Sred as accumulator tiles spread over 16 warps.  k_landmark_reduce / k_obs_v have already laid V out
+// as dense column-major chunk panels in global memory (zeros included), so a panel half (48 columns x rs rows, <= 75 KB) arrives with ONE
 // cp.async.bulk into a 2-stage shared-memory ring while the tensor-core loop works on the other stage: no scatter, no
 // zero fill, no index loads in this kernel.  rs == 4 (mod 16) keeps the m8n8k4 fragment loads bank-conflict free.
 // ---------------------------------------------------------------------------------------------------------------------
@@ -826,6 +730,101 @@ __device__ void speed_regulariser(const double* p, const WinDesc& wd, double r[3
         }
 }
 
+// Views of the reduced system: row-major in global memory (any size), or the lower triangle packed as 8x8 tiles in
+// shared memory (<= 192 rows).  Inside a tile the two 8x4 halves are stored one after the other, which is exactly the
+// m8n8k4 fragment order: lane (fr, fc) reads half h at h*32 + fr*4 + fc -- conflict free.
+struct RowMajorMat {
+    double* p; int ld;
+    __device__ __forceinline__ double& operator()(int r, int c) const { return p[(size_t)r * ld + c]; }
+};
+struct TiledMat {
+    double* p;
+    __device__ __forceinline__ double* tile(int I, int J) const { return p + (size_t)(I * (I + 1) / 2 + J) * 64; }
+    __device__ __forceinline__ double& operator()(int r, int c) const {
+        return tile(r >> 3, c >> 3)[((c & 4) << 3) + ((r & 7) << 2) + (c & 3)];
+    }
+};
+
+// Cholesky of the 32x32 block in D (shared memory, row stride PS, lower part; identity-padded beyond the live rows)
+// by one warp, lane = row.  Two levels: the columns are taken 8 at a time -- a left-looking update from the columns
+// already done (operands from shared memory), then the 8 columns are factored in registers with shuffles.  The pivot
+// uses rsqrt, whose value 1 / L_jj is kept in inv[] for the triangular solves that follow (no division on their
+// critical path).  Returns false on a non-positive pivot.
+__device__ inline bool warp_chol32(double* D, int PS, double* inv, int lane) {
+    bool ok = true;
+#pragma unroll 1
+    for (int jb = 0; jb < 4; ++jb) {
+        const int c0 = 8 * jb;
+        double r[8];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) r[c] = D[lane * PS + c0 + c];
+#pragma unroll 2
+        for (int q = 0; q < c0; ++q) {
+            const double lq = D[lane * PS + q];
+#pragma unroll
+            for (int c = 0; c < 8; ++c) r[c] -= lq * D[(c0 + c) * PS + q];
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const double djj = __shfl_sync(0xffffffffu, r[j], c0 + j);
+            if (!(djj > 0.0) || !isfinite(djj)) ok = false;
+            const double rs = rsqrt(djj);
+            const double lij = (lane == c0 + j) ? djj * rs : r[j] * rs;
+            r[j] = lij;
+            if (lane == c0 + j) inv[c0 + j] = rs;
+#pragma unroll
+            for (int c = j + 1; c < 8; ++c) {
+                const double lcj = __shfl_sync(0xffffffffu, lij, c0 + c);
+                r[c] -= lij * lcj;
+            }
+        }
+        __syncwarp();
+#pragma unroll
+        for (int c = 0; c < 8; ++c) D[lane * PS + c0 + c] = (c0 + c <= lane) ? r[c] : 0.0;
+        __syncwarp();
+    }
+    return ok;
+}
+
+#ifdef KBA_PHASE_CLOCKS  // debug build: cycle counts of the phases of k_reduced_solve for window 0
+#define PHASE_DECL long long clk_[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0}; long long last_ = clock64()
+#define PHASE_MARK(i) do { if (tid == 0 && w == 0) { clk_[i] = clock64(); last_ = clk_[i]; } } while (0)
+#define PHASE_ACC(i) do { if (tid == 0 && w == 0) { const long long t_ = clock64(); clk_[i] += t_ - last_; last_ = t_; } } while (0)
+#define PHASE_PRINT do { if (tid == 0 && w == 0) printf("reduced_solve cycles: sred %lld blocks %lld scale %lld chol %lld (diag %lld panel %lld trail %lld) backsub %lld tail %lld\n", clk_[1] - clk_[0], clk_[2] - clk_[1], clk_[3] - clk_[2], clk_[4] - clk_[3], clk_[8], clk_[9], clk_[10], clk_[5] - clk_[4], clk_[6] - clk_[5]); } while (0)
+#else
+#define PHASE_DECL
+#define PHASE_MARK(i)
+#define PHASE_ACC(i)
+#define PHASE_PRINT
+#endif
+
+// partial Schur sums of the p_split CTAs of a window -> slot 0, fixed order (only launched when p_split > 1, i.e. when
+// the batch is too small to fill the GPU with one CTA per window)
+__global__ void __launch_bounds__(256) k_sred_reduce(BatchDev bd) {
+    const int w = blockIdx.y;
+    const WinState& st = bd.state[w];
+    if (st.phase != PH_ITERATE || st.solve_failed) return;
+    const WinDesc& wd = bd.desc[w];
+    if (wd.landmarks_fixed) return;
+    const int ld = wd.nr_cap, n = st.n_f;
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (n + 1) * ld) return;
+    const int r = idx / ld, c = idx - r * ld;
+    if (c > r) return;
+    double* sp0 = bd.sred + wd.s_off * (size_t)bd.p_split;
+    const size_t pstride = (size_t)ld * ld;
+    double s = 0.0;
+    for (int p0 = 0; p0 < bd.p_split; p0 += 16) {  // 16 independent loads in flight, summed in slot order
+        double v[16];
+#pragma unroll
+        for (int q = 0; q < 16; ++q) v[q] = (p0 + q < bd.p_split) ? sp0[(size_t)(p0 + q) * pstride + idx] : 0.0;
+#pragma unroll
+        for (int q = 0; q < 16; ++q) s += v[q];
+    }
+    sp0[idx] = s;
+}
+
+template <bool kTiled>
 __global__ void __launch_bounds__(512, 1) k_reduced_solve(BatchDev bd, SolveParams sp) {
     const int w = blockIdx.x;
     WinState& st = bd.state[w];
@@ -833,17 +832,24 @@ __global__ void __launch_bounds__(512, 1) k_reduced_solve(BatchDev bd, SolvePara
     const WinDesc& wd = bd.desc[w];
     const int tid = threadIdx.x, nth = blockDim.x;
     const int n = st.n_f, ld = wd.nr_cap;
-    double* A = bd.amat + wd.s_off;
     extern __shared__ double sm[];
     double* s_fdiag = sm;                 // [ld] squared column norms of J (f part)
     double* s_g = s_fdiag + ld;           // [ld] gradient J^T r (f part)
     double* s_y = s_g + ld;               // [ld]
     double* s_lam = s_y + ld;             // [ld]
-    double* s_D = s_lam + ld;             // [kNB][kNB+1]
-    double* s_P = s_D + kNB * (kNB + 1);  // [ld][kNB+1] panel
+    double* s_invd = s_lam + ld;          // [ld] 1 / L_ii (tiled path)
+    double* s_inv = s_invd + ld;          // [kNB] 1 / L_ii of the block being factored
+    double* s_D = s_inv + kNB;            // [kNB][kNB+1]
+    double* s_P = s_D + kNB * (kNB + 1);  // row-major path: [ld][kNB+1] panel; tiled path: the packed lower triangle
+    using Mat = typename std::conditional<kTiled, TiledMat, RowMajorMat>::type;
+    Mat A;
+    if constexpr (kTiled) A.p = s_P;
+    else { A.p = bd.amat + wd.s_off; A.ld = ld; }
     __shared__ int s_fail;
     __shared__ double s_red[16][4];
     if (tid == 0) s_fail = 0;
+    PHASE_DECL;
+    PHASE_MARK(0);
 
     // ---- cost at x and evaluation failure (fresh linearisation only) ----
     if (st.need_linearize && tid == 0) {
@@ -863,16 +869,19 @@ __global__ void __launch_bounds__(512, 1) k_reduced_solve(BatchDev bd, SolvePara
     {
         const double* sp0 = bd.sred + wd.s_off * (size_t)bd.p_split;
         const size_t pstride = (size_t)ld * ld;
-        for (int idx = tid; idx < (n + 1) * ld; idx += nth) {
+        const int np = bd.p_split > 1 ? 1 : bd.p_split;  // k_sred_reduce has folded the partials into slot 0
+        const int rows = kTiled ? ((n + 8) & ~7) : n + 1;  // tiled: whole tile rows, zero padded
+        for (int idx = tid; idx < rows * ld; idx += nth) {
             const int r = idx / ld, c = idx - r * ld;
-            if (c > r || c >= n + 1) continue;
+            if (kTiled ? (c >= rows || (c >> 3) > (r >> 3)) : (c > r || c >= n + 1)) continue;
             double s = 0.0;
-            if (!wd.landmarks_fixed)  // motion-only problem: no landmark blocks were eliminated
-                for (int p = 0; p < bd.p_split; ++p) s += sp0[p * pstride + (size_t)r * ld + c];
-            A[(size_t)r * ld + c] = -s;
+            if (!wd.landmarks_fixed && c <= r && r <= n && !(r == n && c == n))  // motion-only: nothing was eliminated
+                for (int p = 0; p < np; ++p) s += sp0[p * pstride + (size_t)r * ld + c];
+            A(r, c) = -s;
         }
     }
     __syncthreads();
+    PHASE_MARK(1);
     // ---- + per-keyframe Gauss-Newton blocks ----
     for (int idx = tid; idx < wd.n_kf * 27; idx += nth) {
         const int k = idx / 27, q = idx - 27 * k;
@@ -883,7 +892,7 @@ __global__ void __launch_bounds__(512, 1) k_reduced_solve(BatchDev bd, SolvePara
             int a = 0, rem = q;
             while (rem >= 6 - a) { rem -= 6 - a; ++a; }
             const int b = a + rem;  // a <= b
-            A[(size_t)(off + b) * ld + off + a] += v;
+            A(off + b, off + a) += v;
             if (a == b) s_fdiag[off + a] = v;
         } else {
             s_g[off + q - 21] = v;
@@ -925,7 +934,7 @@ __global__ void __launch_bounds__(512, 1) k_reduced_solve(BatchDev bd, SolvePara
                 if (eb[s] < 0) { s_g[ra] += acc[s]; continue; }
                 const int rb = gp_row(bd, wd, k, eb[s]);
                 if (rb < 0) continue;
-                A[(size_t)ra * ld + rb] += acc[s];
+                A(ra, rb) += acc[s];
                 if (ea[s] == eb[s]) s_fdiag[ra] += acc[s];
             }
         }
@@ -950,13 +959,13 @@ __global__ void __launch_bounds__(512, 1) k_reduced_solve(BatchDev bd, SolvePara
                     for (int c = 0; c < 3; ++c) { J[6 * i + c] = sq * P1[3 * i + c]; J[6 * i + 3 + c] = -sq * P0[3 * i + c]; }
                 }
                 const int off[2] = {bd.off_dir[wd.kf_off + k1], bd.off_dir[wd.kf_off + k0]}, sz[2] = {3, 3};
-                warp_add_block(A, ld, s_fdiag, s_g, 3, r, 2, off, sz, J, lane);
+                warp_add_block(A, s_fdiag, s_g, 3, r, 2, off, sz, J, lane);
             }
             {   // GroundPlaneDistanceRegularization(dist1, dist0), weight w
                 const double sq = sqrt(wgt);
                 const double r[1] = {sq * (n1[3] - n0[3])}, J[2] = {sq, -sq};
                 const int off[2] = {bd.off_dist[wd.kf_off + k1], bd.off_dist[wd.kf_off + k0]}, sz[2] = {1, 1};
-                warp_add_block(A, ld, s_fdiag, s_g, 1, r, 2, off, sz, J, lane);
+                warp_add_block(A, s_fdiag, s_g, 1, r, 2, off, sz, J, lane);
             }
             {   // GroundPlaneMotionRegularization(pose0, pose1, dir0), weight 2w
                 const double sq = sqrt(2.0 * wgt);
@@ -967,7 +976,7 @@ __global__ void __launch_bounds__(512, 1) k_reduced_solve(BatchDev bd, SolvePara
                 const double r[1] = {sq * rm};
                 const int off[3] = {bd.off_pose[wd.kf_off + k0], bd.off_pose[wd.kf_off + k1], bd.off_dir[wd.kf_off + k0]};
                 const int sz[3] = {6, 6, 3};
-                warp_add_block(A, ld, s_fdiag, s_g, 1, r, 3, off, sz, J, lane);
+                warp_add_block(A, s_fdiag, s_g, 1, r, 3, off, sz, J, lane);
             }
         }
         for (int k = 0; k < wd.n_kf; ++k) {  // VectorDifferenceRegularization2((0,0,1)), weight w
@@ -977,7 +986,7 @@ __global__ void __launch_bounds__(512, 1) k_reduced_solve(BatchDev bd, SolvePara
             dir_plus_jacobian(n, Pn);
             for (int i = 0; i < 9; ++i) J[i] = -sq * Pn[i];
             const int off[1] = {bd.off_dir[wd.kf_off + k]}, sz[1] = {3};
-            warp_add_block(A, ld, s_fdiag, s_g, 3, r, 1, off, sz, J, lane);
+            warp_add_block(A, s_fdiag, s_g, 3, r, 1, off, sz, J, lane);
         }
         if (lane == 0 && st.need_linearize) st.x_cost += plane_chain_cost(wd, P, PL);
     }
@@ -998,7 +1007,7 @@ __global__ void __launch_bounds__(512, 1) k_reduced_solve(BatchDev bd, SolvePara
         const double rr = sq * r;
         for (int a = 0; a < m; ++a) {
             for (int b = 0; b < m; ++b)
-                if (cols[b] <= cols[a]) A[(size_t)cols[a] * ld + cols[b]] += J[a] * J[b];
+                if (cols[b] <= cols[a]) A(cols[a], cols[b]) += J[a] * J[b];
             s_fdiag[cols[a]] += J[a] * J[a];
             s_g[cols[a]] += J[a] * rr;
         }
@@ -1012,13 +1021,14 @@ __global__ void __launch_bounds__(512, 1) k_reduced_solve(BatchDev bd, SolvePara
             const double wgt = wd.speed_weight;  // rho' = w: J^T J and J^T r scale by w
             for (int a = 0; a < 6; ++a) {
                 for (int b = 0; b <= a; ++b)
-                    A[(size_t)(o + a) * ld + o + b] += wgt * (J[a] * J[b] + J[6 + a] * J[6 + b] + J[12 + a] * J[12 + b]);
+                    A(o + a, o + b) += wgt * (J[a] * J[b] + J[6 + a] * J[6 + b] + J[12 + a] * J[12 + b]);
                 s_fdiag[o + a] += wgt * (J[a] * J[a] + J[6 + a] * J[6 + a] + J[12 + a] * J[12 + a]);
                 s_g[o + a] += wgt * (J[a] * r[0] + J[6 + a] * r[1] + J[12 + a] * r[2]);
             }
         }
     }
     __syncthreads();
+    PHASE_MARK(2);
     // ---- Jacobi scaling, damping, augmented row ----
     double* scale_f = bd.scale_f + (size_t)w * bd.nr_cap_max;
     double* lambda_f = bd.lambda_f + (size_t)w * bd.nr_cap_max;
@@ -1032,86 +1042,189 @@ __global__ void __launch_bounds__(512, 1) k_reduced_solve(BatchDev bd, SolvePara
         s_lam[c] = lam;
         lambda_f[c] = lam;
         grad_f[c] = s_g[c];
-        A[(size_t)c * ld + c] += lam;
-        A[(size_t)n * ld + c] += s_g[c];  // augmented row: g_f - V z
+        A(c, c) += lam;
+        A(n, c) += s_g[c];  // augmented row: g_f - V z
     }
     __syncthreads();
 
-    // ---- blocked right-looking Cholesky of A[0..n) with the augmented row n carried along ----
-    const int PS = kNB + 1;
-    for (int kb = 0; kb < n; kb += kNB) {
-        const int nb = min(kNB, n - kb);
-        for (int idx = tid; idx < nb * nb; idx += nth) {
-            const int r = idx / nb, c = idx - r * nb;
-            s_D[r * PS + c] = (c <= r) ? A[(size_t)(kb + r) * ld + kb + c] : 0.0;
-        }
-        __syncthreads();
-        if (tid < 32) {  // factor the diagonal block with one warp: lane = row
-            const int lane = tid;
-            for (int j = 0; j < nb; ++j) {
-                const double djj = s_D[j * PS + j];
-                if (!(djj > 0.0) || !isfinite(djj)) { if (lane == 0) s_fail = 1; break; }
-                const double piv = sqrt(djj);
-                __syncwarp();
-                if (lane == j) s_D[j * PS + j] = piv;
-                if (lane > j && lane < nb) s_D[lane * PS + j] /= piv;
-                __syncwarp();
-                if (lane > j && lane < nb) {
-                    const double lij = s_D[lane * PS + j];
-                    for (int c = j + 1; c <= lane; ++c) s_D[lane * PS + c] -= lij * s_D[c * PS + j];
+    PHASE_MARK(3);
+    if constexpr (kTiled) {
+        // ---- shared-memory resident blocked Cholesky (NB = 32) with the augmented row n carried along:
+        //      diagonal block in one warp's registers, panel by forward substitution (thread per row), trailing
+        //      update on the FP64 tensor cores straight from the tile-packed storage ----
+        const int lane = tid & 31, warp = tid >> 5, fr = lane >> 2, fc = lane & 3;
+        const int NT = (n + 8) >> 3;  // tile rows, including the one holding the augmented row
+        const int PS = kNB + 1;
+        for (int kb = 0; kb < n; kb += kNB) {
+            const int nb = min(kNB, n - kb);
+            for (int idx = tid; idx < kNB * kNB; idx += nth) {  // stage the diagonal block, identity padded
+                const int r = idx >> 5, c = idx & 31;
+                s_D[r * PS + c] = (r < nb && c <= r) ? A(kb + r, kb + c) : ((r == c) ? 1.0 : 0.0);
+            }
+            __syncthreads();
+            if (warp == 0 && !warp_chol32(s_D, PS, s_inv, lane)) s_fail = 1;
+            __syncthreads();
+            PHASE_ACC(8);
+            if (s_fail) break;
+            for (int idx = tid; idx < nb * kNB; idx += nth) {
+                const int r = idx >> 5, c = idx & 31;
+                if (c <= r) A(kb + r, kb + c) = s_D[r * PS + c];
+            }
+            if (tid < nb) s_invd[kb + tid] = s_inv[tid];
+            // panel: rows below the block, including the augmented row n; X L^T = B column by column, each finished
+            // column is eliminated from the remaining ones right away (independent FMAs, short critical path)
+            const int r0 = kb + nb, m = n + 1 - r0;
+            for (int i = tid; i < m; i += nth) {
+                double x[kNB];
+#pragma unroll
+                for (int c = 0; c < kNB; ++c) x[c] = (c < nb) ? A(r0 + i, kb + c) : 0.0;
+#pragma unroll
+                for (int q = 0; q < kNB; ++q) {
+                    x[q] *= s_inv[q];
+#pragma unroll
+                    for (int c = q + 1; c < kNB; ++c) x[c] -= x[q] * s_D[c * PS + q];
                 }
-                __syncwarp();
+#pragma unroll
+                for (int c = 0; c < kNB; ++c)
+                    if (c < nb) A(r0 + i, kb + c) = x[c];
             }
-        }
-        __syncthreads();
-        if (s_fail) break;
-        for (int idx = tid; idx < nb * nb; idx += nth) {
-            const int r = idx / nb, c = idx - r * nb;
-            if (c <= r) A[(size_t)(kb + r) * ld + kb + c] = s_D[r * PS + c];
-        }
-        // panel: rows below the block, including the augmented row n
-        const int r0 = kb + nb, m = n + 1 - r0;
-        for (int i = tid; i < m; i += nth) {
-            double x[kNB];
-            const double* arow = A + (size_t)(r0 + i) * ld + kb;
-            for (int c = 0; c < nb; ++c) x[c] = arow[c];
-            for (int c = 0; c < nb; ++c) {
-                double s = x[c];
-                for (int q = 0; q < c; ++q) s -= x[q] * s_D[c * PS + q];
-                x[c] = s / s_D[c * PS + c];
+            __syncthreads();
+            PHASE_ACC(9);
+            if (nb < kNB) break;  // last block: only the augmented row is left below it
+            // trailing update: tile (I, J) -= sum_K tile(I, K) tile(J, K)^T over the 4 panel tile columns
+            const int T0 = r0 >> 3, K0 = kb >> 3, mt = NT - T0;
+            for (int t = warp; t < mt * (mt + 1) / 2; t += nth >> 5) {
+                int i = (int)((sqrtf(8.0f * (float)t + 1.0f) - 1.0f) * 0.5f);
+                while ((i + 1) * (i + 2) / 2 <= t) ++i;
+                while (i * (i + 1) / 2 > t) --i;
+                const int j = t - i * (i + 1) / 2;
+                const double* pa = A.tile(T0 + i, K0) + fr * 4 + fc;
+                const double* pb = A.tile(T0 + j, K0) + fr * 4 + fc;
+                double a0 = 0.0, a1 = 0.0, b0 = 0.0, b1 = 0.0;  // two independent accumulator chains
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    dmma(a0, a1, pa[64 * k], pb[64 * k]);
+                    dmma(b0, b1, pa[64 * k + 32], pb[64 * k + 32]);
+                }
+                double2* pc = reinterpret_cast<double2*>(A.tile(T0 + i, T0 + j) + (fc >> 1) * 32 + fr * 4 + (fc & 1) * 2);
+                double2 cv = *pc;
+                cv.x -= a0 + b0;
+                cv.y -= a1 + b1;
+                *pc = cv;
             }
-            double* aw = A + (size_t)(r0 + i) * ld + kb;
-            for (int c = 0; c < nb; ++c) { aw[c] = x[c]; s_P[i * PS + c] = x[c]; }
+            __syncthreads();
+            PHASE_ACC(10);
         }
-        __syncthreads();
-        // trailing update: A[r0+i][r0+j] -= P[i] . P[j], j <= i, skipping the (n, n) corner
-        const long long ntri = (long long)m * (m + 1) / 2;
-        for (long long idx = tid; idx < ntri; idx += nth) {
-            int i = (int)((sqrt(8.0 * (double)idx + 1.0) - 1.0) * 0.5);
-            while ((long long)(i + 1) * (i + 2) / 2 <= idx) ++i;
-            while ((long long)i * (i + 1) / 2 > idx) --i;
-            const int j = (int)(idx - (long long)i * (i + 1) / 2);
-            if (i == m - 1 && j == m - 1) continue;
-            double s = 0.0;
-            for (int c = 0; c < nb; ++c) s += s_P[i * PS + c] * s_P[j * PS + c];
-            A[(size_t)(r0 + i) * ld + r0 + j] -= s;
+        if (s_fail) {
+            if (tid == 0) st.solve_failed = 1;
+            return;
         }
+        PHASE_MARK(4);
+        // ---- blocked back substitution L^T d = y (y = augmented row), delta_f = -d ----
+        for (int c = tid; c < n; c += nth) s_y[c] = A(n, c);
         __syncthreads();
-    }
-    if (s_fail) {
-        if (tid == 0) st.solve_failed = 1;
-        return;
-    }
-    // ---- back substitution L^T d = y (y = augmented row), delta_f = -d ----
-    for (int c = tid; c < n; c += nth) s_y[c] = A[(size_t)n * ld + c];
-    __syncthreads();
-    for (int i = n - 1; i >= 0; --i) {
-        const double di = s_y[i] / A[(size_t)i * ld + i];
+        for (int kb = ((n - 1) / kNB) * kNB; kb >= 0; kb -= kNB) {
+            const int nb = min(kNB, n - kb);
+            for (int idx = tid; idx < kNB * kNB; idx += nth) {  // stage the diagonal block of L
+                const int r = idx >> 5, c = idx & 31;
+                s_D[r * PS + c] = (r < nb && c <= r) ? A(kb + r, kb + c) : 0.0;
+            }
+            __syncthreads();
+            if (warp == 0) {  // lane k owns unknown kb + k of the diagonal block
+                double yk = (lane < nb) ? s_y[kb + lane] : 0.0;
+                const double ik = (lane < nb) ? s_invd[kb + lane] : 0.0;
+#pragma unroll 4
+                for (int i = nb - 1; i >= 0; --i) {
+                    const double lik = s_D[i * PS + lane];  // zero above the diagonal
+                    const double di = __shfl_sync(0xffffffffu, yk * ik, i);
+                    yk = (lane == i) ? di : yk - lik * di;
+                }
+                if (lane < nb) s_y[kb + lane] = yk;
+            }
+            __syncthreads();
+            for (int k = tid; k < kb; k += nth) {
+                double acc = s_y[k];
+                for (int i = 0; i < nb; ++i) acc -= A(kb + i, k) * s_y[kb + i];
+                s_y[k] = acc;
+            }
+            __syncthreads();
+        }
+    } else {
+        // ---- blocked right-looking Cholesky of A[0..n) with the augmented row n carried along ----
+        const int PS = kNB + 1;
+        for (int kb = 0; kb < n; kb += kNB) {
+            const int nb = min(kNB, n - kb);
+            for (int idx = tid; idx < nb * nb; idx += nth) {
+                const int r = idx / nb, c = idx - r * nb;
+                s_D[r * PS + c] = (c <= r) ? A(kb + r, kb + c) : 0.0;
+            }
+            __syncthreads();
+            if (tid < 32) {  // factor the diagonal block with one warp: lane = row
+                const int lane = tid;
+                for (int j = 0; j < nb; ++j) {
+                    const double djj = s_D[j * PS + j];
+                    if (!(djj > 0.0) || !isfinite(djj)) { if (lane == 0) s_fail = 1; break; }
+                    const double piv = sqrt(djj);
+                    __syncwarp();
+                    if (lane == j) s_D[j * PS + j] = piv;
+                    if (lane > j && lane < nb) s_D[lane * PS + j] /= piv;
+                    __syncwarp();
+                    if (lane > j && lane < nb) {
+                        const double lij = s_D[lane * PS + j];
+                        for (int c = j + 1; c <= lane; ++c) s_D[lane * PS + c] -= lij * s_D[c * PS + j];
+                    }
+                    __syncwarp();
+                }
+            }
+            __syncthreads();
+            if (s_fail) break;
+            for (int idx = tid; idx < nb * nb; idx += nth) {
+                const int r = idx / nb, c = idx - r * nb;
+                if (c <= r) A(kb + r, kb + c) = s_D[r * PS + c];
+            }
+            // panel: rows below the block, including the augmented row n
+            const int r0 = kb + nb, m = n + 1 - r0;
+            for (int i = tid; i < m; i += nth) {
+                double x[kNB];
+                for (int c = 0; c < nb; ++c) x[c] = A(r0 + i, kb + c);
+                for (int c = 0; c < nb; ++c) {
+                    double s = x[c];
+                    for (int q = 0; q < c; ++q) s -= x[q] * s_D[c * PS + q];
+                    x[c] = s / s_D[c * PS + c];
+                }
+                for (int c = 0; c < nb; ++c) { A(r0 + i, kb + c) = x[c]; s_P[i * PS + c] = x[c]; }
+            }
+            __syncthreads();
+            // trailing update: A[r0+i][r0+j] -= P[i] . P[j], j <= i, skipping the (n, n) corner
+            const long long ntri = (long long)m * (m + 1) / 2;
+            for (long long idx = tid; idx < ntri; idx += nth) {
+                int i = (int)((sqrt(8.0 * (double)idx + 1.0) - 1.0) * 0.5);
+                while ((long long)(i + 1) * (i + 2) / 2 <= idx) ++i;
+                while ((long long)i * (i + 1) / 2 > idx) --i;
+                const int j = (int)(idx - (long long)i * (i + 1) / 2);
+                if (i == m - 1 && j == m - 1) continue;
+                double s = 0.0;
+                for (int c = 0; c < nb; ++c) s += s_P[i * PS + c] * s_P[j * PS + c];
+                A(r0 + i, r0 + j) -= s;
+            }
+            __syncthreads();
+        }
+        if (s_fail) {
+            if (tid == 0) st.solve_failed = 1;
+            return;
+        }
+        // ---- back substitution L^T d = y (y = augmented row), delta_f = -d ----
+        for (int c = tid; c < n; c += nth) s_y[c] = A(n, c);
         __syncthreads();
-        if (tid == 0) s_y[i] = di;
-        for (int k = tid; k < i; k += nth) s_y[k] -= A[(size_t)i * ld + k] * di;
-        __syncthreads();
+        for (int i = n - 1; i >= 0; --i) {
+            const double di = s_y[i] / A(i, i);
+            __syncthreads();
+            if (tid == 0) s_y[i] = di;
+            for (int k = tid; k < i; k += nth) s_y[k] -= A(i, k) * di;
+            __syncthreads();
+        }
     }
+    PHASE_MARK(5);
     double* delta_f = bd.delta_f + (size_t)w * bd.nr_cap_max;
     double model = 0.0;
     int bad = 0;
@@ -1172,6 +1285,8 @@ __global__ void __launch_bounds__(512, 1) k_reduced_solve(BatchDev bd, SolvePara
         st.f_model = a; st.f_step_sq = b; st.f_xnorm_sq = c; st.f_gmax = g;
         if (s_fail) st.solve_failed = 1;
     }
+    PHASE_MARK(6);
+    PHASE_PRINT;
 }
 
 // =====================================================================================================================
@@ -1464,14 +1579,20 @@ __global__ void __launch_bounds__(256) k_trim_eval(BatchDev bd, SolveParams sp) 
     }
 }
 
-// quantile rejection per group by exact rank (ties broken by landmark index), then start the next solve
+// quantile rejection per group by exact rank (ties broken by landmark index), then start the next solve.  The value
+// of rank `num` (the smallest rejected one) is found with an 8-pass MSB-first radix select over the IEEE bit patterns
+// (non-negative doubles order like unsigned integers); only exact ties with it need the O(n) index count.
 __global__ void __launch_bounds__(512) k_trim_select(BatchDev bd, SolveParams sp) {
     const int w = blockIdx.x;
     WinState& st = bd.state[w];
     if (st.phase != PH_TRIM) return;
     const WinDesc& wd = bd.desc[w];
     __shared__ int s_n;
+    __shared__ unsigned s_hist[256];
+    __shared__ unsigned long long s_prefix;
+    __shared__ int s_k;
     const double quant[3] = {sp.depth_quantile, sp.reprojection_quantile, sp.gp_quantile};
+    const int* orig = bd.lm_orig + wd.lm_off;  // ties are broken by the caller's landmark index
     for (int j = threadIdx.x; j < wd.n_lm; j += blockDim.x) bd.trim_reject[wd.lm_off + j] = 0;
     for (int g = 0; g < 3; ++g) {
         const double* v = bd.trim_val + g * (size_t)bd.tot_lm + wd.lm_off;
@@ -1479,25 +1600,61 @@ __global__ void __launch_bounds__(512) k_trim_select(BatchDev bd, SolveParams sp
         __syncthreads();
         int cnt = 0;
         for (int j = threadIdx.x; j < wd.n_lm; j += blockDim.x) cnt += (v[j] >= 0.0);
-        atomicAdd(&s_n, cnt);
+        if (cnt) atomicAdd(&s_n, cnt);
         __syncthreads();
         const int N = s_n;
         __syncthreads();
         if (N == 0 || N < sp.min_residual_groups) continue;
         const int num = (int)((double)N * quant[g]);
         if (num >= N) continue;
+        if (threadIdx.x == 0) { s_prefix = 0ull; s_k = num; }
+        unsigned long long mask = 0ull;
+        for (int shift = 56; shift >= 0; shift -= 8) {
+            if (threadIdx.x < 256) s_hist[threadIdx.x] = 0u;
+            __syncthreads();
+            const unsigned long long prefix = s_prefix;
+            for (int j = threadIdx.x; j < wd.n_lm; j += blockDim.x) {
+                const double vj = v[j];
+                if (!(vj >= 0.0)) continue;
+                const unsigned long long key = (unsigned long long)__double_as_longlong(vj) & 0x7fffffffffffffffull;
+                if ((key & mask) == prefix) atomicAdd(&s_hist[(key >> shift) & 255ull], 1u);
+            }
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                int k = s_k, bin = 0;
+                for (; bin < 255; ++bin) {
+                    const int h = (int)s_hist[bin];
+                    if (k < h) break;
+                    k -= h;
+                }
+                s_k = k;
+                s_prefix = prefix | ((unsigned long long)bin << shift);
+            }
+            mask |= 255ull << shift;
+            __syncthreads();
+        }
+        const unsigned long long pivot = s_prefix;  // bit pattern of the value with rank `num`
+        const int tie_keep = s_k;                   // ties with fewer than tie_keep smaller-index ties stay
         for (int j = threadIdx.x; j < wd.n_lm; j += blockDim.x) {
             const double vj = v[j];
             if (!(vj >= 0.0)) continue;
-            int rank = 0;
-            const int* orig = bd.lm_orig + wd.lm_off;  // ties are broken by the caller's landmark index
-            const int oj = orig[j];
-            for (int k = 0; k < wd.n_lm; ++k) {
-                const double vk = v[k];
-                rank += (vk >= 0.0) && (vk < vj || (vk == vj && orig[k] < oj));
+            const unsigned long long key = (unsigned long long)__double_as_longlong(vj) & 0x7fffffffffffffffull;
+            if (key < pivot) continue;
+            bool reject = key > pivot;
+            if (!reject) {
+                const int oj = orig[j];
+                int before = 0;
+                for (int k = 0; k < wd.n_lm; ++k) {
+                    const double vk = v[k];
+                    if (!(vk >= 0.0)) continue;
+                    const unsigned long long kk = (unsigned long long)__double_as_longlong(vk) & 0x7fffffffffffffffull;
+                    before += (kk == pivot && orig[k] < oj);
+                }
+                reject = before >= tie_keep;
             }
-            if (rank >= num) bd.trim_reject[wd.lm_off + j] = 1;
+            if (reject) bd.trim_reject[wd.lm_off + j] = 1;
         }
+        __syncthreads();
     }
     __syncthreads();
     for (int j = threadIdx.x; j < wd.n_lm; j += blockDim.x)
@@ -1556,18 +1713,24 @@ __global__ void k_reset_state(BatchDev bd, int rounds_total_override, int min_la
 // launch wrappers
 // =====================================================================================================================
 static inline size_t schur_smem() { return (size_t)2 * 64 * kKS * sizeof(double); }
-static inline size_t schur_small_smem() { return (size_t)kSmallTiles * 8 * kKS * sizeof(double); }
 static inline size_t schur_tma_smem() { return (size_t)2 * kStageDoubles * sizeof(double); }
-static inline size_t solve_smem(int ld) { return ((size_t)4 * ld + kNB * (kNB + 1) + (size_t)ld * (kNB + 1)) * sizeof(double); }
+static inline size_t solve_smem(int ld) { return ((size_t)5 * ld + kNB + kNB * (kNB + 1) + (size_t)ld * (kNB + 1)) * sizeof(double); }
+static inline size_t solve_tiled_smem(int ld) {
+    const int nt = ld / 8;
+    return ((size_t)5 * ld + kNB + kNB * (kNB + 1) + (size_t)nt * (nt + 1) / 2 * 64) * sizeof(double);
+}
 
 cudaError_t configure_kernels(int nr_cap_max) {
     cudaError_t e = cudaFuncSetAttribute(k_schur_syrk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)schur_smem());
     if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(k_schur_syrk_small, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)schur_small_smem());
-    if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(k_schur_syrk_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)schur_tma_smem());
     if (e != cudaSuccess) return e;
-    return cudaFuncSetAttribute(k_reduced_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)solve_smem(nr_cap_max));
+    if (nr_cap_max <= 192) {
+        e = cudaFuncSetAttribute(k_reduced_solve<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)solve_tiled_smem(nr_cap_max));
+        if (e != cudaSuccess) return e;
+    }
+    return cudaFuncSetAttribute(k_reduced_solve<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)solve_smem(nr_cap_max));
 }
 
 void launch_reset(const BatchDev& bd, const LaunchCfg& lc, cudaStream_t s) {
@@ -1591,13 +1754,13 @@ void launch_pass(const BatchDev& bd, const SolveParams& sp, const LaunchCfg& lc,
     if (bd.tot_gp > 0 && bd.use_panel) k_gp_panel<<<dim3((bd.max_gp * 10 + 255) / 256, B), 256, 0, s>>>(bd);
     if (lc.small_syrk && bd.use_panel) {
         k_schur_syrk_tma<<<dim3(bd.p_split, B), 512, schur_tma_smem(), s>>>(bd);
-    } else if (lc.small_syrk) {
-        k_schur_syrk_small<<<dim3(bd.p_split, B), 512, schur_small_smem(), s>>>(bd);
     } else {
         const int nb = lc.nr_cap_max / 64;
         k_schur_syrk<<<dim3(nb * (nb + 1) / 2, bd.p_split, B), 256, schur_smem(), s>>>(bd);
     }
-    k_reduced_solve<<<B, 512, solve_smem(lc.nr_cap_max), s>>>(bd, sp);
+    if (bd.p_split > 1) k_sred_reduce<<<dim3((lc.nr_cap_max * lc.nr_cap_max + 255) / 256, B), 256, 0, s>>>(bd);
+    if (lc.nr_cap_max <= 192 && !bd.solve_row_major) k_reduced_solve<true><<<B, 512, solve_tiled_smem(lc.nr_cap_max), s>>>(bd, sp);
+    else k_reduced_solve<false><<<B, 512, solve_smem(lc.nr_cap_max), s>>>(bd, sp);
     k_backsub<<<dim3((bd.max_lm + 15) / 16, B), 256, 0, s>>>(bd);
     launch_eval_obs<false>(bd, sp, s);
     if (bd.tot_gp > 0) k_gp_eval<false><<<B, 256, 0, s>>>(bd, sp);
@@ -1605,9 +1768,11 @@ void launch_pass(const BatchDev& bd, const SolveParams& sp, const LaunchCfg& lc,
     k_trim_eval<<<g_lm, 256, 0, s>>>(bd, sp);
     k_trim_select<<<B, 512, 0, s>>>(bd, sp);
     if (cnt) {
-        cnt->launches_total += 11;
-        cnt->launches_jacobian += 1; cnt->launches_prep += 2; cnt->launches_schur += 1; cnt->launches_solve += 2;
-        cnt->launches_backsub += 1; cnt->launches_cost += 1; cnt->launches_update += 1; cnt->launches_trim += 2;
+        const int gp = bd.tot_gp > 0 ? 1 : 0;
+        const int prep = 2 + (lc.max_rank + 1) + (gp && bd.use_panel ? 1 : 0);  // pose blocks, landmark blocks, V rows
+        cnt->launches_total += (bd.use_panel ? 1 : 0) + 1 + 1 + gp + prep + 1 + (bd.p_split > 1 ? 1 : 0) + 1 + 1 + 1 + gp + 1 + 2;
+        cnt->launches_jacobian += 1; cnt->launches_prep += prep + gp; cnt->launches_schur += 1; cnt->launches_solve += 2;
+        cnt->launches_backsub += 1; cnt->launches_cost += 1 + gp; cnt->launches_update += 1; cnt->launches_trim += 2;
     }
 }
 

@@ -71,7 +71,8 @@ __device__ inline double plane_motion(const double* p0, const double* p1, const 
 
 // Warp-cooperative J^T J / J^T r accumulation of one residual block (all 32 lanes pass identical arguments).
 // parts: column offsets (or -1 for constant blocks) and sizes; J row-major nres x (sum of sizes), already times sqrt(rho').
-__device__ inline void warp_add_block(double* A, int ld, double* fdiag, double* g, int nres, const double* r, int nparts,
+template <typename Mat>
+__device__ inline void warp_add_block(const Mat& A, double* fdiag, double* g, int nres, const double* r, int nparts,
                                       const int* off, const int* sz, const double* J, int lane) {
     int cols[16];
     double Jc[3][16];
@@ -92,7 +93,7 @@ __device__ inline void warp_add_block(double* A, int ld, double* fdiag, double* 
         if (cols[b] > cols[a]) continue;
         double s = 0.0;
         for (int i = 0; i < nres; ++i) s += Jc[i][a] * Jc[i][b];
-        A[(size_t)cols[a] * ld + cols[b]] += s;
+        A(cols[a], cols[b]) += s;
         if (a == b) {
             fdiag[cols[a]] += s;
             double t = 0.0;
