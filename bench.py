@@ -38,8 +38,8 @@ def usable_cores():
 
 
 def make_windows(n_distinct, rank, config=2):
-    from limo_b200 import synth
-    return [synth.make_window(config, seed=0xBA5E0000 + 1000 * rank + i) for i in range(n_distinct)]
+    from limo_b200 import parallel
+    return parallel.windows_for_rank(n_distinct, rank, config)
 
 
 class ClockSampler:
@@ -153,20 +153,17 @@ def main():
     ap.add_argument("--cpu-sample", type=int, default=16, help="window solves timed for cpu_baseline (~0.7 s each)")
     args = ap.parse_args()
 
-    rank = int(os.environ.get("RANK", "0"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
+    from limo_b200 import parallel
+    rank, local_rank, world = parallel.rank_info()
     if args.impl == "reference":
         run_reference(args, rank, world)
         return
 
     import torch
-    import torch.distributed as dist
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device -- the kba_b200 path has no CPU fallback")
     torch.cuda.set_device(local_rank)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    parallel.init("nccl", torch.device("cuda", local_rank))
     from limo_b200 import capi
 
     n_distinct = max(1, min(args.distinct, args.batch))
@@ -180,9 +177,7 @@ def main():
     batch = h.batch(windows)
 
     def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
+        parallel.barrier(cuda=True)
 
     # ---- warm-up ----
     for _ in range(args.warmup):
@@ -229,10 +224,7 @@ def main():
     clocks = sampler.stop()  # sampled over both timed regions
     h2d, d2h = batch.transfer_bytes()
 
-    t = torch.tensor([ms, ms_e2e], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms, ms_e2e = float(t[0]), float(t[1])
+    ms, ms_e2e = parallel.max_over_ranks([ms, ms_e2e], device="cuda")  # the slowest rank defines the step
 
     if rank == 0:
         total_windows = world * args.batch * args.steps
@@ -273,8 +265,7 @@ def main():
         print(json.dumps(out))
     batch.close()
     h.close()
-    if world > 1:
-        dist.destroy_process_group()
+    parallel.finalize()
 
 
 if __name__ == "__main__":
