@@ -236,6 +236,23 @@ typedef struct kba_counters {
 int kba_get_counters(kba_handle* h, kba_counters* out, int reset);
 int kba_enable_kernel_timing(kba_handle* h, int on);
 
+/* ---- ONE large window sharded over several GPUs by landmark blocks (BASELINE config 5) --------------------------------
+ * Every rank (one process per GPU) holds ALL keyframes and a block of the landmarks with their observations
+ * (limo_b200/parallel.py::shard_window shows the partition).  Per LM iteration the ranks exchange, with NCCL all-reduce
+ * over NVLink, the reduced pose system [S | rhs] their landmarks contribute to, the per-keyframe J^T J blocks and the
+ * cost / model-decrease scalars; the reduced solve and the LM controller then run replicated and bit-identically on
+ * every rank (an NCCL all-reduce delivers the same bits everywhere).  Trimming quantiles are taken over all ranks'
+ * landmarks.  There is no reference counterpart (the reference is single-process); north_star asks for it.
+ * Restrictions: one window per batch, no ground-plane residuals (n_gp = 0), every free keyframe is in the program. */
+typedef struct kba_shard_comm kba_shard_comm;
+#define KBA_SHARD_ID_BYTES 128
+int kba_shard_unique_id(void* id_out);  /* KBA_SHARD_ID_BYTES; rank 0 creates it, the host broadcasts it to all ranks */
+int kba_shard_comm_create(kba_handle* h, int32_t rank, int32_t world, const void* id, kba_shard_comm** out); /* collective */
+void kba_shard_comm_destroy(kba_shard_comm* c);
+/* b holds this rank's shard; lm_begin = index of its first landmark in the whole window, lm_total = landmarks of the
+ * whole window.  Afterwards kba_batch_solve is a collective call: every rank must make it. */
+int kba_batch_set_shard(kba_batch* b, kba_shard_comm* comm, int32_t lm_begin, int32_t lm_total);
+
 /* ---- lidar depth extraction (BASELINE config 4) --------------------------------------------------------------------
  * Replaces the un-vendored mono_lidar_depth::DepthEstimator call the limo front end makes per frame (install_repos.sh:9;
  * in-tree only its parameter file demo_keyframe_bundle_adjustment_meta/res/mono_lidar_fusion_parameters.yaml, whose

@@ -17,7 +17,8 @@ _lib = None
 SYMBOLS = ["kba_version", "kba_last_error", "kba_default_options", "kba_create", "kba_destroy", "kba_set_stream",
            "kba_solve_window", "kba_solve_batch", "kba_eval", "kba_batch_create", "kba_batch_upload",
            "kba_batch_solve", "kba_batch_download", "kba_batch_transfer_bytes", "kba_batch_jacobian_pass", "kba_batch_destroy",
-           "kba_get_counters", "kba_enable_kernel_timing", "kba_lidar_default_options", "kba_lidar_depth"]
+           "kba_get_counters", "kba_enable_kernel_timing", "kba_lidar_default_options", "kba_lidar_depth",
+           "kba_shard_unique_id", "kba_shard_comm_create", "kba_shard_comm_destroy", "kba_batch_set_shard"]
 
 
 class KbaError(RuntimeError):
@@ -52,6 +53,11 @@ def lib():
         L.kba_batch_destroy.restype = None
         L.kba_get_counters.argtypes = [vp, C.POINTER(KbaCounters), C.c_int]
         L.kba_enable_kernel_timing.argtypes = [vp, C.c_int]
+        L.kba_shard_unique_id.argtypes = [C.c_char_p]
+        L.kba_shard_comm_create.argtypes = [vp, C.c_int32, C.c_int32, C.c_char_p, C.POINTER(vp)]
+        L.kba_shard_comm_destroy.argtypes = [vp]
+        L.kba_shard_comm_destroy.restype = None
+        L.kba_batch_set_shard.argtypes = [vp, vp, C.c_int32, C.c_int32]
         L.kba_lidar_default_options.argtypes = [C.POINTER(KbaLidarOptions)]
         L.kba_lidar_default_options.restype = None
         fp = C.POINTER(C.c_float)
@@ -104,6 +110,11 @@ class Batch:
             r.c = c
         return results
 
+    def set_shard(self, comm, lm_begin, lm_total):
+        """this batch holds one rank's shard of a window split by landmark blocks; solve() becomes a collective call"""
+        _check(lib().kba_batch_set_shard(self._p, comm._p, int(lm_begin), int(lm_total)))
+        self._comm = comm
+
     def transfer_bytes(self):
         """(host->device bytes of the last upload, device->host bytes of the last download)"""
         a, b = C.c_int64(), C.c_int64()
@@ -125,6 +136,31 @@ class Batch:
             self.close()
         except Exception:
             pass
+
+
+SHARD_ID_BYTES = 128
+
+
+def shard_unique_id():
+    """NCCL unique id (bytes) -- create on rank 0 and broadcast to the other ranks"""
+    buf = C.create_string_buffer(SHARD_ID_BYTES)
+    _check(lib().kba_shard_unique_id(buf))
+    return bytes(buf.raw)
+
+
+class ShardComm:
+    """NCCL communicator of the sharded window solve (kba_shard_comm_create is collective over all ranks)"""
+
+    def __init__(self, handle, rank, world, unique_id):
+        assert len(unique_id) == SHARD_ID_BYTES
+        self._p = C.c_void_p()
+        self.rank, self.world = rank, world
+        _check(lib().kba_shard_comm_create(handle._p, rank, world, C.c_char_p(unique_id), C.byref(self._p)))
+
+    def close(self):
+        if self._p:
+            lib().kba_shard_comm_destroy(self._p)
+            self._p = C.c_void_p()
 
 
 class Handle:

@@ -97,6 +97,10 @@ struct kba_batch {
         *p = (T*)q;
         return 0;
     }
+    void dev_free(void* q) {
+        scratch.erase(std::remove(scratch.begin(), scratch.end(), q), scratch.end());
+        cudaFree(q);
+    }
     void release() {
         desc.release(); pose0.release(); plane0.release(); cam.release(); lm0.release(); lm_weight.release();
         kf_fixed.release(); lm_ptr.release(); obs_kf.release(); obs_cam.release(); obs_lm.release(); kf_ptr.release();
@@ -236,6 +240,9 @@ static void fill_window(kba_batch* b, int wi, const kba_window* w) {
     }
 }
 
+struct kba_shard_comm;
+kba::Exchange kba_shard_exchange(kba_shard_comm* c);  // kba_shard.cu
+
 extern "C" {
 
 int kba_version(void) { return KBA_VERSION_MAJOR * 100 + KBA_VERSION_MINOR; }
@@ -364,7 +371,7 @@ int kba_batch_create(kba_handle* h, int32_t n_windows, const kba_window* w, kba_
         const int nb = nr_cap_max / 64, pairs = nb * (nb + 1) / 2;
         int max_chunks = 1;
         for (auto& d : b->desc_h) max_chunks = std::max(max_chunks, d.n_chunks);
-        int p = (2 * h->sm_count + n_windows * pairs - 1) / (n_windows * pairs);
+        int p = std::min(16, (6 * h->sm_count + n_windows * pairs - 1) / (n_windows * pairs));
         b->lc.small_syrk = (max_rows <= 184);
         if (b->lc.small_syrk) p = (h->sm_count + n_windows - 1) / n_windows;  // one CTA per SM, each owning all tiles
         bd.p_split = std::max(1, std::min(p, max_chunks));
@@ -376,6 +383,7 @@ int kba_batch_create(kba_handle* h, int32_t n_windows, const kba_window* w, kba_
         bd.eval_tiles_cost = std::max(1, knob("KBA_EVAL_TILES_COST", 8));
         bd.eval_min_blocks = knob("KBA_EVAL_MIN_BLOCKS", 2);
         bd.solve_row_major = knob("KBA_SOLVE_ROW_MAJOR", 0);
+        bd.solve_tiled = (nr_cap_max <= 192 && !bd.solve_row_major) ? 1 : 0;
     }
     bd.bs_parts = (bd.max_lm + 15) / 16;
     int bad = 0;
@@ -390,13 +398,9 @@ int kba_batch_create(kba_handle* h, int32_t n_windows, const kba_window* w, kba_
     bad |= b->chunk_lm0.alloc(chunks, true); bad |= b->chunk_lm1.alloc(chunks, true);
     bad |= b->chunk_k0.alloc(chunks, true); bad |= b->chunk_k1.alloc(chunks, true);
     bad |= b->lm_orig.alloc(lm, true); bad |= b->obs_orig.alloc(obs, true); bad |= b->obs_rank.alloc(obs, true);
-    {   // dense V panels of the TMA-fed Schur kernel: worst case 96 columns x 196 rows per chunk
-        long long cap = 0;
-        for (auto& d : b->desc_h) cap = std::max<long long>(cap, (long long)d.n_chunks * 96 * 196);
-        bd.use_panel = b->lc.small_syrk ? 1 : 0;
-        bd.panel_cap = bd.use_panel ? cap : 0;
-        for (int i = 0; i < n_windows; ++i) b->desc_h[i].panel_off = (long long)i * bd.panel_cap;
-        bad |= b->dev_alloc(&bd.vpanel, (size_t)n_windows * bd.panel_cap);
+    {   // dense V panels of the Schur kernels; sized in kba_batch_upload from the chunks' keyframe ranges
+        bd.panel_cap = 0;
+        bd.vpanel = nullptr;
         bad |= b->dev_alloc(&bd.chunk_poff, chunks); bad |= b->dev_alloc(&bd.chunk_rs, chunks);
     }
     bad |= b->dev_alloc(&bd.chunk_t0, chunks); bad |= b->dev_alloc(&bd.chunk_t1, chunks); bad |= b->dev_alloc(&bd.obs_row, obs);
@@ -416,7 +420,6 @@ int kba_batch_create(kba_handle* h, int32_t n_windows, const kba_window* w, kba_
     bad |= b->dev_alloc(&bd.lm_g, 3 * lm); bad |= b->dev_alloc(&bd.lm_lambda, 3 * lm); bad |= b->dev_alloc(&bd.trim_val, 3 * lm);
     bad |= b->dev_alloc(&bd.trim_reject, lm);
     bad |= b->dev_alloc(&bd.res, 3 * obs); bad |= b->dev_alloc(&bd.jp, 18 * obs); bad |= b->dev_alloc(&bd.jl, 9 * obs);
-    bad |= b->dev_alloc(&bd.vobs, 18 * obs);
     bad |= b->dev_alloc(&bd.cost_part_x, (size_t)n_windows * bd.cost_parts); bad |= b->dev_alloc(&bd.cost_part_c, (size_t)n_windows * bd.cost_parts);
     bad |= b->dev_alloc(&bd.bs_part, (size_t)n_windows * bd.bs_parts * 4);
     bad |= b->dev_alloc(&bd.sred, (size_t)soff * bd.p_split); bad |= b->dev_alloc(&bd.amat, (size_t)soff);
@@ -484,6 +487,27 @@ int kba_batch_upload(kba_batch* b, int32_t n_windows, const kba_window* w) {
         }
     }
     for (int i = 0; i < n_windows; ++i) b->lc.max_rank = std::max(b->lc.max_rank, b->desc_h[i].max_rank);
+    {   // V panel capacity: per chunk 96 columns x (rows of its keyframe range + right-hand-side tile), see k_solve_begin
+        long long need = 0;
+        for (int i = 0; i < n_windows; ++i) {
+            const WinDesc& d = b->desc_h[i];
+            const int rows_per_kf = (w[i].n_gp > 0 || w[i].plane_reg_weight > 0) ? 10 : 6;
+            long long tot = 0;
+            for (int c = 0; c < d.n_chunks; ++c) {
+                const int nk = b->chunk_k1.h[d.chunk_off + c] - b->chunk_k0.h[d.chunk_off + c] + 1;
+                if (nk <= 0) continue;
+                const int rows = 8 * ((rows_per_kf * nk + 14 + 7) / 8) + 8;
+                tot += 96LL * (((rows - 4 + 15) / 16) * 16 + 4);
+            }
+            need = std::max(need, tot);
+        }
+        if (need > b->bd.panel_cap) {
+            if (b->bd.vpanel) { CU(cudaStreamSynchronize(b->h->stream)); b->dev_free(b->bd.vpanel); b->bd.vpanel = nullptr; }
+            b->bd.panel_cap = (need + 1) & ~1LL;
+            if (b->dev_alloc(&b->bd.vpanel, (size_t)n_windows * b->bd.panel_cap)) return fail(KBA_ERR_CUDA, "out of device memory (V panels)");
+        }
+        for (int i = 0; i < n_windows; ++i) { b->desc_h[i].panel_off = (long long)i * b->bd.panel_cap; b->desc.h[i].panel_off = b->desc_h[i].panel_off; }
+    }
     cudaStream_t s = b->h->stream;
     CU(b->desc.upload(s)); CU(b->pose0.upload(s)); CU(b->plane0.upload(s)); CU(b->kf_fixed.upload(s)); CU(b->cam.upload(s));
     CU(b->lm0.upload(s)); CU(b->lm_weight.upload(s)); CU(b->lm_ptr.upload(s));
@@ -542,7 +566,7 @@ int kba_batch_solve(kba_batch* b, const kba_options* opt) {
     const auto t0 = std::chrono::steady_clock::now();
     int check_every = 4;
     for (int pass = 0; pass < max_passes; ++pass) {
-        launch_pass(b->bd, sp, lc, &h->counters, s);
+        if (launch_pass(b->bd, sp, lc, &h->counters, s)) return KBA_ERR_NCCL;  // message set by the exchange
         if ((pass + 1) % check_every == 0 || pass + 1 == max_passes) {
             launch_count_active(b->bd, s);
             CU(b->n_active.download(s));
@@ -565,6 +589,31 @@ int kba_batch_solve(kba_batch* b, const kba_options* opt) {
         CU(cudaEventElapsedTime(&ms, h->ev_pool[i], h->ev_pool[i + 1]));
         h->counters.ms_jacobian += ms;
     }
+    return KBA_OK;
+}
+
+int kba_batch_set_shard(kba_batch* b, kba_shard_comm* comm, int32_t lm_begin, int32_t lm_total) {
+    if (!b || !comm) return fail(KBA_ERR_BAD_ARG, "bad argument to kba_batch_set_shard");
+    BatchDev& bd = b->bd;
+    if (bd.n_win != 1) return fail(KBA_ERR_BAD_ARG, "a sharded batch holds exactly one window (this rank's shard)");
+    if (bd.tot_gp > 0) return fail(KBA_ERR_CAPACITY, "sharded windows with ground-plane residuals are not supported");
+    if (lm_begin < 0 || lm_total < lm_begin + (int)bd.tot_lm) return fail(KBA_ERR_BAD_ARG, "landmark block outside the window");
+    if (bd.sharded) return fail(KBA_ERR_BAD_ARG, "kba_batch_set_shard called twice");
+    const WinDesc& d = b->desc_h[0];
+    int bad = 0;
+    bad |= b->dev_alloc(&bd.xs, 16);
+    bad |= b->dev_alloc(&bd.trim_send, 3 * (size_t)lm_total); bad |= b->dev_alloc(&bd.trim_glob, 3 * (size_t)lm_total);
+    bad |= b->dev_alloc(&bd.reject_glob, (size_t)lm_total);
+    bad |= b->dev_alloc(&b->lc.x_sred, (size_t)d.nr_cap * d.nr_cap);
+    bad |= b->dev_alloc(&b->lc.x_bkf, (size_t)d.n_kf * 27); bad |= b->dev_alloc(&b->lc.x_cost, (size_t)bd.cost_parts);
+    if (bad) return fail(KBA_ERR_CUDA, "out of device memory (shard buffers)");
+    cudaStream_t s = b->h->stream;
+    CU(cudaMemsetAsync(bd.xs, 0, 16 * sizeof(double), s));
+    CU(cudaMemsetAsync(bd.trim_send, 0, 3 * (size_t)lm_total * sizeof(double), s));
+    CU(cudaMemsetAsync(b->lc.x_sred, 0, (size_t)d.nr_cap * d.nr_cap * sizeof(double), s));
+    bd.sharded = 1; bd.lm_begin = lm_begin; bd.lm_total = lm_total;
+    b->lc.xchg = kba_shard_exchange(comm);
+    b->lc.shard_win.nr_cap = d.nr_cap; b->lc.shard_win.n_kf = d.n_kf;
     return KBA_OK;
 }
 

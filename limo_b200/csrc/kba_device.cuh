@@ -125,19 +125,26 @@ struct BatchDev {
     double* res;              // [3][tot_obs]  robustified residual rows (u, v, depth)
     double* jp;               // [18][tot_obs] 3x6 d r~ / d (rot, trans)
     double* jl;               // [9][tot_obs]  3x3 d r~ / d landmark
-    double* vobs;             // [18][tot_obs] V_i = (J_p^T J_l) L^-T, 6x3 (generic Schur kernel)
     // dense per-chunk V panels for the TMA-fed Schur kernel: chunk c of window w occupies 96 columns x chunk_rs[c] rows,
     // column-major ([col][row]), at vpanel + desc.panel_off + chunk_poff[c]; rows = the chunk's 8-row tile range (+ rhs tile)
     double* vpanel;
     long long panel_cap;      // doubles reserved per window
     int* chunk_poff;          // [tot_chunks] offset (doubles) inside the window's panel storage
     int* chunk_rs;            // [tot_chunks] row stride (== 4 mod 16, 0 for chunks without free keyframes)
-    int use_panel;            // 1: V lives in vpanel (register-resident Schur kernel), 0: in vobs
     // reductions
     double* cost_part_x;      // [n_win][cost_parts] cost partials of the linearisation at x
     double* cost_part_c;      // [n_win][cost_parts] cost partials at the candidate
     int cost_parts;
+    // ---- one window sharded by landmark blocks over several GPUs (kba_shard.cu) ----
+    int sharded;              // 1: this batch holds ONE window's shard; sums cross the ranks through LaunchCfg::xchg
+    int lm_begin, lm_total;   // first landmark of this rank's block / landmarks of the whole window (caller's order)
+    double* xs;               // [16] exchanged scalars: 0 model, 1 step^2, 2 |x|^2, 3 candidate cost, 4 eval-failed flag,
+                              //      5 gradient max-norm (MAX), 8 eval_failed at x, 9 landmark block not PD
+    double* trim_send;        // [3][lm_total] this rank's trimming values (+2, 0 where not owned), all-reduced into
+    double* trim_glob;        // [3][lm_total]
+    uint8_t* reject_glob;     // [lm_total]
     int solve_row_major;      // debug knob: force the global-memory Cholesky even when the tiled one fits
+    int solve_tiled;          // 1: k_reduced_solve<true> (<= 192 rows, shared-memory resident)
     int eval_tiles_jac, eval_tiles_cost, eval_min_blocks;  // 256-observation tiles per CTA / CTAs per SM of k_eval_obs
     double* bs_part;          // [n_win][bs_parts][4]: model_e, step_sq, xnorm_sq, gmax_e
     int bs_parts;

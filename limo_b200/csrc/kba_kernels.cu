@@ -54,6 +54,8 @@ __global__ void __launch_bounds__(256) k_solve_begin(BatchDev bd, SolveParams sp
     }
     atomicAdd(&s_cnt[0], n_lm_in);
     atomicAdd(&s_cnt[1], n_blocks);
+    if (bd.sharded)  // another rank's landmarks may be the only ones seen from a keyframe: all free keyframes are variable
+        for (int k = threadIdx.x; k < wd.n_kf; k += blockDim.x) s_has[k] = 1;
     __syncthreads();
     if (threadIdx.x == 0) {
         if (wd.scale_weight > 0) { s_has[wd.scale_kf0] = 1; s_has[wd.scale_kf1] = 1; }
@@ -113,7 +115,7 @@ __global__ void __launch_bounds__(256) k_solve_begin(BatchDev bd, SolveParams sp
         bd.chunk_t0[wd.chunk_off + c] = (r1 < 0) ? 0 : r0 / 8;
         bd.chunk_t1[wd.chunk_off + c] = (r1 < 0) ? 0 : (r1 + 7) / 8;
     }
-    if (bd.use_panel) {  // layout of the dense V panels: per chunk 96 columns x rs rows (rs == 4 mod 16), column-major
+    {  // layout of the dense V panels: per chunk 96 columns x rs rows (rs == 4 mod 16), column-major
         __syncthreads();
         if (threadIdx.x == 0) {
             const int trhs = st.n_f >> 3;
@@ -404,7 +406,6 @@ __global__ void __launch_bounds__(256, 2) k_pose_hessian(BatchDev bd, SolveParam
 // =====================================================================================================================
 constexpr int kLC = 32;            // landmarks per chunk
 constexpr int kKC = 3 * kLC;       // panel columns per chunk
-constexpr int kKS = kKC + 4;       // panel row stride in doubles (== 4 mod 16 -> conflict-free fragment loads)
 
 // reduced-system row of component r (0..5 pose, 6..8 plane normal, 9 plane distance) of keyframe k, -1 if constant
 __device__ __forceinline__ int gp_row(const BatchDev& bd, const WinDesc& wd, int k, int r) {
@@ -419,13 +420,18 @@ __device__ __forceinline__ void dmma(double& c0, double& c1, double a, double b)
                  : "d"(a), "d"(b));
 }
 
+constexpr int kGS = 64 + 4;  // row stride of the column-major 64-row panel slices (== 4 mod 16: conflict-free fragments)
+
 __global__ void __launch_bounds__(256, 2) k_schur_syrk(BatchDev bd) {
+    // Generic kernel for reduced systems of more than 184 rows: CTA = one 64x64 block (bi >= bj) of Sred x a range of
+    // landmark chunks.  The two 64-row slices of a chunk's dense V panel are copied (coalesced, zeros where the chunk has
+    // no rows) into shared memory, column-major like the panel itself; chunks that do not touch both row blocks are
+    // skipped -- landmarks are sorted by first keyframe, so that is most of them.
     const int w = blockIdx.z;
     const WinState& st = bd.state[w];
     if (st.phase != PH_ITERATE || st.solve_failed) return;
     const WinDesc& wd = bd.desc[w];
     if (wd.landmarks_fixed) return;
-    // block pair (bi >= bj) from the linear index
     int bi = 0, rem = blockIdx.x;
     while (rem > bi) { rem -= bi + 1; ++bi; }
     const int bj = rem;
@@ -433,85 +439,55 @@ __global__ void __launch_bounds__(256, 2) k_schur_syrk(BatchDev bd) {
     if (bi * 64 >= nrows) return;
     const bool diag = (bi == bj);
     extern __shared__ double smem[];
-    double* pa = smem;                       // 64 x kKS
-    double* pb = diag ? pa : smem + 64 * kKS;
+    double* pa = smem;                        // [96][kGS]
+    double* pb = diag ? pa : smem + kKC * kGS;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     double acc[8][2];
 #pragma unroll
     for (int t = 0; t < 8; ++t) acc[t][0] = acc[t][1] = 0.0;
-    const int* lm_ptr = bd.lm_ptr + wd.lm_off + w;
-    const size_t T = (size_t)bd.tot_obs, base = (size_t)wd.obs_off;
-    const int rhs_row = st.n_f;
-    const int ra0 = bi * 64, rb0 = bj * 64;
-    // chunks of this CTA: split p of p_split
-    const int per = (wd.n_chunks + bd.p_split - 1) / bd.p_split;
-    const int ch0 = blockIdx.y * per, ch1 = min(wd.n_chunks, ch0 + per);
-    for (int ch = ch0; ch < ch1; ++ch) {
-        const int j0 = bd.chunk_lm0[wd.chunk_off + ch], j1 = bd.chunk_lm1[wd.chunk_off + ch];
-        const int o0 = lm_ptr[j0], o1 = lm_ptr[j1];
-        __syncthreads();  // previous chunk's MMA done before the panel is overwritten
-        for (int i = threadIdx.x; i < (diag ? 1 : 2) * 64 * kKS; i += blockDim.x) smem[i] = 0.0;
-        __syncthreads();
-        // scatter V_i (6x3) into the panel(s)
-        const int nobs = o1 - o0;
-        for (int round = 0; round <= wd.max_rank; ++round) {  // rank > 0: second camera of the rig on the same rows -> add
-            if (round > 0) __syncthreads();
-            for (int idx = threadIdx.x; idx < nobs * 18; idx += blockDim.x) {
-                const int e = idx / nobs, oo = idx - e * nobs;
-                const size_t o = base + o0 + oo;
-                const int jl = bd.obs_lm[o];
-                if (!bd.lm_active[wd.lm_off + jl] || bd.obs_rank[o] != round) continue;
-                const int off = bd.off_pose[wd.kf_off + bd.obs_kf[o]];
-                if (off < 0) continue;
-                const int row = off + e / 3, col = 3 * (jl - j0) + e % 3;
-                const double v = bd.vobs[e * T + o];
-                if (row >= ra0 && row < ra0 + 64) pa[(row - ra0) * kKS + col] += v;
-                if (!diag && row >= rb0 && row < rb0 + 64) pb[(row - rb0) * kKS + col] += v;
-            }
-        }
-        // rhs row: z_j
-        for (int idx = threadIdx.x; idx < (j1 - j0) * 3; idx += blockDim.x) {
-            const int jl = j0 + idx / 3;
-            if (!bd.lm_active[wd.lm_off + jl] || lm_ptr[jl + 1] <= lm_ptr[jl]) continue;
-            const double v = bd.lm_z[3 * (size_t)(wd.lm_off + jl) + idx % 3];
-            if (rhs_row >= ra0 && rhs_row < ra0 + 64) pa[(rhs_row - ra0) * kKS + idx] = v;
-            if (!diag && rhs_row >= rb0 && rhs_row < rb0 + 64) pb[(rhs_row - rb0) * kKS + idx] = v;
-        }
-        if (wd.n_gp > 0) {  // ground-plane rows are ADDED: the pose rows may coincide with an observation's rows
-            __syncthreads();
-            for (int idx = threadIdx.x; idx < (j1 - j0) * 30; idx += blockDim.x) {
-                const int jl = j0 + idx / 30, e = idx % 30;
-                const int gl = bd.gp_of_lm[wd.lm_off + jl];
-                if (gl < 0 || !bd.lm_active[wd.lm_off + jl]) continue;
-                const int row = gp_row(bd, wd, bd.gp_kf[wd.gp_off + gl], e / 3);
-                if (row < 0) continue;
-                const int col = 3 * (jl - j0) + e % 3;
-                const double v = bd.vgp[(size_t)e * bd.tot_gp + wd.gp_off + gl];
-                if (row >= ra0 && row < ra0 + 64) pa[(row - ra0) * kKS + col] += v;
-                if (!diag && row >= rb0 && row < rb0 + 64) pb[(row - rb0) * kKS + col] += v;
-            }
+    const int trhs = st.n_f >> 3;
+    const bool a_rhs = trhs >= 8 * bi && trhs < 8 * bi + 8, b_rhs = trhs >= 8 * bj && trhs < 8 * bj + 8;
+    const double* pbase = bd.vpanel + wd.panel_off;
+    // chunks are dealt round-robin to the p_split CTAs of a block pair: the chunks that touch a given pair are
+    // neighbours in the sorted order, contiguous ranges would leave them all with one CTA
+    for (int ch = blockIdx.y; ch < wd.n_chunks; ch += bd.p_split) {
+        const int t0 = bd.chunk_t0[wd.chunk_off + ch], t1 = bd.chunk_t1[wd.chunk_off + ch];
+        const int rs = bd.chunk_rs[wd.chunk_off + ch];
+        if (rs == 0) continue;
+        const bool a_hit = (8 * bi < t1 && 8 * bi + 8 > t0) || a_rhs, b_hit = (8 * bj < t1 && 8 * bj + 8 > t0) || b_rhs;
+        if (!(a_hit && b_hit)) continue;
+        const double* pan = pbase + bd.chunk_poff[wd.chunk_off + ch];
+        const bool rhs_in = trhs >= t0 && trhs < t1;
+        __syncthreads();  // previous chunk's MMA done before the slices are overwritten
+        for (int idx = threadIdx.x; idx < (diag ? 1 : 2) * kKC * 64; idx += blockDim.x) {
+            const int which = idx / (kKC * 64), e = idx - which * (kKC * 64);
+            const int c = e >> 6, r = e & 63;
+            const int g = 64 * (which ? bj : bi) + r, tile = g >> 3;
+            double v = 0.0;
+            if (tile >= t0 && tile < t1) v = pan[(size_t)c * rs + g - 8 * t0];
+            else if (tile == trhs && !rhs_in) v = pan[(size_t)c * rs + 8 * (t1 - t0) + (g & 7)];
+            (which ? pb : pa)[c * kGS + r] = v;
         }
         __syncthreads();
-        const double* arow = pa + (8 * warp + (lane >> 2)) * kKS + (lane & 3);
-        const double* brow = pb + (lane >> 2) * kKS + (lane & 3);
+        const double* acol = pa + (lane & 3) * kGS + 8 * warp + (lane >> 2);
+        const double* bcol = pb + (lane & 3) * kGS + (lane >> 2);
 #pragma unroll 4
         for (int kk = 0; kk < kKC; kk += 4) {
-            const double a = arow[kk];
+            const double a = acol[kk * kGS];
 #pragma unroll
             for (int t = 0; t < 8; ++t) {
                 if (diag && t > warp) continue;
-                const double b = brow[t * 8 * kKS + kk];
-                dmma(acc[t][0], acc[t][1], a, b);
+                dmma(acc[t][0], acc[t][1], a, bcol[kk * kGS + 8 * t]);
             }
         }
     }
     // store the partial block (row-major, leading dimension nr_cap)
     double* out = bd.sred + wd.s_off * (size_t)bd.p_split + (size_t)blockIdx.y * wd.nr_cap * wd.nr_cap;
-    const int row = ra0 + 8 * warp + (lane >> 2);
+    const int row = bi * 64 + 8 * warp + (lane >> 2);
 #pragma unroll
     for (int t = 0; t < 8; ++t) {
         if (diag && t > warp) continue;
-        const int col = rb0 + 8 * t + 2 * (lane & 3);
+        const int col = bj * 64 + 8 * t + 2 * (lane & 3);
         out[(size_t)row * wd.nr_cap + col] = acc[t][0];
         out[(size_t)row * wd.nr_cap + col + 1] = acc[t][1];
     }
@@ -679,7 +655,8 @@ __global__ void __launch_bounds__(512, 1) k_schur_syrk_tma(BatchDev bd) {
 // reduced system: assemble S = F + Lambda - sum V V^T (+ rhs as an augmented row), blocked Cholesky in place, solve,
 // candidate poses.  One CTA per window.
 // =====================================================================================================================
-constexpr int kNB = 32;  // Cholesky block size
+constexpr int kNB = 32;           // Cholesky block size
+constexpr int kPanelStride = 36;  // row stride of the shared-memory panel copy (row-major path)
 
 // PoseRegularization residual |(T1 T0^-1).t| - s0 with local Jacobians (reference cost_functors_ceres.hpp:224-250).
 __device__ void scale_regulariser(const double* p1, const double* p0, double s0, double& r, double* j1, double* j0) {
@@ -800,7 +777,8 @@ __device__ inline bool warp_chol32(double* D, int PS, double* inv, int lane) {
 
 // partial Schur sums of the p_split CTAs of a window -> slot 0, fixed order (only launched when p_split > 1, i.e. when
 // the batch is too small to fill the GPU with one CTA per window)
-__global__ void __launch_bounds__(256) k_sred_reduce(BatchDev bd) {
+// mode 0: fold the partials and (row-major solve) write A; 1: fold only; 2: write A from slot 0 (after the exchange)
+__global__ void __launch_bounds__(256) k_sred_reduce(BatchDev bd, int mode) {
     const int w = blockIdx.y;
     const WinState& st = bd.state[w];
     if (st.phase != PH_ITERATE || st.solve_failed) return;
@@ -814,6 +792,8 @@ __global__ void __launch_bounds__(256) k_sred_reduce(BatchDev bd) {
     double* sp0 = bd.sred + wd.s_off * (size_t)bd.p_split;
     const size_t pstride = (size_t)ld * ld;
     double s = 0.0;
+    if (mode == 2) s = sp0[idx];
+    else
     for (int p0 = 0; p0 < bd.p_split; p0 += 16) {  // 16 independent loads in flight, summed in slot order
         double v[16];
 #pragma unroll
@@ -821,7 +801,9 @@ __global__ void __launch_bounds__(256) k_sred_reduce(BatchDev bd) {
 #pragma unroll
         for (int q = 0; q < 16; ++q) s += v[q];
     }
-    sp0[idx] = s;
+    if (mode != 2) sp0[idx] = s;
+    // row-major solve: A = -Sred is written here by the whole GPU instead of by the single CTA of the solve kernel
+    if (mode != 1 && !bd.solve_tiled) bd.amat[wd.s_off + idx] = (r == n && c == n) ? 0.0 : -s;
 }
 
 template <bool kTiled>
@@ -869,9 +851,10 @@ __global__ void __launch_bounds__(512, 1) k_reduced_solve(BatchDev bd, SolvePara
     {
         const double* sp0 = bd.sred + wd.s_off * (size_t)bd.p_split;
         const size_t pstride = (size_t)ld * ld;
-        const int np = bd.p_split > 1 ? 1 : bd.p_split;  // k_sred_reduce has folded the partials into slot 0
+        const int np = 1;  // with p_split > 1, k_sred_reduce has folded the partials into slot 0
         const int rows = kTiled ? ((n + 8) & ~7) : n + 1;  // tiled: whole tile rows, zero padded
-        for (int idx = tid; idx < rows * ld; idx += nth) {
+        const bool done_by_reduce = !kTiled && (bd.p_split > 1 || bd.sharded) && !wd.landmarks_fixed;  // see k_sred_reduce
+        for (int idx = tid; idx < (done_by_reduce ? 0 : rows * ld); idx += nth) {
             const int r = idx / ld, c = idx - r * ld;
             if (kTiled ? (c >= rows || (c >> 3) > (r >> 3)) : (c > r || c >= n + 1)) continue;
             double s = 0.0;
@@ -1048,59 +1031,83 @@ __global__ void __launch_bounds__(512, 1) k_reduced_solve(BatchDev bd, SolvePara
     __syncthreads();
 
     PHASE_MARK(3);
-    if constexpr (kTiled) {
-        // ---- shared-memory resident blocked Cholesky (NB = 32) with the augmented row n carried along:
-        //      diagonal block in one warp's registers, panel by forward substitution (thread per row), trailing
-        //      update on the FP64 tensor cores straight from the tile-packed storage ----
-        const int lane = tid & 31, warp = tid >> 5, fr = lane >> 2, fc = lane & 3;
-        const int NT = (n + 8) >> 3;  // tile rows, including the one holding the augmented row
-        const int PS = kNB + 1;
-        for (int kb = 0; kb < n; kb += kNB) {
-            const int nb = min(kNB, n - kb);
-            for (int idx = tid; idx < kNB * kNB; idx += nth) {  // stage the diagonal block, identity padded
-                const int r = idx >> 5, c = idx & 31;
-                s_D[r * PS + c] = (r < nb && c <= r) ? A(kb + r, kb + c) : ((r == c) ? 1.0 : 0.0);
+    // ---- blocked Cholesky (NB = 32) with the augmented row n carried along: diagonal block by one warp (registers +
+    //      shuffles), panel by forward substitution (thread per row), trailing update on the FP64 tensor cores --
+    //      tiled: operands and result straight from the tile-packed shared-memory storage; row-major: operands from
+    //      the shared-memory copy of the panel (s_P, row stride 36: conflict-free fragments), result tiles in global ----
+    const int lane = tid & 31, warp = tid >> 5, fr = lane >> 2, fc = lane & 3;
+    const int NT = (n + 8) >> 3;  // tile rows, including the one holding the augmented row
+    const int PS = kNB + 1;
+    for (int kb = 0; kb < n; kb += kNB) {
+        const int nb = min(kNB, n - kb);
+        for (int idx = tid; idx < kNB * kNB; idx += nth) {  // stage the diagonal block, identity padded
+            const int r = idx >> 5, c = idx & 31;
+            s_D[r * PS + c] = (r < nb && c <= r) ? A(kb + r, kb + c) : ((r == c) ? 1.0 : 0.0);
+        }
+        __syncthreads();
+        if (warp == 0 && !warp_chol32(s_D, PS, s_inv, lane)) s_fail = 1;
+        __syncthreads();
+        PHASE_ACC(8);
+        if (s_fail) break;
+        for (int idx = tid; idx < nb * kNB; idx += nth) {
+            const int r = idx >> 5, c = idx & 31;
+            if (c <= r) A(kb + r, kb + c) = s_D[r * PS + c];
+        }
+        if (tid < nb) s_invd[kb + tid] = s_inv[tid];
+        // panel: rows below the block, including the augmented row n; X L^T = B column by column, each finished
+        // column is eliminated from the remaining ones right away (independent FMAs, short critical path)
+        const int r0 = kb + nb, m = n + 1 - r0;
+        if constexpr (!kTiled) {  // coalesced copy of the panel rows into shared memory, zero padded to whole tiles
+            for (int idx = tid; idx < ((m + 7) & ~7) * kNB; idx += nth) {
+                const int i = idx >> 5, c = idx & 31;
+                s_P[i * kPanelStride + c] = (i < m && c < nb) ? A(r0 + i, kb + c) : 0.0;
             }
             __syncthreads();
-            if (warp == 0 && !warp_chol32(s_D, PS, s_inv, lane)) s_fail = 1;
-            __syncthreads();
-            PHASE_ACC(8);
-            if (s_fail) break;
-            for (int idx = tid; idx < nb * kNB; idx += nth) {
-                const int r = idx >> 5, c = idx & 31;
-                if (c <= r) A(kb + r, kb + c) = s_D[r * PS + c];
+        }
+        for (int i = tid; i < m; i += nth) {
+            double x[kNB];
+#pragma unroll
+            for (int c = 0; c < kNB; ++c) {
+                if constexpr (kTiled) x[c] = (c < nb) ? A(r0 + i, kb + c) : 0.0;
+                else x[c] = s_P[i * kPanelStride + c];
             }
-            if (tid < nb) s_invd[kb + tid] = s_inv[tid];
-            // panel: rows below the block, including the augmented row n; X L^T = B column by column, each finished
-            // column is eliminated from the remaining ones right away (independent FMAs, short critical path)
-            const int r0 = kb + nb, m = n + 1 - r0;
-            for (int i = tid; i < m; i += nth) {
-                double x[kNB];
+            const volatile double* vD = s_D;  // volatile: keeps the 496 factor entries from being hoisted out of the row loop
 #pragma unroll
-                for (int c = 0; c < kNB; ++c) x[c] = (c < nb) ? A(r0 + i, kb + c) : 0.0;
+            for (int q = 0; q < kNB; ++q) {
+                x[q] *= s_inv[q];
 #pragma unroll
-                for (int q = 0; q < kNB; ++q) {
-                    x[q] *= s_inv[q];
-#pragma unroll
-                    for (int c = q + 1; c < kNB; ++c) x[c] -= x[q] * s_D[c * PS + q];
-                }
-#pragma unroll
-                for (int c = 0; c < kNB; ++c)
-                    if (c < nb) A(r0 + i, kb + c) = x[c];
+                for (int c = q + 1; c < kNB; ++c) x[c] -= x[q] * vD[c * PS + q];
             }
-            __syncthreads();
-            PHASE_ACC(9);
-            if (nb < kNB) break;  // last block: only the augmented row is left below it
-            // trailing update: tile (I, J) -= sum_K tile(I, K) tile(J, K)^T over the 4 panel tile columns
-            const int T0 = r0 >> 3, K0 = kb >> 3, mt = NT - T0;
-            for (int t = warp; t < mt * (mt + 1) / 2; t += nth >> 5) {
-                int i = (int)((sqrtf(8.0f * (float)t + 1.0f) - 1.0f) * 0.5f);
-                while ((i + 1) * (i + 2) / 2 <= t) ++i;
-                while (i * (i + 1) / 2 > t) --i;
-                const int j = t - i * (i + 1) / 2;
-                const double* pa = A.tile(T0 + i, K0) + fr * 4 + fc;
-                const double* pb = A.tile(T0 + j, K0) + fr * 4 + fc;
+#pragma unroll
+            for (int c = 0; c < kNB; ++c) {
+                if constexpr (kTiled) { if (c < nb) A(r0 + i, kb + c) = x[c]; }
+                else s_P[i * kPanelStride + c] = x[c];
+            }
+        }
+        __syncthreads();
+        if constexpr (!kTiled) {  // the factor's panel back to global memory (coalesced); s_P feeds the tensor cores
+            for (int idx = tid; idx < m * kNB; idx += nth) {
+                const int i = idx >> 5, c = idx & 31;
+                if (c < nb) A(r0 + i, kb + c) = s_P[i * kPanelStride + c];
+            }
+        }
+        PHASE_ACC(9);
+        if (nb < kNB) break;  // last block: only the augmented row is left below it
+        // trailing update: tile (I, J) -= sum_K tile(I, K) tile(J, K)^T over the 4 panel tile columns
+        const int T0 = r0 >> 3, mt = NT - T0, ntile = mt * (mt + 1) / 2;
+        auto tile_ij = [](int t, int& i, int& j) {
+            i = (int)((sqrtf(8.0f * (float)t + 1.0f) - 1.0f) * 0.5f);
+            while ((i + 1) * (i + 2) / 2 <= t) ++i;
+            while (i * (i + 1) / 2 > t) --i;
+            j = t - i * (i + 1) / 2;
+        };
+        if constexpr (kTiled) {
+            for (int t = warp; t < ntile; t += nth >> 5) {
+                int i, j;
+                tile_ij(t, i, j);
                 double a0 = 0.0, a1 = 0.0, b0 = 0.0, b1 = 0.0;  // two independent accumulator chains
+                const double* pa = A.tile(T0 + i, kb >> 3) + fr * 4 + fc;
+                const double* pb = A.tile(T0 + j, kb >> 3) + fr * 4 + fc;
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
                     dmma(a0, a1, pa[64 * k], pb[64 * k]);
@@ -1112,117 +1119,80 @@ __global__ void __launch_bounds__(512, 1) k_reduced_solve(BatchDev bd, SolvePara
                 cv.y -= a1 + b1;
                 *pc = cv;
             }
-            __syncthreads();
-            PHASE_ACC(10);
-        }
-        if (s_fail) {
-            if (tid == 0) st.solve_failed = 1;
-            return;
-        }
-        PHASE_MARK(4);
-        // ---- blocked back substitution L^T d = y (y = augmented row), delta_f = -d ----
-        for (int c = tid; c < n; c += nth) s_y[c] = A(n, c);
-        __syncthreads();
-        for (int kb = ((n - 1) / kNB) * kNB; kb >= 0; kb -= kNB) {
-            const int nb = min(kNB, n - kb);
-            for (int idx = tid; idx < kNB * kNB; idx += nth) {  // stage the diagonal block of L
-                const int r = idx >> 5, c = idx & 31;
-                s_D[r * PS + c] = (r < nb && c <= r) ? A(kb + r, kb + c) : 0.0;
+        } else {
+            // result tiles live in global memory (L2): the tile of the NEXT iteration is requested before this one's
+            // tensor-core work so that its latency is hidden
+            struct Req { int i, j; double2* pc; bool wr; double2 cv; };
+            auto fetch = [=](int t) {
+                Req q;
+                q.i = (int)((sqrtf(8.0f * (float)t + 1.0f) - 1.0f) * 0.5f);
+                while ((q.i + 1) * (q.i + 2) / 2 <= t) ++q.i;
+                while (q.i * (q.i + 1) / 2 > t) --q.i;
+                q.j = t - q.i * (q.i + 1) / 2;
+                const int gr = r0 + 8 * q.i + fr, gc = r0 + 8 * q.j + 2 * fc;
+                q.wr = gr <= n;  // rows past the augmented row do not exist in the row-major storage
+                q.pc = reinterpret_cast<double2*>(A.p + (size_t)(q.wr ? gr : n) * A.ld + gc);
+                q.cv = q.wr ? *q.pc : make_double2(0.0, 0.0);
+                return q;
+            };
+            int t = warp;
+            Req cur = fetch(t < ntile ? t : 0);
+            while (t < ntile) {
+                const int tn = t + (nth >> 5);
+                const Req nxt = fetch(tn < ntile ? tn : t);
+                double a0 = 0.0, a1 = 0.0, b0 = 0.0, b1 = 0.0;
+                const double* pa = s_P + (8 * cur.i + fr) * kPanelStride + fc;
+                const double* pb = s_P + (8 * cur.j + fr) * kPanelStride + fc;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    dmma(a0, a1, pa[8 * k], pb[8 * k]);
+                    dmma(b0, b1, pa[8 * k + 4], pb[8 * k + 4]);
+                }
+                if (cur.wr) {
+                    cur.cv.x -= a0 + b0;
+                    cur.cv.y -= a1 + b1;
+                    *cur.pc = cur.cv;
+                }
+                t = tn;
+                cur = nxt;
             }
-            __syncthreads();
-            if (warp == 0) {  // lane k owns unknown kb + k of the diagonal block
-                double yk = (lane < nb) ? s_y[kb + lane] : 0.0;
-                const double ik = (lane < nb) ? s_invd[kb + lane] : 0.0;
+        }
+        __syncthreads();
+        PHASE_ACC(10);
+    }
+    if (s_fail) {
+        if (tid == 0) st.solve_failed = 1;
+        return;
+    }
+    PHASE_MARK(4);
+    // ---- blocked back substitution L^T d = y (y = augmented row), delta_f = -d ----
+    for (int c = tid; c < n; c += nth) s_y[c] = A(n, c);
+    __syncthreads();
+    for (int kb = ((n - 1) / kNB) * kNB; kb >= 0; kb -= kNB) {
+        const int nb = min(kNB, n - kb);
+        for (int idx = tid; idx < kNB * kNB; idx += nth) {  // stage the diagonal block of L
+            const int r = idx >> 5, c = idx & 31;
+            s_D[r * PS + c] = (r < nb && c <= r) ? A(kb + r, kb + c) : 0.0;
+        }
+        __syncthreads();
+        if (warp == 0) {  // lane k owns unknown kb + k of the diagonal block
+            double yk = (lane < nb) ? s_y[kb + lane] : 0.0;
+            const double ik = (lane < nb) ? s_invd[kb + lane] : 0.0;
 #pragma unroll 4
-                for (int i = nb - 1; i >= 0; --i) {
-                    const double lik = s_D[i * PS + lane];  // zero above the diagonal
-                    const double di = __shfl_sync(0xffffffffu, yk * ik, i);
-                    yk = (lane == i) ? di : yk - lik * di;
-                }
-                if (lane < nb) s_y[kb + lane] = yk;
+            for (int i = nb - 1; i >= 0; --i) {
+                const double lik = s_D[i * PS + lane];  // zero above the diagonal
+                const double di = __shfl_sync(0xffffffffu, yk * ik, i);
+                yk = (lane == i) ? di : yk - lik * di;
             }
-            __syncthreads();
-            for (int k = tid; k < kb; k += nth) {
-                double acc = s_y[k];
-                for (int i = 0; i < nb; ++i) acc -= A(kb + i, k) * s_y[kb + i];
-                s_y[k] = acc;
-            }
-            __syncthreads();
+            if (lane < nb) s_y[kb + lane] = yk;
         }
-    } else {
-        // ---- blocked right-looking Cholesky of A[0..n) with the augmented row n carried along ----
-        const int PS = kNB + 1;
-        for (int kb = 0; kb < n; kb += kNB) {
-            const int nb = min(kNB, n - kb);
-            for (int idx = tid; idx < nb * nb; idx += nth) {
-                const int r = idx / nb, c = idx - r * nb;
-                s_D[r * PS + c] = (c <= r) ? A(kb + r, kb + c) : 0.0;
-            }
-            __syncthreads();
-            if (tid < 32) {  // factor the diagonal block with one warp: lane = row
-                const int lane = tid;
-                for (int j = 0; j < nb; ++j) {
-                    const double djj = s_D[j * PS + j];
-                    if (!(djj > 0.0) || !isfinite(djj)) { if (lane == 0) s_fail = 1; break; }
-                    const double piv = sqrt(djj);
-                    __syncwarp();
-                    if (lane == j) s_D[j * PS + j] = piv;
-                    if (lane > j && lane < nb) s_D[lane * PS + j] /= piv;
-                    __syncwarp();
-                    if (lane > j && lane < nb) {
-                        const double lij = s_D[lane * PS + j];
-                        for (int c = j + 1; c <= lane; ++c) s_D[lane * PS + c] -= lij * s_D[c * PS + j];
-                    }
-                    __syncwarp();
-                }
-            }
-            __syncthreads();
-            if (s_fail) break;
-            for (int idx = tid; idx < nb * nb; idx += nth) {
-                const int r = idx / nb, c = idx - r * nb;
-                if (c <= r) A(kb + r, kb + c) = s_D[r * PS + c];
-            }
-            // panel: rows below the block, including the augmented row n
-            const int r0 = kb + nb, m = n + 1 - r0;
-            for (int i = tid; i < m; i += nth) {
-                double x[kNB];
-                for (int c = 0; c < nb; ++c) x[c] = A(r0 + i, kb + c);
-                for (int c = 0; c < nb; ++c) {
-                    double s = x[c];
-                    for (int q = 0; q < c; ++q) s -= x[q] * s_D[c * PS + q];
-                    x[c] = s / s_D[c * PS + c];
-                }
-                for (int c = 0; c < nb; ++c) { A(r0 + i, kb + c) = x[c]; s_P[i * PS + c] = x[c]; }
-            }
-            __syncthreads();
-            // trailing update: A[r0+i][r0+j] -= P[i] . P[j], j <= i, skipping the (n, n) corner
-            const long long ntri = (long long)m * (m + 1) / 2;
-            for (long long idx = tid; idx < ntri; idx += nth) {
-                int i = (int)((sqrt(8.0 * (double)idx + 1.0) - 1.0) * 0.5);
-                while ((long long)(i + 1) * (i + 2) / 2 <= idx) ++i;
-                while ((long long)i * (i + 1) / 2 > idx) --i;
-                const int j = (int)(idx - (long long)i * (i + 1) / 2);
-                if (i == m - 1 && j == m - 1) continue;
-                double s = 0.0;
-                for (int c = 0; c < nb; ++c) s += s_P[i * PS + c] * s_P[j * PS + c];
-                A(r0 + i, r0 + j) -= s;
-            }
-            __syncthreads();
-        }
-        if (s_fail) {
-            if (tid == 0) st.solve_failed = 1;
-            return;
-        }
-        // ---- back substitution L^T d = y (y = augmented row), delta_f = -d ----
-        for (int c = tid; c < n; c += nth) s_y[c] = A(n, c);
         __syncthreads();
-        for (int i = n - 1; i >= 0; --i) {
-            const double di = s_y[i] / A(i, i);
-            __syncthreads();
-            if (tid == 0) s_y[i] = di;
-            for (int k = tid; k < i; k += nth) s_y[k] -= A(i, k) * di;
-            __syncthreads();
+        for (int k = tid; k < kb; k += nth) {
+            double acc = s_y[k];
+            for (int i = 0; i < nb; ++i) acc -= A(kb + i, k) * s_y[kb + i];
+            s_y[k] = acc;
         }
+        __syncthreads();
     }
     PHASE_MARK(5);
     double* delta_f = bd.delta_f + (size_t)w * bd.nr_cap_max;
@@ -1309,7 +1279,7 @@ __global__ void __launch_bounds__(256) k_backsub(BatchDev bd) {
     const int* lm_ptr = bd.lm_ptr + wd.lm_off + w;
     const int o0 = have ? lm_ptr[j] : 0, o1 = have ? lm_ptr[j + 1] : 0;
     const bool in = have && bd.lm_active[L] && o1 > o0 && !wd.landmarks_fixed && !st.solve_failed;
-    const size_t T = (size_t)bd.tot_obs, base = (size_t)wd.obs_off;
+    const size_t base = (size_t)wd.obs_off;
     const double* delta_f = bd.delta_f + (size_t)w * bd.nr_cap_max;
     double t[3] = {0, 0, 0};
     const int gl = (in && wd.n_gp > 0) ? bd.gp_of_lm[L] : -1;
@@ -1317,33 +1287,25 @@ __global__ void __launch_bounds__(256) k_backsub(BatchDev bd) {
     if (in) {
         const double* pcol = nullptr;
         int prs = 0, prow0 = 0;
-        if (bd.use_panel) {
+        {
             const int ch = wd.chunk_off + (j >> 5);
             prs = bd.chunk_rs[ch];
             prow0 = 8 * bd.chunk_t0[ch];
             pcol = bd.vpanel + wd.panel_off + bd.chunk_poff[ch] + (size_t)(3 * (j & 31)) * prs;
         }
-        const int gk = (gl >= 0 && bd.use_panel) ? bd.gp_kf[wd.gp_off + gl] : -1;
+        const int gk = (gl >= 0) ? bd.gp_kf[wd.gp_off + gl] : -1;
         for (int o = o0 + hl; o < o1; o += 16) {
             const int k = bd.obs_kf[base + o];
             mine |= (k == gk);
             const int off = bd.off_pose[wd.kf_off + k];
             if (off < 0) continue;
-            if (bd.use_panel) {  // the panel rows hold the sum over the rig's cameras: read them once (rank 0)
-                if (bd.obs_rank[base + o] != 0) continue;
-                const double* q = pcol + (off - prow0);
+            // the panel rows hold the sum over the rig's cameras: read them once (rank 0)
+            if (bd.obs_rank[base + o] != 0) continue;
+            const double* q = pcol + (off - prow0);
 #pragma unroll
-                for (int r = 0; r < 6; ++r) {
-                    const double d = delta_f[off + r];
-                    t[0] += q[r] * d; t[1] += q[prs + r] * d; t[2] += q[2 * prs + r] * d;
-                }
-            } else {
-#pragma unroll
-                for (int r = 0; r < 6; ++r) {
-                    const double d = delta_f[off + r];
-#pragma unroll
-                    for (int c = 0; c < 3; ++c) t[c] += bd.vobs[(3 * r + c) * T + base + o] * d;
-                }
+            for (int r = 0; r < 6; ++r) {
+                const double d = delta_f[off + r];
+                t[0] += q[r] * d; t[1] += q[prs + r] * d; t[2] += q[2 * prs + r] * d;
             }
         }
     }
@@ -1418,6 +1380,58 @@ __device__ void solve_end(WinState& st, int termination) {
     st.phase = PH_TRIM;
 }
 
+// ---- sharded window: local partial sums -> the exchanged scalar block; flags out of / into the window state ----
+__global__ void __launch_bounds__(256) k_shard_scalars(BatchDev bd) {  // after k_backsub and k_eval_obs<false>
+    const WinState& st = bd.state[0];
+    const WinDesc& wd = bd.desc[0];
+    __shared__ double s_red[8][5];
+    double a = 0, b = 0, c = 0, cc = 0, g = 0;
+    if (st.phase == PH_ITERATE) {
+        for (int q = threadIdx.x; q < (wd.n_lm + 15) / 16; q += blockDim.x) {
+            const double* p = bd.bs_part + (size_t)q * 4;
+            a += p[0]; b += p[1]; c += p[2]; g = fmax(g, p[3]);
+        }
+        for (int q = threadIdx.x; q < bd.cost_parts; q += blockDim.x) cc += bd.cost_part_c[q];
+    }
+    a = warp_sum(a); b = warp_sum(b); c = warp_sum(c); cc = warp_sum(cc); g = warp_max(g);
+    if ((threadIdx.x & 31) == 0) {
+        double* r = s_red[threadIdx.x >> 5];
+        r[0] = a; r[1] = b; r[2] = c; r[3] = cc; r[4] = g;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t[5] = {0, 0, 0, 0, 0};
+        for (int q = 0; q < 8; ++q) { for (int e = 0; e < 4; ++e) t[e] += s_red[q][e]; t[4] = fmax(t[4], s_red[q][4]); }
+        bd.xs[0] = t[0]; bd.xs[1] = t[1]; bd.xs[2] = t[2]; bd.xs[3] = t[3];
+        bd.xs[4] = (st.phase == PH_ITERATE && st.eval_failed) ? 1.0 : 0.0;
+        bd.xs[5] = t[4];
+    }
+}
+__global__ void k_shard_flags(BatchDev bd, int post) {  // around the exchange that follows the linearisation kernels
+    WinState& st = bd.state[0];
+    if (threadIdx.x != 0 || st.phase != PH_ITERATE) {
+        if (threadIdx.x == 0 && !post) { bd.xs[8] = 0.0; bd.xs[9] = 0.0; }
+        return;
+    }
+    if (!post) {
+        bd.xs[8] = st.eval_failed ? 1.0 : 0.0;
+        bd.xs[9] = st.solve_failed ? 1.0 : 0.0;
+    } else {
+        if (bd.xs[8] > 0.0) st.eval_failed = 1;
+        if (bd.xs[9] > 0.0 && !st.solve_failed) st.solve_failed = 1;
+    }
+}
+// trimming values of this rank's landmarks into their slots of the window-wide array (0 = not mine, v + 2 otherwise)
+__global__ void __launch_bounds__(256) k_shard_trim_scatter(BatchDev bd) {
+    const WinState& st = bd.state[0];
+    if (st.phase != PH_TRIM) return;
+    const WinDesc& wd = bd.desc[0];
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= wd.n_lm) return;
+    const int gidx = bd.lm_begin + bd.lm_orig[j];
+    for (int g = 0; g < 3; ++g) bd.trim_send[(size_t)g * bd.lm_total + gidx] = bd.trim_val[(size_t)g * bd.tot_lm + j] + 2.0;
+}
+
 __global__ void __launch_bounds__(128) k_lm_update(BatchDev bd, SolveParams sp) {
     // one warp per window: the lanes reduce the partial sums (fixed shape: strided partials, then a butterfly), lane 0
     // then runs the controller
@@ -1436,6 +1450,10 @@ __global__ void __launch_bounds__(128) k_lm_update(BatchDev bd, SolveParams sp) 
     e_model = warp_sum(e_model); e_step = warp_sum(e_step); e_xn = warp_sum(e_xn); e_g = warp_max(e_g);
     cand_sum = warp_sum(cand_sum);
     if (lane != 0) return;
+    if (bd.sharded) {  // sums over all ranks (k_shard_scalars + all-reduce), identical on every rank
+        e_model = bd.xs[0]; e_step = bd.xs[1]; e_xn = bd.xs[2]; cand_sum = bd.xs[3]; e_g = bd.xs[5];
+        if (bd.xs[4] > 0.0) st.eval_failed = 1;
+    }
     if (st.solve_failed == 2) {  // evaluation failed at iteration zero
         sum.initial_cost = sum.final_cost = -1.0;
         st.solve_failed = 0; st.eval_failed = 0;
@@ -1592,14 +1610,22 @@ __global__ void __launch_bounds__(512) k_trim_select(BatchDev bd, SolveParams sp
     __shared__ unsigned long long s_prefix;
     __shared__ int s_k;
     const double quant[3] = {sp.depth_quantile, sp.reprojection_quantile, sp.gp_quantile};
+    // sharded window: the values of ALL ranks' landmarks (k_shard_trim_scatter + all-reduce), indexed by the caller's
+    // window-wide landmark index, stored as v + 2; every rank takes the same decisions and applies them to its own block
+    const bool sh = bd.sharded != 0;
+    const int n_items = sh ? bd.lm_total : wd.n_lm;
     const int* orig = bd.lm_orig + wd.lm_off;  // ties are broken by the caller's landmark index
-    for (int j = threadIdx.x; j < wd.n_lm; j += blockDim.x) bd.trim_reject[wd.lm_off + j] = 0;
+    auto oid = [&](int j) { return sh ? j : orig[j]; };
+    uint8_t* rej = sh ? bd.reject_glob : bd.trim_reject + wd.lm_off;
+    for (int j = threadIdx.x; j < n_items; j += blockDim.x) rej[j] = 0;
     for (int g = 0; g < 3; ++g) {
-        const double* v = bd.trim_val + g * (size_t)bd.tot_lm + wd.lm_off;
+        const double* vbase = sh ? bd.trim_glob + g * (size_t)bd.lm_total : bd.trim_val + g * (size_t)bd.tot_lm + wd.lm_off;
+        const double voff = sh ? 2.0 : 0.0;
+        auto val = [&](int j) { return vbase[j] - voff; };
         if (threadIdx.x == 0) s_n = 0;
         __syncthreads();
         int cnt = 0;
-        for (int j = threadIdx.x; j < wd.n_lm; j += blockDim.x) cnt += (v[j] >= 0.0);
+        for (int j = threadIdx.x; j < n_items; j += blockDim.x) cnt += (val(j) >= 0.0);
         if (cnt) atomicAdd(&s_n, cnt);
         __syncthreads();
         const int N = s_n;
@@ -1609,56 +1635,87 @@ __global__ void __launch_bounds__(512) k_trim_select(BatchDev bd, SolveParams sp
         if (num >= N) continue;
         if (threadIdx.x == 0) { s_prefix = 0ull; s_k = num; }
         unsigned long long mask = 0ull;
+        constexpr unsigned long long kInvalid = ~0ull;  // not a non-negative double
+        auto load_key = [&](int j) -> unsigned long long {
+            const double vj = (j < n_items) ? val(j) : -1.0;
+            return (vj >= 0.0) ? ((unsigned long long)__double_as_longlong(vj) & 0x7fffffffffffffffull) : kInvalid;
+        };
+        // up to 8 keys per thread stay in registers over the 8 passes (windows of <= 4096 landmarks: every key)
+        unsigned long long kreg[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) kreg[q] = load_key(threadIdx.x + q * (int)blockDim.x);
+        const int n_reg = 8 * (int)blockDim.x;
         for (int shift = 56; shift >= 0; shift -= 8) {
             if (threadIdx.x < 256) s_hist[threadIdx.x] = 0u;
             __syncthreads();
             const unsigned long long prefix = s_prefix;
-            for (int j = threadIdx.x; j < wd.n_lm; j += blockDim.x) {
-                const double vj = v[j];
-                if (!(vj >= 0.0)) continue;
-                const unsigned long long key = (unsigned long long)__double_as_longlong(vj) & 0x7fffffffffffffffull;
-                if ((key & mask) == prefix) atomicAdd(&s_hist[(key >> shift) & 255ull], 1u);
+            auto count = [&](unsigned long long key) {  // every lane of the warp calls this (warp vote inside)
+                const bool in = key != kInvalid && (key & mask) == prefix;
+                // the leading bytes are nearly constant (exponent): aggregate equal bins inside the warp first
+                const unsigned bin = in ? (unsigned)((key >> shift) & 255ull) : 256u;
+                const unsigned peers = __match_any_sync(0xffffffffu, bin);
+                if (in && (threadIdx.x & 31) == (unsigned)(__ffs(peers) - 1)) atomicAdd(&s_hist[bin], (unsigned)__popc(peers));
+            };
+#pragma unroll
+            for (int q = 0; q < 8; ++q) count(kreg[q]);
+            for (int j0 = n_reg; j0 < n_items; j0 += 4 * blockDim.x) {  // larger windows: 4 independent loads per round
+                unsigned long long k4[4];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) k4[q] = load_key(j0 + q * (int)blockDim.x + threadIdx.x);
+#pragma unroll
+                for (int q = 0; q < 4; ++q) count(k4[q]);
             }
             __syncthreads();
-            if (threadIdx.x == 0) {
-                int k = s_k, bin = 0;
-                for (; bin < 255; ++bin) {
-                    const int h = (int)s_hist[bin];
-                    if (k < h) break;
-                    k -= h;
+            if (threadIdx.x < 32) {  // warp 0 finds the bin holding rank s_k: 8 bins per lane, shuffle prefix sum
+                const int lane = threadIdx.x;
+                unsigned h[8], tot = 0;
+#pragma unroll
+                for (int q = 0; q < 8; ++q) { h[q] = s_hist[8 * lane + q]; tot += h[q]; }
+                unsigned incl = tot;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const unsigned up = __shfl_up_sync(0xffffffffu, incl, o);
+                    if (lane >= o) incl += up;
                 }
-                s_k = k;
-                s_prefix = prefix | ((unsigned long long)bin << shift);
+                const unsigned k = (unsigned)s_k, excl = incl - tot;
+                const bool mine = k >= excl && k < incl;  // exactly one lane (k < total count)
+                if (mine) {
+                    unsigned rem = k - excl;
+                    int q = 0;
+                    for (; q < 7; ++q) { if (rem < h[q]) break; rem -= h[q]; }
+                    s_k = (int)rem;
+                    s_prefix = prefix | ((unsigned long long)(8 * lane + q) << shift);
+                }
             }
             mask |= 255ull << shift;
             __syncthreads();
         }
         const unsigned long long pivot = s_prefix;  // bit pattern of the value with rank `num`
         const int tie_keep = s_k;                   // ties with fewer than tie_keep smaller-index ties stay
-        for (int j = threadIdx.x; j < wd.n_lm; j += blockDim.x) {
-            const double vj = v[j];
+        for (int j = threadIdx.x; j < n_items; j += blockDim.x) {
+            const double vj = val(j);
             if (!(vj >= 0.0)) continue;
             const unsigned long long key = (unsigned long long)__double_as_longlong(vj) & 0x7fffffffffffffffull;
             if (key < pivot) continue;
             bool reject = key > pivot;
             if (!reject) {
-                const int oj = orig[j];
+                const int oj = oid(j);
                 int before = 0;
-                for (int k = 0; k < wd.n_lm; ++k) {
-                    const double vk = v[k];
+                for (int k = 0; k < n_items; ++k) {
+                    const double vk = val(k);
                     if (!(vk >= 0.0)) continue;
                     const unsigned long long kk = (unsigned long long)__double_as_longlong(vk) & 0x7fffffffffffffffull;
-                    before += (kk == pivot && orig[k] < oj);
+                    before += (kk == pivot && oid(k) < oj);
                 }
                 reject = before >= tie_keep;
             }
-            if (reject) bd.trim_reject[wd.lm_off + j] = 1;
+            if (reject) rej[j] = 1;
         }
         __syncthreads();
     }
     __syncthreads();
     for (int j = threadIdx.x; j < wd.n_lm; j += blockDim.x)
-        if (bd.trim_reject[wd.lm_off + j]) bd.lm_active[wd.lm_off + j] = 0;
+        if (rej[sh ? bd.lm_begin + orig[j] : j]) bd.lm_active[wd.lm_off + j] = 0;
     __syncthreads();
     if (threadIdx.x == 0) {
         st.round++;
@@ -1701,7 +1758,7 @@ __global__ void k_reset_state(BatchDev bd, int rounds_total_override, int min_la
         st.cur = 0;
         st.solve_index = 0; st.round = 0; st.retried = 0; st.log_n = 0; st.n_solves = 0;
         int rounds = rounds_total_override;
-        if (rounds < 0) rounds = (wd.n_lm > min_landmarks_for_trimming) ? num_rounds_option : 0;
+        if (rounds < 0) rounds = ((bd.sharded ? bd.lm_total : wd.n_lm) > min_landmarks_for_trimming) ? num_rounds_option : 0;
         if (rounds > 6) rounds = 6;
         st.rounds_total = rounds;
         st.is_final = (rounds == 0);
@@ -1712,9 +1769,9 @@ __global__ void k_reset_state(BatchDev bd, int rounds_total_override, int min_la
 // =====================================================================================================================
 // launch wrappers
 // =====================================================================================================================
-static inline size_t schur_smem() { return (size_t)2 * 64 * kKS * sizeof(double); }
+static inline size_t schur_smem() { return (size_t)2 * kKC * kGS * sizeof(double); }
 static inline size_t schur_tma_smem() { return (size_t)2 * kStageDoubles * sizeof(double); }
-static inline size_t solve_smem(int ld) { return ((size_t)5 * ld + kNB + kNB * (kNB + 1) + (size_t)ld * (kNB + 1)) * sizeof(double); }
+static inline size_t solve_smem(int ld) { return ((size_t)5 * ld + kNB + kNB * (kNB + 1) + (size_t)(ld + 8) * kPanelStride) * sizeof(double); }
 static inline size_t solve_tiled_smem(int ld) {
     const int nt = ld / 8;
     return ((size_t)5 * ld + kNB + kNB * (kNB + 1) + (size_t)nt * (nt + 1) / 2 * 64) * sizeof(double);
@@ -1737,11 +1794,11 @@ void launch_reset(const BatchDev& bd, const LaunchCfg& lc, cudaStream_t s) {
     k_reset_state<<<bd.n_win, 256, 0, s>>>(bd, lc.rounds_override, lc.min_landmarks_for_trimming, lc.num_rounds_option);
 }
 
-void launch_pass(const BatchDev& bd, const SolveParams& sp, const LaunchCfg& lc, Counters* cnt, cudaStream_t s) {
+int launch_pass(const BatchDev& bd, const SolveParams& sp, const LaunchCfg& lc, Counters* cnt, cudaStream_t s) {
     const int B = bd.n_win;
     const dim3 g_obs((bd.max_obs + 255) / 256, B);
     const dim3 g_lm((bd.max_lm + 7) / 8, B);
-    if (bd.use_panel) k_panel_zero<<<dim3(64, B), 256, 0, s>>>(bd);
+    k_panel_zero<<<dim3(64, B), 256, 0, s>>>(bd);
     k_solve_begin<<<B, 256, 0, s>>>(bd, sp);
     const bool timed = lc.time_jacobian && lc.ev_pool && *lc.ev_used + 2 <= lc.ev_cap;
     if (timed) cudaEventRecord(lc.ev_pool[(*lc.ev_used)++], s);
@@ -1751,29 +1808,59 @@ void launch_pass(const BatchDev& bd, const SolveParams& sp, const LaunchCfg& lc,
     k_pose_hessian<<<dim3(bd.max_kf, B), 256, 0, s>>>(bd, sp);
     k_landmark_reduce<<<dim3((bd.max_lm + 15) / 16, B), 256, 0, s>>>(bd, sp);
     for (int round = 0; round <= lc.max_rank; ++round) k_obs_v<<<g_obs, 256, 0, s>>>(bd, round);
-    if (bd.tot_gp > 0 && bd.use_panel) k_gp_panel<<<dim3((bd.max_gp * 10 + 255) / 256, B), 256, 0, s>>>(bd);
-    if (lc.small_syrk && bd.use_panel) {
+    if (bd.tot_gp > 0) k_gp_panel<<<dim3((bd.max_gp * 10 + 255) / 256, B), 256, 0, s>>>(bd);
+    if (lc.small_syrk) {
         k_schur_syrk_tma<<<dim3(bd.p_split, B), 512, schur_tma_smem(), s>>>(bd);
     } else {
         const int nb = lc.nr_cap_max / 64;
         k_schur_syrk<<<dim3(nb * (nb + 1) / 2, bd.p_split, B), 256, schur_smem(), s>>>(bd);
     }
-    if (bd.p_split > 1) k_sred_reduce<<<dim3((lc.nr_cap_max * lc.nr_cap_max + 255) / 256, B), 256, 0, s>>>(bd);
-    if (lc.nr_cap_max <= 192 && !bd.solve_row_major) k_reduced_solve<true><<<B, 512, solve_tiled_smem(lc.nr_cap_max), s>>>(bd, sp);
-    else k_reduced_solve<false><<<B, 512, solve_smem(lc.nr_cap_max), s>>>(bd, sp);
+    const dim3 g_red((lc.nr_cap_max * lc.nr_cap_max + 255) / 256, B);
+    BatchDev bc = bd;  // consumer view of the reduced system
+    if (bd.sharded) {
+        // the one exchange of the linearisation: reduced system (Schur sums + right-hand side), pose blocks, cost at x
+        if (bd.p_split > 1) k_sred_reduce<<<g_red, 256, 0, s>>>(bd, 1);
+        k_shard_flags<<<1, 32, 0, s>>>(bd, 0);
+        // out of place: a pass that does not re-linearise (rejected step) leaves bkf / cost_part_x untouched, and summing
+        // an already summed buffer again would scale it by the number of ranks
+        const LaunchCfg::WinDescHost& wh = lc.shard_win;
+        int rc = lc.xchg.allreduce(lc.xchg.user, bd.sred, lc.x_sred, (long long)wh.nr_cap * wh.nr_cap, 0, s);
+        rc |= lc.xchg.allreduce(lc.xchg.user, bd.bkf, lc.x_bkf, (long long)wh.n_kf * 27, 0, s);
+        rc |= lc.xchg.allreduce(lc.xchg.user, bd.cost_part_x, lc.x_cost, bd.cost_parts, 0, s);
+        rc |= lc.xchg.allreduce(lc.xchg.user, bd.xs + 8, bd.xs + 8, 2, 0, s);
+        if (rc) return rc;
+        k_shard_flags<<<1, 32, 0, s>>>(bd, 1);
+        bc.sred = lc.x_sred; bc.bkf = lc.x_bkf; bc.cost_part_x = lc.x_cost;  // the solve reads the window-wide sums
+        k_sred_reduce<<<g_red, 256, 0, s>>>(bc, 2);
+    } else if (bd.p_split > 1) {
+        k_sred_reduce<<<g_red, 256, 0, s>>>(bd, 0);
+    }
+    if (bd.solve_tiled) k_reduced_solve<true><<<B, 512, solve_tiled_smem(lc.nr_cap_max), s>>>(bc, sp);
+    else k_reduced_solve<false><<<B, 512, solve_smem(lc.nr_cap_max), s>>>(bc, sp);
     k_backsub<<<dim3((bd.max_lm + 15) / 16, B), 256, 0, s>>>(bd);
     launch_eval_obs<false>(bd, sp, s);
     if (bd.tot_gp > 0) k_gp_eval<false><<<B, 256, 0, s>>>(bd, sp);
+    if (bd.sharded) {  // model decrease / step norm / candidate cost over all ranks
+        k_shard_scalars<<<1, 256, 0, s>>>(bd);
+        int rc = lc.xchg.allreduce(lc.xchg.user, bd.xs, bd.xs, 5, 0, s);
+        rc |= lc.xchg.allreduce(lc.xchg.user, bd.xs + 5, bd.xs + 5, 1, 1, s);
+        if (rc) return rc;
+    }
     k_lm_update<<<(B * 32 + 127) / 128, 128, 0, s>>>(bd, sp);
     k_trim_eval<<<g_lm, 256, 0, s>>>(bd, sp);
+    if (bd.sharded) {  // quantiles are taken over the landmarks of all ranks
+        k_shard_trim_scatter<<<(bd.max_lm + 255) / 256, 256, 0, s>>>(bd);
+        if (int rc = lc.xchg.allreduce(lc.xchg.user, bd.trim_send, bd.trim_glob, 3LL * bd.lm_total, 0, s)) return rc;
+    }
     k_trim_select<<<B, 512, 0, s>>>(bd, sp);
     if (cnt) {
         const int gp = bd.tot_gp > 0 ? 1 : 0;
-        const int prep = 2 + (lc.max_rank + 1) + (gp && bd.use_panel ? 1 : 0);  // pose blocks, landmark blocks, V rows
-        cnt->launches_total += (bd.use_panel ? 1 : 0) + 1 + 1 + gp + prep + 1 + (bd.p_split > 1 ? 1 : 0) + 1 + 1 + 1 + gp + 1 + 2;
+        const int prep = 2 + (lc.max_rank + 1) + gp;  // pose blocks, landmark blocks, V rows
+        cnt->launches_total += 1 + 1 + 1 + gp + prep + 1 + (bd.p_split > 1 ? 1 : 0) + 1 + 1 + 1 + gp + 1 + 2;
         cnt->launches_jacobian += 1; cnt->launches_prep += prep + gp; cnt->launches_schur += 1; cnt->launches_solve += 2;
         cnt->launches_backsub += 1; cnt->launches_cost += 1 + gp; cnt->launches_update += 1; cnt->launches_trim += 2;
     }
+    return 0;
 }
 
 void launch_count_active(const BatchDev& bd, cudaStream_t s) {

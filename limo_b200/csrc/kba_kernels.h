@@ -14,6 +14,13 @@ struct Counters {
     long long jacobian_obs = 0;
 };
 
+// cross-rank reduction hook of the sharded solve: out-of-place all-reduce of `count` doubles on stream s
+// (op 0 = sum, 1 = max); returns 0 on success.  Implemented over NCCL in kba_shard.cu.
+struct Exchange {
+    int (*allreduce)(void* user, const double* send, double* recv, long long count, int op, cudaStream_t s) = nullptr;
+    void* user = nullptr;
+};
+
 struct LaunchCfg {
     int nr_cap_max = 64;
     int max_rank = 0;         // largest observation rank in the batch (multi-camera rigs)
@@ -23,11 +30,14 @@ struct LaunchCfg {
     cudaEvent_t* ev_pool = nullptr;  // pairs of events bracketing each residual/Jacobian launch
     int ev_cap = 0;
     int* ev_used = nullptr;
+    Exchange xchg;  // used when BatchDev::sharded
+    struct WinDescHost { int nr_cap = 0, n_kf = 0; } shard_win;  // shapes of the sharded window (host copy)
+    double *x_sred = nullptr, *x_bkf = nullptr, *x_cost = nullptr;  // window-wide sums (receive buffers of the exchange)
 };
 
 cudaError_t configure_kernels(int nr_cap_max);
 void launch_reset(const BatchDev& bd, const LaunchCfg& lc, cudaStream_t s);
-void launch_pass(const BatchDev& bd, const SolveParams& sp, const LaunchCfg& lc, Counters* cnt, cudaStream_t s);
+int launch_pass(const BatchDev& bd, const SolveParams& sp, const LaunchCfg& lc, Counters* cnt, cudaStream_t s);
 void launch_count_active(const BatchDev& bd, cudaStream_t s);
 void launch_force_linearize(const BatchDev& bd, cudaStream_t s);
 void launch_jacobian_only(const BatchDev& bd, const SolveParams& sp, cudaStream_t s);

@@ -2,7 +2,7 @@
 //   k_landmark_reduce : 16 lanes per landmark -> C_j = sum J_l^T J_l, g_j = sum J_l^T r (shuffle tree), Jacobi-scaled LM
 //                       damping, 3x3 Cholesky, L^-1, z_j = L^-1 g_j, V rows of the landmark's ground-plane block
 //   k_obs_v           : one thread per observation (fully coalesced SoA loads) -> V_i = (J_p^T J_l) L^-T, written either
-//                       into the dense column-major chunk panel the TMA-fed Schur kernel bulk-loads, or to vobs
+//                       into the dense column-major chunk panel the Schur kernels load
 //   k_gp_panel        : ground-plane V rows into the panel (added onto an observation's pose rows when they coincide)
 #pragma once
 #include "kba_device.cuh"
@@ -104,7 +104,7 @@ __global__ void __launch_bounds__(256) k_landmark_reduce(BatchDev bd, SolveParam
             bd.lm_lambda[3 * (size_t)L + a] = lam[a];
             if (st.iter0) bd.lm_scale[3 * (size_t)L + a] = sc[a];
         }
-        if (bd.use_panel) {  // right-hand-side row z_j of the chunk panel
+        {  // right-hand-side row z_j of the chunk panel
             const int ch = wd.chunk_off + (j >> 5);
             const int prs = bd.chunk_rs[ch];
             if (prs > 0) {
@@ -152,13 +152,6 @@ __global__ void __launch_bounds__(256) k_obs_v(BatchDev bd, int round) {
         const double e1 = jp[r] * jl[1] + jp[6 + r] * jl[4] + jp[12 + r] * jl[7];
         const double e2 = jp[r] * jl[2] + jp[6 + r] * jl[5] + jp[12 + r] * jl[8];
         vv[0][r] = e0 * i00; vv[1][r] = e0 * i10 + e1 * i11; vv[2][r] = e0 * i20 + e1 * i21 + e2 * i22;
-    }
-    if (!bd.use_panel) {
-#pragma unroll
-        for (int r = 0; r < 6; ++r)
-#pragma unroll
-            for (int c = 0; c < 3; ++c) bd.vobs[(3 * r + c) * T + o] = vv[c][r];
-        return;
     }
     const int ch = wd.chunk_off + (j >> 5);
     const int prs = bd.chunk_rs[ch];

@@ -116,6 +116,10 @@ def make_window(config=2, seed=None, n_kf=None, n_lm=None, n_obs=None, depth_fra
     for _attempt in range(5000):
         if len(todo) == 0:
             break
+        if _attempt >= 400 and _attempt % 10 == 0:
+            # tracks that cannot be placed in the field of view over their whole length (long tracks on the 100-keyframe
+            # trajectory of config 5) are shortened step by step; configs 1-3 never get here (< 100 attempts)
+            ell[todo] = np.maximum(2, ell[todo] - 1)
         m = len(todo)
         s = start[todo]
         # candidate position: pixel uniform in the image, depth U(4, 60) in the first observing camera

@@ -33,3 +33,5 @@ if __name__ == "__main__":
     if "2" in which: show(synth.make_window(2), "config2")
     if "3" in which: show(synth.make_window(3, seed=41), "config3")
     if "3s" in which: show(synth.make_window(3, seed=41, n_kf=14, n_lm=500, n_obs=4500), "config3-small")
+    if "5" in which: show(synth.make_window(5), "config5")
+    if "5s" in which: show(synth.make_window(5, n_kf=40, n_lm=3000, n_obs=45000), "config5-small")
