@@ -223,3 +223,33 @@ def test_bad_arguments(handle):
     win = synth.make_window(1, n_kf=2, n_lm=20, n_obs=40)
     with pytest.raises(capi.KbaError, match="error 3"):
         handle.solve_window(win)
+
+
+def test_large_window_generic_path_matches_oracle(handle, oracle):
+    """BASELINE config 5 scaled to 40 keyframes (234 reduced rows): the panel-based generic Schur kernel and the
+    global-memory Cholesky with tensor-core trailing update, GPU vs oracle"""
+    win = synth.make_window(5, n_kf=40, n_lm=3000, n_obs=45000)
+    rg = handle.solve_window(win)
+    rc = oracle.solve_window(win, num_threads=8)
+    _compare_solves(rg, rc, win, "config5-small")
+
+
+def test_sharded_solve_with_one_rank_equals_plain_solve(handle):
+    """the landmark-sharded multi-GPU path (NCCL exchange points, window-wide trimming) run with a single rank must
+    reproduce the plain solve bit for bit; with 2 GPUs it is exercised by scripts/config5_sharded.py (profiles/)"""
+    from limo_b200 import capi, parallel
+    win = synth.make_window(5, n_kf=40, n_lm=3000, n_obs=45000)
+    sub, j0, j1 = parallel.shard_window(win, 0, 1)
+    assert (j0, j1) == (0, win.n_lm)
+    comm = capi.ShardComm(handle, 0, 1, capi.shard_unique_id())
+    batch = handle.batch([sub])
+    batch.set_shard(comm, j0, win.n_lm)
+    batch.solve(capi.default_options())
+    rs = batch.download()[0]
+    rp = handle.solve_window(win)
+    assert [s.num_iterations for s in rs.solves] == [s.num_iterations for s in rp.solves]
+    assert np.array_equal(rs.kf_pose, rp.kf_pose)
+    assert np.array_equal(rs.lm_pos[:win.n_lm], rp.lm_pos[:win.n_lm])
+    assert np.array_equal(rs.lm_rejected[:win.n_lm], rp.lm_rejected[:win.n_lm])
+    batch.close()
+    comm.close()
