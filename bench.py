@@ -220,11 +220,41 @@ def main():
         t_up += t1 - t0; t_dn += time.perf_counter() - t2
     e1.record(stream)
     barrier()
-    ms_e2e = max(e0.elapsed_time(e1), 1e3 * (time.perf_counter() - t_wall))
-    clocks = sampler.stop()  # sampled over both timed regions
+    ms_e2e_seq = max(e0.elapsed_time(e1), 1e3 * (time.perf_counter() - t_wall))
+
+    # ---- end-to-end, two steps in flight: a second handle (own stream, own device buffers) lets the host pack and copy
+    #      step i+1 while the GPU solves step i.  Every step still does its own pack + H2D + solve + D2H inside the
+    #      timed region; ctypes releases the GIL during the C calls, so two Python threads are enough. ----
+    stream2 = torch.cuda.Stream()
+    h2 = capi.Handle(local_rank, stream=stream2.cuda_stream)
+    batch2 = h2.batch(windows)
+    results2 = batch2.download()
+    lanes = [(batch, results), (batch2, results2)]
+    for b_, r_ in lanes:  # warm-up of both lanes
+        b_.upload(); b_.solve(opt); b_.download(results=r_)
+    barrier()
+
+    def lane(idx, n_steps):
+        torch.cuda.set_device(local_rank)
+        b_, r_ = lanes[idx]
+        for _ in range(n_steps):
+            b_.upload(); b_.solve(opt); b_.download(results=r_)
+
+    split = [(args.steps + 1) // 2, args.steps // 2]
+    threads = [threading.Thread(target=lane, args=(i, split[i])) for i in range(2) if split[i] > 0]
+    t_wall = time.perf_counter()
+    for t_ in threads:
+        t_.start()
+    for t_ in threads:
+        t_.join()
+    torch.cuda.synchronize()
+    ms_e2e = 1e3 * (time.perf_counter() - t_wall)
+    barrier()
+    ok = ok and all(r.c.status == 0 for r in results2)
+    clocks = sampler.stop()  # sampled over all timed regions
     h2d, d2h = batch.transfer_bytes()
 
-    ms, ms_e2e = parallel.max_over_ranks([ms, ms_e2e], device="cuda")  # the slowest rank defines the step
+    ms, ms_e2e, ms_e2e_seq = parallel.max_over_ranks([ms, ms_e2e, ms_e2e_seq], device="cuda")  # slowest rank
 
     if rank == 0:
         total_windows = world * args.batch * args.steps
@@ -246,6 +276,7 @@ def main():
                        "all_windows_converged": bool(ok)},
             "e2e": {"value": total_windows / (ms_e2e * 1e-3), "unit": "windows/s",
                     "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                    "steps_in_flight": 2, "sequential_value": total_windows / (ms_e2e_seq * 1e-3),
                     "host_pack_upload_ms_per_step": 1e3 * t_up / args.steps,
                     "download_ms_per_step": 1e3 * t_dn / args.steps},
             "gpu_launches": int(cnt.launches_total),
@@ -263,6 +294,8 @@ def main():
             "clocks": clocks,
         }
         print(json.dumps(out))
+    batch2.close()
+    h2.close()
     batch.close()
     h.close()
     parallel.finalize()

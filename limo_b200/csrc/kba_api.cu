@@ -455,6 +455,7 @@ int kba_batch_create(kba_handle* h, int32_t n_windows, const kba_window* w, kba_
 
 int kba_batch_upload(kba_batch* b, int32_t n_windows, const kba_window* w) {
     if (!b || !w || n_windows != b->bd.n_win) return fail(KBA_ERR_BAD_ARG, "bad argument to kba_batch_upload");
+    CU(cudaSetDevice(b->h->device));  // callers may drive several handles from several host threads
     for (int i = 0; i < n_windows; ++i) {
         const WinDesc& d = b->desc_h[i];
         if (w[i].n_kf != d.n_kf || w[i].n_lm != d.n_lm || w[i].n_obs != d.n_obs || w[i].n_cam != d.n_cam)
@@ -541,7 +542,8 @@ static SolveParams make_params(const kba_options* o) {
 
 int kba_batch_solve(kba_batch* b, const kba_options* opt) {
     if (!b || !opt) return fail(KBA_ERR_BAD_ARG, "bad argument to kba_batch_solve");
-    if (opt->precision != 0) return fail(KBA_ERR_CAPACITY, "only the FP64 kernels (precision = 0) are built");
+    if (opt->precision != 0 && opt->precision != 1) return fail(KBA_ERR_BAD_ARG, "kba_options.precision must be 0 (FP64) or 1 (FP32 linearisation)");
+    b->bd.precision = opt->precision;
     kba_handle* h = b->h;
     CU(cudaSetDevice(h->device));
     cudaStream_t s = h->stream;
@@ -619,6 +621,7 @@ int kba_batch_set_shard(kba_batch* b, kba_shard_comm* comm, int32_t lm_begin, in
 
 int kba_batch_download(kba_batch* b, kba_result* res) {
     if (!b || !res) return fail(KBA_ERR_BAD_ARG, "bad argument to kba_batch_download");
+    CU(cudaSetDevice(b->h->device));
     cudaStream_t s = b->h->stream;
     CU(b->state.download(s)); CU(b->log.download(s));
     CU(b->pose_out[0].download(s)); CU(b->pose_out[1].download(s));
@@ -684,6 +687,8 @@ int kba_batch_jacobian_pass(kba_batch* b, const kba_options* opt, int32_t repeat
     kba_handle* h = b->h;
     cudaStream_t s = h->stream;
     const SolveParams sp = make_params(opt);
+    if (opt->precision != 0 && opt->precision != 1) return fail(KBA_ERR_BAD_ARG, "kba_options.precision must be 0 or 1");
+    b->bd.precision = opt->precision;
     launch_reset(b->bd, b->lc, s);
     launch_force_linearize(b->bd, s);
     CU(cudaEventRecord(b->ev_a, s));
@@ -741,9 +746,13 @@ int kba_eval(kba_handle* h, const kba_window* w, const kba_options* opt, kba_eva
     for (size_t e = 0; e < n; ++e) {  // e: internal (sorted) observation slot, o: the caller's observation index
         const size_t o = (size_t)b->obs_orig.h[e];
         const bool fixed = offp[w->obs_kf[o]] < 0;
-        if (out->residual) for (int q = 0; q < 3; ++q) out->residual[3 * o + q] = res_h[q * n + e];
-        if (out->jac_pose) for (int q = 0; q < 18; ++q) out->jac_pose[18 * o + q] = fixed ? 0.0 : jp_h[q * n + e];
-        if (out->jac_lm) for (int q = 0; q < 9; ++q) out->jac_lm[9 * o + q] = jl_h[q * n + e];
+        // precision 1: the streams hold floats (same component-major layout)
+        auto at = [&](const std::vector<double>& v, size_t idx) {
+            return opt->precision ? (double)reinterpret_cast<const float*>(v.data())[idx] : v[idx];
+        };
+        if (out->residual) for (int q = 0; q < 3; ++q) out->residual[3 * o + q] = at(res_h, q * n + e);
+        if (out->jac_pose) for (int q = 0; q < 18; ++q) out->jac_pose[18 * o + q] = fixed ? 0.0 : at(jp_h, q * n + e);
+        if (out->jac_lm) for (int q = 0; q < 9; ++q) out->jac_lm[9 * o + q] = at(jl_h, q * n + e);
     }
     if (out->cost) { double c = 0; for (int q = 0; q < bd.cost_parts; ++q) c += cost_h[q]; out->cost[0] = c; }
     if (out->failed) out->failed[0] = st.eval_failed;

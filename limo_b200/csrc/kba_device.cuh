@@ -143,6 +143,8 @@ struct BatchDev {
     double* trim_send;        // [3][lm_total] this rank's trimming values (+2, 0 where not owned), all-reduced into
     double* trim_glob;        // [3][lm_total]
     uint8_t* reject_glob;     // [lm_total]
+    int precision;            // 0: FP64; 1: residual / Jacobian blocks evaluated and stored in FP32 (res, jp, jl hold floats),
+                              //    every accumulation (landmark blocks, Schur products, solve, cost) stays FP64
     int solve_row_major;      // debug knob: force the global-memory Cholesky even when the tiled one fits
     int solve_tiled;          // 1: k_reduced_solve<true> (<= 192 rows, shared-memory resident)
     int eval_tiles_jac, eval_tiles_cost, eval_min_blocks;  // 256-observation tiles per CTA / CTAs per SM of k_eval_obs
@@ -340,6 +342,11 @@ __device__ inline bool eval_observation_store(const T* __restrict__ pose, const 
         q[2 * stride] = m0 * pose[2] + m1 * pose[5] + m2 * pose[8];
     }
     return true;
+}
+
+// entry `idx` of a materialised linearisation stream (res / jp / jl): doubles, or floats when BatchDev::precision == 1
+__device__ __forceinline__ double lin_load(const double* base, size_t idx, int precision) {
+    return precision ? (double)reinterpret_cast<const float*>(base)[idx] : base[idx];
 }
 
 // stage keyframe poses (as R|t) and cameras of one window into shared memory

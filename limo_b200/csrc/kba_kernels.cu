@@ -152,7 +152,7 @@ __global__ void __launch_bounds__(256) k_panel_zero(BatchDev bd) {
 //   kJac = false: cost only, at the candidate point
 // Algorithmic HBM bytes per observation (FP64, with depth row): 20 read + 240 written.
 // =====================================================================================================================
-template <bool kJac, int kMinBlocks>
+template <bool kJac, int kMinBlocks, typename TLin>
 __global__ void __launch_bounds__(256, kMinBlocks) k_eval_obs(BatchDev bd, SolveParams sp, int tiles) {
     // A CTA walks `tiles` consecutive 256-observation tiles of one window with a two-deep software pipeline: while tile
     // t is evaluated, the measurement / landmark loads of tile t+1 and the landmark-index load of tile t+2 are in
@@ -168,6 +168,9 @@ __global__ void __launch_bounds__(256, kMinBlocks) k_eval_obs(BatchDev bd, Solve
     __shared__ double s_cam[kMaxCam * kCamStride];
     __shared__ double s_red[8];
     __shared__ int s_cnt[8];
+    constexpr bool kF32 = sizeof(TLin) == 4;  // FP32 evaluation + storage of the linearisation (precision 1)
+    __shared__ float s_pose_f[kF32 ? kMaxKf * kPoseStride : 1];
+    __shared__ float s_cam_f[kF32 ? kMaxCam * kCamStride : 1];
     const int buf = kJac ? st.cur : 1 - st.cur;
     const double* __restrict__ lm_buf = bd.lm[buf];
     const int i0 = blockIdx.x * tiles * 256 + threadIdx.x;
@@ -189,6 +192,11 @@ __global__ void __launch_bounds__(256, kMinBlocks) k_eval_obs(BatchDev bd, Solve
     }
     stage_window(wd, bd.pose[buf], bd.cam, s_pose, s_cam);
     __syncthreads();
+    if (kF32) {
+        for (int i = threadIdx.x; i < wd.n_kf * kPoseStride; i += blockDim.x) s_pose_f[i] = (float)s_pose[i];
+        for (int i = threadIdx.x; i < wd.n_cam * kCamStride; i += blockDim.x) s_cam_f[i] = (float)s_cam[i];
+        __syncthreads();
+    }
     double cost = 0.0;
     int done = 0;
 #pragma unroll 1
@@ -215,7 +223,26 @@ __global__ void __launch_bounds__(256, kMinBlocks) k_eval_obs(BatchDev bd, Solve
             const double p[3] = {p0, p1, p2};
             double hr = 0.0;
             bool ok;
-            if (kJac) {  // rows are stored to their SoA slots as they are formed
+            if (kJac && kF32) {
+                // FP32 linearisation; the cost at x keeps the FP64 evaluation so that the step acceptance test compares
+                // like with like (the candidate cost pass is FP64)
+                double r[3], raw[2];
+                ok = eval_observation<double, false>(
+                    s_pose + kPoseStride * k, s_cam + kCamStride * c, p, (double)u, (double)v, (double)d, wgt,
+                    sp.reprojection_thres * sp.reprojection_thres, sp.depth_thres * sp.depth_thres, r, nullptr, nullptr, hr,
+                    raw);
+                if (ok) {
+                    const float pf[3] = {(float)p0, (float)p1, (float)p2};
+                    float hrf;
+                    float* resf = reinterpret_cast<float*>(bd.res) + o;
+                    float* jpf = reinterpret_cast<float*>(bd.jp) + o;
+                    float* jlf = reinterpret_cast<float*>(bd.jl) + o;
+                    eval_observation_store<float>(
+                        s_pose_f + kPoseStride * k, s_cam_f + kCamStride * c, pf, u, v, d, (float)wgt,
+                        (float)(sp.reprojection_thres * sp.reprojection_thres), (float)(sp.depth_thres * sp.depth_thres),
+                        resf, jpf, jlf, (size_t)bd.tot_obs, bd.off_pose[wd.kf_off + k] >= 0, hrf);
+                }
+            } else if (kJac) {  // rows are stored to their SoA slots as they are formed
                 ok = eval_observation_store<double>(
                     s_pose + kPoseStride * k, s_cam + kCamStride * c, p, (double)u, (double)v, (double)d, wgt,
                     sp.reprojection_thres * sp.reprojection_thres, sp.depth_thres * sp.depth_thres, bd.res + o, bd.jp + o,
@@ -259,9 +286,10 @@ static void launch_eval_obs(const BatchDev& bd, const SolveParams& sp, cudaStrea
     const int tiles = kJac ? bd.eval_tiles_jac : bd.eval_tiles_cost;
     const dim3 g((bd.max_obs + 256 * tiles - 1) / (256 * tiles), bd.n_win);
     const int mb = kJac ? bd.eval_min_blocks : 4;
-    if (mb == 2) k_eval_obs<kJac, 2><<<g, 256, 0, s>>>(bd, sp, tiles);
-    else if (mb == 3) k_eval_obs<kJac, 3><<<g, 256, 0, s>>>(bd, sp, tiles);
-    else k_eval_obs<kJac, 4><<<g, 256, 0, s>>>(bd, sp, tiles);
+    if (kJac && bd.precision == 1) k_eval_obs<kJac, 2, float><<<g, 256, 0, s>>>(bd, sp, tiles);
+    else if (mb == 2) k_eval_obs<kJac, 2, double><<<g, 256, 0, s>>>(bd, sp, tiles);
+    else if (mb == 3) k_eval_obs<kJac, 3, double><<<g, 256, 0, s>>>(bd, sp, tiles);
+    else k_eval_obs<kJac, 4, double><<<g, 256, 0, s>>>(bd, sp, tiles);
 }
 
 // =====================================================================================================================
@@ -525,6 +553,17 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 }
 
 constexpr int kBlockSlots = 5;  // ceil(12*13/2 / 16) 16x16 blocks per warp for up to 184 reduced rows
+// Which 16x16 blocks (linear index bi (bi + 1) / 2 + bj of the 12-row lower triangle) a warp owns.  The accumulators are
+// registers, so the map is static; a chunk only touches the blocks inside its keyframe row range (a sub-square of the
+// triangle plus the right-hand-side row), and with the plain cyclic map the busiest warp of such a chunk owns ~1.5x the
+// mean number of active tiles while the per-stage barrier waits for it.  This table was searched offline (random swaps,
+// objective = sum over chunks of the busiest warp's tile count, on config-2 windows plus generic sliding ranges):
+// balance 0.65 -> 0.75 on windows that were not part of the search.
+__constant__ signed char kSyrkBlockOfSlot[16][kBlockSlots] = {
+    {8, 29, 44, 60, 76}, {2, 24, 35, 49, 55}, {14, 22, 47, 61, 77}, {15, 34, 38, 58, 69}, {5, 20, 28, 52, 56},
+    {4, 19, 36, 63, 73}, {3, 17, 40, 62, 72}, {6, 30, 42, 59, 70},  {13, 33, 37, 54, 66}, {7, 18, 41, 45, 75},
+    {1, 23, 39, 64, 71}, {10, 27, 31, 50, 67}, {0, 25, 51, 57, 68}, {11, 26, 46, 65, 74}, {9, 16, 43, 48, -1},
+    {12, 21, 32, 53, -1}};
 
 __global__ void __launch_bounds__(512, 1) k_schur_syrk_tma(BatchDev bd) {
     const int w = blockIdx.y;
@@ -550,6 +589,19 @@ __global__ void __launch_bounds__(512, 1) k_schur_syrk_tma(BatchDev bd) {
 #pragma unroll
         for (int q = 0; q < 4; ++q) acc[s][q][0] = acc[s][q][1] = 0.0;
     const int nb2 = (nt + 1) >> 1;
+    int my_bi[kBlockSlots], my_bj[kBlockSlots];  // this warp's blocks (an empty slot gets a row past the triangle)
+#pragma unroll
+    for (int s = 0; s < kBlockSlots; ++s) {
+        const int t = kSyrkBlockOfSlot[warp][s];
+        int bi = 1 << 20, bj = 0;
+        if (t >= 0) {
+            bi = (int)((sqrtf(8.0f * (float)t + 1.0f) - 1.0f) * 0.5f);
+            while ((bi + 1) * (bi + 2) / 2 <= t) ++bi;
+            while (bi * (bi + 1) / 2 > t) --bi;
+            bj = t - bi * (bi + 1) / 2;
+        }
+        my_bi[s] = bi; my_bj[s] = bj;
+    }
     const int per = (wd.n_chunks + bd.p_split - 1) / bd.p_split;
     const int ch0 = blockIdx.x * per, ch1 = min(wd.n_chunks, ch0 + per);
     const int* crs = bd.chunk_rs + wd.chunk_off;
@@ -586,11 +638,7 @@ __global__ void __launch_bounds__(512, 1) k_schur_syrk_tma(BatchDev bd) {
         };
 #pragma unroll
         for (int s = 0; s < kBlockSlots; ++s) {
-            const int t = s * 16 + warp;
-            int bi = (int)((sqrtf(8.0f * (float)t + 1.0f) - 1.0f) * 0.5f);
-            while ((bi + 1) * (bi + 2) / 2 <= t) ++bi;
-            while (bi * (bi + 1) / 2 > t) --bi;
-            const int bj = t - bi * (bi + 1) / 2;
+            const int bi = my_bi[s], bj = my_bj[s];
             if (bi >= nb2) continue;
             const int ri0 = tile_row(2 * bi), ri1 = tile_row(2 * bi + 1), rj0 = tile_row(2 * bj), rj1 = tile_row(2 * bj + 1);
             if ((ri0 < 0 && ri1 < 0) || (rj0 < 0 && rj1 < 0)) continue;
@@ -634,11 +682,7 @@ __global__ void __launch_bounds__(512, 1) k_schur_syrk_tma(BatchDev bd) {
     double* out = bd.sred + wd.s_off * (size_t)bd.p_split + (size_t)blockIdx.x * wd.nr_cap * wd.nr_cap;
 #pragma unroll
     for (int s = 0; s < kBlockSlots; ++s) {
-        const int t = s * 16 + warp;
-        int bi = (int)((sqrtf(8.0f * (float)t + 1.0f) - 1.0f) * 0.5f);
-        while ((bi + 1) * (bi + 2) / 2 <= t) ++bi;
-        while (bi * (bi + 1) / 2 > t) --bi;
-        const int bj = t - bi * (bi + 1) / 2;
+        const int bi = my_bi[s], bj = my_bj[s];
         if (bi >= nb2) continue;
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
@@ -1295,9 +1339,8 @@ __global__ void __launch_bounds__(256) k_backsub(BatchDev bd) {
         }
         const int gk = (gl >= 0) ? bd.gp_kf[wd.gp_off + gl] : -1;
         for (int o = o0 + hl; o < o1; o += 16) {
-            const int k = bd.obs_kf[base + o];
-            mine |= (k == gk);
-            const int off = bd.off_pose[wd.kf_off + k];
+            if (gk >= 0) mine |= (bd.obs_kf[base + o] == gk);
+            const int off = bd.obs_row[base + o];  // row of the observation's pose block (k_solve_begin), -1: constant
             if (off < 0) continue;
             // the panel rows hold the sum over the rig's cameras: read them once (rank 0)
             if (bd.obs_rank[base + o] != 0) continue;

@@ -30,9 +30,9 @@ __global__ void __launch_bounds__(256) k_landmark_reduce(BatchDev bd, SolveParam
         for (int o = o0 + sl; o < o1; o += 16) {
             double jl[9], r[3];
 #pragma unroll
-            for (int q = 0; q < 9; ++q) jl[q] = bd.jl[q * T + base + o];
+            for (int q = 0; q < 9; ++q) jl[q] = lin_load(bd.jl, q * T + base + o, bd.precision);
 #pragma unroll
-            for (int q = 0; q < 3; ++q) r[q] = bd.res[q * T + base + o];
+            for (int q = 0; q < 3; ++q) r[q] = lin_load(bd.res, q * T + base + o, bd.precision);
             c[0] += jl[0] * jl[0] + jl[3] * jl[3] + jl[6] * jl[6];
             c[1] += jl[0] * jl[1] + jl[3] * jl[4] + jl[6] * jl[7];
             c[2] += jl[0] * jl[2] + jl[3] * jl[5] + jl[6] * jl[8];
@@ -142,9 +142,9 @@ __global__ void __launch_bounds__(256) k_obs_v(BatchDev bd, int round) {
     const double i00 = li[0], i10 = li[1], i11 = li[2], i20 = li[3], i21 = li[4], i22 = li[5];
     double jl[9], jp[18];
 #pragma unroll
-    for (int q = 0; q < 9; ++q) jl[q] = bd.jl[q * T + o];
+    for (int q = 0; q < 9; ++q) jl[q] = lin_load(bd.jl, q * T + o, bd.precision);
 #pragma unroll
-    for (int q = 0; q < 18; ++q) jp[q] = bd.jp[q * T + o];
+    for (int q = 0; q < 18; ++q) jp[q] = lin_load(bd.jp, q * T + o, bd.precision);
     double vv[3][6];  // [column][row]
 #pragma unroll
     for (int r = 0; r < 6; ++r) {
