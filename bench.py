@@ -26,8 +26,8 @@ METRIC = "BA windows/s (30 KF, 3k LM, 40k obs)"
 B_OBS_ALGORITHMIC = 259.0  # bytes per observation of the residual/Jacobian kernel, mono + depth FP64
 # dram__bytes_read.sum + dram__bytes_write.sum of one k_eval_obs<true> launch / its observations, from the ncu --set full
 # capture summarised in profiles/ (re-measured whenever the kernel changes)
-B_OBS_DRAM_MEASURED = 293.0
-TRAFFIC_SOURCE = "ncu --set full, profiles/r01_v5_ncu_summary.md: (0.214 GB read + 1.410 GB written) / 5.54 M observations"
+B_OBS_DRAM_MEASURED = 277.0
+TRAFFIC_SOURCE = "ncu --set full, profiles/r01_v11_ncu_summary.md: (0.200 GB read + 1.293 GB written) / 5.39 M observations"
 
 
 def usable_cores():

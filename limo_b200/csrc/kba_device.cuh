@@ -220,10 +220,10 @@ __host__ __device__ inline void pose_plus(const double* p, const double* d, doub
 }
 
 // Robust loss of one residual block: ScaledLoss(CauchyLoss(a), w): rho = w b log(1 + s/b), rho' = w / (1 + s/b)
-template <typename T>
+template <typename T, bool kCost = true>
 __device__ inline void cauchy(T b, T w, T s, T& half_rho, T& sqrt_rho1) {
     const T sum = T(1) + s / b;
-    half_rho = T(0.5) * w * b * log(sum);
+    half_rho = kCost ? T(0.5) * w * b * log(sum) : T(0);  // callers that only need the Jacobian rows skip the log
     sqrt_rho1 = sqrt(w / sum);
 }
 
@@ -231,7 +231,7 @@ __device__ inline void cauchy(T b, T w, T s, T& half_rho, T& sqrt_rho1) {
 // pose: staged R(9)+t(3); cam: staged Rc(9)+tc(3)+f,cx,cy.  Jacobian rows: d/d(delta_rot) = -2 (m x a), d/d(delta_t) = m,
 // d/d(p) = m R, with m = (row of Pi) * Rc and a = R p   (reference cost_functors_ceres.hpp:91-155,193-212).
 // Returns false when |z_cam| < 0.01 (evaluation failure, cost_functors_ceres.hpp:78-83).
-template <typename T, bool kJac>
+template <typename T, bool kJac, bool kCost = true>
 __device__ inline bool eval_observation(const T* __restrict__ pose, const T* __restrict__ cam, const T p[3], T u, T v,
                                         T d, T wt, T b_repr, T b_depth, T r[3], T jp[18], T jl[9], T& half_rho_sum,
                                         T raw[2]) {
@@ -248,7 +248,7 @@ __device__ inline bool eval_observation(const T* __restrict__ pose, const T* __r
     const T ru = f * xn + cam[13] - u, rv = f * yn + cam[14] - v;
     const T s = ru * ru + rv * rv;
     T hr, sq;
-    cauchy<T>(b_repr, wt, s, hr, sq);
+    cauchy<T, kCost>(b_repr, wt, s, hr, sq);
     half_rho_sum = hr;
     raw[0] = sqrt(s);
     raw[1] = T(-1);
@@ -258,7 +258,7 @@ __device__ inline bool eval_observation(const T* __restrict__ pose, const T* __r
     if (has_d) {
         rd = c2 - d;
         T hrd;
-        cauchy<T>(b_depth, wt, rd * rd, hrd, sqd);
+        cauchy<T, kCost>(b_depth, wt, rd * rd, hrd, sqd);
         half_rho_sum += hrd;
         raw[1] = fabs(rd);
         r[2] = sqd * rd;

@@ -177,14 +177,15 @@ __global__ void __launch_bounds__(256, kMinBlocks) k_eval_obs(BatchDev bd, Solve
     // stage A: landmark index of a tile; stage B: everything else the evaluation reads
     int idx_b = (i0 < n_obs) ? bd.obs_lm[(size_t)obs_off + i0] : -1;                  // tile 0
     int idx_a = (tiles > 1 && i0 + 256 < n_obs) ? bd.obs_lm[(size_t)obs_off + i0 + 256] : -1;  // tile 1
-    int L = -1, kc = 0;
+    int L = -1, kfi = 0, cami = 0, row = -1;  // loaded values are not touched before their tile is evaluated; row: reduced-system row of the pose block (k_solve_begin), < 0: constant keyframe
     float u = 0.f, v = 0.f, d = 0.f;
     double p0 = 0, p1 = 0, p2 = 0, wgt = 0;
     unsigned char act = 0;
     if (idx_b >= 0) {
         const size_t o = (size_t)obs_off + i0;
         L = lm_off + idx_b;
-        kc = bd.obs_kf[o] | (bd.obs_cam[o] << 16);
+        kfi = bd.obs_kf[o]; cami = bd.obs_cam[o];
+        if (kJac) row = bd.obs_row[o];
         u = bd.obs_u[o]; v = bd.obs_v[o]; d = bd.obs_d[o];
         p0 = lm_buf[3 * (size_t)L]; p1 = lm_buf[3 * (size_t)L + 1]; p2 = lm_buf[3 * (size_t)L + 2];
         wgt = bd.lm_weight[L];
@@ -203,14 +204,15 @@ __global__ void __launch_bounds__(256, kMinBlocks) k_eval_obs(BatchDev bd, Solve
     for (int t = 0; t < tiles; ++t) {
         // issue the next tile's loads (stage B of t+1, stage A of t+2) before touching this tile's values
         const int i_n = i0 + (t + 1) * 256;
-        int Ln = -1, kcn = 0;
+        int Ln = -1, kfn = 0, camn = 0, rown = -1;
         float un = 0.f, vn = 0.f, dn = 0.f;
         double q0 = 0, q1 = 0, q2 = 0, wn = 0;
         unsigned char actn = 0;
         if (idx_a >= 0) {
             const size_t o = (size_t)obs_off + i_n;
             Ln = lm_off + idx_a;
-            kcn = bd.obs_kf[o] | (bd.obs_cam[o] << 16);
+            kfn = bd.obs_kf[o]; camn = bd.obs_cam[o];
+            if (kJac) rown = bd.obs_row[o];
             un = bd.obs_u[o]; vn = bd.obs_v[o]; dn = bd.obs_d[o];
             q0 = lm_buf[3 * (size_t)Ln]; q1 = lm_buf[3 * (size_t)Ln + 1]; q2 = lm_buf[3 * (size_t)Ln + 2];
             wn = bd.lm_weight[Ln];
@@ -219,7 +221,7 @@ __global__ void __launch_bounds__(256, kMinBlocks) k_eval_obs(BatchDev bd, Solve
         idx_a = (t + 2 < tiles && i_n + 256 < n_obs) ? bd.obs_lm[(size_t)obs_off + i_n + 256] : -1;
         if (L >= 0 && act) {
             const size_t o = (size_t)obs_off + i0 + t * 256;
-            const int k = kc & 0xffff, c = kc >> 16;
+            const int k = kfi, c = cami;
             const double p[3] = {p0, p1, p2};
             double hr = 0.0;
             bool ok;
@@ -240,13 +242,13 @@ __global__ void __launch_bounds__(256, kMinBlocks) k_eval_obs(BatchDev bd, Solve
                     eval_observation_store<float>(
                         s_pose_f + kPoseStride * k, s_cam_f + kCamStride * c, pf, u, v, d, (float)wgt,
                         (float)(sp.reprojection_thres * sp.reprojection_thres), (float)(sp.depth_thres * sp.depth_thres),
-                        resf, jpf, jlf, (size_t)bd.tot_obs, bd.off_pose[wd.kf_off + k] >= 0, hrf);
+                        resf, jpf, jlf, (size_t)bd.tot_obs, row >= 0, hrf);
                 }
             } else if (kJac) {  // rows are stored to their SoA slots as they are formed
                 ok = eval_observation_store<double>(
                     s_pose + kPoseStride * k, s_cam + kCamStride * c, p, (double)u, (double)v, (double)d, wgt,
                     sp.reprojection_thres * sp.reprojection_thres, sp.depth_thres * sp.depth_thres, bd.res + o, bd.jp + o,
-                    bd.jl + o, (size_t)bd.tot_obs, bd.off_pose[wd.kf_off + k] >= 0, hr);
+                    bd.jl + o, (size_t)bd.tot_obs, row >= 0, hr);
             } else {
                 double r[3], raw[2];
                 ok = eval_observation<double, false>(
@@ -261,7 +263,7 @@ __global__ void __launch_bounds__(256, kMinBlocks) k_eval_obs(BatchDev bd, Solve
                 ++done;
             }
         }
-        L = Ln; kc = kcn; u = un; v = vn; d = dn; p0 = q0; p1 = q1; p2 = q2; wgt = wn; act = actn;
+        L = Ln; kfi = kfn; cami = camn; row = rown; u = un; v = vn; d = dn; p0 = q0; p1 = q1; p2 = q2; wgt = wn; act = actn;
     }
     cost = warp_sum(cost);
     if (kJac) done = __reduce_add_sync(0xffffffffu, done);
@@ -397,7 +399,7 @@ __global__ void __launch_bounds__(256, 2) k_pose_hessian(BatchDev bd, SolveParam
         const double* lm = bd.lm[st.cur] + 3 * (size_t)L;
         const double p[3] = {lm[0], lm[1], lm[2]};
         double r[3], jp[18], jl[9], raw[2], hr;
-        if (!eval_observation<double, true>(s_pose, s_cam + kCamStride * bd.pm_cam[o], p, (double)bd.pm_u[o],
+        if (!eval_observation<double, true, false>(s_pose, s_cam + kCamStride * bd.pm_cam[o], p, (double)bd.pm_u[o],
                                             (double)bd.pm_v[o], (double)bd.pm_d[o], bd.lm_weight[L],
                                             sp.reprojection_thres * sp.reprojection_thres,
                                             sp.depth_thres * sp.depth_thres, r, jp, jl, hr, raw))

@@ -11,7 +11,7 @@ namespace kba {
 
 __device__ __forceinline__ int gp_row(const BatchDev& bd, const WinDesc& wd, int k, int r);
 
-__global__ void __launch_bounds__(256) k_landmark_reduce(BatchDev bd, SolveParams sp) {
+__global__ void __launch_bounds__(256, 4) k_landmark_reduce(BatchDev bd, SolveParams sp) {
     const int w = blockIdx.y;
     WinState& st = bd.state[w];
     if (st.phase != PH_ITERATE) return;
