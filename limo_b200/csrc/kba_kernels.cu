@@ -392,28 +392,56 @@ __global__ void __launch_bounds__(256, 2) k_pose_hessian(BatchDev bd, SolveParam
     for (int q = 0; q < 27; ++q) acc[q] = 0.0;
     const int* kp = bd.kf_ptr + wd.kf_off + w;
     const int e0 = kp[k], e1 = kp[k + 1];
-    for (int e = e0 + threadIdx.x; e < e1; e += blockDim.x) {
-        const size_t o = (size_t)wd.obs_off + e;
-        const int L = wd.lm_off + bd.pm_lm[o];
-        if (!bd.lm_active[L]) continue;
-        const double* lm = bd.lm[st.cur] + 3 * (size_t)L;
-        const double p[3] = {lm[0], lm[1], lm[2]};
-        double r[3], jp[18], jl[9], raw[2], hr;
-        if (!eval_observation<double, true, false>(s_pose, s_cam + kCamStride * bd.pm_cam[o], p, (double)bd.pm_u[o],
-                                            (double)bd.pm_v[o], (double)bd.pm_d[o], bd.lm_weight[L],
-                                            sp.reprojection_thres * sp.reprojection_thres,
-                                            sp.depth_thres * sp.depth_thres, r, jp, jl, hr, raw))
-            continue;  // flagged by k_eval_obs
-        int q = 0;
+    // two-deep software pipeline like k_eval_obs: the landmark index of iteration i+2 and the measurement / landmark
+    // loads of iteration i+1 are in flight while iteration i is evaluated; loaded values are not touched before use
+    const double* __restrict__ lm_buf = bd.lm[st.cur];
+    const size_t ob = (size_t)wd.obs_off;
+    int e = e0 + threadIdx.x;
+    int idx_b = (e < e1) ? bd.pm_lm[ob + e] : -1;
+    int idx_a = (e + (int)blockDim.x < e1) ? bd.pm_lm[ob + e + blockDim.x] : -1;
+    int L = -1, cam = 0;
+    float u = 0.f, v = 0.f, d = 0.f;
+    double p0 = 0, p1 = 0, p2 = 0, wgt = 0;
+    unsigned char act = 0;
+    if (idx_b >= 0) {
+        L = wd.lm_off + idx_b;
+        cam = bd.pm_cam[ob + e]; u = bd.pm_u[ob + e]; v = bd.pm_v[ob + e]; d = bd.pm_d[ob + e];
+        p0 = lm_buf[3 * (size_t)L]; p1 = lm_buf[3 * (size_t)L + 1]; p2 = lm_buf[3 * (size_t)L + 2];
+        wgt = bd.lm_weight[L]; act = bd.lm_active[L];
+    }
+#pragma unroll 1
+    for (; e < e1; e += blockDim.x) {
+        const int en = e + blockDim.x;
+        int Ln = -1, camn = 0;
+        float un = 0.f, vn = 0.f, dn = 0.f;
+        double q0 = 0, q1 = 0, q2 = 0, wn = 0;
+        unsigned char actn = 0;
+        if (idx_a >= 0) {
+            Ln = wd.lm_off + idx_a;
+            camn = bd.pm_cam[ob + en]; un = bd.pm_u[ob + en]; vn = bd.pm_v[ob + en]; dn = bd.pm_d[ob + en];
+            q0 = lm_buf[3 * (size_t)Ln]; q1 = lm_buf[3 * (size_t)Ln + 1]; q2 = lm_buf[3 * (size_t)Ln + 2];
+            wn = bd.lm_weight[Ln]; actn = bd.lm_active[Ln];
+        }
+        idx_a = (en + (int)blockDim.x < e1) ? bd.pm_lm[ob + en + blockDim.x] : -1;
+        if (act) {
+            const double p[3] = {p0, p1, p2};
+            double r[3], jp[18], jl[9], raw[2], hr;
+            if (eval_observation<double, true, false>(s_pose, s_cam + kCamStride * cam, p, (double)u, (double)v, (double)d,
+                                                      wgt, sp.reprojection_thres * sp.reprojection_thres,
+                                                      sp.depth_thres * sp.depth_thres, r, jp, jl, hr, raw)) {
+                int q = 0;
 #pragma unroll
-        for (int a = 0; a < 6; ++a)
+                for (int a = 0; a < 6; ++a)
 #pragma unroll
-            for (int b = a; b < 6; ++b) {
-                acc[q] += jp[a] * jp[b] + jp[6 + a] * jp[6 + b] + jp[12 + a] * jp[12 + b];
-                ++q;
-            }
+                    for (int b = a; b < 6; ++b) {
+                        acc[q] += jp[a] * jp[b] + jp[6 + a] * jp[6 + b] + jp[12 + a] * jp[12 + b];
+                        ++q;
+                    }
 #pragma unroll
-        for (int a = 0; a < 6; ++a) acc[21 + a] += jp[a] * r[0] + jp[6 + a] * r[1] + jp[12 + a] * r[2];
+                for (int a = 0; a < 6; ++a) acc[21 + a] += jp[a] * r[0] + jp[6 + a] * r[1] + jp[12 + a] * r[2];
+            }  // an evaluation failure is flagged by k_eval_obs
+        }
+        L = Ln; cam = camn; u = un; v = vn; d = dn; p0 = q0; p1 = q1; p2 = q2; wgt = wn; act = actn;
     }
 #pragma unroll
     for (int q = 0; q < 27; ++q) {
