@@ -165,6 +165,8 @@ def main():
     torch.cuda.set_device(local_rank)
     parallel.init("nccl", torch.device("cuda", local_rank))
     from limo_b200 import capi
+    # host threads that pack a step's windows: share the box's cores between the ranks and the two steps in flight
+    os.environ.setdefault("KBA_HOST_THREADS", str(max(2, min(16, usable_cores() // (2 * world)))))
 
     n_distinct = max(1, min(args.distinct, args.batch))
     base = make_windows(n_distinct, rank)
