@@ -147,7 +147,8 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--batch", type=int, default=148, help="windows per GPU per step (one per SM)")
+    ap.add_argument("--batch", type=int, default=296, help="windows per GPU per step (two per SM: the windows of a batch\n"
+                    "advance in lock-step passes, a larger batch amortises the passes in which only the slowest windows are left)")
     ap.add_argument("--distinct", type=int, default=16, help="distinct synthetic windows per GPU (tiled to --batch)")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--cpu-sample", type=int, default=16, help="window solves timed for cpu_baseline (~0.7 s each)")
