@@ -384,6 +384,9 @@ int kba_batch_create(kba_handle* h, int32_t n_windows, const kba_window* w, kba_
         bd.eval_min_blocks = knob("KBA_EVAL_MIN_BLOCKS", 2);
         bd.solve_row_major = knob("KBA_SOLVE_ROW_MAJOR", 0);
         bd.solve_tiled = (nr_cap_max <= 192 && !bd.solve_row_major) ? 1 : 0;
+        // a single SM's FP64 rate bounds the one-CTA factorisation of a large system: with few windows spread it
+        const int split_dflt = (!bd.solve_tiled && n_windows <= 16) ? std::max(1, std::min(32, h->sm_count / n_windows)) : 0;
+        bd.solve_split = bd.solve_tiled ? 0 : knob("KBA_SOLVE_SPLIT", split_dflt);
     }
     bd.bs_parts = (bd.max_lm + 15) / 16;
     int bad = 0;
@@ -423,6 +426,7 @@ int kba_batch_create(kba_handle* h, int32_t n_windows, const kba_window* w, kba_
     bad |= b->dev_alloc(&bd.cost_part_x, (size_t)n_windows * bd.cost_parts); bad |= b->dev_alloc(&bd.cost_part_c, (size_t)n_windows * bd.cost_parts);
     bad |= b->dev_alloc(&bd.bs_part, (size_t)n_windows * bd.bs_parts * 4);
     bad |= b->dev_alloc(&bd.sred, (size_t)soff * bd.p_split); bad |= b->dev_alloc(&bd.amat, (size_t)soff);
+    bad |= b->dev_alloc(&bd.chol_w, (size_t)n_windows * 32 * 32); bad |= b->dev_alloc(&bd.chol_invd, (size_t)n_windows * nr_cap_max);
     if (bad) {
         const std::string msg = std::string("device/pinned allocation failed: ") + cudaGetErrorString(cudaGetLastError());
         b->release(); delete b;

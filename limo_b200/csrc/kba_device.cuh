@@ -147,6 +147,9 @@ struct BatchDev {
                               //    every accumulation (landmark blocks, Schur products, solve, cost) stays FP64
     int solve_row_major;      // debug knob: force the global-memory Cholesky even when the tiled one fits
     int solve_tiled;          // 1: k_reduced_solve<true> (<= 192 rows, shared-memory resident)
+    int solve_split;          // > 0: large system of a small batch, factorisation spread over this many CTAs per window
+    double* chol_w;           // [n_win][32*32] inverse of the current diagonal block's factor (split factorisation)
+    double* chol_invd;        // [n_win][nr_cap_max] 1 / L_ii
     int eval_tiles_jac, eval_tiles_cost, eval_min_blocks;  // 256-observation tiles per CTA / CTAs per SM of k_eval_obs
     double* bs_part;          // [n_win][bs_parts][4]: model_e, step_sq, xnorm_sq, gmax_e
     int bs_parts;

@@ -880,8 +880,12 @@ __global__ void __launch_bounds__(256) k_sred_reduce(BatchDev bd, int mode) {
     if (mode != 1 && !bd.solve_tiled) bd.amat[wd.s_off + idx] = (r == n && c == n) ? 0.0 : -s;
 }
 
+// stage 0: the whole solve in this one CTA.  Large reduced systems of small batches split it (launch_pass): stage 1 =
+// assembly, Jacobi scaling and damping only; then per 32-column block k_chol_diag / k_chol_panel / k_chol_trail spread
+// the factorisation over many SMs (one SM's FP64 throughput bounds the n^3/3 trailing flops of a 594-row system at
+// 0.55 ms); stage 2 = back substitution and candidate state only.
 template <bool kTiled>
-__global__ void __launch_bounds__(512, 1) k_reduced_solve(BatchDev bd, SolveParams sp) {
+__global__ void __launch_bounds__(512, 1) k_reduced_solve(BatchDev bd, SolveParams sp, int stage) {
     const int w = blockIdx.x;
     WinState& st = bd.state[w];
     if (st.phase != PH_ITERATE) return;
@@ -906,7 +910,16 @@ __global__ void __launch_bounds__(512, 1) k_reduced_solve(BatchDev bd, SolvePara
     if (tid == 0) s_fail = 0;
     PHASE_DECL;
     PHASE_MARK(0);
-
+    if (stage == 2) {  // the factor is in A (global), what the tail needs comes back from global memory
+        if (st.solve_failed) return;  // also set by stage 1 (evaluation failure) and by k_chol_diag (not positive definite)
+        for (int c = tid; c < n; c += nth) {
+            s_g[c] = bd.grad_f[(size_t)w * bd.nr_cap_max + c];
+            s_lam[c] = bd.lambda_f[(size_t)w * bd.nr_cap_max + c];
+            s_invd[c] = bd.chol_invd[(size_t)w * bd.nr_cap_max + c];
+        }
+        __syncthreads();
+    }
+    if (stage != 2) {
     // ---- cost at x and evaluation failure (fresh linearisation only) ----
     if (st.need_linearize && tid == 0) {
         double c = 0.0;
@@ -1103,6 +1116,8 @@ __global__ void __launch_bounds__(512, 1) k_reduced_solve(BatchDev bd, SolvePara
         A(n, c) += s_g[c];  // augmented row: g_f - V z
     }
     __syncthreads();
+    }  // stage != 2
+    if (stage == 1) return;
 
     PHASE_MARK(3);
     // ---- blocked Cholesky (NB = 32) with the augmented row n carried along: diagonal block by one warp (registers +
@@ -1112,7 +1127,7 @@ __global__ void __launch_bounds__(512, 1) k_reduced_solve(BatchDev bd, SolvePara
     const int lane = tid & 31, warp = tid >> 5, fr = lane >> 2, fc = lane & 3;
     const int NT = (n + 8) >> 3;  // tile rows, including the one holding the augmented row
     const int PS = kNB + 1;
-    for (int kb = 0; kb < n; kb += kNB) {
+    for (int kb = 0; kb < (stage == 0 ? n : 0); kb += kNB) {
         const int nb = min(kNB, n - kb);
         for (int idx = tid; idx < kNB * kNB; idx += nth) {  // stage the diagonal block, identity padded
             const int r = idx >> 5, c = idx & 31;
@@ -1331,6 +1346,122 @@ __global__ void __launch_bounds__(512, 1) k_reduced_solve(BatchDev bd, SolvePara
     }
     PHASE_MARK(6);
     PHASE_PRINT;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Split factorisation of a large reduced system (row-major A in global memory), one 32-column block per launch triple.
+// ---------------------------------------------------------------------------------------------------------------------
+// diagonal block: Cholesky by one warp, then W = L11^-1 (lane j solves column j), both to global memory
+__global__ void __launch_bounds__(32) k_chol_diag(BatchDev bd, int kb) {
+    const int w = blockIdx.x, lane = threadIdx.x;
+    WinState& st = bd.state[w];
+    if (st.phase != PH_ITERATE || st.solve_failed || kb >= st.n_f) return;
+    const WinDesc& wd = bd.desc[w];
+    const int n = st.n_f, ld = wd.nr_cap, nb = min(kNB, n - kb), PS = kNB + 1;
+    double* A = bd.amat + wd.s_off;
+    __shared__ double s_D[kNB * (kNB + 1)];
+    __shared__ double s_inv[kNB];
+    for (int r = 0; r < kNB; ++r)  // row r of the block: coalesced, identity padded
+        s_D[r * PS + lane] = (r < nb && lane <= r) ? A[(size_t)(kb + r) * ld + kb + lane] : ((r == lane) ? 1.0 : 0.0);
+    __syncwarp();
+    if (!warp_chol32(s_D, PS, s_inv, lane)) { if (lane == 0) st.solve_failed = 1; return; }
+    for (int r = 0; r < nb; ++r)
+        if (lane <= r) A[(size_t)(kb + r) * ld + kb + lane] = s_D[r * PS + lane];
+    if (lane < nb) bd.chol_invd[(size_t)w * bd.nr_cap_max + kb + lane] = s_inv[lane];
+    // column `lane` of L11^-1 by forward substitution (the identity padding keeps rows >= nb trivial)
+    double wv[kNB];
+#pragma unroll
+    for (int i = 0; i < kNB; ++i) {
+        double acc = (i == lane) ? 1.0 : 0.0;
+#pragma unroll
+        for (int k = 0; k < i; ++k) acc -= s_D[i * PS + k] * wv[k];
+        wv[i] = acc * s_inv[i];
+    }
+    double* W = bd.chol_w + (size_t)w * kNB * kNB;  // row-major: W[c][q] = (L11^-1)[c][q]
+#pragma unroll
+    for (int i = 0; i < kNB; ++i) W[i * kNB + lane] = wv[i];
+}
+
+// panel: X = B L11^-T = B W^T on the tensor cores, one warp per 8-row strip below the block (incl. the augmented row)
+__global__ void __launch_bounds__(512) k_chol_panel(BatchDev bd, int kb) {
+    const int w = blockIdx.y;
+    const WinState& st = bd.state[w];
+    if (st.phase != PH_ITERATE || st.solve_failed || kb >= st.n_f) return;
+    const WinDesc& wd = bd.desc[w];
+    const int n = st.n_f, ld = wd.nr_cap, nb = min(kNB, n - kb);
+    const int r0 = kb + nb, m = n + 1 - r0;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, fr = lane >> 2, fc = lane & 3;
+    __shared__ double s_W[kNB * kPanelStride];
+    for (int idx = tid; idx < kNB * kNB; idx += blockDim.x)
+        s_W[(idx >> 5) * kPanelStride + (idx & 31)] = bd.chol_w[(size_t)w * kNB * kNB + idx];
+    __syncthreads();
+    const int strip = blockIdx.x * 16 + warp;
+    if (8 * strip >= m) return;
+    double* A = bd.amat + wd.s_off;
+    const int gr = r0 + 8 * strip + fr;
+    const bool live = gr <= n;
+    double a[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) a[k] = (live && 4 * k + fc < nb) ? A[(size_t)gr * ld + kb + 4 * k + fc] : 0.0;
+    double c[4][2];
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+        c[t][0] = c[t][1] = 0.0;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) dmma(c[t][0], c[t][1], a[k], s_W[(8 * t + fr) * kPanelStride + 4 * k + fc]);
+    }
+    __syncwarp();  // every lane has read its part of the strip before any of it is overwritten
+    if (live) {
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+            const int cc = 8 * t + 2 * fc;
+            if (cc < nb) A[(size_t)gr * ld + kb + cc] = c[t][0];
+            if (cc + 1 < nb) A[(size_t)gr * ld + kb + cc + 1] = c[t][1];
+        }
+    }
+}
+
+// trailing update A22 -= X X^T: every CTA copies the panel into shared memory and takes every gridDim.x-th share of
+// the result tiles (tensor cores, result tiles read-modify-written in global memory)
+__global__ void __launch_bounds__(512, 1) k_chol_trail(BatchDev bd, int kb) {
+    const int w = blockIdx.y;
+    const WinState& st = bd.state[w];
+    if (st.phase != PH_ITERATE || st.solve_failed || kb + kNB >= st.n_f) return;  // nothing below a last, partial block
+    const WinDesc& wd = bd.desc[w];
+    const int n = st.n_f, ld = wd.nr_cap;
+    const int r0 = kb + kNB, m = n + 1 - r0, mt = (m + 7) >> 3, ntile = mt * (mt + 1) / 2;
+    const int tid = threadIdx.x, lane = tid & 31, fr = lane >> 2, fc = lane & 3;
+    extern __shared__ double s_P[];  // [8 * mt][kPanelStride]
+    double* A = bd.amat + wd.s_off;
+    for (int idx = tid; idx < 8 * mt * kNB; idx += blockDim.x) {
+        const int i = idx >> 5, c = idx & 31;
+        s_P[i * kPanelStride + c] = (i < m) ? A[(size_t)(r0 + i) * ld + kb + c] : 0.0;
+    }
+    __syncthreads();
+    const int nw = gridDim.x * (blockDim.x >> 5);
+    for (int t = blockIdx.x * (blockDim.x >> 5) + (tid >> 5); t < ntile; t += nw) {
+        int i = (int)((sqrtf(8.0f * (float)t + 1.0f) - 1.0f) * 0.5f);
+        while ((i + 1) * (i + 2) / 2 <= t) ++i;
+        while (i * (i + 1) / 2 > t) --i;
+        const int j = t - i * (i + 1) / 2;
+        const int gr = r0 + 8 * i + fr, gc = r0 + 8 * j + 2 * fc;
+        const bool wr = gr <= n;
+        double2* pc = reinterpret_cast<double2*>(A + (size_t)(wr ? gr : n) * ld + gc);
+        double2 cv = wr ? *pc : make_double2(0.0, 0.0);  // requested before the tensor-core work
+        double a0 = 0.0, a1 = 0.0, b0 = 0.0, b1 = 0.0;
+        const double* pa = s_P + (8 * i + fr) * kPanelStride + fc;
+        const double* pb = s_P + (8 * j + fr) * kPanelStride + fc;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            dmma(a0, a1, pa[8 * k], pb[8 * k]);
+            dmma(b0, b1, pa[8 * k + 4], pb[8 * k + 4]);
+        }
+        if (wr) {
+            cv.x -= a0 + b0;
+            cv.y -= a1 + b1;
+            *pc = cv;
+        }
+    }
 }
 
 // =====================================================================================================================
@@ -1845,6 +1976,7 @@ __global__ void k_reset_state(BatchDev bd, int rounds_total_override, int min_la
 static inline size_t schur_smem() { return (size_t)2 * kKC * kGS * sizeof(double); }
 static inline size_t schur_tma_smem() { return (size_t)2 * kStageDoubles * sizeof(double); }
 static inline size_t solve_smem(int ld) { return ((size_t)5 * ld + kNB + kNB * (kNB + 1) + (size_t)(ld + 8) * kPanelStride) * sizeof(double); }
+static inline size_t trail_smem(int ld) { return (size_t)(ld + 8) * kPanelStride * sizeof(double); }
 static inline size_t solve_tiled_smem(int ld) {
     const int nt = ld / 8;
     return ((size_t)5 * ld + kNB + kNB * (kNB + 1) + (size_t)nt * (nt + 1) / 2 * 64) * sizeof(double);
@@ -1860,6 +1992,8 @@ cudaError_t configure_kernels(int nr_cap_max) {
                                  (int)solve_tiled_smem(nr_cap_max));
         if (e != cudaSuccess) return e;
     }
+    e = cudaFuncSetAttribute(k_chol_trail, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)trail_smem(nr_cap_max));
+    if (e != cudaSuccess) return e;
     return cudaFuncSetAttribute(k_reduced_solve<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)solve_smem(nr_cap_max));
 }
 
@@ -1908,8 +2042,20 @@ int launch_pass(const BatchDev& bd, const SolveParams& sp, const LaunchCfg& lc, 
     } else if (bd.p_split > 1) {
         k_sred_reduce<<<g_red, 256, 0, s>>>(bd, 0);
     }
-    if (bd.solve_tiled) k_reduced_solve<true><<<B, 512, solve_tiled_smem(lc.nr_cap_max), s>>>(bc, sp);
-    else k_reduced_solve<false><<<B, 512, solve_smem(lc.nr_cap_max), s>>>(bc, sp);
+    if (bd.solve_tiled) {
+        k_reduced_solve<true><<<B, 512, solve_tiled_smem(lc.nr_cap_max), s>>>(bc, sp, 0);
+    } else if (!bd.solve_split) {
+        k_reduced_solve<false><<<B, 512, solve_smem(lc.nr_cap_max), s>>>(bc, sp, 0);
+    } else {  // few large windows: the factorisation is spread over the GPU, one 32-column block at a time
+        k_reduced_solve<false><<<B, 512, solve_smem(lc.nr_cap_max), s>>>(bc, sp, 1);
+        const int strips = (lc.nr_cap_max + 7) / 8;
+        for (int kb = 0; kb < lc.nr_cap_max; kb += kNB) {
+            k_chol_diag<<<B, 32, 0, s>>>(bc, kb);
+            k_chol_panel<<<dim3((strips + 15) / 16, B), 512, 0, s>>>(bc, kb);
+            k_chol_trail<<<dim3(bd.solve_split, B), 512, trail_smem(lc.nr_cap_max), s>>>(bc, kb);
+        }
+        k_reduced_solve<false><<<B, 512, solve_smem(lc.nr_cap_max), s>>>(bc, sp, 2);
+    }
     k_backsub<<<dim3((bd.max_lm + 15) / 16, B), 256, 0, s>>>(bd);
     launch_eval_obs<false>(bd, sp, s);
     if (bd.tot_gp > 0) k_gp_eval<false><<<B, 256, 0, s>>>(bd, sp);
@@ -1929,7 +2075,8 @@ int launch_pass(const BatchDev& bd, const SolveParams& sp, const LaunchCfg& lc, 
     if (cnt) {
         const int gp = bd.tot_gp > 0 ? 1 : 0;
         const int prep = 2 + (lc.max_rank + 1) + gp;  // pose blocks, landmark blocks, V rows
-        cnt->launches_total += 1 + 1 + 1 + gp + prep + 1 + (bd.p_split > 1 ? 1 : 0) + 1 + 1 + 1 + gp + 1 + 2;
+        const int split = (!bd.solve_tiled && bd.solve_split) ? 1 + 3 * ((lc.nr_cap_max + kNB - 1) / kNB) : 0;
+        cnt->launches_total += 1 + 1 + 1 + gp + prep + 1 + (bd.p_split > 1 ? 1 : 0) + 1 + split + 1 + 1 + gp + 1 + 2;
         cnt->launches_jacobian += 1; cnt->launches_prep += prep + gp; cnt->launches_schur += 1; cnt->launches_solve += 2;
         cnt->launches_backsub += 1; cnt->launches_cost += 1 + gp; cnt->launches_update += 1; cnt->launches_trim += 2;
     }
