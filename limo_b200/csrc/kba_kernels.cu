@@ -1,7 +1,10 @@
 // kba_kernels.cu -- sm_100a kernels of the window solver.  One LM "pass" over a batch of windows is
-//   k_solve_begin -> k_eval_obs<true> (residual/Jacobian, HBM streaming) -> k_pose_hessian -> k_landmark_prep
-//   -> k_schur_syrk (FP64 tensor-core SYRK) -> k_reduced_solve -> k_backsub -> k_eval_obs<false> (candidate cost)
-//   -> k_lm_update [-> k_trim_eval -> k_trim_select]
+//   k_panel_zero -> k_solve_begin -> k_eval_obs<true> (residual/Jacobian, HBM streaming) [-> k_gp_eval<true>]
+//   -> k_pose_hessian -> k_landmark_reduce -> k_obs_v [-> k_gp_panel]          (kba_prep.cuh: landmark blocks, V panels)
+//   -> k_schur_syrk_tma | k_schur_syrk (FP64 tensor-core SYRK) [-> k_sred_reduce]
+//   -> k_reduced_solve (or, for large systems of small batches: stage 1, k_chol_diag/panel/trail per block, stage 2)
+//   -> k_backsub -> k_eval_obs<false> (candidate cost) [-> k_gp_eval<false>] -> k_lm_update -> k_trim_eval -> k_trim_select
+// with the k_shard_* kernels and NCCL all-reduces in between when one window is sharded over several GPUs (launch_pass).
 // Every kernel looks at the per-window state and returns immediately for windows that have nothing to do, so the
 // host launches a fixed sequence without synchronising per iteration.
 #include "kba_device.cuh"
