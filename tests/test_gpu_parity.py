@@ -24,7 +24,7 @@ def handle():
     h.close()
 
 
-def _compare_solves(res_gpu, res_cpu, win, label="", iter_slack=0):
+def _compare_solves(res_gpu, res_cpu, win, label="", iter_slack=0, lm_p95=1e-6, lm_max=0.1):
     assert res_gpu.c.status == 0, label
     assert res_gpu.c.num_solves == res_cpu.c.num_solves, label
     for a, b in zip(res_gpu.solves, res_cpu.solves):
@@ -45,7 +45,7 @@ def _compare_solves(res_gpu, res_cpu, win, label="", iter_slack=0):
     assert dq <= 1e-7, (label, dq)
     # Landmarks seen twice with almost no parallax are nearly unobservable along the ray (condition ~1e10), so rounding
     # differences show up there first; north_star's tolerances are on poses and cost.  Typical landmarks agree to 1e-6.
-    assert np.percentile(dl, 95) <= 1e-6 and dl.max() <= 0.1, (label, np.percentile(dl, 95), dl.max())
+    assert np.percentile(dl, 95) <= lm_p95 and dl.max() <= lm_max, (label, np.percentile(dl, 95), dl.max())
 
 
 def test_eval_matches_oracle(handle, oracle):
@@ -278,3 +278,23 @@ def test_fp32_linearisation_mode(handle, oracle):
         assert rg.c.final_cost == pytest.approx(rc.c.final_cost, rel=1e-5)
         assert np.linalg.norm(rg.kf_pose[:, 4:] - rc.kf_pose[:, 4:], axis=1).max() <= 5e-3
         assert (rg.lm_rejected[:win.n_lm] != rc.lm_rejected[:win.n_lm]).mean() <= 0.005
+
+
+@pytest.mark.parametrize("case", ["ragged", "all_keyframes_fixed", "evaluation_failure", "tiny"])
+def test_edge_case_windows_match_oracle(handle, oracle, case):
+    """ragged CSR rows (landmarks with zero / one observation), a window whose keyframes are all constant (no reduced
+    system), an evaluation failure at the first iterate (FAILURE termination, then trimming removes the culprit) and a
+    window below min_landmarks_for_trimming: same terminations, iterates and results as the oracle"""
+    from tests import edge_windows as ew
+    win = ew.CASES[case]()
+    rg = handle.solve_window(win)
+    rc = oracle.solve_window(win)
+    # landmarks seen once have a rank-2 block that only the LM damping regularises, and with constant keyframes nothing
+    # couples a badly observed landmark to the rest: their positions are flat directions (cost and poses are not)
+    tol = {"ragged": dict(lm_p95=1e-4, lm_max=1.0), "all_keyframes_fixed": dict(lm_max=np.inf)}.get(case, {})
+    _compare_solves(rg, rc, win, case, **tol)
+    if case == "all_keyframes_fixed":
+        assert np.array_equal(rg.kf_pose, win.kf_pose)
+    if case == "ragged":
+        empty = np.diff(win.lm_obs_ptr) == 0
+        assert empty.sum() == 4 and np.array_equal(rg.lm_pos[:win.n_lm][empty], win.lm_pos[empty])
