@@ -152,6 +152,7 @@ def main():
     ap.add_argument("--distinct", type=int, default=16, help="distinct synthetic windows per GPU (tiled to --batch)")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--cpu-sample", type=int, default=16, help="window solves timed for cpu_baseline (~0.7 s each)")
+    ap.add_argument("--in-flight", type=int, default=4, help="steps in flight of the end-to-end measurement (handles / streams)")
     args = ap.parse_args()
 
     from limo_b200 import parallel
@@ -167,7 +168,7 @@ def main():
     parallel.init("nccl", torch.device("cuda", local_rank))
     from limo_b200 import capi
     # host threads that pack a step's windows: share the box's cores between the ranks and the two steps in flight
-    os.environ.setdefault("KBA_HOST_THREADS", str(max(2, min(16, usable_cores() // (2 * world)))))
+    os.environ.setdefault("KBA_HOST_THREADS", str(max(2, min(16, usable_cores() // (max(2, args.in_flight) * world)))))
 
     n_distinct = max(1, min(args.distinct, args.batch))
     base = make_windows(n_distinct, rank)
@@ -228,11 +229,15 @@ def main():
     # ---- end-to-end, two steps in flight: a second handle (own stream, own device buffers) lets the host pack and copy
     #      step i+1 while the GPU solves step i.  Every step still does its own pack + H2D + solve + D2H inside the
     #      timed region; ctypes releases the GIL during the C calls, so two Python threads are enough. ----
-    stream2 = torch.cuda.Stream()
-    h2 = capi.Handle(local_rank, stream=stream2.cuda_stream)
-    batch2 = h2.batch(windows)
-    results2 = batch2.download()
-    lanes = [(batch, results), (batch2, results2)]
+    n_lanes = max(1, args.in_flight)
+    extra = []
+    lanes = [(batch, results)]
+    for _ in range(n_lanes - 1):
+        st_ = torch.cuda.Stream()
+        h_ = capi.Handle(local_rank, stream=st_.cuda_stream)
+        b_ = h_.batch(windows)
+        extra.append((st_, h_, b_))
+        lanes.append((b_, b_.download()))
     for b_, r_ in lanes:  # warm-up of both lanes
         b_.upload(); b_.solve(opt); b_.download(results=r_)
     barrier()
@@ -243,8 +248,8 @@ def main():
         for _ in range(n_steps):
             b_.upload(); b_.solve(opt); b_.download(results=r_)
 
-    split = [(args.steps + 1) // 2, args.steps // 2]
-    threads = [threading.Thread(target=lane, args=(i, split[i])) for i in range(2) if split[i] > 0]
+    split = [args.steps // n_lanes + (1 if i < args.steps % n_lanes else 0) for i in range(n_lanes)]
+    threads = [threading.Thread(target=lane, args=(i, split[i])) for i in range(n_lanes) if split[i] > 0]
     t_wall = time.perf_counter()
     for t_ in threads:
         t_.start()
@@ -253,7 +258,7 @@ def main():
     torch.cuda.synchronize()
     ms_e2e = 1e3 * (time.perf_counter() - t_wall)
     barrier()
-    ok = ok and all(r.c.status == 0 for r in results2)
+    ok = ok and all(r.c.status == 0 for _, rs in lanes[1:] for r in rs)
     clocks = sampler.stop()  # sampled over all timed regions
     h2d, d2h = batch.transfer_bytes()
 
@@ -274,12 +279,13 @@ def main():
                        "batch_windows_per_gpu": args.batch, "distinct_windows_per_gpu": n_distinct,
                        "parallelism": "independent windows per GPU (no data-path collective)" if world > 1 else "1 GPU",
                        "lm_iterations_per_window_mean": float(np.mean(iters)),
+                       "lm_iterations_per_window_max": int(np.max(iters)),
                        "l2_policy": "inputs larger than L2 (%.1f GB of Jacobian blocks per pass)"
                                     % (args.batch * n_obs_win * 240 / 1e9),
                        "all_windows_converged": bool(ok)},
             "e2e": {"value": total_windows / (ms_e2e * 1e-3), "unit": "windows/s",
                     "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                    "steps_in_flight": 2, "sequential_value": total_windows / (ms_e2e_seq * 1e-3),
+                    "steps_in_flight": n_lanes, "sequential_value": total_windows / (ms_e2e_seq * 1e-3),
                     "host_pack_upload_ms_per_step": 1e3 * t_up / args.steps,
                     "download_ms_per_step": 1e3 * t_dn / args.steps},
             "gpu_launches": int(cnt.launches_total),
@@ -297,8 +303,9 @@ def main():
             "clocks": clocks,
         }
         print(json.dumps(out))
-    batch2.close()
-    h2.close()
+    for _, h_, b_ in extra:
+        b_.close()
+        h_.close()
     batch.close()
     h.close()
     parallel.finalize()
