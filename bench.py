@@ -167,7 +167,7 @@ def main():
     torch.cuda.set_device(local_rank)
     parallel.init("nccl", torch.device("cuda", local_rank))
     from limo_b200 import capi
-    # host threads that pack a step's windows: share the box's cores between the ranks and the two steps in flight
+    # host threads that pack a step's windows: share the box's cores between the ranks and the steps in flight
     os.environ.setdefault("KBA_HOST_THREADS", str(max(2, min(16, usable_cores() // (max(2, args.in_flight) * world)))))
 
     n_distinct = max(1, min(args.distinct, args.batch))
@@ -226,7 +226,7 @@ def main():
     barrier()
     ms_e2e_seq = max(e0.elapsed_time(e1), 1e3 * (time.perf_counter() - t_wall))
 
-    # ---- end-to-end, two steps in flight: a second handle (own stream, own device buffers) lets the host pack and copy
+    # ---- end-to-end, several steps in flight: further handles (own stream, own device buffers) let the host pack and copy
     #      step i+1 while the GPU solves step i.  Every step still does its own pack + H2D + solve + D2H inside the
     #      timed region; ctypes releases the GIL during the C calls, so two Python threads are enough. ----
     n_lanes = max(1, args.in_flight)
@@ -242,14 +242,20 @@ def main():
         b_.upload(); b_.solve(opt); b_.download(results=r_)
     barrier()
 
-    def lane(idx, n_steps):
+    todo = {"left": args.steps}
+    todo_lock = threading.Lock()
+
+    def lane(idx):
         torch.cuda.set_device(local_rank)
         b_, r_ = lanes[idx]
-        for _ in range(n_steps):
+        while True:
+            with todo_lock:  # the lanes pull steps from one counter: balanced for any K
+                if todo["left"] <= 0:
+                    return
+                todo["left"] -= 1
             b_.upload(); b_.solve(opt); b_.download(results=r_)
 
-    split = [args.steps // n_lanes + (1 if i < args.steps % n_lanes else 0) for i in range(n_lanes)]
-    threads = [threading.Thread(target=lane, args=(i, split[i])) for i in range(n_lanes) if split[i] > 0]
+    threads = [threading.Thread(target=lane, args=(i,)) for i in range(min(n_lanes, args.steps))]
     t_wall = time.perf_counter()
     for t_ in threads:
         t_.start()
