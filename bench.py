@@ -302,6 +302,7 @@ def main():
                          "traffic_unit": "bytes per launch", "traffic_source": TRAFFIC_SOURCE,
                          "algorithmic_bytes_per_obs": B_OBS_ALGORITHMIC,
                          "launch_ms_mean": cnt.ms_jacobian / max(cnt.launches_jacobian, 1),
+                         "launches": int(cnt.launches_jacobian), "share_of_timed_region": cnt.ms_jacobian / ms,
                          "obs_per_launch_mean": cnt.jacobian_obs / max(cnt.launches_jacobian, 1)},
             "cpu_baseline": {"value": cpu_val, "unit": "windows/s", "cores": threads, "kind": "port",
                              "sample": "%d full window solves of the same workload, %.1f s (oracle/, OpenMP)"
