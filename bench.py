@@ -168,7 +168,7 @@ def main():
     parallel.init("nccl", torch.device("cuda", local_rank))
     from limo_b200 import capi
     # host threads that pack a step's windows: share the box's cores between the ranks and the steps in flight
-    os.environ.setdefault("KBA_HOST_THREADS", str(max(2, min(16, usable_cores() // (max(2, args.in_flight) * world)))))
+    os.environ.setdefault("KBA_HOST_THREADS", str(max(2, min(16, usable_cores() // (max(1, min(args.in_flight, usable_cores() // (4 * world))) * world)))))
 
     n_distinct = max(1, min(args.distinct, args.batch))
     base = make_windows(n_distinct, rank)
@@ -229,9 +229,12 @@ def main():
     # ---- end-to-end, several steps in flight: further handles (own stream, own device buffers) let the host pack and copy
     #      step i+1 while the GPU solves step i.  Every step still does its own pack + H2D + solve + D2H inside the
     #      timed region; ctypes releases the GIL during the C calls, so two Python threads are enough. ----
-    n_lanes = max(1, args.in_flight)
+    # a lane needs a host thread for the launches plus a few packing threads: fewer lanes when the ranks share few cores
+    n_lanes = max(1, min(args.in_flight, usable_cores() // (4 * world)))
     extra = []
     lanes = [(batch, results)]
+    if n_lanes * world > 1:  # the additional handles sleep while they wait for the GPU (see kba_api.cu wait_stream)
+        os.environ["KBA_BLOCKING_SYNC"] = "1"
     for _ in range(n_lanes - 1):
         st_ = torch.cuda.Stream()
         h_ = capi.Handle(local_rank, stream=st_.cuda_stream)
@@ -304,6 +307,7 @@ def main():
                          "launch_ms_mean": cnt.ms_jacobian / max(cnt.launches_jacobian, 1),
                          "launches": int(cnt.launches_jacobian), "share_of_timed_region": cnt.ms_jacobian / ms,
                          "obs_per_launch_mean": cnt.jacobian_obs / max(cnt.launches_jacobian, 1)},
+            "host_cores": usable_cores(),
             "cpu_baseline": {"value": cpu_val, "unit": "windows/s", "cores": threads, "kind": "port",
                              "sample": "%d full window solves of the same workload, %.1f s (oracle/, OpenMP)"
                                        % (args.cpu_sample, cpu_dt)},

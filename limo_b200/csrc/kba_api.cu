@@ -39,7 +39,23 @@ struct kba_handle {
     std::vector<cudaEvent_t> ev_pool;  // event pairs around every residual/Jacobian launch (kernel timing)
     int ev_used = 0;
     int sm_count = 148;
+    cudaEvent_t ev_block = nullptr;  // blocking-sync event: waiting host threads sleep instead of spinning on a core
+    bool blocking_sync = false;      // KBA_BLOCKING_SYNC=1 at kba_create
 };
+
+// Wait for the handle's stream.  With KBA_BLOCKING_SYNC=1 (read at kba_create) the host thread sleeps on a blocking-sync
+// event instead of spinning on a core (cudaStreamSynchronize spins under the default scheduling policy): for several
+// handles per process / one process per GPU that share the box's cores with the packing threads.
+static cudaError_t wait_stream(kba_handle* h) {
+    if (!h->blocking_sync) return cudaStreamSynchronize(h->stream);  // lowest latency: the default for a lone handle
+    if (!h->ev_block) {
+        const cudaError_t e = cudaEventCreateWithFlags(&h->ev_block, cudaEventBlockingSync | cudaEventDisableTiming);
+        if (e != cudaSuccess) return e;
+    }
+    const cudaError_t e = cudaEventRecord(h->ev_block, h->stream);
+    if (e != cudaSuccess) return e;
+    return cudaEventSynchronize(h->ev_block);
+}
 
 // ---- a device + pinned-host buffer pair, filled on the host and uploaded with one async copy ----------------------------
 template <typename T>
@@ -282,6 +298,7 @@ int kba_create(kba_handle** out, int device) {
     kba_handle* h = new kba_handle();
     h->device = device;
     h->sm_count = prop.multiProcessorCount;
+    { const char* e = std::getenv("KBA_BLOCKING_SYNC"); h->blocking_sync = e && std::atoi(e) != 0; }
     CU(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
     h->own_stream = true;
     CU(cudaEventCreate(&h->ev0));
@@ -295,6 +312,8 @@ void kba_destroy(kba_handle* h) {
     if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
+    if (h->ev_block) cudaEventDestroy(h->ev_block);
+    for (auto& e : h->ev_pool) cudaEventDestroy(e);
     delete h;
 }
 
@@ -576,7 +595,7 @@ int kba_batch_solve(kba_batch* b, const kba_options* opt) {
         if ((pass + 1) % check_every == 0 || pass + 1 == max_passes) {
             launch_count_active(b->bd, s);
             CU(b->n_active.download(s));
-            CU(cudaStreamSynchronize(s));
+            CU(wait_stream(h));
             if (b->n_active.h[0] == 0) break;
             if (opt->solver_time_sec > 0) {
                 const double el = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
@@ -586,7 +605,7 @@ int kba_batch_solve(kba_batch* b, const kba_options* opt) {
     }
     CU(cudaEventRecord(b->ev_b, s));
     CU(b->jac_obs.download(s));
-    CU(cudaStreamSynchronize(s));
+    CU(wait_stream(h));
     CU(cudaGetLastError());
     CU(cudaEventElapsedTime(&b->last_solve_ms, b->ev_a, b->ev_b));
     h->counters.jacobian_obs += (long long)b->jac_obs.h[0];
@@ -631,7 +650,7 @@ int kba_batch_download(kba_batch* b, kba_result* res) {
     CU(b->pose_out[0].download(s)); CU(b->pose_out[1].download(s));
     CU(b->lm_out[0].download(s)); CU(b->lm_out[1].download(s)); CU(b->lm_active.download(s));
     CU(b->plane_out[0].download(s)); CU(b->plane_out[1].download(s));
-    CU(cudaStreamSynchronize(s));
+    CU(wait_stream(b->h));
     const BatchDev& bd = b->bd;
     b->d2h_bytes = sizeof(WinState) * bd.n_win + 2 * (7 * 8 * bd.tot_kf + 3 * 8 * bd.tot_lm) + bd.tot_lm;
     for (int i = 0; i < bd.n_win; ++i) {
