@@ -139,7 +139,7 @@ __global__ void __launch_bounds__(256) k_solve_begin(BatchDev bd, SolveParams sp
 }
 
 // zero the dense V panels of windows that are about to start a solve (the sparsity pattern is fixed within a solve:
-// k_landmark_prep overwrites every structurally non-zero entry in each pass)
+// k_landmark_reduce / k_obs_v / k_gp_panel overwrite every structurally non-zero entry in each pass)
 __global__ void __launch_bounds__(256) k_panel_zero(BatchDev bd) {
     const int w = blockIdx.y;
     if (bd.state[w].phase != PH_SOLVE_BEGIN || bd.desc[w].landmarks_fixed) return;
