@@ -253,6 +253,16 @@ void kba_shard_comm_destroy(kba_shard_comm* c);
  * whole window.  Afterwards kba_batch_solve is a collective call: every rank must make it. */
 int kba_batch_set_shard(kba_batch* b, kba_shard_comm* comm, int32_t lm_begin, int32_t lm_total);
 
+/* ---- landmark initialisation of push() for a whole window ------------------------------------------
+ * Replaces, for all landmarks of `w` at once, what BundleAdjusterKeyframes::push() does per new landmark on the host:
+ * the first observation with a lidar depth (d >= 0) is back-projected (bundle_adjuster_keyframes.cpp:332-355); without
+ * one, the point closest to all viewing rays is taken when there are at least two (cpp:125-159,358-382,
+ * internal/triangulator.hpp:51-75); then the cheirality test of the landmark selector
+ * (landmark_selection_scheme_cheirality.cpp:22-60).  Batch semantics: "first observation" is CSR order (keyframe, then
+ * camera), where the incremental reference looks at the keyframe being pushed.  w->lm_pos is not read.
+ * flags_out[j]: bit 0 = a position was computed, bit 1 = it lies in front of every observing camera. */
+int kba_init_landmarks(kba_handle* h, const kba_window* w, double* lm_pos_out, uint8_t* flags_out, float* device_ms);
+
 /* ---- lidar depth extraction (BASELINE config 4) --------------------------------------------------------------------
  * Replaces the un-vendored mono_lidar_depth::DepthEstimator call the limo front end makes per frame (install_repos.sh:9;
  * in-tree only its parameter file demo_keyframe_bundle_adjustment_meta/res/mono_lidar_fusion_parameters.yaml, whose

@@ -18,7 +18,8 @@ SYMBOLS = ["kba_version", "kba_last_error", "kba_default_options", "kba_create",
            "kba_solve_window", "kba_solve_batch", "kba_eval", "kba_batch_create", "kba_batch_upload",
            "kba_batch_solve", "kba_batch_download", "kba_batch_transfer_bytes", "kba_batch_jacobian_pass", "kba_batch_destroy",
            "kba_get_counters", "kba_enable_kernel_timing", "kba_lidar_default_options", "kba_lidar_depth",
-           "kba_shard_unique_id", "kba_shard_comm_create", "kba_shard_comm_destroy", "kba_batch_set_shard"]
+           "kba_shard_unique_id", "kba_shard_comm_create", "kba_shard_comm_destroy", "kba_batch_set_shard",
+           "kba_init_landmarks"]
 
 
 class KbaError(RuntimeError):
@@ -58,6 +59,7 @@ def lib():
         L.kba_shard_comm_destroy.argtypes = [vp]
         L.kba_shard_comm_destroy.restype = None
         L.kba_batch_set_shard.argtypes = [vp, vp, C.c_int32, C.c_int32]
+        L.kba_init_landmarks.argtypes = [vp, C.POINTER(KbaWindow), c_double_p, C.POINTER(C.c_uint8), C.POINTER(C.c_float)]
         L.kba_lidar_default_options.argtypes = [C.POINTER(KbaLidarOptions)]
         L.kba_lidar_default_options.restype = None
         fp = C.POINTER(C.c_float)
@@ -203,6 +205,16 @@ class Handle:
 
     def batch(self, windows):
         return Batch(self, windows)
+
+    def init_landmarks(self, win):
+        """push() landmark initialisation for every landmark of `win` on the device: (positions, flags, device ms);
+        flags bit 0 = created, bit 1 = in front of every observing camera"""
+        pos = np.zeros((max(win.n_lm, 1), 3))
+        flags = np.zeros(max(win.n_lm, 1), dtype=np.uint8)
+        ms = C.c_float()
+        _check(lib().kba_init_landmarks(self._p, C.byref(win.c), pos.ctypes.data_as(c_double_p),
+                                        flags.ctypes.data_as(C.POINTER(C.c_uint8)), C.byref(ms)))
+        return pos[:win.n_lm], flags[:win.n_lm], ms.value
 
     def lidar_depth(self, cloud, T_cam_lidar, intr, features_uv, opt=None):
         """cloud [n, stride>=3] float32, features_uv [m, 2] float32 -> (depth [m] float32 (-1 = none), device ms)"""

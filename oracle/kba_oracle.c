@@ -1345,3 +1345,75 @@ void kbo_triangulate_rays(int n, const double* R_oc, const double* t_oc, const d
     inv[6] = (A[3] * A[7] - A[4] * A[6]) / det; inv[7] = (A[1] * A[6] - A[0] * A[7]) / det; inv[8] = (A[0] * A[4] - A[1] * A[3]) / det;
     matvec3(inv, b, out);
 }
+
+/* Landmark initialisation of BundleAdjusterKeyframes::push() for every landmark of a window (batch restatement, see
+ * kba_init_landmarks in include/kba_b200.h): back-projection of the first observation with a lidar depth
+ * (bundle_adjuster_keyframes.cpp:332-355), else Triangulator::triangulate_rays over all viewing rays when there are at
+ * least two (cpp:125-159,358-382), then the cheirality test (landmark_selection_scheme_cheirality.cpp:22-60). */
+void kbo_init_landmarks(const kba_window* w, double* lm_pos_out, unsigned char* flags_out) {
+    for (int j = 0; j < w->n_lm; ++j) {
+        const int o0 = w->lm_obs_ptr[j], o1 = w->lm_obs_ptr[j + 1];
+        double p[3] = {0, 0, 0};
+        int created = 0;
+        for (int o = o0; o < o1 && !created; ++o) {
+            if (w->obs_d[o] < 0.f) continue;
+            const int c = w->obs_cam ? w->obs_cam[o] : 0;
+            const double* pose = w->kf_pose + 7 * w->obs_kf[o];
+            const double* cam = w->cam_pose + 7 * c;
+            const double f = w->cam_intr[3 * c], cx = w->cam_intr[3 * c + 1], cy = w->cam_intr[3 * c + 2];
+            double R[9], Rc[9];
+            quat_to_R(pose, R);
+            quat_to_R(cam, Rc);
+            const double z = (double)w->obs_d[o];
+            const double pc[3] = {((double)w->obs_u[o] - cx) * z / f, ((double)w->obs_v[o] - cy) * z / f, z};
+            /* (T_cam_vehicle * T_kf)^-1 * pc = R^T (Rc^T (pc - tc) - t) */
+            double a[3], b[3];
+            for (int i = 0; i < 3; ++i) a[i] = pc[i] - cam[4 + i];
+            for (int i = 0; i < 3; ++i) b[i] = Rc[i] * a[0] + Rc[3 + i] * a[1] + Rc[6 + i] * a[2] - pose[4 + i];
+            for (int i = 0; i < 3; ++i) p[i] = R[i] * b[0] + R[3 + i] * b[1] + R[6 + i] * b[2];
+            created = 1;
+        }
+        if (!created && o1 - o0 >= 2) {
+            const int n = o1 - o0;
+            double* R_oc = (double*)malloc(sizeof(double) * 9 * n);
+            double* t_oc = (double*)malloc(sizeof(double) * 3 * n);
+            double* rays = (double*)malloc(sizeof(double) * 3 * n);
+            for (int q = 0; q < n; ++q) {
+                const int o = o0 + q, c = w->obs_cam ? w->obs_cam[o] : 0;
+                const double* pose = w->kf_pose + 7 * w->obs_kf[o];
+                const double* cam = w->cam_pose + 7 * c;
+                const double f = w->cam_intr[3 * c], cx = w->cam_intr[3 * c + 1], cy = w->cam_intr[3 * c + 2];
+                double R[9], Rc[9];
+                quat_to_R(pose, R);
+                quat_to_R(cam, Rc);
+                double r[3] = {((double)w->obs_u[o] - cx) / f, ((double)w->obs_v[o] - cy) / f, 1.0};
+                const double nr = sqrt(r[0] * r[0] + r[1] * r[1] + r[2] * r[2]);
+                for (int i = 0; i < 3; ++i) rays[3 * q + i] = r[i] / nr;
+                for (int i = 0; i < 3; ++i)  /* R_oc = R^T Rc^T */
+                    for (int k = 0; k < 3; ++k)
+                        R_oc[9 * q + 3 * i + k] = R[i] * Rc[3 * k] + R[3 + i] * Rc[3 * k + 1] + R[6 + i] * Rc[3 * k + 2];
+                double a[3];
+                for (int i = 0; i < 3; ++i) a[i] = Rc[i] * cam[4] + Rc[3 + i] * cam[5] + Rc[6 + i] * cam[6] + pose[4 + i];
+                for (int i = 0; i < 3; ++i) t_oc[3 * q + i] = -(R[i] * a[0] + R[3 + i] * a[1] + R[6 + i] * a[2]);
+            }
+            kbo_triangulate_rays(n, R_oc, t_oc, rays, p);
+            free(R_oc); free(t_oc); free(rays);
+            created = 1;
+        }
+        int front = created;
+        for (int o = o0; o < o1 && front; ++o) {
+            const int c = w->obs_cam ? w->obs_cam[o] : 0;
+            const double* pose = w->kf_pose + 7 * w->obs_kf[o];
+            const double* cam = w->cam_pose + 7 * c;
+            double R[9], Rc[9], x[3];
+            quat_to_R(pose, R);
+            quat_to_R(cam, Rc);
+            for (int i = 0; i < 3; ++i) x[i] = R[3 * i] * p[0] + R[3 * i + 1] * p[1] + R[3 * i + 2] * p[2] + pose[4 + i];
+            const double zc = Rc[6] * x[0] + Rc[7] * x[1] + Rc[8] * x[2] + cam[6];
+            if (zc < 0.0) front = 0;
+        }
+        lm_pos_out[3 * j] = p[0]; lm_pos_out[3 * j + 1] = p[1]; lm_pos_out[3 * j + 2] = p[2];
+        flags_out[j] = (unsigned char)(created | (front << 1));
+    }
+}
+

@@ -62,6 +62,11 @@ int kbo_trimmer_quantile(const double* values, int n, double quantile, unsigned 
 /* Triangulator::triangulate_rays (internal/triangulator.hpp:51-75): R_oc [n*9] row-major, t_oc [n*3], rays [n*3] (unit, camera frame). */
 void kbo_triangulate_rays(int n, const double* R_oc, const double* t_oc, const double* rays, double out[3]);
 
+/* push() landmark initialisation for a whole window: back-projection / ray triangulation / cheirality (batch form of
+ * bundle_adjuster_keyframes.cpp:125-159,332-382 and landmark_selection_scheme_cheirality.cpp:22-60);
+ * flags: bit 0 created, bit 1 in front of every observing camera. */
+void kbo_init_landmarks(const kba_window* w, double* lm_pos_out, unsigned char* flags_out);
+
 /* lidar depth extraction per the parameter file's specification (lidar_oracle.c; parity unpinned, see there) */
 void kbo_lidar_default_options(kba_lidar_options* opt);
 int kbo_lidar_depth(const float* cloud, int n_points, int stride, const double* T_cam_lidar, const double* intr,

@@ -167,6 +167,17 @@ def triangulate_rays(R_oc, t_oc, rays):
     return out
 
 
+def init_landmarks(win):
+    """push() landmark initialisation for every landmark of `win`: (positions [n_lm, 3], flags [n_lm] uint8)"""
+    pos = np.zeros((max(win.n_lm, 1), 3))
+    flags = np.zeros(max(win.n_lm, 1), dtype=np.uint8)
+    L = lib()
+    L.kbo_init_landmarks.argtypes = [C.POINTER(type(win.c)), c_double_p, C.POINTER(C.c_uint8)]
+    L.kbo_init_landmarks.restype = None
+    L.kbo_init_landmarks(C.byref(win.c), pos.ctypes.data_as(c_double_p), flags.ctypes.data_as(C.POINTER(C.c_uint8)))
+    return pos[:win.n_lm], flags[:win.n_lm]
+
+
 def lidar_default_options():
     o = KbaLidarOptions()
     lib().kbo_lidar_default_options(C.byref(o))
