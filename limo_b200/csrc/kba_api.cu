@@ -382,6 +382,10 @@ int kba_batch_create(kba_handle* h, int32_t n_windows, const kba_window* w, kba_
         bd.max_kf = std::max(bd.max_kf, w[i].n_kf); bd.max_gp = std::max(bd.max_gp, w[i].n_gp);
     }
     if (obs > 2000000000LL) { delete b; return fail(KBA_ERR_CAPACITY, "batch exceeds 2^31 observations"); }
+    if (nr_cap_max > 640) {  // shared-memory budget of the panel copies in k_reduced_solve / k_chol_trail (227 KB per CTA)
+        delete b;
+        return fail(KBA_ERR_CAPACITY, "reduced system larger than 640 rows (106 keyframes, or 63 with ground-plane blocks)");
+    }
     bd.tot_kf = kf; bd.tot_cam = cam; bd.tot_lm = lm; bd.tot_obs = obs; bd.tot_chunks = (int)chunks; bd.tot_gp = gp;
     bd.nr_cap_max = nr_cap_max;
     b->lc.nr_cap_max = nr_cap_max;
@@ -466,10 +470,13 @@ int kba_batch_create(kba_handle* h, int32_t n_windows, const kba_window* w, kba_
     bd.gp_lm = b->gp_lm.d; bd.gp_kf = b->gp_kf.d; bd.gp_weight = b->gp_weight.d; bd.gp_of_lm = b->gp_of_lm.d; bd.gp_shared = b->gp_shared.d;
     bd.n_active = b->n_active.d;
     bd.jac_obs = b->jac_obs.d;
-    CU(cudaMemset(bd.jac_obs, 0, sizeof(unsigned long long)));
-    CU(cudaEventCreate(&b->ev_a));
-    CU(cudaEventCreate(&b->ev_b));
-    CU(configure_kernels(nr_cap_max));
+    {   // failures from here on must give the allocations back
+        cudaError_t e = cudaMemset(bd.jac_obs, 0, sizeof(unsigned long long));
+        if (e == cudaSuccess) e = cudaEventCreate(&b->ev_a);
+        if (e == cudaSuccess) e = cudaEventCreate(&b->ev_b);
+        if (e == cudaSuccess) e = configure_kernels(nr_cap_max);
+        if (e != cudaSuccess) { b->release(); delete b; return fail(KBA_ERR_CUDA, cudaGetErrorString(e)); }
+    }
     *out = b;
     const int rc = kba_batch_upload(b, n_windows, w);
     if (rc != KBA_OK) { b->release(); delete b; *out = nullptr; }
