@@ -157,11 +157,38 @@ static void test_motion_only() {  // BundleAdjusterKeyframes.adjustMotionOnly :1
     CHECK(kf.getEigenPose().isApprox(s.gt[4], 0.5));
 }
 
+static void test_landmark_selector() {  // LandmarkSelector.base, cheirality part :649-707
+    const std::vector<Eigen::Vector3d> lms{{0.5, 3., 5.5}, {0., 1., -20.}, {1., -5., 4.}, {2.0, 1., 1.5}, {-2.0, -1., 10.}};
+    std::map<LandmarkId, Landmark::ConstPtr> lm_ptrs;
+    for (size_t i = 0; i < lms.size(); ++i) lm_ptrs[i] = std::make_shared<const Landmark>(lms[i]);
+    const auto poses = getPoses(0., std::make_tuple(0., 0., 0.));
+    auto cam = std::make_shared<Camera>(600., Eigen::Vector2d(300., 200.), Eigen::Isometry3d::Identity());
+    Tracklets ts;
+    ts.stamps = {0, 1, 2, 3, 4};
+    ts.tracks.resize(lms.size());
+    for (size_t i = 0; i < lms.size(); ++i) ts.tracks[i].id = i;
+    for (const auto& pose : poses)  // makeTrackletsDepth :359-417
+        for (size_t i = 0; i < lms.size(); ++i) {
+            const Eigen::Vector3d lm_cam = (cam->getEigenPose() * pose) * lms[i];
+            Eigen::Vector3d proj = cam->getIntrinsicMatrix() * lm_cam;
+            proj /= proj[2];
+            ts.tracks[i].feature_points.push_back(FeaturePoint(float(proj[0]), float(proj[1]), float(lm_cam[2])));
+        }
+    std::map<KeyframeId, Keyframe::ConstPtr> kfs;
+    for (size_t i = 0; i < poses.size(); ++i) kfs[i] = std::make_shared<const Keyframe>(Keyframe(i, ts, cam, poses[i]));
+    LandmarkSelector selector;
+    selector.addScheme(LandmarkRejectionSchemeCheirality::create());
+    const auto selected = selector.select(lm_ptrs, kfs);
+    CHECK(selected.size() == 3);     // the reference's expected count
+    CHECK(selected.count(1) == 0);   // landmark 1 is behind the image plane
+}
+
 int main(int argc, char** argv) {
     const bool gpu = argc > 1 && std::strcmp(argv[1], "gpu") == 0;
     test_triangulator();
     test_landmark_creation();
     test_bookkeeping();
+    test_landmark_selector();
     if (gpu) { test_solve(false); test_solve(true); test_motion_only(); }
     std::printf("%s: %d failed checks\n", gpu ? "gpu" : "cpu", g_fail);
     return g_fail ? 1 : 0;

@@ -188,3 +188,23 @@ def test_deactivate_keyframes(oracle):
     ordered = sorted(b.active_keyframe_ids_)
     assert b.keyframes_[ordered[0]].fixation_status_ == Keyframe.FIX_POSE
     assert b.keyframes_[ordered[1]].fixation_status_ == Keyframe.FIX_SCALE
+
+
+def test_landmark_selector_cheirality():
+    """LandmarkSelector.base, cheirality part (reference test :649-707): five landmarks seen from the five test poses
+    through an identity-extrinsic camera (f = 600, pp = (300, 200)); the library-default rejection scheme keeps exactly
+    three of them (landmark 1 at z = -20 lies behind the image plane, landmark 3 at z = 1.5 falls behind the later
+    poses).  Host logic of the drop-in (A17): the Python mirror here, the C++ facade in tests/cpp/test_facade.cpp."""
+    from limo_b200.adjuster import Camera, Keyframe, Landmark, LandmarkSelector
+    lms = [np.array(p) for p in ((0.5, 3., 5.5), (0., 1., -20.), (1., -5., 4.), (2.0, 1., 1.5), (-2.0, -1., 10.))]
+    poses = rs.get_poses(0.0, (0.0, 0.0, 0.0))
+    cam = Camera(600.0, (300.0, 200.0), np.eye(4))
+    ts = rs.make_tracklets(poses, lms, {0: cam}, (0.0, 0.0, 0.0), {i: [0] for i in range(len(lms))}, with_depth=True)
+    landmarks = {i: Landmark(p) for i, p in enumerate(lms)}
+    kfs = {i: Keyframe(i, ts, cam, pose) for i, pose in enumerate(poses)}
+    selected = LandmarkSelector().select(landmarks, kfs)
+    assert len(selected) == 3 and 1 not in selected
+    # the batch restatement used by the device kernel agrees on which landmarks are in front of every camera
+    behind = {i for i, p in enumerate(lms)
+              if any((cam.getEigenPose() @ pose @ np.append(p, 1.0))[2] < 0 for pose in poses)}
+    assert selected == set(range(5)) - behind
