@@ -23,7 +23,11 @@ sys.path.insert(0, ROOT)
 import numpy as np  # noqa: E402
 
 METRIC = "BA windows/s (30 KF, 3k LM, 40k obs)"
-B_OBS_ALGORITHMIC = 259.0  # bytes per observation of the residual/Jacobian kernel, mono + depth FP64
+# Algorithmic bytes per observation of the residual/Jacobian kernel, mono + depth FP64: reads u, v, d (12) +
+# keyframe index (4) + landmark data (~3); writes residual 3x8 + J_pose 3x6x8 [+ J_landmark 3x3x8].  Since round 2 the
+# small-window path does not materialise J_landmark (its consumers re-form it as J_pose[:, 3:6] R): 259 - 72 = 187 B.
+FUSED = os.environ.get("KBA_FUSED", "1") != "0"
+B_OBS_ALGORITHMIC = 187.0 if FUSED else 259.0
 # dram__bytes_read.sum + dram__bytes_write.sum of one k_eval_obs<true> launch / its observations, from the ncu --set full
 # capture summarised in profiles/ (re-measured whenever the kernel changes)
 B_OBS_DRAM_MEASURED = 277.0

@@ -11,22 +11,42 @@
 #include <cmath>
 #include <cstddef>
 
+#include <limits>
+
 #define EIGEN_MAKE_ALIGNED_OPERATOR_NEW
+
+// Real Eigen leaves default-constructed fixed-size objects UNINITIALISED.  This subset only exposes spellings that exist
+// in Eigen 3.3; to make sure the facade does not lean on anything else either, default construction fills with NaN when
+// KBA_EIGEN_POISON_UNINIT is defined (the strict build leg of tests/test_cpp_facade.py): code that reads a
+// default-constructed vector or matrix before writing it then fails its tests instead of silently seeing zeros.
+#ifdef KBA_EIGEN_POISON_UNINIT
+#define KBA_EIGEN_FILL std::numeric_limits<double>::quiet_NaN()
+#else
+#define KBA_EIGEN_FILL 0.0
+#endif
 
 namespace Eigen {
 
 struct Vector2d {
-    double v[2]{0, 0};
+    double v[2]{KBA_EIGEN_FILL, KBA_EIGEN_FILL};
     Vector2d() = default;
     Vector2d(double a, double b) : v{a, b} {}
     double& operator[](int i) { return v[i]; }
     double operator[](int i) const { return v[i]; }
     double x() const { return v[0]; }
     double y() const { return v[1]; }
+    Vector2d operator-(const Vector2d& o) const { return {v[0] - o.v[0], v[1] - o.v[1]}; }
+    Vector2d operator+(const Vector2d& o) const { return {v[0] + o.v[0], v[1] + o.v[1]}; }
+    double norm() const { return std::sqrt(v[0] * v[0] + v[1] * v[1]); }
+    static Vector2d Zero() { return {0., 0.}; }
+};
+
+struct RowVector3d {  // what Vector3d::transpose() yields: only usable as the right factor of an outer product
+    double v[3];
 };
 
 struct Vector3d {
-    double v[3]{0, 0, 0};
+    double v[3]{KBA_EIGEN_FILL, KBA_EIGEN_FILL, KBA_EIGEN_FILL};
     Vector3d() = default;
     Vector3d(double a, double b, double c) : v{a, b, c} {}
     explicit Vector3d(const double* p) : v{p[0], p[1], p[2]} {}
@@ -54,16 +74,18 @@ struct Vector3d {
     Vector3d operator/(double s) const { return {v[0] / s, v[1] / s, v[2] / s}; }
     Vector3d& operator+=(const Vector3d& o) { v[0] += o.v[0]; v[1] += o.v[1]; v[2] += o.v[2]; return *this; }
     Vector3d& operator/=(double s) { v[0] /= s; v[1] /= s; v[2] /= s; return *this; }
-    static Vector3d Zero() { return {}; }
+    RowVector3d transpose() const { return {{v[0], v[1], v[2]}}; }
+    static Vector3d Zero() { return {0., 0., 0.}; }
 };
 inline Vector3d operator*(double s, const Vector3d& a) { return a * s; }
 
 struct Matrix3d {
-    double m[9]{0, 0, 0, 0, 0, 0, 0, 0, 0};  // row-major
+    double m[9]{KBA_EIGEN_FILL, KBA_EIGEN_FILL, KBA_EIGEN_FILL, KBA_EIGEN_FILL, KBA_EIGEN_FILL,
+                KBA_EIGEN_FILL, KBA_EIGEN_FILL, KBA_EIGEN_FILL, KBA_EIGEN_FILL};  // row-major
     double& operator()(int i, int j) { return m[3 * i + j]; }
     double operator()(int i, int j) const { return m[3 * i + j]; }
-    static Matrix3d Identity() { Matrix3d r; r.m[0] = r.m[4] = r.m[8] = 1; return r; }
-    static Matrix3d Zero() { return {}; }
+    static Matrix3d Zero() { Matrix3d r; for (int i = 0; i < 9; ++i) r.m[i] = 0.; return r; }
+    static Matrix3d Identity() { Matrix3d r = Zero(); r.m[0] = r.m[4] = r.m[8] = 1; return r; }
     Matrix3d transpose() const { Matrix3d r; for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) r(i, j) = (*this)(j, i); return r; }
     Matrix3d operator*(const Matrix3d& o) const {
         Matrix3d r;
@@ -88,7 +110,11 @@ struct Matrix3d {
         return r;
     }
 };
-inline Matrix3d outer(const Vector3d& a, const Vector3d& b) { Matrix3d r; for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) r(i, j) = a[i] * b[j]; return r; }
+inline Matrix3d operator*(const Vector3d& a, const RowVector3d& b) {  // a * b.transpose()
+    Matrix3d r;
+    for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) r(i, j) = a[i] * b.v[j];
+    return r;
+}
 
 struct Quaterniond;
 struct AngleAxisd {
@@ -167,7 +193,7 @@ inline AngleAxisd::AngleAxisd(const Quaterniond& q) {  // Eigen/src/Geometry/Ang
 inline Matrix3d operator*(const AngleAxisd& a, const AngleAxisd& b) { return a.toRotationMatrix() * b.toRotationMatrix(); }
 
 struct Matrix4d {
-    double m[16]{};
+    double m[16]{0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
     double operator()(int i, int j) const { return m[4 * i + j]; }
     double& operator()(int i, int j) { return m[4 * i + j]; }
     bool isApprox(const Matrix4d& o, double prec = 1e-12) const {
@@ -179,8 +205,8 @@ struct Matrix4d {
 
 // Transform<double, 3, Isometry>
 struct Isometry3d {
-    Matrix3d R = Matrix3d::Identity();
-    Vector3d t;
+    Matrix3d R = Matrix3d::Identity();   // (a default-constructed Eigen::Transform is uninitialised too; every use in the
+    Vector3d t = Vector3d::Zero();       //  facade starts from Identity())
     static Isometry3d Identity() { return {}; }
     void setIdentity() { *this = Isometry3d(); }
     Isometry3d& translate(const Vector3d& v) { t += R * v; return *this; }

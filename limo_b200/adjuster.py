@@ -363,12 +363,16 @@ class BundleAdjusterKeyframes:
     def _pack(self, kfs, lm_ids, landmarks_fixed=False):
         """addKeyframeToProblem (cpp:564-627) as a landmark-major CSR.  kfs: keyframes in ascending id order."""
         kf_index = {kf.timestamp_: i for i, kf in enumerate(kfs)}
+        # cameras are de-duplicated by VALUE: the production node creates a new Camera object per frame
+        # (mono_lidar.cpp:112), object identity would give one camera per keyframe
+        def cam_key(cam):
+            return (cam.focal_length, *np.asarray(cam.principal_point, dtype=float), *np.asarray(cam.pose_camera_vehicle, dtype=float))
         cam_list, cam_index = [], {}
         for kf in kfs:
             for cam_id in sorted(kf.cameras_):
                 cam = kf.cameras_[cam_id]
-                if id(cam) not in cam_index:
-                    cam_index[id(cam)] = len(cam_list)
+                if cam_key(cam) not in cam_index:
+                    cam_index[cam_key(cam)] = len(cam_list)
                     cam_list.append(cam)
         lm_ids = sorted(lm_ids)
         ptr, okf, ocam, ou, ov, od = [0], [], [], [], [], []
@@ -379,7 +383,7 @@ class BundleAdjusterKeyframes:
                     continue
                 for cam_id in sorted(m):
                     fp = m[cam_id]
-                    okf.append(kf_index[kf.timestamp_]); ocam.append(cam_index[id(kf.cameras_[cam_id])])
+                    okf.append(kf_index[kf.timestamp_]); ocam.append(cam_index[cam_key(kf.cameras_[cam_id])])
                     ou.append(fp.u); ov.append(fp.v); od.append(fp.d)
             ptr.append(len(okf))
         return dict(

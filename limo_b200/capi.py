@@ -11,7 +11,7 @@ import numpy as np
 from .capi_types import (KbaCounters, KbaEvalOut, KbaLidarOptions, KbaOptions, KbaResult, KbaWindow, Result, c_double_p, c_int32_p)
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libkba_b200.so")
+LIB_PATH = os.environ.get("KBA_LIB_PATH") or os.path.join(_HERE, "libkba_b200.so")  # KBA_LIB_PATH: instrumented builds
 _lib = None
 
 SYMBOLS = ["kba_version", "kba_last_error", "kba_default_options", "kba_create", "kba_destroy", "kba_set_stream",

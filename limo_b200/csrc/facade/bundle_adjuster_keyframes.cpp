@@ -1,9 +1,11 @@
 // bundle_adjuster_keyframes.cpp -- the replacement translation unit for limo's
-// keyframe_bundle_adjustment/src/{bundle_adjuster_keyframes,keyframe,definitions,landmark_selection_scheme_cheirality}.cpp:
-// window bookkeeping on the host exactly as the reference does it, the solve through the C ABI (kba_b200.h).
+// keyframe_bundle_adjustment/src/bundle_adjuster_keyframes.cpp (the other sources of the facade: definitions.cpp,
+// keyframe.cpp, landmark_selection.cpp): window bookkeeping on the host exactly as the reference does it, the solve
+// through the C ABI (kba_b200.h).
 #include "keyframe_bundle_adjustment/bundle_adjuster_keyframes.hpp"
 
 #include <algorithm>
+#include <array>
 #include <cmath>
 #include <iterator>
 #include <sstream>
@@ -13,153 +15,13 @@
 
 namespace keyframe_bundle_adjustment {
 
-// ---- definitions.cpp ---------------------------------------------------------------------------------------------------
-Pose convert(EigenPose p) {
-    Eigen::Quaterniond q(p.rotation());
-    return Pose{{q.w(), q.x(), q.y(), q.z(), p.translation()[0], p.translation()[1], p.translation()[2]}};
-}
-EigenPose convert(const Pose& pose) {
-    EigenPose p = EigenPose::Identity();
-    p.translate(Eigen::Vector3d(pose[4], pose[5], pose[6]));
-    p.rotate(Eigen::Quaterniond(pose[0], pose[1], pose[2], pose[3]));
-    return p;
-}
-TimestampSec convert(const TimestampNSec& ts) { return static_cast<TimestampSec>(ts * 1e-09); }
-TimestampNSec convert(const TimestampSec& ts) { return static_cast<TimestampNSec>(ts * 1e09); }
-double calcQuaternionDiff(const Pose& p0, const Pose& p1) {
-    Eigen::Quaterniond q0(p0[0], p0[1], p0[2], p0[3]), q1(p1[0], p1[1], p1[2], p1[3]);
-    return Eigen::AngleAxisd(q1.inverse() * q0).angle();
-}
-
-Camera::Camera(double f, const Eigen::Vector2d& pp, const EigenPose& pose_cam_veh) : focal_length(f), principal_point(pp) {
-    pose_camera_vehicle = convert(pose_cam_veh);
-    intrin_inv = getIntrinsicMatrix().inverse();
-}
-Eigen::Matrix3d Camera::getIntrinsicMatrix() const {
-    Eigen::Matrix3d K;
-    K(0, 0) = focal_length; K(0, 2) = principal_point[0]; K(1, 1) = focal_length; K(1, 2) = principal_point[1]; K(2, 2) = 1.;
-    return K;
-}
-EigenPose Camera::getEigenPose() const { return convert(pose_camera_vehicle); }
-
-// ---- keyframe.cpp -------------------------------------------------------------------------------------------------------
-Keyframe::Keyframe(TimestampNSec timestamp, const Tracklets& tracklets, std::map<CameraId, Camera::Ptr> cameras,
-                   std::map<LandmarkId, CameraIds> landmark_to_cameras, EigenPose p, FixationStatus fix_stat,
-                   Plane ground_plane)
-        : timestamp_(timestamp), cameras_(cameras), fixation_status_(fix_stat), local_ground_plane_(ground_plane),
-          is_active_(true) {
-    assignMeasurements(tracklets, landmark_to_cameras);
-    assignPose(p);
-}
-Keyframe::Keyframe(TimestampNSec timestamp, const Tracklets& tracklets, Camera::Ptr camera, EigenPose p,
-                   FixationStatus fix_stat, Plane ground_plane)
-        : timestamp_(timestamp), fixation_status_(fix_stat), local_ground_plane_(ground_plane), is_active_(true) {
-    cameras_[0] = camera;
-    assignMeasurements(tracklets, CameraId(0));
-    assignPose(p);
-}
-void Keyframe::assignMeasurements(const Tracklets& tracklets, const std::map<LandmarkId, CameraIds>& lookup) {
-    std::map<CameraId, Tracklets> out;
-    for (const auto& track : tracklets.tracks)
-        for (const auto& cam_id : lookup.at(track.id)) {
-            out[cam_id].stamps = tracklets.stamps;
-            out[cam_id].tracks.push_back(track);
-        }
-    for (const auto& el : out) assignMeasurements(el.second, el.first);
-}
-void Keyframe::assignMeasurements(const Tracklets& tracklets, const CameraId& cam_id) {
-    auto iter = std::find(tracklets.stamps.begin(), tracklets.stamps.end(), this->timestamp_);
-    const int index = int(std::distance(tracklets.stamps.begin(), iter));
-    for (const auto& track : tracklets.tracks)
-        if (index < int(track.feature_points.size())) measurements_[track.id][cam_id] = track.feature_points[index];
-}
-std::map<CameraId, Measurement> Keyframe::getMeasurements(LandmarkId lm_id) const {
-    std::map<CameraId, Measurement> out;
-    for (const auto& cam : cameras_)
-        if (hasMeasurement(lm_id, cam.first)) out[cam.first] = getMeasurement(lm_id, cam.first);
-    return out;
-}
-bool Keyframe::hasMeasurement(const LandmarkId& lm_id, const CameraId& cam_id) const {
-    auto it = measurements_.find(lm_id);
-    return it != measurements_.cend() && it->second.find(cam_id) != it->second.cend();
-}
-bool Keyframe::hasMeasurement(LandmarkId lm_id) const {
-    for (const auto& cam : cameras_)
-        if (hasMeasurement(lm_id, cam.first)) return true;
-    return false;
-}
-std::map<CameraId, Eigen::Vector3d> Keyframe::getProjectedLandmarkPosition(
-    const std::pair<LandmarkId, Landmark::ConstPtr>& id_lm) const {
-    std::map<CameraId, Eigen::Vector3d> out;
-    auto it = measurements_.find(id_lm.first);
-    if (it == measurements_.cend()) return out;
-    const Eigen::Vector3d p_vehicle = getEigenPose() * Eigen::Vector3d(id_lm.second->pos.data());
-    for (const auto& cam_meas : it->second) out[cam_meas.first] = cameras_.at(cam_meas.first)->getEigenPose() * p_vehicle;
-    return out;
-}
-
-// ---- landmark selection ---------------------------------------------------------------------------------------------------
-std::set<LandmarkId> LandmarkRejectionSchemeCheirality::getSelection(const LandmarkMap& landmarks,
-                                                                     const KeyframeMap& keyframes) const {
-    std::set<LandmarkId> out;
-    for (const auto& lm_el : landmarks) {
-        bool ok = true;
-        for (const auto& id_kf : keyframes) {
-            if (!id_kf.second->is_active_) continue;
-            for (const auto& cam_lm : id_kf.second->getProjectedLandmarkPosition(lm_el))
-                if (cam_lm.second.z() < 0.) { ok = false; break; }
-            if (!ok) break;
-        }
-        if (ok) out.insert(lm_el.first);
-    }
-    return out;
-}
-
-std::set<LandmarkId> LandmarkSelector::select(const std::map<LandmarkId, Landmark::ConstPtr>& landmarks,
-                                              const std::map<KeyframeId, Keyframe::ConstPtr>& kfs) {
-    std::map<LandmarkId, Landmark::ConstPtr> non_rejected = landmarks;  // landmark_selector.hpp:118-253
-    for (const auto& id : outlier_ids_) non_rejected.erase(id);
-    auto add_to_map = [&](const std::map<LandmarkId, Landmark::ConstPtr>& src, const std::set<LandmarkId>& sel,
-                          std::map<LandmarkId, Landmark::ConstPtr>& dst) {
-        for (const auto& id : sel) { auto it = src.find(id); if (it != src.cend()) dst[id] = it->second; }
-    };
-    for (const auto& scheme : rejection_schemes_) {
-        auto cur = scheme->getSelection(non_rejected, kfs);
-        non_rejected.clear();
-        add_to_map(landmarks, cur, non_rejected);
-    }
-    std::map<LandmarkId, Landmark::ConstPtr> selected;
-    for (const auto& scheme : selection_schemes_) add_to_map(non_rejected, scheme->getSelection(non_rejected, kfs), selected);
-    std::map<LandmarkId, Landmark::ConstPtr> sparsified = non_rejected;
-    for (const auto& scheme : sparsification_schemes_) {
-        auto cur = scheme->getSelection(sparsified, kfs);
-        sparsified.clear();
-        add_to_map(non_rejected, cur, sparsified);
-    }
-    for (const auto& el : selected) sparsified[el.first] = el.second;
-    std::set<LandmarkId> selection;
-    for (const auto& el : sparsified) selection.insert(el.first);
-    TimestampNSec cur_ts = 0;
-    for (const auto& kf : kfs) cur_ts = std::max(cur_ts, kf.second->timestamp_);
-    for (const auto& lm : landmarks)
-        if (!selection.count(lm.first)) { unselected_lms_[lm.first] += 1; last_time_seen_[lm.first] = cur_ts; }
-    const TimestampNSec ten = convert(TimestampSec(10.));
-    const TimestampNSec oldest = cur_ts > ten ? cur_ts - ten : 0;
-    for (auto it = last_time_seen_.begin(); it != last_time_seen_.end();) {
-        if (it->second < oldest) { unselected_lms_.erase(it->first); it = last_time_seen_.erase(it); }
-        else ++it;
-    }
-    last_selected_lms_ = selection;
-    return selection;
-}
-
 // ---- triangulation ---------------------------------------------------------------------------------------------------------
 Eigen::Vector3d triangulate_rays(const std::vector<std::pair<EigenPose, Eigen::Vector3d>>& poses_rays) {
     Eigen::Matrix3d sum = Eigen::Matrix3d::Zero();
-    Eigen::Vector3d rhs;
+    Eigen::Vector3d rhs = Eigen::Vector3d::Zero();
     for (const auto& p_r : poses_rays) {
         const Eigen::Vector3d r = p_r.first.rotation() * p_r.second;
-        const Eigen::Matrix3d cur = Eigen::Matrix3d::Identity() - Eigen::outer(r, r);
+        const Eigen::Matrix3d cur = Eigen::Matrix3d::Identity() - r * r.transpose();
         sum += cur;
         rhs += cur * p_r.first.translation();
     }
@@ -329,14 +191,22 @@ std::string BundleAdjusterKeyframes::runWindow(const std::vector<Keyframe*>& kfs
     std::vector<uint8_t> kf_fixed;
     std::vector<int32_t> lm_obs_ptr{0}, obs_kf, obs_cam, gp_lm, gp_kf;
     std::vector<float> obs_u, obs_v, obs_d;
-    std::map<const Camera*, int> cam_index;
+    // Cameras are de-duplicated BY VALUE: the production node makes a new Camera object for every frame
+    // (mono_lidar.cpp:112, mono_standalone.cpp:101), so pointer identity would give one "camera" per keyframe.
+    using CamKey = std::array<double, 10>;  // focal length, principal point, pose_camera_vehicle
+    auto cam_key = [](const Camera& c) {
+        CamKey k{{c.focal_length, c.principal_point[0], c.principal_point[1]}};
+        std::copy(c.pose_camera_vehicle.begin(), c.pose_camera_vehicle.end(), k.begin() + 3);
+        return k;
+    };
+    std::map<CamKey, int> cam_index;
     for (const Keyframe* kf : kfs) {
         kf_pose.insert(kf_pose.end(), kf->pose_.begin(), kf->pose_.end());
         kf_fixed.push_back(!motion_only && kf->fixation_status_ == Keyframe::FixationStatus::Pose);  // cpp:198-219
         kf_plane.insert(kf_plane.end(), kf->local_ground_plane_.direction.begin(), kf->local_ground_plane_.direction.end());
         kf_plane.push_back(kf->local_ground_plane_.distance);
         for (const auto& c : kf->cameras_)
-            if (cam_index.emplace(c.second.get(), int(cam_index.size())).second) {
+            if (cam_index.emplace(cam_key(*c.second), int(cam_index.size())).second) {
                 cam_intr.insert(cam_intr.end(), {c.second->focal_length, c.second->principal_point[0], c.second->principal_point[1]});
                 cam_pose.insert(cam_pose.end(), c.second->pose_camera_vehicle.begin(), c.second->pose_camera_vehicle.end());
             }
@@ -351,7 +221,7 @@ std::string BundleAdjusterKeyframes::runWindow(const std::vector<Keyframe*>& kfs
             if (it == kfs[k]->measurements_.end()) continue;
             for (const auto& cm : it->second) {
                 obs_kf.push_back(int32_t(k));
-                obs_cam.push_back(cam_index.at(kfs[k]->cameras_.at(cm.first).get()));
+                obs_cam.push_back(cam_index.at(cam_key(*kfs[k]->cameras_.at(cm.first))));
                 obs_u.push_back(cm.second.u); obs_v.push_back(cm.second.v); obs_d.push_back(cm.second.d);
                 n_depth += cm.second.d > 0.0f;
             }

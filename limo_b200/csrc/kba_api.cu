@@ -88,6 +88,7 @@ struct kba_batch {
     Staged<double> pose0, plane0, cam, lm0, lm_weight;
     Staged<uint8_t> kf_fixed;
     Staged<int> lm_ptr, obs_kf, obs_cam, obs_lm, kf_ptr, pm_lm, pm_cam, chunk_lm0, chunk_lm1, chunk_k0, chunk_k1, lm_orig, obs_orig;
+    Staged<int> grp_k0, grp_k1;
     Staged<int> obs_rank;
     Staged<float> obs_u, obs_v, obs_d, pm_u, pm_v, pm_d;
     // outputs
@@ -122,6 +123,7 @@ struct kba_batch {
         kf_fixed.release(); lm_ptr.release(); obs_kf.release(); obs_cam.release(); obs_lm.release(); kf_ptr.release();
         pm_lm.release(); pm_cam.release(); chunk_lm0.release(); chunk_lm1.release(); chunk_k0.release(); chunk_k1.release();
         lm_orig.release(); obs_orig.release(); obs_rank.release(); obs_u.release(); obs_v.release();
+        grp_k0.release(); grp_k1.release();
         obs_d.release(); pm_u.release(); pm_v.release(); pm_d.release(); state.release(); log.release();
         pose_out[0].release(); pose_out[1].release(); lm_out[0].release(); lm_out[1].release(); lm_active.release();
         n_active.release(); jac_obs.release(); plane_out[0].release(); plane_out[1].release();
@@ -254,6 +256,26 @@ static void fill_window(kba_batch* b, int wi, const kba_window* w) {
         b->chunk_k0.h[d.chunk_off + c] = k0;
         b->chunk_k1.h[d.chunk_off + c] = k1;
     }
+    for (int c = 0; c < d.n_groups; ++c) {  // 8-landmark groups of the fused Schur kernel
+        const int j0 = c * 8, j1 = std::min(nl, (c + 1) * 8);
+        int k0 = w->n_kf, k1 = -1;
+        for (int o = lp[j0]; o < lp[j1]; ++o) {
+            const int k = b->obs_kf.h[(size_t)d.obs_off + o];
+            k0 = std::min(k0, k); k1 = std::max(k1, k);
+        }
+        for (int j = j0; j < j1; ++j)
+            if (gp_kf_of_lm[j] >= 0) { k0 = std::min(k0, gp_kf_of_lm[j]); k1 = std::max(k1, gp_kf_of_lm[j]); }
+        b->grp_k0.h[d.grp_off + c] = k0;
+        b->grp_k1.h[d.grp_off + c] = k1;
+    }
+}
+
+// reduced-system rows a window can have given its constant keyframes (k_solve_begin may leave out more)
+static int window_rows(const kba_window& w) {
+    const bool planes = w.n_gp > 0 || w.plane_reg_weight > 0;
+    int n_free = 0;
+    for (int k = 0; k < w.n_kf; ++k) n_free += w.kf_fixed[k] ? 0 : 1;
+    return (planes ? 10 : 6) * n_free + 1;
 }
 
 struct kba_shard_comm;
@@ -358,8 +380,8 @@ int kba_batch_create(kba_handle* h, int32_t n_windows, const kba_window* w, kba_
     BatchDev& bd = b->bd;
     bd.n_win = n_windows;
     b->desc_h.resize(n_windows);
-    long long kf = 0, cam = 0, lm = 0, obs = 0, chunks = 0, soff = 0, gp = 0;
-    int max_rows = 0;
+    long long kf = 0, cam = 0, lm = 0, obs = 0, chunks = 0, soff = 0, gp = 0, groups = 0;
+    int max_rows = 0, max_rows_free = 0, max_groups = 1;
     int nr_cap_max = 64;
     for (int i = 0; i < n_windows; ++i) {
         WinDesc& d = b->desc_h[i];
@@ -367,6 +389,9 @@ int kba_batch_create(kba_handle* h, int32_t n_windows, const kba_window* w, kba_
         d.n_kf = w[i].n_kf; d.n_cam = w[i].n_cam; d.n_lm = w[i].n_lm; d.n_obs = w[i].n_obs; d.n_gp = w[i].n_gp;
         d.kf_off = (int)kf; d.cam_off = (int)cam; d.lm_off = (int)lm; d.obs_off = (int)obs; d.gp_off = (int)gp;
         d.chunk_off = (int)chunks; d.n_chunks = (w[i].n_lm + 31) / 32;
+        d.grp_off = (int)groups; d.n_groups = (w[i].n_lm + 7) / 8;
+        groups += d.n_groups; max_groups = std::max(max_groups, d.n_groups);
+        max_rows_free = std::max(max_rows_free, window_rows(w[i]));
         d.scale_kf0 = w[i].scale_kf0; d.scale_kf1 = w[i].scale_kf1;
         d.scale_weight = w[i].scale_weight; d.scale_value = w[i].scale_value;
         const bool planes = w[i].n_gp > 0 || w[i].plane_reg_weight > 0;
@@ -387,6 +412,7 @@ int kba_batch_create(kba_handle* h, int32_t n_windows, const kba_window* w, kba_
         return fail(KBA_ERR_CAPACITY, "reduced system larger than 640 rows (106 keyframes, or 63 with ground-plane blocks)");
     }
     bd.tot_kf = kf; bd.tot_cam = cam; bd.tot_lm = lm; bd.tot_obs = obs; bd.tot_chunks = (int)chunks; bd.tot_gp = gp;
+    bd.tot_groups = (int)groups;
     bd.nr_cap_max = nr_cap_max;
     b->lc.nr_cap_max = nr_cap_max;
     // split the landmark chunks of each window over several CTAs when the batch alone cannot fill the GPU
@@ -398,6 +424,15 @@ int kba_batch_create(kba_handle* h, int32_t n_windows, const kba_window* w, kba_
         b->lc.small_syrk = (max_rows <= 184);
         if (b->lc.small_syrk) p = (h->sm_count + n_windows - 1) / n_windows;  // one CTA per SM, each owning all tiles
         bd.p_split = std::max(1, std::min(p, max_chunks));
+        // fused small-window path (kba_schur_fused.cuh): no J_l, no global V panels; KBA_FUSED=0 keeps the round-1 kernels
+        const char* fe = std::getenv("KBA_FUSED");
+        bd.fused = (b->lc.small_syrk && bd.max_kf <= kFusedMaxKf && !(fe && std::atoi(fe) == 0)) ? 1 : 0;
+        // KBA_P_SPLIT pins the number of CTAs a window's landmark groups are split over.  The partial Schur sums are folded in
+        // a fixed order, so results are bit-reproducible for a given split; the default split follows the batch size.
+        if (const char* pe = std::getenv("KBA_P_SPLIT")) { if (std::atoi(pe) > 0) p = std::atoi(pe); }
+        if (bd.fused) bd.p_split = std::max(1, std::min(p, max_groups));
+        else if (std::getenv("KBA_P_SPLIT")) bd.p_split = std::max(1, std::min(p, max_chunks));
+        b->lc.fused_slots = (max_rows_free <= 176) ? 6 : 7;
     }
     bd.cost_parts = (bd.max_obs + 255) / 256;
     {  // tuning knobs of the residual/Jacobian kernel (defaults measured on B200)
@@ -424,6 +459,13 @@ int kba_batch_create(kba_handle* h, int32_t n_windows, const kba_window* w, kba_
     bad |= b->chunk_lm0.alloc(chunks, true); bad |= b->chunk_lm1.alloc(chunks, true);
     bad |= b->chunk_k0.alloc(chunks, true); bad |= b->chunk_k1.alloc(chunks, true);
     bad |= b->lm_orig.alloc(lm, true); bad |= b->obs_orig.alloc(obs, true); bad |= b->obs_rank.alloc(obs, true);
+    bad |= b->grp_k0.alloc(groups, true); bad |= b->grp_k1.alloc(groups, true);
+    bad |= b->dev_alloc(&bd.grp_t0, groups); bad |= b->dev_alloc(&bd.grp_t1, groups); bad |= b->dev_alloc(&bd.grp_rs, groups);
+#ifdef KBA_PROF
+    bad |= b->dev_alloc(&bd.prof, 16);
+    if (!bad) cudaMemset(bd.prof, 0, 16 * sizeof(unsigned long long));
+#endif
+    bad |= b->dev_alloc(&bd.rt[0], (size_t)kPoseStride * kf); bad |= b->dev_alloc(&bd.rt[1], (size_t)kPoseStride * kf);
     {   // dense V panels of the Schur kernels; sized in kba_batch_upload from the chunks' keyframe ranges
         bd.panel_cap = 0;
         bd.vpanel = nullptr;
@@ -445,7 +487,8 @@ int kba_batch_create(kba_handle* h, int32_t n_windows, const kba_window* w, kba_
     bad |= b->dev_alloc(&bd.lm_scale, 3 * lm); bad |= b->dev_alloc(&bd.lm_linv, 6 * lm); bad |= b->dev_alloc(&bd.lm_z, 3 * lm);
     bad |= b->dev_alloc(&bd.lm_g, 3 * lm); bad |= b->dev_alloc(&bd.lm_lambda, 3 * lm); bad |= b->dev_alloc(&bd.trim_val, 3 * lm);
     bad |= b->dev_alloc(&bd.trim_reject, lm);
-    bad |= b->dev_alloc(&bd.res, 3 * obs); bad |= b->dev_alloc(&bd.jp, 18 * obs); bad |= b->dev_alloc(&bd.jl, 9 * obs);
+    bad |= b->dev_alloc(&bd.res, 3 * obs); bad |= b->dev_alloc(&bd.jp, 18 * obs);
+    if (!bd.fused) bad |= b->dev_alloc(&bd.jl, 9 * obs);  // fused path: J_l is re-formed from J_p by its consumers
     bad |= b->dev_alloc(&bd.cost_part_x, (size_t)n_windows * bd.cost_parts); bad |= b->dev_alloc(&bd.cost_part_c, (size_t)n_windows * bd.cost_parts);
     bad |= b->dev_alloc(&bd.bs_part, (size_t)n_windows * bd.bs_parts * 4);
     bad |= b->dev_alloc(&bd.sred, (size_t)soff * bd.p_split); bad |= b->dev_alloc(&bd.amat, (size_t)soff);
@@ -466,6 +509,7 @@ int kba_batch_create(kba_handle* h, int32_t n_windows, const kba_window* w, kba_
     bd.chunk_lm0 = b->chunk_lm0.d; bd.chunk_lm1 = b->chunk_lm1.d; bd.chunk_k0 = b->chunk_k0.d; bd.chunk_k1 = b->chunk_k1.d;
     bd.lm_orig = b->lm_orig.d;
     bd.obs_rank = b->obs_rank.d;
+    bd.grp_k0 = b->grp_k0.d; bd.grp_k1 = b->grp_k1.d;
     bd.plane[0] = b->plane_out[0].d; bd.plane[1] = b->plane_out[1].d;
     bd.gp_lm = b->gp_lm.d; bd.gp_kf = b->gp_kf.d; bd.gp_weight = b->gp_weight.d; bd.gp_of_lm = b->gp_of_lm.d; bd.gp_shared = b->gp_shared.d;
     bd.n_active = b->n_active.d;
@@ -518,7 +562,12 @@ int kba_batch_upload(kba_batch* b, int32_t n_windows, const kba_window* w) {
         }
     }
     for (int i = 0; i < n_windows; ++i) b->lc.max_rank = std::max(b->lc.max_rank, b->desc_h[i].max_rank);
-    {   // V panel capacity: per chunk 96 columns x (rows of its keyframe range + right-hand-side tile), see k_solve_begin
+    if (b->bd.fused) {
+        int rows = 0;
+        for (int i = 0; i < n_windows; ++i) rows = std::max(rows, window_rows(w[i]));
+        b->lc.fused_slots = (rows <= 176) ? 6 : 7;
+    }
+    if (!b->bd.fused) {   // V panel capacity: per chunk 96 columns x (rows of its keyframe range + right-hand-side tile), see k_solve_begin
         long long need = 0;
         for (int i = 0; i < n_windows; ++i) {
             const WinDesc& d = b->desc_h[i];
@@ -546,12 +595,13 @@ int kba_batch_upload(kba_batch* b, int32_t n_windows, const kba_window* w) {
     CU(b->obs_u.upload(s)); CU(b->obs_v.upload(s)); CU(b->obs_d.upload(s));
     CU(b->kf_ptr.upload(s)); CU(b->pm_lm.upload(s)); CU(b->pm_cam.upload(s)); CU(b->pm_u.upload(s)); CU(b->pm_v.upload(s)); CU(b->pm_d.upload(s));
     CU(b->chunk_lm0.upload(s)); CU(b->chunk_lm1.upload(s)); CU(b->chunk_k0.upload(s)); CU(b->chunk_k1.upload(s));
+    CU(b->grp_k0.upload(s)); CU(b->grp_k1.upload(s));
     CU(b->lm_orig.upload(s)); CU(b->obs_rank.upload(s));
     CU(b->gp_lm.upload(s)); CU(b->gp_kf.upload(s)); CU(b->gp_weight.upload(s)); CU(b->gp_of_lm.upload(s)); CU(b->gp_shared.upload(s));
     const BatchDev& bd = b->bd;
     b->h2d_bytes = sizeof(WinDesc) * bd.n_win + (7 + 4) * 8 * bd.tot_kf + bd.tot_kf + kCamStride * 8 * bd.tot_cam +
                    (3 + 1) * 8 * bd.tot_lm + 4 * (bd.tot_lm + bd.n_win) + (3 * 4 + 3 * 4) * bd.tot_obs +
-                   4 * (bd.tot_kf + bd.n_win) + (2 * 4 + 3 * 4) * bd.tot_obs + 8 * bd.tot_chunks;
+                   4 * (bd.tot_kf + bd.n_win) + (2 * 4 + 3 * 4) * bd.tot_obs + 8 * bd.tot_chunks + 8 * bd.tot_groups;
     return KBA_OK;
 }
 
@@ -708,6 +758,14 @@ int kba_batch_transfer_bytes(kba_batch* b, int64_t* h2d, int64_t* d2h) {
 void kba_batch_destroy(kba_batch* b) {
     if (!b) return;
     cudaStreamSynchronize(b->h->stream);
+#ifdef KBA_PROF
+    if (b->bd.prof) {
+        unsigned long long c[16];
+        cudaMemcpy(c, b->bd.prof, sizeof c, cudaMemcpyDeviceToHost);
+        fprintf(stderr, "[kba prof] fused Schur kernel, cycles summed over warps: consumers wait %llu multiply %llu | producers "
+                "wait-empty %llu zero+copy-wait %llu scatter %llu\n", c[0], c[1], c[4], c[5], c[6]);
+    }
+#endif
     b->release();
     delete b;
 }
@@ -767,7 +825,12 @@ int kba_eval(kba_handle* h, const kba_window* w, const kba_options* opt, kba_eva
     cudaStream_t s = h->stream;
     cudaMemcpyAsync(res_h.data(), bd.res, 3 * n * sizeof(double), cudaMemcpyDeviceToHost, s);
     cudaMemcpyAsync(jp_h.data(), bd.jp, 18 * n * sizeof(double), cudaMemcpyDeviceToHost, s);
-    cudaMemcpyAsync(jl_h.data(), bd.jl, 9 * n * sizeof(double), cudaMemcpyDeviceToHost, s);
+    double* jl_dev = bd.jl;
+    if (bd.fused) {  // J_l is not materialised on the fused path: expand it on the device the way its consumers do
+        if (b->dev_alloc(&jl_dev, 9 * n)) { kba_batch_destroy(b); return fail(KBA_ERR_CUDA, "out of device memory (kba_eval)"); }
+        launch_expand_jl(bd, jl_dev, s);
+    }
+    cudaMemcpyAsync(jl_h.data(), jl_dev, 9 * n * sizeof(double), cudaMemcpyDeviceToHost, s);
     cudaMemcpyAsync(cost_h.data(), bd.cost_part_x, bd.cost_parts * sizeof(double), cudaMemcpyDeviceToHost, s);
     cudaMemcpyAsync(offp.data(), bd.off_pose, w->n_kf * sizeof(int), cudaMemcpyDeviceToHost, s);
     cudaMemcpyAsync(&st, bd.state, sizeof(WinState), cudaMemcpyDeviceToHost, s);

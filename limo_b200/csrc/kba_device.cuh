@@ -14,12 +14,14 @@ constexpr int kMaxCam = 8;
 constexpr int kPoseStride = 12;     // staged pose: R (9, row-major) + t (3)
 constexpr int kCamStride = 16;      // staged camera: Rc (9) + tc (3) + f, cx, cy, pad
 constexpr int kIterLogCap = 160;    // iteration records kept per window
+constexpr int kFusedMaxKf = 32;     // keyframes of a window on the fused small-window path (<= 184 reduced rows)
 
 // ---- per-window descriptor (immutable after upload) --------------------------------------------------------------
 struct WinDesc {
     int n_kf, n_cam, n_lm, n_obs, n_gp;
     int kf_off, cam_off, lm_off, obs_off, gp_off;  // offsets into the batch-flat arrays
-    int chunk_off, n_chunks;                        // landmark chunks of the Schur kernel
+    int chunk_off, n_chunks;                        // landmark chunks (32 landmarks) of the panel-based Schur kernel
+    int grp_off, n_groups;                          // landmark groups (8 landmarks) of the fused Schur kernel
     int scale_kf0, scale_kf1;
     double scale_weight, scale_value;
     double plane_reg_weight;
@@ -87,6 +89,8 @@ struct BatchDev {
     double* pose0;            // [tot_kf*7] uploaded state
     double* plane0;           // [tot_kf*4]
     double* pose[2];          // [tot_kf*7] x / candidate (ping-pong)
+    double* rt[2];            // [tot_kf*12] the same poses as R (9, row-major) | t (3): what the observation kernels stage
+                              //             with one bulk copy (written by whoever writes pose[])
     double* plane[2];         // [tot_kf*4]
     uint8_t* kf_fixed;        // [tot_kf]
     int* off_pose;            // [tot_kf] column offset in the reduced system or -1
@@ -171,6 +175,17 @@ struct BatchDev {
     int* obs_row;             // [tot_obs] first reduced-system row of the observation's pose block, -1: constant / inactive
     int* lm_orig;             // [tot_lm] caller's landmark index (landmarks are stored sorted by first keyframe)
     int tot_chunks;
+    // fused small-window path (k_schur_fused): J_l is not materialised (J_l = translation columns of J_p times R), the V
+    // panels exist only in shared memory; per 8-landmark group the keyframe range (host, static) and, per solve, the
+    // 8-row tile range of the reduced system it touches and the row stride of its shared-memory panel
+    int fused;                // 1: every window of the batch has <= 184 reduced rows -> fused path, jl / vpanel unused
+    int* grp_k0;              // [tot_groups]
+    int* grp_k1;
+    int* grp_t0;              // [tot_groups]
+    int* grp_t1;
+    int* grp_rs;              // [tot_groups] == 4 mod 16, 0: no free keyframe rows
+    unsigned long long* prof; // [16] cycle counters of a KBA_PROF build (nullptr otherwise)
+    int tot_groups;
     int* n_active;            // [1] windows still running (device counter)
     unsigned long long* jac_obs;  // [1] observations linearised by the residual/Jacobian kernel since the last reset
     // ground-plane height residuals (one per ground landmark, attached to a keyframe by the host)
@@ -298,7 +313,7 @@ template <typename T>
 __device__ inline bool eval_observation_store(const T* __restrict__ pose, const T* __restrict__ cam, const T p[3], T u,
                                               T v, T d, T wt, T b_repr, T b_depth, T* __restrict__ res,
                                               T* __restrict__ jp, T* __restrict__ jl, size_t stride, bool write_jp,
-                                              T& half_rho_sum) {
+                                              bool write_jl, T& half_rho_sum) {
     const T a0 = pose[0] * p[0] + pose[1] * p[1] + pose[2] * p[2];
     const T a1 = pose[3] * p[0] + pose[4] * p[1] + pose[5] * p[2];
     const T a2 = pose[6] * p[0] + pose[7] * p[1] + pose[8] * p[2];
@@ -339,10 +354,12 @@ __device__ inline bool eval_observation_store(const T* __restrict__ pose, const 
             o[4 * stride] = m1;
             o[5 * stride] = m2;
         }
-        T* q = jl + (size_t)(3 * i) * stride;
-        q[0] = m0 * pose[0] + m1 * pose[3] + m2 * pose[6];
-        q[stride] = m0 * pose[1] + m1 * pose[4] + m2 * pose[7];
-        q[2 * stride] = m0 * pose[2] + m1 * pose[5] + m2 * pose[8];
+        if (write_jl) {
+            T* q = jl + (size_t)(3 * i) * stride;
+            q[0] = m0 * pose[0] + m1 * pose[3] + m2 * pose[6];
+            q[stride] = m0 * pose[1] + m1 * pose[4] + m2 * pose[7];
+            q[2 * stride] = m0 * pose[2] + m1 * pose[5] + m2 * pose[8];
+        }
     }
     return true;
 }
@@ -366,6 +383,53 @@ __device__ inline void stage_window(const WinDesc& wd, const double* __restrict_
         s_pose[kPoseStride * k + 11] = p[6];
     }
     for (int i = threadIdx.x; i < wd.n_cam * kCamStride; i += blockDim.x) s_cam[i] = cam16[(size_t)wd.cam_off * kCamStride + i];
+}
+
+// staged form of a pose: R (9, row-major) | t (3); kept next to pose[] by every kernel that writes a pose
+__device__ inline void write_rt(double* rt12, const double* p7) {
+    quat_to_rot<double>(p7, rt12);
+    rt12[9] = p7[4]; rt12[10] = p7[5]; rt12[11] = p7[6];
+}
+
+// ---- mbarrier / bulk-copy (TMA) primitives ------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_load_1d(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t done = 0;
+    while (!done)
+        asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
+                     : "=r"(done)
+                     : "r"(smem_u32(bar)), "r"(parity)
+                     : "memory");
+}
+
+// Keyframe poses (R | t, BatchDev::rt) and cameras of one window into shared memory with two bulk copies issued by one
+// thread (cp.async.bulk + mbarrier): the consuming CTA does no per-pose arithmetic and no scalar staging loads.
+// s_pose / s_cam must be 16-byte aligned; `bar` is a CTA-local mbarrier used once.  Every thread of the CTA calls this.
+__device__ inline void stage_window_bulk(const WinDesc& wd, const double* __restrict__ rt, const double* __restrict__ cam16,
+                                         double* s_pose, double* s_cam, uint64_t* bar) {
+    if (threadIdx.x == 0) {
+        mbar_init(bar, 1);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const uint32_t bp = (uint32_t)(wd.n_kf * kPoseStride * sizeof(double)), bc = (uint32_t)(wd.n_cam * kCamStride * sizeof(double));
+        mbar_expect_tx(bar, bp + bc);
+        tma_load_1d(s_pose, rt + (size_t)kPoseStride * wd.kf_off, bp, bar);
+        tma_load_1d(s_cam, cam16 + (size_t)kCamStride * wd.cam_off, bc, bar);
+    }
+    mbar_wait(bar, 0);
 }
 
 __device__ inline double warp_sum(double v) {

@@ -118,7 +118,29 @@ __global__ void __launch_bounds__(256) k_solve_begin(BatchDev bd, SolveParams sp
         bd.chunk_t0[wd.chunk_off + c] = (r1 < 0) ? 0 : r0 / 8;
         bd.chunk_t1[wd.chunk_off + c] = (r1 < 0) ? 0 : (r1 + 7) / 8;
     }
-    {  // layout of the dense V panels: per chunk 96 columns x rs rows (rs == 4 mod 16), column-major
+    // fused path: 8-row tile range and shared-memory row stride (== 4 mod 16) of each 8-landmark group
+    if (bd.fused) {
+        const int trhs = st.n_f >> 3;
+        for (int c = threadIdx.x; c < wd.n_groups; c += blockDim.x) {
+            int r0 = 1 << 30, r1 = -1;
+            for (int k = bd.grp_k0[wd.grp_off + c]; k <= bd.grp_k1[wd.grp_off + c]; ++k) {
+                const int off = bd.off_pose[wd.kf_off + k], od = bd.off_dir[wd.kf_off + k], oz = bd.off_dist[wd.kf_off + k];
+                if (off >= 0) { r0 = min(r0, off); r1 = max(r1, off + 6); }
+                if (od >= 0) { r0 = min(r0, od); r1 = max(r1, od + 3); }
+                if (oz >= 0) { r0 = min(r0, oz); r1 = max(r1, oz + 1); }
+            }
+            const int t0 = (r1 < 0) ? 0 : r0 / 8, t1 = (r1 < 0) ? 0 : (r1 + 7) / 8;
+            int rs = 0;
+            if (t1 > t0) {
+                const int rows = 8 * (t1 - t0) + ((trhs >= t0 && trhs < t1) ? 0 : 8);
+                rs = ((rows - 4 + 15) / 16) * 16 + 4;
+            }
+            bd.grp_t0[wd.grp_off + c] = t0;
+            bd.grp_t1[wd.grp_off + c] = t1;
+            bd.grp_rs[wd.grp_off + c] = rs;
+        }
+    }
+    if (!bd.fused) {  // layout of the dense V panels: per chunk 96 columns x rs rows (rs == 4 mod 16), column-major
         __syncthreads();
         if (threadIdx.x == 0) {
             const int trhs = st.n_f >> 3;
@@ -142,7 +164,7 @@ __global__ void __launch_bounds__(256) k_solve_begin(BatchDev bd, SolveParams sp
 // k_landmark_reduce / k_obs_v / k_gp_panel overwrite every structurally non-zero entry in each pass)
 __global__ void __launch_bounds__(256) k_panel_zero(BatchDev bd) {
     const int w = blockIdx.y;
-    if (bd.state[w].phase != PH_SOLVE_BEGIN || bd.desc[w].landmarks_fixed) return;
+    if (bd.fused || bd.state[w].phase != PH_SOLVE_BEGIN || bd.desc[w].landmarks_fixed) return;
     double2* p = reinterpret_cast<double2*>(bd.vpanel + bd.desc[w].panel_off);
     const long long n2 = bd.panel_cap / 2;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n2; i += (long long)gridDim.x * blockDim.x)
@@ -167,8 +189,9 @@ __global__ void __launch_bounds__(256, kMinBlocks) k_eval_obs(BatchDev bd, Solve
     if (st.phase != PH_ITERATE) return;
     if (kJac && !st.need_linearize) return;
     if (!kJac && st.solve_failed) return;
-    __shared__ double s_pose[kMaxKf * kPoseStride];
-    __shared__ double s_cam[kMaxCam * kCamStride];
+    __shared__ __align__(16) double s_pose[kMaxKf * kPoseStride];
+    __shared__ __align__(16) double s_cam[kMaxCam * kCamStride];
+    __shared__ __align__(8) uint64_t s_bar;
     __shared__ double s_red[8];
     __shared__ int s_cnt[8];
     constexpr bool kF32 = sizeof(TLin) == 4;  // FP32 evaluation + storage of the linearisation (precision 1)
@@ -194,8 +217,8 @@ __global__ void __launch_bounds__(256, kMinBlocks) k_eval_obs(BatchDev bd, Solve
         wgt = bd.lm_weight[L];
         act = bd.lm_active[L];
     }
-    stage_window(wd, bd.pose[buf], bd.cam, s_pose, s_cam);
-    __syncthreads();
+    stage_window_bulk(wd, bd.rt[buf], bd.cam, s_pose, s_cam, &s_bar);  // poses (R | t) and cameras: two bulk copies
+    const bool write_jl = !bd.fused;  // fused path: consumers form J_l = (translation columns of J_p) R themselves
     if (kF32) {
         for (int i = threadIdx.x; i < wd.n_kf * kPoseStride; i += blockDim.x) s_pose_f[i] = (float)s_pose[i];
         for (int i = threadIdx.x; i < wd.n_cam * kCamStride; i += blockDim.x) s_cam_f[i] = (float)s_cam[i];
@@ -245,13 +268,13 @@ __global__ void __launch_bounds__(256, kMinBlocks) k_eval_obs(BatchDev bd, Solve
                     eval_observation_store<float>(
                         s_pose_f + kPoseStride * k, s_cam_f + kCamStride * c, pf, u, v, d, (float)wgt,
                         (float)(sp.reprojection_thres * sp.reprojection_thres), (float)(sp.depth_thres * sp.depth_thres),
-                        resf, jpf, jlf, (size_t)bd.tot_obs, row >= 0, hrf);
+                        resf, jpf, jlf, (size_t)bd.tot_obs, row >= 0 || !write_jl, write_jl, hrf);
                 }
             } else if (kJac) {  // rows are stored to their SoA slots as they are formed
                 ok = eval_observation_store<double>(
                     s_pose + kPoseStride * k, s_cam + kCamStride * c, p, (double)u, (double)v, (double)d, wgt,
                     sp.reprojection_thres * sp.reprojection_thres, sp.depth_thres * sp.depth_thres, bd.res + o, bd.jp + o,
-                    bd.jl + o, (size_t)bd.tot_obs, row >= 0, hr);
+                    bd.jl + o, (size_t)bd.tot_obs, row >= 0 || !write_jl, write_jl, hr);
             } else {
                 double r[3], raw[2];
                 ok = eval_observation<double, false>(
@@ -564,26 +587,9 @@ __global__ void __launch_bounds__(256, 2) k_schur_syrk(BatchDev bd) {
 constexpr int kHalfCols = 48;
 constexpr int kStageDoubles = kHalfCols * 196;  // 184 rows -> rs = 196
 
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void tma_load_1d(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
-                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
-                 : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-    uint32_t done = 0;
-    while (!done)
-        asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
-                     : "=r"(done)
-                     : "r"(smem_u32(bar)), "r"(parity)
-                     : "memory");
-}
+}  // namespace kba
+#include "kba_schur_fused.cuh"
+namespace kba {
 
 constexpr int kBlockSlots = 5;  // ceil(12*13/2 / 16) 16x16 blocks per warp for up to 184 reduced rows
 // Which 16x16 blocks (linear index bi (bi + 1) / 2 + bj of the 12-row lower triangle) a warp owns.  The accumulators are
@@ -1304,13 +1310,16 @@ __global__ void __launch_bounds__(512, 1) k_reduced_solve(BatchDev bd, SolvePara
         const double* p = Pc + 7 * (size_t)(wd.kf_off + k);
         double* q = Pn + 7 * (size_t)(wd.kf_off + k);
         const int off = bd.off_pose[wd.kf_off + k];
+        double* qrt = bd.rt[1 - st.cur] + kPoseStride * (size_t)(wd.kf_off + k);
         if (off < 0) {
             for (int i = 0; i < 7; ++i) q[i] = p[i];
+            write_rt(qrt, p);
             continue;
         }
         double d[6], gneg[6], out[7];
         for (int i = 0; i < 6; ++i) { d[i] = -s_y[off + i]; gneg[i] = -s_g[off + i]; }
         pose_plus(p, d, out);
+        write_rt(qrt, out);
         for (int i = 0; i < 7; ++i) { q[i] = out[i]; const double e = out[i] - p[i]; step_sq += e * e; xn_sq += p[i] * p[i]; }
         pose_plus(p, gneg, out);
         for (int i = 0; i < 7; ++i) gmax = fmax(gmax, fabs(out[i] - p[i]));
@@ -1536,6 +1545,110 @@ __global__ void __launch_bounds__(256) k_backsub(BatchDev bd) {
             const double* z = bd.lm_z + 3 * (size_t)L;
             const double* li = bd.lm_linv + 6 * (size_t)L;  // i00; i10 i11; i20 i21 i22
             const double t0 = t[0] + z[0], t1 = t[1] + z[1], t2 = t[2] + z[2];
+            // delta_p = -Linv^T t
+            const double d0 = -(li[0] * t0 + li[1] * t1 + li[3] * t2);
+            const double d1 = -(li[2] * t1 + li[4] * t2);
+            const double d2 = -(li[5] * t2);
+            const double* g = bd.lm_g + 3 * (size_t)L;
+            const double* lam = bd.lm_lambda + 3 * (size_t)L;
+            pn[0] = pc[0] + d0; pn[1] = pc[1] + d1; pn[2] = pc[2] + d2;
+            model = -(g[0] * d0 + g[1] * d1 + g[2] * d2) + lam[0] * d0 * d0 + lam[1] * d1 * d1 + lam[2] * d2 * d2;
+            step_sq = d0 * d0 + d1 * d1 + d2 * d2;
+            xn_sq = pc[0] * pc[0] + pc[1] * pc[1] + pc[2] * pc[2];
+            gmax = fmax(fabs(g[0]), fmax(fabs(g[1]), fabs(g[2])));
+            if (!isfinite(d0) || !isfinite(d1) || !isfinite(d2)) model = nan("");
+        }
+    }
+    if (hl == 0) { s_red[grp][0] = model; s_red[grp][1] = step_sq; s_red[grp][2] = xn_sq; s_red[grp][3] = gmax; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double a = 0, b = 0, c = 0, g = 0;
+        for (int q = 0; q < 16; ++q) { a += s_red[q][0]; b += s_red[q][1]; c += s_red[q][2]; g = fmax(g, s_red[q][3]); }
+        double* out = bd.bs_part + ((size_t)w * bd.bs_parts + blockIdx.x) * 4;
+        out[0] = a; out[1] = b; out[2] = c; out[3] = g;
+    }
+}
+
+// Fused path: no V panels exist in global memory.  With V_i = (J_p^T J_l) L^-T the sum over the landmark's observations
+// is  sum_i V_i^T delta_f,i = L^-1 sum_i J_l^T (J_p delta_f,i):  J_p streams in coalesced (144 B per observation), J_l is
+// re-formed from its translation columns and the staged rotation, and no gather of 48-byte panel segments is left.
+__global__ void __launch_bounds__(256) k_backsub_jp(BatchDev bd) {
+    const int w = blockIdx.y;
+    const WinState& st = bd.state[w];
+    if (st.phase != PH_ITERATE) return;
+    const WinDesc& wd = bd.desc[w];
+    __shared__ __align__(16) double s_pose[kFusedMaxKf * kPoseStride];
+    __shared__ __align__(8) uint64_t s_bar;
+    __shared__ double s_red[16][4];
+    if (threadIdx.x == 0) {
+        mbar_init(&s_bar, 1);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const uint32_t bytes = (uint32_t)(wd.n_kf * kPoseStride * sizeof(double));
+        mbar_expect_tx(&s_bar, bytes);
+        tma_load_1d(s_pose, bd.rt[st.cur] + (size_t)kPoseStride * wd.kf_off, bytes, &s_bar);
+    }
+    const int hl = threadIdx.x & 15, grp = threadIdx.x >> 4;
+    const int j = blockIdx.x * 16 + grp;
+    double model = 0.0, step_sq = 0.0, xn_sq = 0.0, gmax = 0.0;
+    const bool have = j < wd.n_lm;
+    const int L = wd.lm_off + (have ? j : 0);
+    const double* pc = bd.lm[st.cur] + 3 * (size_t)L;
+    double* pn = bd.lm[1 - st.cur] + 3 * (size_t)L;
+    const int* lm_ptr = bd.lm_ptr + wd.lm_off + w;
+    const int o0 = have ? lm_ptr[j] : 0, o1 = have ? lm_ptr[j + 1] : 0;
+    const bool in = have && bd.lm_active[L] && o1 > o0 && !wd.landmarks_fixed && !st.solve_failed;
+    const size_t base = (size_t)wd.obs_off, T = (size_t)bd.tot_obs;
+    const double* delta_f = bd.delta_f + (size_t)w * bd.nr_cap_max;
+    double sv[3] = {0, 0, 0};  // sum_i J_l^T (J_p delta_i)
+    double tg[3] = {0, 0, 0};  // ground-plane block: V rows are stored (10 x 3), already multiplied by L^-T
+    mbar_wait(&s_bar, 0);
+    if (in) {
+        for (int o = o0 + hl; o < o1; o += 16) {
+            const int off = bd.obs_row[base + o];  // row of the observation's pose block (k_solve_begin), -1: constant
+            if (off < 0) continue;
+            const double* R = s_pose + kPoseStride * bd.obs_kf[base + o];
+            double d[6];
+#pragma unroll
+            for (int r = 0; r < 6; ++r) d[r] = delta_f[off + r];
+#pragma unroll
+            for (int i = 0; i < 3; ++i) {
+                double jp[6];
+#pragma unroll
+                for (int r = 0; r < 6; ++r) jp[r] = lin_load(bd.jp, (6 * i + r) * T + base + o, bd.precision);
+                const double wi = jp[0] * d[0] + jp[1] * d[1] + jp[2] * d[2] + jp[3] * d[3] + jp[4] * d[4] + jp[5] * d[5];
+#pragma unroll
+                for (int c = 0; c < 3; ++c) sv[c] += (jp[3] * R[c] + jp[4] * R[3 + c] + jp[5] * R[6 + c]) * wi;
+            }
+        }
+        const int gl = (wd.n_gp > 0) ? bd.gp_of_lm[L] : -1;
+        if (gl >= 0 && hl < 10) {  // row `hl` of the gp block's 10 x 3 V
+            const int row = gp_row(bd, wd, bd.gp_kf[wd.gp_off + gl], hl);
+            if (row >= 0) {
+                const double d = delta_f[row];
+#pragma unroll
+                for (int c = 0; c < 3; ++c) tg[c] = bd.vgp[(size_t)(3 * hl + c) * bd.tot_gp + wd.gp_off + gl] * d;
+            }
+        }
+    }
+#pragma unroll
+    for (int c = 0; c < 3; ++c)
+#pragma unroll
+        for (int m = 8; m >= 1; m >>= 1) {
+            sv[c] += __shfl_xor_sync(0xffffffffu, sv[c], m);
+            tg[c] += __shfl_xor_sync(0xffffffffu, tg[c], m);
+        }
+    if (have && hl == 0) {
+        if (!in) {
+            pn[0] = pc[0]; pn[1] = pc[1]; pn[2] = pc[2];
+        } else {
+            const double* z = bd.lm_z + 3 * (size_t)L;
+            const double* li = bd.lm_linv + 6 * (size_t)L;  // i00; i10 i11; i20 i21 i22
+            const double t0 = li[0] * sv[0] + tg[0] + z[0];
+            const double t1 = li[1] * sv[0] + li[2] * sv[1] + tg[1] + z[1];
+            const double t2 = li[3] * sv[0] + li[4] * sv[1] + li[5] * sv[2] + tg[2] + z[2];
             // delta_p = -Linv^T t
             const double d0 = -(li[0] * t0 + li[1] * t1 + li[3] * t2);
             const double d1 = -(li[2] * t1 + li[4] * t2);
@@ -1948,6 +2061,14 @@ __global__ void k_reset_state(BatchDev bd, int rounds_total_override, int min_la
         bd.pose[0][(size_t)wd.kf_off * 7 + i] = v;
         bd.pose[1][(size_t)wd.kf_off * 7 + i] = v;
     }
+    for (int k = threadIdx.x; k < wd.n_kf; k += blockDim.x) {
+        double rt12[kPoseStride];
+        write_rt(rt12, bd.pose0 + 7 * (size_t)(wd.kf_off + k));
+        for (int i = 0; i < kPoseStride; ++i) {
+            bd.rt[0][kPoseStride * (size_t)(wd.kf_off + k) + i] = rt12[i];
+            bd.rt[1][kPoseStride * (size_t)(wd.kf_off + k) + i] = rt12[i];
+        }
+    }
     for (int i = threadIdx.x; i < wd.n_kf * 4; i += blockDim.x) {
         const double v = bd.plane0[(size_t)wd.kf_off * 4 + i];
         bd.plane[0][(size_t)wd.kf_off * 4 + i] = v;
@@ -1990,6 +2111,14 @@ cudaError_t configure_kernels(int nr_cap_max) {
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(k_schur_syrk_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)schur_tma_smem());
     if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(k_schur_fused<6, double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)schur_fused_smem());
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(k_schur_fused<7, double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)schur_fused_smem());
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(k_schur_fused<6, float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)schur_fused_smem());
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(k_schur_fused<7, float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)schur_fused_smem());
+    if (e != cudaSuccess) return e;
     if (nr_cap_max <= 192) {
         e = cudaFuncSetAttribute(k_reduced_solve<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  (int)solve_tiled_smem(nr_cap_max));
@@ -2016,10 +2145,23 @@ int launch_pass(const BatchDev& bd, const SolveParams& sp, const LaunchCfg& lc, 
     if (timed) cudaEventRecord(lc.ev_pool[(*lc.ev_used)++], s);
     if (bd.tot_gp > 0) k_gp_eval<true><<<B, 256, 0, s>>>(bd, sp);
     k_pose_hessian<<<dim3(bd.max_kf, B), 256, 0, s>>>(bd, sp);
-    k_landmark_reduce<<<dim3((bd.max_lm + 15) / 16, B), 256, 0, s>>>(bd, sp);
-    for (int round = 0; round <= lc.max_rank; ++round) k_obs_v<<<g_obs, 256, 0, s>>>(bd, round);
-    if (bd.tot_gp > 0) k_gp_panel<<<dim3((bd.max_gp * 10 + 255) / 256, B), 256, 0, s>>>(bd);
-    if (lc.small_syrk) {
+    if (bd.fused) {
+        k_landmark_reduce<true><<<dim3((bd.max_lm + 15) / 16, B), 256, 0, s>>>(bd, sp);
+        const dim3 gf(bd.p_split, B);
+        if (lc.fused_slots == 7) {
+            if (bd.precision) k_schur_fused<7, float><<<gf, 512, schur_fused_smem(), s>>>(bd);
+            else k_schur_fused<7, double><<<gf, 512, schur_fused_smem(), s>>>(bd);
+        } else {
+            if (bd.precision) k_schur_fused<6, float><<<gf, 512, schur_fused_smem(), s>>>(bd);
+            else k_schur_fused<6, double><<<gf, 512, schur_fused_smem(), s>>>(bd);
+        }
+    } else {
+        k_landmark_reduce<false><<<dim3((bd.max_lm + 15) / 16, B), 256, 0, s>>>(bd, sp);
+        for (int round = 0; round <= lc.max_rank; ++round) k_obs_v<<<g_obs, 256, 0, s>>>(bd, round);
+        if (bd.tot_gp > 0) k_gp_panel<<<dim3((bd.max_gp * 10 + 255) / 256, B), 256, 0, s>>>(bd);
+    }
+    if (bd.fused) {
+    } else if (lc.small_syrk) {
         k_schur_syrk_tma<<<dim3(bd.p_split, B), 512, schur_tma_smem(), s>>>(bd);
     } else {
         const int nb = lc.nr_cap_max / 64;
@@ -2059,7 +2201,8 @@ int launch_pass(const BatchDev& bd, const SolveParams& sp, const LaunchCfg& lc, 
         }
         k_reduced_solve<false><<<B, 512, solve_smem(lc.nr_cap_max), s>>>(bc, sp, 2);
     }
-    k_backsub<<<dim3((bd.max_lm + 15) / 16, B), 256, 0, s>>>(bd);
+    if (bd.fused) k_backsub_jp<<<dim3((bd.max_lm + 15) / 16, B), 256, 0, s>>>(bd);
+    else k_backsub<<<dim3((bd.max_lm + 15) / 16, B), 256, 0, s>>>(bd);
     launch_eval_obs<false>(bd, sp, s);
     if (bd.tot_gp > 0) k_gp_eval<false><<<B, 256, 0, s>>>(bd, sp);
     if (bd.sharded) {  // model decrease / step norm / candidate cost over all ranks
@@ -2101,6 +2244,26 @@ __global__ void k_force_linearize(BatchDev bd) {
 void launch_jacobian_only(const BatchDev& bd, const SolveParams& sp, cudaStream_t s) {
     const dim3 g_obs((bd.max_obs + 255) / 256, bd.n_win);
     launch_eval_obs<true>(bd, sp, s);
+}
+// inspection entry point (kba_eval) on the fused path: J_l of every observation, formed exactly as the consumers of the
+// linearisation form it -- translation columns of the materialised J_p times the staged rotation of the keyframe
+template <typename TLin>
+__global__ void k_expand_jl(BatchDev bd, TLin* out) {
+    const WinDesc& wd = bd.desc[0];
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= wd.n_obs) return;
+    const size_t o = (size_t)wd.obs_off + i, T = (size_t)bd.tot_obs;
+    const double* R = bd.rt[0] + kPoseStride * (size_t)(wd.kf_off + bd.obs_kf[o]);
+    const TLin* jp = reinterpret_cast<const TLin*>(bd.jp);
+    for (int r = 0; r < 3; ++r) {
+        const double m0 = (double)jp[(6 * r + 3) * T + o], m1 = (double)jp[(6 * r + 4) * T + o], m2 = (double)jp[(6 * r + 5) * T + o];
+        for (int c = 0; c < 3; ++c) out[(size_t)(3 * r + c) * T + o] = (TLin)(m0 * R[c] + m1 * R[3 + c] + m2 * R[6 + c]);
+    }
+}
+void launch_expand_jl(const BatchDev& bd, double* out, cudaStream_t s) {
+    const int n = (int)bd.tot_obs;
+    if (bd.precision) k_expand_jl<float><<<(n + 255) / 256, 256, 0, s>>>(bd, reinterpret_cast<float*>(out));
+    else k_expand_jl<double><<<(n + 255) / 256, 256, 0, s>>>(bd, out);
 }
 void launch_force_linearize(const BatchDev& bd, cudaStream_t s) {
     k_solve_begin<<<bd.n_win, 256, 0, s>>>(bd, SolveParams{});  // layout (off_pose) for the eval entry point

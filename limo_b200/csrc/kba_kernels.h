@@ -25,6 +25,7 @@ struct LaunchCfg {
     int nr_cap_max = 64;
     int max_rank = 0;         // largest observation rank in the batch (multi-camera rigs)
     bool small_syrk = false;  // every window has <= 184 reduced rows: register-resident Schur kernel
+    int fused_slots = 6;      // fused Schur kernel instance: 6 accumulator blocks per warp (<= 176 rows) or 7 (<= 184)
     int rounds_override = -1, min_landmarks_for_trimming = 100, num_rounds_option = 1;
     bool time_jacobian = false;
     cudaEvent_t* ev_pool = nullptr;  // pairs of events bracketing each residual/Jacobian launch
@@ -41,5 +42,6 @@ int launch_pass(const BatchDev& bd, const SolveParams& sp, const LaunchCfg& lc, 
 void launch_count_active(const BatchDev& bd, cudaStream_t s);
 void launch_force_linearize(const BatchDev& bd, cudaStream_t s);
 void launch_jacobian_only(const BatchDev& bd, const SolveParams& sp, cudaStream_t s);
+void launch_expand_jl(const BatchDev& bd, double* out, cudaStream_t s);  // fused path: J_l as its consumers form it
 
 }  // namespace kba

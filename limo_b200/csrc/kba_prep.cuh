@@ -11,12 +11,29 @@ namespace kba {
 
 __device__ __forceinline__ int gp_row(const BatchDev& bd, const WinDesc& wd, int k, int r);
 
+// kFused: J_l is not materialised; it is formed here as (translation columns of J_p) R(keyframe), the rotations staged by
+// one bulk copy, and the z row goes to global memory only (lm_z) -- the fused Schur kernel builds its panels itself.
+template <bool kFused>
 __global__ void __launch_bounds__(256, 4) k_landmark_reduce(BatchDev bd, SolveParams sp) {
     const int w = blockIdx.y;
     WinState& st = bd.state[w];
     if (st.phase != PH_ITERATE) return;
     const WinDesc& wd = bd.desc[w];
     if (wd.landmarks_fixed) return;
+    __shared__ __align__(16) double s_pose[kFused ? kFusedMaxKf * kPoseStride : 2];
+    __shared__ __align__(8) uint64_t s_bar;
+    if (kFused) {
+        if (threadIdx.x == 0) {
+            mbar_init(&s_bar, 1);
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            const uint32_t bytes = (uint32_t)(wd.n_kf * kPoseStride * sizeof(double));
+            mbar_expect_tx(&s_bar, bytes);
+            tma_load_1d(s_pose, bd.rt[st.cur] + (size_t)kPoseStride * wd.kf_off, bytes, &s_bar);
+        }
+    }
     const int sl = threadIdx.x & 15;                       // lane inside the 16-lane group
     const int j = blockIdx.x * 16 + (threadIdx.x >> 4);    // one landmark per half warp
     const int L = wd.lm_off + min(j, wd.n_lm - 1);
@@ -26,11 +43,24 @@ __global__ void __launch_bounds__(256, 4) k_landmark_reduce(BatchDev bd, SolvePa
     if (valid) { o0 = lm_ptr[j]; o1 = lm_ptr[j + 1]; valid = o1 > o0; }
     const size_t T = (size_t)bd.tot_obs, base = (size_t)wd.obs_off;
     double c[6] = {0, 0, 0, 0, 0, 0}, g[3] = {0, 0, 0};
+    if (kFused) mbar_wait(&s_bar, 0);
     if (valid) {
         for (int o = o0 + sl; o < o1; o += 16) {
             double jl[9], r[3];
+            if (kFused) {
+                const double* R = s_pose + kPoseStride * bd.obs_kf[base + o];
 #pragma unroll
-            for (int q = 0; q < 9; ++q) jl[q] = lin_load(bd.jl, q * T + base + o, bd.precision);
+                for (int i = 0; i < 3; ++i) {
+                    const double m0 = lin_load(bd.jp, (6 * i + 3) * T + base + o, bd.precision);
+                    const double m1 = lin_load(bd.jp, (6 * i + 4) * T + base + o, bd.precision);
+                    const double m2 = lin_load(bd.jp, (6 * i + 5) * T + base + o, bd.precision);
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) jl[3 * i + c] = m0 * R[c] + m1 * R[3 + c] + m2 * R[6 + c];
+                }
+            } else {
+#pragma unroll
+                for (int q = 0; q < 9; ++q) jl[q] = lin_load(bd.jl, q * T + base + o, bd.precision);
+            }
 #pragma unroll
             for (int q = 0; q < 3; ++q) r[q] = lin_load(bd.res, q * T + base + o, bd.precision);
             c[0] += jl[0] * jl[0] + jl[3] * jl[3] + jl[6] * jl[6];
@@ -104,7 +134,7 @@ __global__ void __launch_bounds__(256, 4) k_landmark_reduce(BatchDev bd, SolvePa
             bd.lm_lambda[3 * (size_t)L + a] = lam[a];
             if (st.iter0) bd.lm_scale[3 * (size_t)L + a] = sc[a];
         }
-        {  // right-hand-side row z_j of the chunk panel
+        if (!kFused) {  // right-hand-side row z_j of the chunk panel
             const int ch = wd.chunk_off + (j >> 5);
             const int prs = bd.chunk_rs[ch];
             if (prs > 0) {

@@ -15,9 +15,18 @@ def _build():
 
 def test_facade_host_logic():
     """Triangulator.process, LandmarkCreator.CreateWithDepth, deactivateKeyframes, NotEnoughKeyframesException,
-    cheirality selection -- no GPU needed"""
+    cheirality selection, LandmarkSelector.voxel, the add-depth scheme -- no GPU needed"""
     _build()
     out = subprocess.run([EXE, "cpu"], capture_output=True, text=True)
+    assert out.returncode == 0, out.stdout + out.stderr
+
+
+def test_facade_host_logic_strict_eigen():
+    """the same cases on the strict build leg: the facade sources compiled with -DKBA_EIGEN_POISON_UNINIT, where the Eigen
+    subset offers only spellings that exist in Eigen 3.3 and default-constructed vectors / matrices are NaN-filled (real
+    Eigen leaves them uninitialised) -- an accumulation into a default-constructed object would poison the results"""
+    _build()
+    out = subprocess.run([EXE + "_strict", "cpu"], capture_output=True, text=True)
     assert out.returncode == 0, out.stdout + out.stderr
 
 
