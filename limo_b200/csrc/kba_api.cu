@@ -41,6 +41,9 @@ struct kba_handle {
     int sm_count = 148;
     cudaEvent_t ev_block = nullptr;  // blocking-sync event: waiting host threads sleep instead of spinning on a core
     bool blocking_sync = false;      // KBA_BLOCKING_SYNC=1 at kba_create
+    // grow-only device workspace of the single-shot entry points (kba_lidar_depth): no cudaMalloc / cudaFree per call
+    void* ws = nullptr;
+    size_t ws_cap = 0;
 };
 
 // Wait for the handle's stream.  With KBA_BLOCKING_SYNC=1 (read at kba_create) the host thread sleeps on a blocking-sync
@@ -291,6 +294,21 @@ int kba_internal_stream(kba_handle* h, cudaStream_t* s, int* device) {
     return KBA_OK;
 }
 int kba_internal_fail(int code, const char* msg) { return fail(code, msg ? msg : ""); }
+// at least `bytes` of device memory owned by the handle, 256-byte aligned, valid until the next call that asks for more
+int kba_internal_workspace(kba_handle* h, size_t bytes, void** out) {
+    if (!h || !out) return fail(KBA_ERR_BAD_ARG, "null handle");
+    if (bytes > h->ws_cap) {
+        CU(cudaSetDevice(h->device));
+        CU(cudaStreamSynchronize(h->stream));
+        if (h->ws) cudaFree(h->ws);
+        h->ws = nullptr; h->ws_cap = 0;
+        const size_t cap = bytes + bytes / 4 + 4096;
+        CU(cudaMalloc(&h->ws, cap));
+        h->ws_cap = cap;
+    }
+    *out = h->ws;
+    return KBA_OK;
+}
 const char* kba_last_error(void) { return g_last_error.c_str(); }
 
 void kba_default_options(kba_options* o) {
@@ -335,6 +353,7 @@ void kba_destroy(kba_handle* h) {
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
     if (h->ev_block) cudaEventDestroy(h->ev_block);
+    if (h->ws) cudaFree(h->ws);
     for (auto& e : h->ev_pool) cudaEventDestroy(e);
     delete h;
 }

@@ -222,6 +222,7 @@ extern "C" void kba_lidar_default_options(kba_lidar_options* o) {
 // implemented in kba_api.cu
 extern "C" int kba_internal_stream(kba_handle* h, cudaStream_t* s, int* device);
 extern "C" int kba_internal_fail(int code, const char* msg);
+extern "C" int kba_internal_workspace(kba_handle* h, size_t bytes, void** out);
 
 extern "C" int kba_lidar_depth(kba_handle* h, const float* cloud, int32_t n_points, int32_t stride, const double* T,
                                const double* intr, const float* feats, int32_t n_feats, const kba_lidar_options* o,
@@ -244,23 +245,30 @@ extern "C" int kba_lidar_depth(kba_handle* h, const float* cloud, int32_t n_poin
     P.local_enabled = o->local_rel_tolerance >= 0; P.local_tol = (float)o->local_rel_tolerance;
     P.crossnorm_min = (float)o->triangle_crossnorm_min; P.viewray_min = (float)o->viewray_plane_min;
     const int ncell = P.cells_x * P.cells_y;
-    float* d_cloud = nullptr; float* d_feats = nullptr; float* d_out = nullptr;
-    int* d_cnt = nullptr; int* d_start = nullptr; int* d_cur = nullptr; ProjPt* d_sorted = nullptr;
+    // one device workspace owned by the handle (grow-only): cloud | features | depths | cell counts, starts, cursors | sorted points
+    auto al = [](size_t b) { return (b + 255) & ~(size_t)255; };
+    const size_t b_cloud = al(sizeof(float) * (size_t)std::max(n_points, 1) * stride), b_feat = al(sizeof(float) * 2 * (size_t)std::max(n_feats, 1)),
+                 b_out = al(sizeof(float) * (size_t)std::max(n_feats, 1)), b_cell = al(sizeof(int) * (size_t)(ncell + 1)),
+                 b_sorted = al(sizeof(ProjPt) * (size_t)std::max(n_points, 1));
+    void* ws = nullptr;
+    if (kba_internal_workspace(h, b_cloud + b_feat + b_out + 3 * b_cell + b_sorted, &ws) != KBA_OK) return KBA_ERR_CUDA;
+    char* wp = (char*)ws;
+    float* d_cloud = (float*)wp; wp += b_cloud;
+    float* d_feats = (float*)wp; wp += b_feat;
+    float* d_out = (float*)wp; wp += b_out;
+    int* d_cnt = (int*)wp; wp += b_cell;
+    int* d_start = (int*)wp; wp += b_cell;
+    int* d_cur = (int*)wp; wp += b_cell;
+    ProjPt* d_sorted = (ProjPt*)wp;
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     cudaError_t err = cudaSuccess;
     auto chk = [&](cudaError_t e) { if (err == cudaSuccess && e != cudaSuccess) err = e; };
     chk(cudaSetDevice(device));
-    chk(cudaMalloc(&d_cloud, sizeof(float) * (size_t)std::max(n_points, 1) * stride));
-    chk(cudaMalloc(&d_feats, sizeof(float) * 2 * (size_t)std::max(n_feats, 1)));
-    chk(cudaMalloc(&d_out, sizeof(float) * (size_t)std::max(n_feats, 1)));
-    chk(cudaMalloc(&d_cnt, sizeof(int) * ncell)); chk(cudaMalloc(&d_start, sizeof(int) * (ncell + 1)));
-    chk(cudaMalloc(&d_cur, sizeof(int) * ncell));
-    chk(cudaMalloc(&d_sorted, sizeof(ProjPt) * (size_t)std::max(n_points, 1)));
-    chk(cudaEventCreate(&e0)); chk(cudaEventCreate(&e1));
+    if (device_ms) { chk(cudaEventCreate(&e0)); chk(cudaEventCreate(&e1)); }
     if (err == cudaSuccess) {
         chk(cudaMemcpyAsync(d_cloud, cloud, sizeof(float) * (size_t)n_points * stride, cudaMemcpyHostToDevice, s));
         chk(cudaMemcpyAsync(d_feats, feats, sizeof(float) * 2 * (size_t)n_feats, cudaMemcpyHostToDevice, s));
-        chk(cudaEventRecord(e0, s));
+        if (e0) chk(cudaEventRecord(e0, s));
         chk(cudaMemsetAsync(d_cnt, 0, sizeof(int) * ncell, s));
         chk(cudaMemsetAsync(d_cur, 0, sizeof(int) * ncell, s));
         const int gp = (n_points + 255) / 256;
@@ -268,13 +276,12 @@ extern "C" int kba_lidar_depth(kba_handle* h, const float* cloud, int32_t n_poin
         k_lidar_scan<<<1, 1024, 0, s>>>(d_cnt, d_start, ncell);
         if (n_points > 0) k_lidar_bin<true><<<gp, 256, 0, s>>>(P, d_cloud, n_points, stride, d_cnt, d_start, d_cur, d_sorted);
         if (n_feats > 0) k_lidar_feature<<<(n_feats + 3) / 4, 128, 0, s>>>(P, d_sorted, d_start, d_feats, n_feats, d_out);
-        chk(cudaEventRecord(e1, s));
+        if (e1) chk(cudaEventRecord(e1, s));
         chk(cudaMemcpyAsync(depth_out, d_out, sizeof(float) * (size_t)n_feats, cudaMemcpyDeviceToHost, s));
         chk(cudaStreamSynchronize(s));
         chk(cudaGetLastError());
         if (err == cudaSuccess && device_ms) chk(cudaEventElapsedTime(device_ms, e0, e1));
     }
-    cudaFree(d_cloud); cudaFree(d_feats); cudaFree(d_out); cudaFree(d_cnt); cudaFree(d_start); cudaFree(d_cur); cudaFree(d_sorted);
     if (e0) cudaEventDestroy(e0);
     if (e1) cudaEventDestroy(e1);
     if (err != cudaSuccess) return kba_internal_fail(KBA_ERR_CUDA, cudaGetErrorString(err));

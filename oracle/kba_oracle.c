@@ -17,6 +17,11 @@
 #include <time.h>
 #ifdef _OPENMP
 #include <omp.h>
+
+/* 0: ceres 1.13 order of the tolerance tests (candidate not applied), 1: the <= 1.12 order of SURVEY A.6 (see lm_solve) */
+static int g_tolerance_order = 0;
+void kbo_set_tolerance_order(int order) { g_tolerance_order = order ? 1 : 0; }
+
 #endif
 
 /* ------------------------------------------------------------------------------------------------ */
@@ -1060,20 +1065,29 @@ static void ceres_solve(program* P, state_t* x, int max_num_iterations, double m
         double cand_cost;
         if (!program_evaluate(P, &cand, 0, &cand_cost)) cand_cost = DBL_MAX;
 
-        /* ---- ParameterToleranceReached ---- */
+        /* ---- ParameterToleranceReached / FunctionToleranceReached ----
+         * Order of ceres 1.13: both tests look at the CANDIDATE and, when one fires, the solve ends with x
+         * unchanged.  g_tolerance_order = 1 is the other order SURVEY A.6 names for ceres <= 1.12 ("as recalled"): the
+         * same tests, but a candidate that passes the acceptance test is applied before the solve ends.  The reference pins
+         * neither (no golden vectors, Ceres not installable); scripts/ceres_order_sensitivity.py measures how far the two
+         * move the result -- that is the error bar on "parity with Ceres" this restatement carries. */
         double sq;
         state_diff_norms(P, x, &cand, &sq, NULL);
         const double step_norm = sqrt(sq);
-        if (step_norm <= opt->parameter_tolerance * (x_norm + opt->parameter_tolerance)) {
-            sum->termination = KBA_TERM_CONVERGENCE;
-            log_iteration(L, solve_index, iteration, x_cost, 0, gmax, step_norm, 0, radius, 1, 0);
-            break;
-        }
-        /* ---- FunctionToleranceReached ---- */
         const double cost_change = x_cost - cand_cost;
-        if (fabs(cost_change) <= opt->function_tolerance * x_cost) {
+        const int tol_param = step_norm <= opt->parameter_tolerance * (x_norm + opt->parameter_tolerance);
+        const int tol_func = !tol_param && fabs(cost_change) <= opt->function_tolerance * x_cost;
+        if (tol_param || tol_func) {
             sum->termination = KBA_TERM_CONVERGENCE;
-            log_iteration(L, solve_index, iteration, x_cost, cost_change, gmax, step_norm, 0, radius, 1, 0);
+            if (g_tolerance_order == 1 && cost_change / model_change > opt->min_relative_decrease) {
+                state_copy(x, &cand, P->n_kf, nl);
+                if (!program_evaluate(P, x, 1, &x_cost)) { sum->termination = KBA_TERM_FAILURE; break; }
+                sum->num_successful_steps++;
+                if (x_cost < sum->final_cost) sum->final_cost = x_cost;
+                log_iteration(L, solve_index, iteration, x_cost, cost_change, gmax, step_norm, cost_change / model_change, radius, 1, 1);
+            } else {
+                log_iteration(L, solve_index, iteration, x_cost, tol_param ? 0 : cost_change, gmax, step_norm, 0, radius, 1, 0);
+            }
             break;
         }
         /* ---- IsStepSuccessful (monotonic: relative == historical decrease) ---- */

@@ -33,6 +33,11 @@ int kbo_eval(const kba_window* w, const kba_options* opt, kba_eval_out* out);
 
 void kbo_default_options(kba_options* opt);
 
+/* Order of the parameter / function tolerance tests inside the trust-region loop: 0 (default) = ceres 1.13, the tests
+ * look at the candidate and a firing test leaves x unchanged; 1 = the order SURVEY.md A.6 recalls for ceres <= 1.12, where
+ * an acceptable candidate is applied before the solve ends.  Process-wide; used by scripts/ceres_order_sensitivity.py. */
+void kbo_set_tolerance_order(int order);
+
 /* ---- single-residual entry points, for the reference's known-answer tests and finite-difference checks ---- */
 /* ReprojectionErrorWithQuaternions::operator() (cost_functors_ceres.hpp:91-155); returns 0 on failure (|z|<0.01). */
 int kbo_reprojection(const double pose[7], const double cam_pose[7], const double intr[3], const double point[3],
