@@ -38,7 +38,8 @@ enum {
     KBA_ERR_CUDA = 2,          /* no device / CUDA runtime error (see kba_last_error) */
     KBA_ERR_NOT_ENOUGH_KF = 3, /* fewer than 3 keyframes: NotEnoughKeyframesException, cpp:630 */
     KBA_ERR_CAPACITY = 4,      /* window larger than the limits compiled into the kernels */
-    KBA_ERR_NCCL = 5
+    KBA_ERR_NCCL = 5,
+    KBA_ERR_TIMEOUT = 6        /* kba_result.status only: the host's safety cap ended the batch before this window finished */
 };
 
 /* ---- termination of one inner solve (mirrors ceres::TerminationType as used via Summary) ---- */
@@ -127,8 +128,11 @@ typedef struct kba_options {
     int32_t min_landmarks_for_trimming; /* 100 for solve() (cpp:741), 30 for adjustPoseOnly (cpp:865) */
     int32_t min_residual_groups;   /* 30    (cpp:762, robust_solving.cpp:109)               */
     int32_t num_rounds_option;     /* outlier_rejection_options_.num_iterations, default 1  */
-    double solver_time_sec;        /* wall-clock cap checked between iterations; <= 0: none. Parity runs use 20 s as
-                                      the reference tests do (test/keyframe_bundle_adjustment.cpp:486) */
+    double solver_time_sec;        /* max_solver_time_in_seconds of EVERY inner ceres::Solve (robust_solving.cpp:233-238), checked on
+                                      the device between iterations: the solve ends NO_CONVERGENCE with its accepted iterate and
+                                      solveTrimmed continues, so the final solve always runs.  <= 0: none; ignored by sharded
+                                      solves (collective).  Parity runs use 20 s as the reference tests do
+                                      (test/keyframe_bundle_adjustment.cpp:486) */
     /* ceres defaults, never overridden by the reference (robust_solving.hpp:101-103 are commented out) */
     double function_tolerance;     /* 1e-6  */
     double gradient_tolerance;     /* 1e-10 */

@@ -315,6 +315,8 @@ std::string BundleAdjusterKeyframes::runWindow(const std::vector<Keyframe*>& kfs
            << s.initial_cost << ", final cost " << s.final_cost << ", iterations " << s.num_iterations << " (successful "
            << s.num_successful_steps << "), termination " << term[s.termination < 3 ? s.termination : 2] << "\n";
     }
+    if (r.status != KBA_OK)  // like a Ceres failure, not surfaced as an exception (reference: only text in the report)
+        ss << "\nsolver did not finish (kba status " << r.status << "): the last accepted iterate was written back\n";
     ss << "\nDuration solveTrimmed=" << r.time_sec << " sec\n";
     return ss.str();
 }

@@ -151,7 +151,19 @@ static int validate_window(const kba_window* w, std::string& why) {
     for (int g = 0; g < w->n_gp; ++g)
         if (w->gp_lm[g] < 0 || w->gp_lm[g] >= w->n_lm || w->gp_kf[g] < 0 || w->gp_kf[g] >= w->n_kf) { why = "ground-plane index out of range"; return KBA_ERR_BAD_ARG; }
     if (w->speed_weight > 0 && (w->speed_kf < 0 || w->speed_kf >= w->n_kf || !(w->speed_dt > 0))) { why = "speed prior: keyframe out of range or dt <= 0"; return KBA_ERR_BAD_ARG; }
-    if (w->n_lm > 0 && w->lm_obs_ptr[w->n_lm] != w->n_obs) { why = "lm_obs_ptr[n_lm] != n_obs"; return KBA_ERR_BAD_ARG; }
+    if (w->n_lm > 0) {
+        if (w->lm_obs_ptr[0] != 0) { why = "lm_obs_ptr[0] != 0"; return KBA_ERR_BAD_ARG; }
+        for (int j = 0; j < w->n_lm; ++j)
+            if (w->lm_obs_ptr[j + 1] < w->lm_obs_ptr[j]) { why = "lm_obs_ptr is not non-decreasing"; return KBA_ERR_BAD_ARG; }
+        if (w->lm_obs_ptr[w->n_lm] != w->n_obs) { why = "lm_obs_ptr[n_lm] != n_obs"; return KBA_ERR_BAD_ARG; }
+    } else if (w->n_obs != 0) { why = "observations without landmarks"; return KBA_ERR_BAD_ARG; }
+    if (w->n_gp > 0) {  // at most one ground-plane residual per landmark (one Landmark::is_ground_plane flag, cpp:519-560)
+        std::vector<unsigned char> seen((size_t)w->n_lm, 0);
+        for (int g = 0; g < w->n_gp; ++g) {
+            if (seen[w->gp_lm[g]]) { why = "two ground-plane residuals on one landmark"; return KBA_ERR_BAD_ARG; }
+            seen[w->gp_lm[g]] = 1;
+        }
+    }
     for (int o = 0; o < w->n_obs; ++o) {
         if (w->obs_kf[o] < 0 || w->obs_kf[o] >= w->n_kf) { why = "obs_kf out of range"; return KBA_ERR_BAD_ARG; }
         if (w->obs_cam && (w->obs_cam[o] < 0 || w->obs_cam[o] >= w->n_cam)) { why = "obs_cam out of range"; return KBA_ERR_BAD_ARG; }
@@ -425,8 +437,9 @@ int kba_batch_create(kba_handle* h, int32_t n_windows, const kba_window* w, kba_
         bd.max_obs = std::max(bd.max_obs, w[i].n_obs); bd.max_lm = std::max(bd.max_lm, w[i].n_lm);
         bd.max_kf = std::max(bd.max_kf, w[i].n_kf); bd.max_gp = std::max(bd.max_gp, w[i].n_gp);
     }
-    if (obs > 2000000000LL) { delete b; return fail(KBA_ERR_CAPACITY, "batch exceeds 2^31 observations"); }
+    if (obs > 2000000000LL) { b->release(); delete b; return fail(KBA_ERR_CAPACITY, "batch exceeds 2^31 observations"); }
     if (nr_cap_max > 640) {  // shared-memory budget of the panel copies in k_reduced_solve / k_chol_trail (227 KB per CTA)
+        b->release();
         delete b;
         return fail(KBA_ERR_CAPACITY, "reduced system larger than 640 rows (106 keyframes, or 63 with ground-plane blocks)");
     }
@@ -508,6 +521,7 @@ int kba_batch_create(kba_handle* h, int32_t n_windows, const kba_window* w, kba_
     bad |= b->dev_alloc(&bd.trim_reject, lm);
     bad |= b->dev_alloc(&bd.res, 3 * obs); bad |= b->dev_alloc(&bd.jp, 18 * obs);
     if (!bd.fused) bad |= b->dev_alloc(&bd.jl, 9 * obs);  // fused path: J_l is re-formed from J_p by its consumers
+    else bad |= b->dev_alloc(&bd.vobs, 18 * obs);         // ... and V is kept per observation, unpadded
     bad |= b->dev_alloc(&bd.cost_part_x, (size_t)n_windows * bd.cost_parts); bad |= b->dev_alloc(&bd.cost_part_c, (size_t)n_windows * bd.cost_parts);
     bad |= b->dev_alloc(&bd.bs_part, (size_t)n_windows * bd.bs_parts * 4);
     bad |= b->dev_alloc(&bd.sred, (size_t)soff * bd.p_split); bad |= b->dev_alloc(&bd.amat, (size_t)soff);
@@ -551,8 +565,16 @@ int kba_batch_upload(kba_batch* b, int32_t n_windows, const kba_window* w) {
     CU(cudaSetDevice(b->h->device));  // callers may drive several handles from several host threads
     for (int i = 0; i < n_windows; ++i) {
         const WinDesc& d = b->desc_h[i];
-        if (w[i].n_kf != d.n_kf || w[i].n_lm != d.n_lm || w[i].n_obs != d.n_obs || w[i].n_cam != d.n_cam)
-            return fail(KBA_ERR_BAD_ARG, "kba_batch_upload: window shapes differ from kba_batch_create");
+        std::string why;
+        const int rc = validate_window(&w[i], why);  // indices of the new contents are checked like at create
+        if (rc != KBA_OK) return fail(rc, "kba_batch_upload: window " + std::to_string(i) + ": " + why);
+        if (w[i].n_kf != d.n_kf || w[i].n_lm != d.n_lm || w[i].n_obs != d.n_obs || w[i].n_cam != d.n_cam || w[i].n_gp != d.n_gp)
+            return fail(KBA_ERR_BAD_ARG, "kba_batch_upload: window shapes (keyframes, cameras, landmarks, observations, ground-plane "
+                                         "residuals) differ from kba_batch_create");
+        // the reduced system was sized at create: 6 rows per keyframe, 10 with plane blocks
+        const bool planes = w[i].n_gp > 0 || w[i].plane_reg_weight > 0;
+        if (((planes ? 10 : 6) * w[i].n_kf + 1 + 63) / 64 * 64 > d.nr_cap)
+            return fail(KBA_ERR_BAD_ARG, "kba_batch_upload: window " + std::to_string(i) + " needs plane blocks the batch was not created with");
     }
     // packing (landmark sort, observation permutation, keyframe-major copy) is independent per window: host threads
     auto pack = [&](int i) {
@@ -636,12 +658,15 @@ static SolveParams make_params(const kba_options* o) {
     sp.max_lm_diagonal = o->max_lm_diagonal; sp.trim_solver_iterations = o->trim_solver_iterations;
     sp.final_solver_iterations = o->final_solver_iterations; sp.min_residual_groups = o->min_residual_groups;
     sp.max_consecutive_invalid_steps = o->max_consecutive_invalid_steps;
+    sp.max_solver_time = o->solver_time_sec;
     return sp;
 }
 
 int kba_batch_solve(kba_batch* b, const kba_options* opt) {
     if (!b || !opt) return fail(KBA_ERR_BAD_ARG, "bad argument to kba_batch_solve");
     if (opt->precision != 0 && opt->precision != 1) return fail(KBA_ERR_BAD_ARG, "kba_options.precision must be 0 (FP64) or 1 (FP32 linearisation)");
+    if (opt->num_trim_rounds > 6 || (opt->num_trim_rounds < 0 && opt->num_rounds_option > 6))
+        return fail(KBA_ERR_CAPACITY, "at most 6 trimming rounds (KBA_MAX_SOLVES = 8 inner solves incl. one retry and the final solve)");
     b->bd.precision = opt->precision;
     kba_handle* h = b->h;
     CU(cudaSetDevice(h->device));
@@ -666,19 +691,28 @@ int kba_batch_solve(kba_batch* b, const kba_options* opt) {
     const int max_passes = rounds_max * (3 * opt->trim_solver_iterations + 4) + opt->final_solver_iterations + 8;
     const auto t0 = std::chrono::steady_clock::now();
     int check_every = 4;
+    bool timed_out = false;
     for (int pass = 0; pass < max_passes; ++pass) {
-        if (launch_pass(b->bd, sp, lc, &h->counters, s)) return KBA_ERR_NCCL;  // message set by the exchange
+        if (launch_pass(b->bd, sp, lc, &h->counters, s)) {  // message set by the exchange
+            cudaEventRecord(b->ev_b, s);
+            return KBA_ERR_NCCL;
+        }
         if ((pass + 1) % check_every == 0 || pass + 1 == max_passes) {
             launch_count_active(b->bd, s);
             CU(b->n_active.download(s));
             CU(wait_stream(h));
             if (b->n_active.h[0] == 0) break;
-            if (opt->solver_time_sec > 0) {
+            // max_solver_time_in_seconds is applied PER INNER SOLVE on the device (k_lm_update, like ceres), which always
+            // lets the final solve start; the host only guards against a stuck device with the budget of every possible
+            // inner solve.  A sharded solve is collective: its ranks must issue the same passes, so no rank may leave on
+            // its own clock (the iteration caps bound it).
+            if (opt->solver_time_sec > 0 && !b->bd.sharded) {
                 const double el = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
-                if (el > opt->solver_time_sec) break;  // wall-clock cap: the accepted iterate stands
+                if (el > KBA_MAX_SOLVES * opt->solver_time_sec + 2.0) { timed_out = true; break; }
             }
         }
     }
+    if (timed_out) g_last_error = "kba_batch_solve: host safety cap reached, unfinished windows carry KBA_ERR_TIMEOUT in kba_result.status";
     CU(cudaEventRecord(b->ev_b, s));
     CU(b->jac_obs.download(s));
     CU(wait_stream(h));
@@ -750,7 +784,7 @@ int kba_batch_download(kba_batch* b, kba_result* res) {
         }
         r.initial_cost = st.n_solves > 0 ? st.solves[0].initial_cost : 0.0;
         r.final_cost = st.n_solves > 0 ? st.solves[st.n_solves - 1].final_cost : 0.0;
-        r.status = (st.phase == PH_DONE) ? KBA_OK : KBA_ERR_CAPACITY;
+        r.status = (st.phase == PH_DONE) ? KBA_OK : KBA_ERR_TIMEOUT;  // host safety cap hit (see kba_batch_solve)
         r.time_sec = 1e-3 * b->last_solve_ms;
         int n = 0;
         if (r.iterations) {
@@ -842,19 +876,23 @@ int kba_eval(kba_handle* h, const kba_window* w, const kba_options* opt, kba_eva
     std::vector<int> offp(w->n_kf);
     WinState st;
     cudaStream_t s = h->stream;
-    cudaMemcpyAsync(res_h.data(), bd.res, 3 * n * sizeof(double), cudaMemcpyDeviceToHost, s);
-    cudaMemcpyAsync(jp_h.data(), bd.jp, 18 * n * sizeof(double), cudaMemcpyDeviceToHost, s);
+    cudaError_t ce = cudaSuccess;
+    auto cp = [&](void* dst, const void* src, size_t bytes) {
+        if (ce == cudaSuccess) ce = cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, s);
+    };
+    cp(res_h.data(), bd.res, 3 * n * sizeof(double));
+    cp(jp_h.data(), bd.jp, 18 * n * sizeof(double));
     double* jl_dev = bd.jl;
     if (bd.fused) {  // J_l is not materialised on the fused path: expand it on the device the way its consumers do
         if (b->dev_alloc(&jl_dev, 9 * n)) { kba_batch_destroy(b); return fail(KBA_ERR_CUDA, "out of device memory (kba_eval)"); }
         launch_expand_jl(bd, jl_dev, s);
     }
-    cudaMemcpyAsync(jl_h.data(), jl_dev, 9 * n * sizeof(double), cudaMemcpyDeviceToHost, s);
-    cudaMemcpyAsync(cost_h.data(), bd.cost_part_x, bd.cost_parts * sizeof(double), cudaMemcpyDeviceToHost, s);
-    cudaMemcpyAsync(offp.data(), bd.off_pose, w->n_kf * sizeof(int), cudaMemcpyDeviceToHost, s);
-    cudaMemcpyAsync(&st, bd.state, sizeof(WinState), cudaMemcpyDeviceToHost, s);
-    cudaError_t e = cudaStreamSynchronize(s);
-    if (e != cudaSuccess) { kba_batch_destroy(b); return fail(KBA_ERR_CUDA, cudaGetErrorString(e)); }
+    cp(jl_h.data(), jl_dev, 9 * n * sizeof(double));
+    cp(cost_h.data(), bd.cost_part_x, bd.cost_parts * sizeof(double));
+    cp(offp.data(), bd.off_pose, w->n_kf * sizeof(int));
+    cp(&st, bd.state, sizeof(WinState));
+    if (ce == cudaSuccess) ce = cudaStreamSynchronize(s);
+    if (ce != cudaSuccess) { kba_batch_destroy(b); return fail(KBA_ERR_CUDA, cudaGetErrorString(ce)); }
     for (size_t e = 0; e < n; ++e) {  // e: internal (sorted) observation slot, o: the caller's observation index
         const size_t o = (size_t)b->obs_orig.h[e];
         const bool fixed = offp[w->obs_kf[o]] < 0;

@@ -74,6 +74,7 @@ struct WinState {
     double x_cost, x_norm, gmax;
     // pose-side scalars of the current step (written by the reduced solve)
     double f_model, f_step_sq, f_xnorm_sq, f_gmax;
+    unsigned long long t_solve_start;  // %globaltimer (ns) when the current inner solve began: max_solver_time is per solve
     SolveSummary solves[8];
 };
 
@@ -184,6 +185,7 @@ struct BatchDev {
     int* grp_t0;              // [tot_groups]
     int* grp_t1;
     int* grp_rs;              // [tot_groups] == 4 mod 16, 0: no free keyframe rows
+    double* vobs;             // [tot_obs][18] V_i = (J_p^T J_l) L^-T of every observation, 3 columns x 6 rows, unpadded
     unsigned long long* prof; // [16] cycle counters of a KBA_PROF build (nullptr otherwise)
     int tot_groups;
     int* n_active;            // [1] windows still running (device counter)
@@ -206,7 +208,14 @@ struct SolveParams {  // kba_options subset used on the device
     double function_tolerance, gradient_tolerance, parameter_tolerance;
     double initial_radius, max_radius, min_radius, min_relative_decrease, min_lm_diagonal, max_lm_diagonal;
     int trim_solver_iterations, final_solver_iterations, min_residual_groups, max_consecutive_invalid_steps;
+    double max_solver_time;  // seconds per inner solve (ceres max_solver_time_in_seconds), <= 0: none
 };
+
+__device__ __forceinline__ unsigned long long global_timer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
 
 // ---- small math ----------------------------------------------------------------------------------------------------------
 template <typename T>

@@ -97,6 +97,7 @@ __global__ void __launch_bounds__(256) k_solve_begin(BatchDev bd, SolveParams sp
         s.num_iterations = 0; s.num_successful_steps = 0; s.termination = 1;
         s.num_landmarks = s_cnt[0];
         s.num_residual_blocks = s_cnt[1] + s_cnt[2] + n_reg + (wd.scale_weight > 0 ? 1 : 0) + (wd.speed_weight > 0 ? 1 : 0);
+        st.t_solve_start = global_timer_ns();
         st.phase = PH_ITERATE;
     }
     __syncthreads();
@@ -129,15 +130,14 @@ __global__ void __launch_bounds__(256) k_solve_begin(BatchDev bd, SolveParams sp
                 if (od >= 0) { r0 = min(r0, od); r1 = max(r1, od + 3); }
                 if (oz >= 0) { r0 = min(r0, oz); r1 = max(r1, oz + 1); }
             }
-            const int t0 = (r1 < 0) ? 0 : r0 / 8, t1 = (r1 < 0) ? 0 : (r1 + 7) / 8;
-            int rs = 0;
-            if (t1 > t0) {
-                const int rows = 8 * (t1 - t0) + ((trhs >= t0 && trhs < t1) ? 0 : 8);
-                rs = ((rows - 4 + 15) / 16) * 16 + 4;
-            }
+            // range aligned to 16-row blocks (two tiles): every block of the range has both its tiles, the fused kernel then
+            // needs no partial-block variants except for the right-hand-side tile
+            const int t0 = (r1 < 0) ? 0 : (r0 / 16) * 2, t1 = (r1 < 0) ? 0 : ((r1 + 15) / 16) * 2;
+            int rows = 0;  // rows of the group's shared-memory panel (the column stride is the constant kFMaxRs)
+            if (t1 > t0) rows = 8 * (t1 - t0) + ((trhs >= t0 && trhs < t1) ? 0 : 8);
             bd.grp_t0[wd.grp_off + c] = t0;
             bd.grp_t1[wd.grp_off + c] = t1;
-            bd.grp_rs[wd.grp_off + c] = rs;
+            bd.grp_rs[wd.grp_off + c] = rows;
         }
     }
     if (!bd.fused) {  // layout of the dense V panels: per chunk 96 columns x rs rows (rs == 4 mod 16), column-major
@@ -1569,27 +1569,14 @@ __global__ void __launch_bounds__(256) k_backsub(BatchDev bd) {
     }
 }
 
-// Fused path: no V panels exist in global memory.  With V_i = (J_p^T J_l) L^-T the sum over the landmark's observations
-// is  sum_i V_i^T delta_f,i = L^-1 sum_i J_l^T (J_p delta_f,i):  J_p streams in coalesced (144 B per observation), J_l is
-// re-formed from its translation columns and the staged rotation, and no gather of 48-byte panel segments is left.
-__global__ void __launch_bounds__(256) k_backsub_jp(BatchDev bd) {
+// Fused path: sum_i V_i^T delta_f,i from the compact per-observation V (18 doubles, k_obs_v2): each lane reads its
+// observation's 144 contiguous bytes with nine 128-bit loads.
+__global__ void __launch_bounds__(256) k_backsub_v(BatchDev bd) {
     const int w = blockIdx.y;
     const WinState& st = bd.state[w];
     if (st.phase != PH_ITERATE) return;
     const WinDesc& wd = bd.desc[w];
-    __shared__ __align__(16) double s_pose[kFusedMaxKf * kPoseStride];
-    __shared__ __align__(8) uint64_t s_bar;
     __shared__ double s_red[16][4];
-    if (threadIdx.x == 0) {
-        mbar_init(&s_bar, 1);
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        const uint32_t bytes = (uint32_t)(wd.n_kf * kPoseStride * sizeof(double));
-        mbar_expect_tx(&s_bar, bytes);
-        tma_load_1d(s_pose, bd.rt[st.cur] + (size_t)kPoseStride * wd.kf_off, bytes, &s_bar);
-    }
     const int hl = threadIdx.x & 15, grp = threadIdx.x >> 4;
     const int j = blockIdx.x * 16 + grp;
     double model = 0.0, step_sq = 0.0, xn_sq = 0.0, gmax = 0.0;
@@ -1600,28 +1587,24 @@ __global__ void __launch_bounds__(256) k_backsub_jp(BatchDev bd) {
     const int* lm_ptr = bd.lm_ptr + wd.lm_off + w;
     const int o0 = have ? lm_ptr[j] : 0, o1 = have ? lm_ptr[j + 1] : 0;
     const bool in = have && bd.lm_active[L] && o1 > o0 && !wd.landmarks_fixed && !st.solve_failed;
-    const size_t base = (size_t)wd.obs_off, T = (size_t)bd.tot_obs;
+    const size_t base = (size_t)wd.obs_off;
     const double* delta_f = bd.delta_f + (size_t)w * bd.nr_cap_max;
-    double sv[3] = {0, 0, 0};  // sum_i J_l^T (J_p delta_i)
-    double tg[3] = {0, 0, 0};  // ground-plane block: V rows are stored (10 x 3), already multiplied by L^-T
-    mbar_wait(&s_bar, 0);
+    double t[3] = {0, 0, 0};
     if (in) {
         for (int o = o0 + hl; o < o1; o += 16) {
             const int off = bd.obs_row[base + o];  // row of the observation's pose block (k_solve_begin), -1: constant
             if (off < 0) continue;
-            const double* R = s_pose + kPoseStride * bd.obs_kf[base + o];
+            const double2* v = reinterpret_cast<const double2*>(bd.vobs + 18 * (base + o));
             double d[6];
 #pragma unroll
             for (int r = 0; r < 6; ++r) d[r] = delta_f[off + r];
 #pragma unroll
-            for (int i = 0; i < 3; ++i) {
-                double jp[6];
+            for (int c = 0; c < 3; ++c)
 #pragma unroll
-                for (int r = 0; r < 6; ++r) jp[r] = lin_load(bd.jp, (6 * i + r) * T + base + o, bd.precision);
-                const double wi = jp[0] * d[0] + jp[1] * d[1] + jp[2] * d[2] + jp[3] * d[3] + jp[4] * d[4] + jp[5] * d[5];
-#pragma unroll
-                for (int c = 0; c < 3; ++c) sv[c] += (jp[3] * R[c] + jp[4] * R[3 + c] + jp[5] * R[6 + c]) * wi;
-            }
+                for (int h = 0; h < 3; ++h) {
+                    const double2 x = v[3 * c + h];
+                    t[c] += x.x * d[2 * h] + x.y * d[2 * h + 1];
+                }
         }
         const int gl = (wd.n_gp > 0) ? bd.gp_of_lm[L] : -1;
         if (gl >= 0 && hl < 10) {  // row `hl` of the gp block's 10 x 3 V
@@ -1629,26 +1612,21 @@ __global__ void __launch_bounds__(256) k_backsub_jp(BatchDev bd) {
             if (row >= 0) {
                 const double d = delta_f[row];
 #pragma unroll
-                for (int c = 0; c < 3; ++c) tg[c] = bd.vgp[(size_t)(3 * hl + c) * bd.tot_gp + wd.gp_off + gl] * d;
+                for (int c = 0; c < 3; ++c) t[c] += bd.vgp[(size_t)(3 * hl + c) * bd.tot_gp + wd.gp_off + gl] * d;
             }
         }
     }
 #pragma unroll
     for (int c = 0; c < 3; ++c)
 #pragma unroll
-        for (int m = 8; m >= 1; m >>= 1) {
-            sv[c] += __shfl_xor_sync(0xffffffffu, sv[c], m);
-            tg[c] += __shfl_xor_sync(0xffffffffu, tg[c], m);
-        }
+        for (int m = 8; m >= 1; m >>= 1) t[c] += __shfl_xor_sync(0xffffffffu, t[c], m);
     if (have && hl == 0) {
         if (!in) {
             pn[0] = pc[0]; pn[1] = pc[1]; pn[2] = pc[2];
         } else {
             const double* z = bd.lm_z + 3 * (size_t)L;
             const double* li = bd.lm_linv + 6 * (size_t)L;  // i00; i10 i11; i20 i21 i22
-            const double t0 = li[0] * sv[0] + tg[0] + z[0];
-            const double t1 = li[1] * sv[0] + li[2] * sv[1] + tg[1] + z[1];
-            const double t2 = li[3] * sv[0] + li[4] * sv[1] + li[5] * sv[2] + tg[2] + z[2];
+            const double t0 = t[0] + z[0], t1 = t[1] + z[1], t2 = t[2] + z[2];
             // delta_p = -Linv^T t
             const double d0 = -(li[0] * t0 + li[1] * t1 + li[3] * t2);
             const double d1 = -(li[2] * t1 + li[4] * t2);
@@ -1802,6 +1780,10 @@ __global__ void __launch_bounds__(128) k_lm_update(BatchDev bd, SolveParams sp) 
     }
     // ---- loop head of the next iteration (FinalizeIterationAndCheckIfMinimizerCanContinue) ----
     if (st.iteration >= st.max_iter) { st.solve_failed = 0; solve_end(st, 1); return; }
+    // max_solver_time_in_seconds of THIS inner solve (robust_solving.cpp:233-238 sets it per ceres::Solve): NO_CONVERGENCE, the
+    // accepted iterate stands and solveTrimmed goes on to its next solve.  Not in a sharded solve: the ranks' clocks differ.
+    if (sp.max_solver_time > 0 && !bd.sharded &&
+        (double)(global_timer_ns() - st.t_solve_start) * 1e-9 >= sp.max_solver_time) { st.solve_failed = 0; solve_end(st, 1); return; }
     if (st.last_successful && st.gmax <= sp.gradient_tolerance) { st.solve_failed = 0; solve_end(st, 0); return; }
     if (st.radius <= sp.min_radius) { st.solve_failed = 0; solve_end(st, 0); return; }
     st.iteration++;
@@ -2111,13 +2093,9 @@ cudaError_t configure_kernels(int nr_cap_max) {
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(k_schur_syrk_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)schur_tma_smem());
     if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(k_schur_fused<6, double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)schur_fused_smem());
+    e = cudaFuncSetAttribute(k_schur_fused<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)schur_fused_smem());
     if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(k_schur_fused<7, double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)schur_fused_smem());
-    if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(k_schur_fused<6, float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)schur_fused_smem());
-    if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(k_schur_fused<7, float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)schur_fused_smem());
+    e = cudaFuncSetAttribute(k_schur_fused<7>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)schur_fused_smem());
     if (e != cudaSuccess) return e;
     if (nr_cap_max <= 192) {
         e = cudaFuncSetAttribute(k_reduced_solve<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -2147,14 +2125,10 @@ int launch_pass(const BatchDev& bd, const SolveParams& sp, const LaunchCfg& lc, 
     k_pose_hessian<<<dim3(bd.max_kf, B), 256, 0, s>>>(bd, sp);
     if (bd.fused) {
         k_landmark_reduce<true><<<dim3((bd.max_lm + 15) / 16, B), 256, 0, s>>>(bd, sp);
+        k_obs_v2<<<g_obs, 256, 0, s>>>(bd);
         const dim3 gf(bd.p_split, B);
-        if (lc.fused_slots == 7) {
-            if (bd.precision) k_schur_fused<7, float><<<gf, 512, schur_fused_smem(), s>>>(bd);
-            else k_schur_fused<7, double><<<gf, 512, schur_fused_smem(), s>>>(bd);
-        } else {
-            if (bd.precision) k_schur_fused<6, float><<<gf, 512, schur_fused_smem(), s>>>(bd);
-            else k_schur_fused<6, double><<<gf, 512, schur_fused_smem(), s>>>(bd);
-        }
+        if (lc.fused_slots == 7) k_schur_fused<7><<<gf, 512, schur_fused_smem(), s>>>(bd);
+        else k_schur_fused<6><<<gf, 512, schur_fused_smem(), s>>>(bd);
     } else {
         k_landmark_reduce<false><<<dim3((bd.max_lm + 15) / 16, B), 256, 0, s>>>(bd, sp);
         for (int round = 0; round <= lc.max_rank; ++round) k_obs_v<<<g_obs, 256, 0, s>>>(bd, round);
@@ -2201,7 +2175,7 @@ int launch_pass(const BatchDev& bd, const SolveParams& sp, const LaunchCfg& lc, 
         }
         k_reduced_solve<false><<<B, 512, solve_smem(lc.nr_cap_max), s>>>(bc, sp, 2);
     }
-    if (bd.fused) k_backsub_jp<<<dim3((bd.max_lm + 15) / 16, B), 256, 0, s>>>(bd);
+    if (bd.fused) k_backsub_v<<<dim3((bd.max_lm + 15) / 16, B), 256, 0, s>>>(bd);
     else k_backsub<<<dim3((bd.max_lm + 15) / 16, B), 256, 0, s>>>(bd);
     launch_eval_obs<false>(bd, sp, s);
     if (bd.tot_gp > 0) k_gp_eval<false><<<B, 256, 0, s>>>(bd, sp);

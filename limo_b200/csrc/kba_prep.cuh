@@ -207,6 +207,66 @@ __global__ void __launch_bounds__(256) k_obs_v(BatchDev bd, int round) {
     }
 }
 
+// Fused path: V_i = (J_p^T J_l) L^-T per observation, written compactly (18 doubles: 3 columns x 6 rows) -- the fused Schur
+// kernel copies these straight into its shared-memory panels and the back substitution reads them again.  J_l is formed
+// as (translation columns of J_p) R(keyframe) from the staged rotations; W = J_l L^-T first keeps the dependency chains short.
+// HBM per observation: 144 B of J_p read + 144 B written.
+__global__ void __launch_bounds__(256) k_obs_v2(BatchDev bd) {
+    const int w = blockIdx.y;
+    const WinState& st = bd.state[w];
+    if (st.phase != PH_ITERATE || st.solve_failed) return;
+    const WinDesc& wd = bd.desc[w];
+    if (wd.landmarks_fixed) return;
+    if ((int)(blockIdx.x * blockDim.x) >= wd.n_obs) return;
+    __shared__ __align__(16) double s_pose[kFusedMaxKf * kPoseStride];
+    __shared__ __align__(8) uint64_t s_bar;
+    if (threadIdx.x == 0) {
+        mbar_init(&s_bar, 1);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const uint32_t bytes = (uint32_t)(wd.n_kf * kPoseStride * sizeof(double));
+        mbar_expect_tx(&s_bar, bytes);
+        tma_load_1d(s_pose, bd.rt[st.cur] + (size_t)kPoseStride * wd.kf_off, bytes, &s_bar);
+    }
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool have = i < wd.n_obs;
+    const size_t o = (size_t)wd.obs_off + (have ? i : 0), T = (size_t)bd.tot_obs;
+    const int row0 = have ? bd.obs_row[o] : -1;  // -1: constant pose or trimmed landmark
+    double jp[18], li[6];
+    int kf = 0;
+    if (row0 >= 0) {
+        kf = bd.obs_kf[o];
+        const double* lp = bd.lm_linv + 6 * (size_t)(wd.lm_off + bd.obs_lm[o]);
+#pragma unroll
+        for (int q = 0; q < 6; ++q) li[q] = lp[q];
+#pragma unroll
+        for (int q = 0; q < 18; ++q) jp[q] = lin_load(bd.jp, q * T + o, bd.precision);
+    }
+    mbar_wait(&s_bar, 0);
+    if (row0 < 0) return;
+    const double* R = s_pose + kPoseStride * kf;
+    double wm[9];  // W = J_l L^-T, J_l = M R with M = J_p[:, 3:6];  L^-1 = [i00; i10 i11; i20 i21 i22]
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+        const double m0 = jp[6 * r + 3], m1 = jp[6 * r + 4], m2 = jp[6 * r + 5];
+        const double l0 = m0 * R[0] + m1 * R[3] + m2 * R[6], l1 = m0 * R[1] + m1 * R[4] + m2 * R[7], l2 = m0 * R[2] + m1 * R[5] + m2 * R[8];
+        wm[3 * r + 0] = l0 * li[0];
+        wm[3 * r + 1] = l0 * li[1] + l1 * li[2];
+        wm[3 * r + 2] = l0 * li[3] + l1 * li[4] + l2 * li[5];
+    }
+    double2* out = reinterpret_cast<double2*>(bd.vobs + 18 * o);  // 144 B per observation, 16-byte aligned
+#pragma unroll
+    for (int c = 0; c < 3; ++c)
+#pragma unroll
+        for (int h = 0; h < 3; ++h) {
+            const int r0 = 2 * h, r1 = 2 * h + 1;  // V[r][c] = sum_k J_p[k][r] W[k][c]
+            out[3 * c + h] = make_double2(jp[r0] * wm[c] + jp[6 + r0] * wm[3 + c] + jp[12 + r0] * wm[6 + c],
+                                          jp[r1] * wm[c] + jp[6 + r1] * wm[3 + c] + jp[12 + r1] * wm[6 + c]);
+        }
+}
+
 // ground-plane V rows into the chunk panels: one thread per (gp residual, row of its 10 x 3 block)
 __global__ void __launch_bounds__(256) k_gp_panel(BatchDev bd) {
     const int w = blockIdx.y;

@@ -1,25 +1,31 @@
 // kba_schur_fused.cuh -- Schur complement of a small window (<= 184 reduced rows) in ONE warp-specialised kernel:
 //
-//   producers (4 warps)  : per group of 8 landmarks, V_i = (J_p^T J_l) L^-T of every observation is formed straight into a
-//                          shared-memory panel (24 columns x the group's reduced-system rows, column-major, zeros
-//                          included), from the materialised J_p (cp.async-prefetched one group ahead), J_l = (translation
-//                          columns of J_p) R(keyframe) and the landmark's L^-1; plus the right-hand-side row z_j and the
-//                          ground-plane rows.  Nothing of V ever goes to global memory.
+//   k_obs_v2 (kba_prep.cuh, one thread per observation, full occupancy) has written V_i = (J_p^T J_l) L^-T compactly:
+//   18 doubles per observation (3 columns x 6 rows), no padding.
+//   producers (4 warps)  : per group of 8 landmarks the panel (24 columns x the group's reduced-system rows, column-major,
+//                          zeros included) is assembled in shared memory by ASYNCHRONOUS copies: every lane owns one
+//                          observation and issues nine 16-byte cp.async from the compact V straight to the panel
+//                          positions of its pose rows, plus the z row; the stage's "full" mbarrier is armed with
+//                          cp.async.mbarrier.arrive, so no producer thread ever waits for data and the ring runs four groups
+//                          ahead.  Windows with ground-plane rows or several cameras per keyframe (rows that ADD onto
+//                          others) take a synchronous variant of the same loop.
 //   consumers (12 warps) : Sred += V V^T on the FP64 tensor cores (mma.sync m8n8k4).  The whole lower triangle lives in
 //                          the consumers' registers as 16x16 blocks (2x2 tiles: one shared-memory load per DMMA); only
 //                          the tile pairs inside the group's row range are multiplied.
-//   ring                 : 4 panel stages with full / empty mbarriers, so warps drift up to three groups apart and the
+//   ring                 : 6 panel stages with full / empty mbarriers, so warps drift up to five groups apart and the
 //                          per-group imbalance of the static block -> warp map (scripts/syrk_map_search.py) averages out.
 //
 // Replaces k_obs_v + k_gp_panel + k_schur_syrk_tma of round 1 (2.2 GB of zero-padded panels written and re-read per pass of
-// a 148-window batch).  Included by kba_kernels.cu after dmma(), the mbarrier helpers and gp_row().
+// a 148-window batch; now 144 B per observation).  Forming V inside the producer warps was measured too: with only four
+// warps the ~250 dependent instructions per observation are latency-bound (5400 cycles per group against 1900 of tensor
+// work), see profiles/.  Included by kba_kernels.cu after dmma(), the mbarrier helpers and gp_row().
 #pragma once
 
 namespace kba {
 
 constexpr int kLG = 8;                           // landmarks per group
 constexpr int kGC = 3 * kLG;                     // panel columns per group
-constexpr int kFStages = 4;
+constexpr int kFStages = 6;                     // 6 x 37.6 KB: the async copies of up to five groups are in flight
 constexpr int kFMaxRs = 196;                     // 184 rows -> row stride 196 (== 4 mod 16)
 constexpr int kFStageDoubles = kGC * kFMaxRs;
 constexpr int kFObs = 128;                       // observations staged per group = producer lanes
@@ -42,6 +48,17 @@ __device__ __forceinline__ void cp_async_elem(double* dst, const double* src) {
 __device__ __forceinline__ void cp_async_elem(float* dst, const float* src) {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
 }
+__device__ __forceinline__ void cp_async16(double* dst, const double* src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async8(double* dst, const double* src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
+}
+// the mbarrier gets one arrival from this thread once all its earlier cp.async have landed (.noinc: the arrival is part of
+// the barrier's expected count)
+__device__ __forceinline__ void cp_async_arrive(uint64_t* bar) {
+    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
@@ -51,50 +68,7 @@ __device__ __forceinline__ void reg_dec() { asm volatile("setmaxnreg.dec.sync.al
 template <int N>
 __device__ __forceinline__ void reg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
 
-constexpr size_t schur_fused_smem() {
-    return (size_t)kFStages * kFStageDoubles * sizeof(double) + (size_t)3 * 18 * kFObs * sizeof(double) +
-           (size_t)kFMaxKf * kPoseStride * sizeof(double) + 16 * sizeof(uint64_t);
-}
-
-// V rows of one observation into the group's panel.  jp(q): entry q of the 3x6 pose block; li: L^-1 (i00; i10 i11; i20
-// i21 i22); R: the keyframe's rotation; col0: panel entry (row of the pose block, first column of the landmark).
-template <typename JpLoad>
-__device__ __forceinline__ void fused_emit(JpLoad jp, const double* __restrict__ li, const double* __restrict__ R,
-                                           double* col0, int rs, bool add) {
-    double jl[9];
-#pragma unroll
-    for (int i = 0; i < 3; ++i) {
-        const double m0 = jp(6 * i + 3), m1 = jp(6 * i + 4), m2 = jp(6 * i + 5);
-#pragma unroll
-        for (int c = 0; c < 3; ++c) jl[3 * i + c] = m0 * R[c] + m1 * R[3 + c] + m2 * R[6 + c];
-    }
-    const double i00 = li[0], i10 = li[1], i11 = li[2], i20 = li[3], i21 = li[4], i22 = li[5];
-    const bool even = ((size_t)col0 & 15) == 0 && (rs & 1) == 0;
-#pragma unroll
-    for (int r = 0; r < 6; r += 2) {
-        double v[2][3];
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-            const double a = jp(r + h), b = jp(6 + r + h), c = jp(12 + r + h);
-            const double e0 = a * jl[0] + b * jl[3] + c * jl[6];
-            const double e1 = a * jl[1] + b * jl[4] + c * jl[7];
-            const double e2 = a * jl[2] + b * jl[5] + c * jl[8];
-            v[h][0] = e0 * i00; v[h][1] = e0 * i10 + e1 * i11; v[h][2] = e0 * i20 + e1 * i21 + e2 * i22;
-        }
-#pragma unroll
-        for (int c = 0; c < 3; ++c) {
-            double* q = col0 + (size_t)c * rs + r;
-            if (even) {
-                double2 t = make_double2(v[0][c], v[1][c]);
-                if (add) { const double2 old = *reinterpret_cast<double2*>(q); t.x += old.x; t.y += old.y; }
-                *reinterpret_cast<double2*>(q) = t;
-            } else {
-                q[0] = add ? q[0] + v[0][c] : v[0][c];
-                q[1] = add ? q[1] + v[1][c] : v[1][c];
-            }
-        }
-    }
-}
+constexpr size_t schur_fused_smem() { return (size_t)kFStages * kFStageDoubles * sizeof(double) + 16 * sizeof(uint64_t); }
 
 // KBA_PROF build: cycles per role (lane 0 of every warp, summed over CTAs into BatchDev::prof) --
 //   consumers: [0] waiting for a full panel, [1] multiplying;  producers: [4] waiting for an empty stage, [5] zero fill +
@@ -111,7 +85,7 @@ __device__ __forceinline__ void fused_emit(JpLoad jp, const double* __restrict__
 #define KBA_PROF_FLUSH(base)
 #endif
 
-template <int kSlots, typename TLin>
+template <int kSlots>
 __global__ void __launch_bounds__(512, 1) k_schur_fused(BatchDev bd) {
     const int w = blockIdx.y;
     const WinState& st = bd.state[w];
@@ -120,12 +94,8 @@ __global__ void __launch_bounds__(512, 1) k_schur_fused(BatchDev bd) {
     if (wd.landmarks_fixed) return;
     extern __shared__ __align__(128) unsigned char fsm[];
     double* stage = reinterpret_cast<double*>(fsm);
-    TLin* jpbuf = reinterpret_cast<TLin*>(fsm + (size_t)kFStages * kFStageDoubles * sizeof(double));
-    double* s_pose = reinterpret_cast<double*>(fsm + (size_t)kFStages * kFStageDoubles * sizeof(double) +
-                                               (size_t)3 * 18 * kFObs * sizeof(double));
-    uint64_t* full = reinterpret_cast<uint64_t*>(s_pose + kFMaxKf * kPoseStride);
+    uint64_t* full = reinterpret_cast<uint64_t*>(fsm + (size_t)kFStages * kFStageDoubles * sizeof(double));
     uint64_t* empty = full + kFStages;
-    uint64_t* pose_bar = empty + kFStages;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int n_f = st.n_f, nt = (n_f + 8) >> 3, trhs = n_f >> 3;
     const int per = (wd.n_groups + (int)gridDim.x - 1) / (int)gridDim.x;
@@ -135,8 +105,6 @@ __global__ void __launch_bounds__(512, 1) k_schur_fused(BatchDev bd) {
     const int* gt1 = bd.grp_t1 + wd.grp_off;
     if (tid == 0) {
         for (int i = 0; i < kFStages; ++i) { mbar_init(&full[i], 128); mbar_init(&empty[i], kFConsumerWarps); }
-        mbar_init(pose_bar, 1);
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
     __syncthreads();
     auto next_group = [&](int g) { while (g < g1 && grs[g] == 0) ++g; return g; };
@@ -144,140 +112,136 @@ __global__ void __launch_bounds__(512, 1) k_schur_fused(BatchDev bd) {
     if (warp >= kFConsumerWarps) {
         // =============================== producers ===============================
         if (kSlots == 7) reg_dec<56>(); else reg_dec<104>();
+
         const int ptid = tid - 32 * kFConsumerWarps;
-        if (ptid == 0) {  // keyframe rotations (R | t as written next to the poses) with one bulk copy
-            const uint32_t bytes = (uint32_t)(wd.n_kf * kPoseStride * sizeof(double));
-            mbar_expect_tx(pose_bar, bytes);
-            tma_load_1d(s_pose, bd.rt[st.cur] + (size_t)kPoseStride * wd.kf_off, bytes, pose_bar);
-        }
-        mbar_wait(pose_bar, 0);
         const int* lm_ptr = bd.lm_ptr + wd.lm_off + w;
-        const size_t T = (size_t)bd.tot_obs, base = (size_t)wd.obs_off, TG = (size_t)bd.tot_gp;
-        const TLin* jpg = reinterpret_cast<const TLin*>(bd.jp);
-        // Software pipeline over the groups, three deep, so that no global-memory latency sits on the per-group critical
-        // path (a group's panel has to be ready every ~2000 cycles):
-        //   P3 (group g+3): observation range of the group                              -> a_*
-        //   P2 (group g+2): this lane's observation: row / keyframe / landmark / rank   -> m2_*, J_p by cp.async -> jpbuf
-        //   P1 (group g+1): L^-1 of the observation's landmark, the group's tile range, z row and validity -> *1
-        //   P0 (group g)  : zero the panel stage, scatter V, right-hand-side and ground-plane rows, hand over
-        int a_ob = 0, a_oe = 0, b_ob = 0, b_oe = 0, c_ob = 0, c_oe = 0, d_ob = 0, d_oe = 0;
-        int m2_row = -1, m2_kf = 0, m2_lm = 0, m2_rank = 0, m1_row = -1, m1_kf = 0, m1_lm = 0, m1_rank = 0;
-        int m0_row = -1, m0_kf = 0, m0_lm = 0, m0_rank = 0;
+        const size_t base = (size_t)wd.obs_off, TG = (size_t)bd.tot_gp;
+        // rows that ADD onto others (ground-plane rows, further cameras of a rig) cannot be async copies
+        const bool sync_path = wd.n_gp > 0 || wd.max_rank > 0;
+        // Two-deep register pipeline in front of the copies: P2 (group g+2) observation range; P1 (group g+1) this lane's
+        // observation (row, landmark, rank), the group's tile range and the validity of "its" landmark (lanes 0..7);
+        // P0 (group g): zero the stage, issue the copies, arm the barrier.  No load result is consumed in the iteration that
+        // issues it.
+        int a_ob = 0, a_oe = 0, b_ob = 0, b_oe = 0, c_ob = 0, c_oe = 0;
+        int m1_o = 0, m1_row = -1, m1_lm = 0, m1_rank = 0, m0_o = 0, m0_row = -1, m0_lm = 0, m0_rank = 0;
         int rs1 = 0, t01 = 0, t11 = 0, rs0 = 0, t00 = 0, t10 = 0;
-        int zok1 = 0, zok0 = 0, gl1 = -1, gl0 = -1;
-        double l1[6], l0[6], z1[3], z0[3];
-#pragma unroll
-        for (int q = 0; q < 6; ++q) l1[q] = l0[q] = 0.0;
-#pragma unroll
-        for (int q = 0; q < 3; ++q) z1[q] = z0[q] = 0.0;
-        const int zj = ptid / 10, zr = ptid - 10 * zj;  // lanes 0..79: landmark zj of the group, ground-plane row zr (z row: zr == 0)
+        int act1 = 0, p01 = 0, p11 = 0, act0 = 0, p00 = 0, p10 = 0;  // lanes 0..7: lm_active and CSR bounds of landmark 8 g + lane
         int gi = 0;
         KBA_PROF_DECL;
-        for (int gg = g0 - 3; gg < g1; ++gg) {
-            {   // ---- P3
-                const int g = gg + 3;
+        for (int gg = g0 - 2; gg < g1; ++gg) {
+            {   // ---- P2
+                const int g = gg + 2;
                 if (g >= g0 && g < g1) {
                     a_ob = lm_ptr[g * kLG];
                     a_oe = lm_ptr[min(wd.n_lm, g * kLG + kLG)];
                 }
             }
-            {   // ---- P2 (b_* = range of group gg + 2)
-                const int g = gg + 2;
-                m2_row = -1;
-                if (g >= g0 && g < g1) {
-                    const int o = b_ob + ptid;
-                    if (o < b_oe) {
-                        const size_t oo = base + o;
-                        m2_row = bd.obs_row[oo]; m2_kf = bd.obs_kf[oo]; m2_lm = bd.obs_lm[oo]; m2_rank = bd.obs_rank[oo];
-                        TLin* dst = jpbuf + (size_t)(g % 3) * 18 * kFObs + ptid;
-#pragma unroll
-                        for (int q = 0; q < 18; ++q) cp_async_elem(dst + q * kFObs, jpg + q * T + oo);
-                    }
-                }
-                cp_async_commit();
-            }
-            {   // ---- P1 (m1_* = this lane's observation of group gg + 1)
+            {   // ---- P1 (b_* = observation range of group gg + 1)
                 const int g = gg + 1;
-                zok1 = 0; gl1 = -1;
+                m1_row = -1; act1 = 0;
                 if (g >= g0 && g < g1) {
                     rs1 = grs[g]; t01 = gt0[g]; t11 = gt1[g];
-                    if (m1_row >= 0) {
-                        const double* lp = bd.lm_linv + 6 * (size_t)(wd.lm_off + m1_lm);
-#pragma unroll
-                        for (int q = 0; q < 6; ++q) l1[q] = lp[q];
+                    m1_o = b_ob + ptid;
+                    if (m1_o < b_oe) {
+                        const size_t oo = base + m1_o;
+                        m1_row = bd.obs_row[oo]; m1_lm = bd.obs_lm[oo]; m1_rank = bd.obs_rank[oo];
                     }
-                    const int j = g * kLG + zj;
-                    if (ptid < 80 && j < wd.n_lm) {
-                        const int L = wd.lm_off + j;
-                        zok1 = bd.lm_active[L] && lm_ptr[j + 1] > lm_ptr[j];
-                        if (zr == 0) { const double* zz = bd.lm_z + 3 * (size_t)L; z1[0] = zz[0]; z1[1] = zz[1]; z1[2] = zz[2]; }
-                        if (wd.n_gp > 0) gl1 = bd.gp_of_lm[L];
-                    }
+                    const int j = g * kLG + ptid;
+                    if (ptid < kLG && j < wd.n_lm) { act1 = bd.lm_active[wd.lm_off + j]; p01 = lm_ptr[j]; p11 = lm_ptr[j + 1]; }
                 }
             }
             if (gg >= g0 && rs0 != 0) {   // ---- P0
                 const int g = gg, rs = rs0, t0 = t00, t1 = t10;
-                const int slot = gi & (kFStages - 1);
+                const int slot = gi % kFStages;
                 KBA_PROF_T0;
                 if (gi >= kFStages) mbar_wait(&empty[slot], ((gi / kFStages) - 1) & 1);
                 KBA_PROF_ACC(0);
                 double* sb = stage + (size_t)slot * kFStageDoubles;
-                {
-                    double2* z = reinterpret_cast<double2*>(sb);
-                    for (int i = ptid; i < (kGC / 2) * rs; i += 128) z[i] = make_double2(0.0, 0.0);
+                {   // rs = rows of this group's panel (multiple of 8); the column stride is the constant kFMaxRs
+                    const int h = rs >> 1;
+                    for (int i = ptid; i < kGC * h; i += 128) {
+                        const int c = i / h, r2 = i - c * h;
+                        reinterpret_cast<double2*>(sb + (size_t)c * kFMaxRs)[r2] = make_double2(0.0, 0.0);
+                    }
                 }
-                cp_async_wait<2>();  // all but the two newest commit groups (groups g+1, g+2) have landed
-                producer_sync();
+                producer_sync();  // the stage is zero before any copy lands in it
                 KBA_PROF_ACC(1);
                 const int j0 = g * kLG;
-                const TLin* jb = jpbuf + (size_t)(g % 3) * 18 * kFObs + ptid;
-                for (int round = 0; round <= wd.max_rank; ++round) {
-                    if (round > 0) producer_sync();
-                    if (m0_row >= 0 && m0_rank == round)
-                        fused_emit([&](int q) { return (double)jb[q * kFObs]; }, l0, s_pose + kPoseStride * m0_kf,
-                                   sb + (size_t)(3 * (m0_lm - j0)) * rs + (m0_row - 8 * t0), rs, round > 0);
-                    for (int o = d_ob + kFObs + ptid; o < d_oe; o += kFObs) {  // groups of more than 128 observations (rare)
-                        const size_t oo = base + o;
-                        const int row = bd.obs_row[oo];
-                        if (row < 0 || bd.obs_rank[oo] != round) continue;
-                        const int jj = bd.obs_lm[oo] - j0;
-                        fused_emit([&](int q) { return (double)jpg[q * T + oo]; }, bd.lm_linv + 6 * (size_t)(wd.lm_off + j0 + jj),
-                                   s_pose + kPoseStride * bd.obs_kf[oo], sb + (size_t)(3 * jj) * rs + (row - 8 * t0), rs, round > 0);
+                const int rl = (trhs >= t0 && trhs < t1) ? n_f - 8 * t0 : 8 * (t1 - t0) + (n_f - 8 * trhs);  // t0, t1: block aligned
+                auto copy_obs = [&](int o, int row, int jj) {  // 3 columns x 6 rows of one observation, asynchronously
+                    const double* src = bd.vobs + 18 * (base + o);
+                    double* dst = sb + (size_t)(3 * jj) * kFMaxRs + (row - 8 * t0);
+                    if (((row - 8 * t0) & 1) == 0) {
+#pragma unroll
+                        for (int c = 0; c < 3; ++c)
+#pragma unroll
+                            for (int h = 0; h < 3; ++h) cp_async16(dst + c * kFMaxRs + 2 * h, src + 6 * c + 2 * h);
+                    } else {
+#pragma unroll
+                        for (int c = 0; c < 3; ++c)
+#pragma unroll
+                            for (int r = 0; r < 6; ++r) cp_async8(dst + c * kFMaxRs + r, src + 6 * c + r);
                     }
+                };
+                if (m0_row >= 0 && m0_rank == 0) copy_obs(m0_o, m0_row, m0_lm - j0);
+                for (int o = c_ob + kFObs + ptid; o < c_oe; o += kFObs) {  // groups of more than 128 observations (rare)
+                    const size_t oo = base + o;
+                    const int row = bd.obs_row[oo];
+                    if (row >= 0 && bd.obs_rank[oo] == 0) copy_obs(o, row, bd.obs_lm[oo] - j0);
                 }
-                producer_sync();  // every V row is in place: the ground-plane rows may add onto them
-                if (zok0) {       // lanes 0..79 of valid landmarks: z row (zr == 0) and ground-plane row zr
-                    double* col = sb + (size_t)(3 * zj) * rs;
-                    if (zr == 0) {
-                        const int rl = (trhs >= t0 && trhs < t1) ? n_f - 8 * t0 : 8 * (t1 - t0) + (n_f - 8 * trhs);
-                        col[rl] = z0[0]; col[rs + rl] = z0[1]; col[2 * rs + rl] = z0[2];
+                const bool zvalid = ptid < kLG && act0 && p10 > p00;
+                if (zvalid) {  // right-hand-side row z_j
+                    const double* zz = bd.lm_z + 3 * (size_t)(wd.lm_off + j0 + ptid);
+                    double* col = sb + (size_t)(3 * ptid) * kFMaxRs + rl;
+                    cp_async8(col, zz); cp_async8(col + kFMaxRs, zz + 1); cp_async8(col + 2 * kFMaxRs, zz + 2);
+                }
+                if (!sync_path) {
+                    cp_async_arrive(&full[slot]);  // this thread's arrival fires when its copies have landed
+                } else {
+                    cp_async_commit();
+                    cp_async_wait<0>();
+                    producer_sync();
+                    for (int round = 1; round <= wd.max_rank; ++round) {  // further cameras of a rig: add onto the same rows
+                        for (int o = c_ob + ptid; o < c_oe; o += kFObs) {
+                            const size_t oo = base + o;
+                            const int row = bd.obs_row[oo];
+                            if (row < 0 || bd.obs_rank[oo] != round) continue;
+                            const double* src = bd.vobs + 18 * oo;
+                            double* dst = sb + (size_t)(3 * (bd.obs_lm[oo] - j0)) * kFMaxRs + (row - 8 * t0);
+                            for (int c = 0; c < 3; ++c)
+                                for (int r = 0; r < 6; ++r) dst[c * kFMaxRs + r] += src[6 * c + r];
+                        }
+                        producer_sync();
                     }
-                    if (gl0 >= 0) {
-                        const size_t G = (size_t)wd.gp_off + gl0;
-                        const int row = gp_row(bd, wd, bd.gp_kf[G], zr);
-                        if (row >= 0) {
-                            double* q = col + (row - 8 * t0);
-                            q[0] += bd.vgp[(3 * zr + 0) * TG + G];
-                            q[rs] += bd.vgp[(3 * zr + 1) * TG + G];
-                            q[2 * rs] += bd.vgp[(3 * zr + 2) * TG + G];
+                    if (wd.n_gp > 0 && ptid < 80) {  // ground-plane rows: 8 landmarks x 10 rows, added onto the pose rows
+                        const int jj = ptid / 10, r = ptid - 10 * jj, j = j0 + jj;
+                        const int L = wd.lm_off + j;
+                        if (j < wd.n_lm && bd.lm_active[L] && lm_ptr[j + 1] > lm_ptr[j]) {
+                            const int gl = bd.gp_of_lm[L];
+                            if (gl >= 0) {
+                                const size_t G = (size_t)wd.gp_off + gl;
+                                const int row = gp_row(bd, wd, bd.gp_kf[G], r);
+                                if (row >= 0) {
+                                    double* q = sb + (size_t)(3 * jj) * kFMaxRs + (row - 8 * t0);
+                                    q[0] += bd.vgp[(3 * r + 0) * TG + G];
+                                    q[kFMaxRs] += bd.vgp[(3 * r + 1) * TG + G];
+                                    q[2 * kFMaxRs] += bd.vgp[(3 * r + 2) * TG + G];
+                                }
+                            }
                         }
                     }
+                    mbar_arrive(&full[slot]);  // release: this thread's panel writes are visible to the consumers' acquire
                 }
-                mbar_arrive(&full[slot]);  // release: this thread's panel writes are visible to the consumers' acquire
                 KBA_PROF_ACC(2);
                 ++gi;
             }
             KBA_PROF_T0;
             // ---- shift the pipeline registers
-            d_ob = c_ob; d_oe = c_oe; c_ob = b_ob; c_oe = b_oe; b_ob = a_ob; b_oe = a_oe;
-            m0_row = m1_row; m0_kf = m1_kf; m0_lm = m1_lm; m0_rank = m1_rank;
-            m1_row = m2_row; m1_kf = m2_kf; m1_lm = m2_lm; m1_rank = m2_rank;
-            rs0 = rs1; t00 = t01; t10 = t11; zok0 = zok1; gl0 = gl1;
-#pragma unroll
-            for (int q = 0; q < 6; ++q) l0[q] = l1[q];
-#pragma unroll
-            for (int q = 0; q < 3; ++q) z0[q] = z1[q];
+            c_ob = b_ob; c_oe = b_oe; b_ob = a_ob; b_oe = a_oe;
+            m0_o = m1_o; m0_row = m1_row; m0_lm = m1_lm; m0_rank = m1_rank;
+            rs0 = rs1; t00 = t01; t10 = t11; act0 = act1; p00 = p01; p10 = p11;
         }
+        cp_async_commit();
         cp_async_wait<0>();
         KBA_PROF_FLUSH(4);
         return;
@@ -286,7 +250,7 @@ __global__ void __launch_bounds__(512, 1) k_schur_fused(BatchDev bd) {
     // =============================== consumers ===============================
     if (kSlots == 7) reg_inc<152>(); else reg_inc<136>();
     const int fr = lane >> 2, fc = lane & 3;
-    const int nb2 = (nt + 1) >> 1;
+    const int nb2 = (nt + 1) >> 1, brhs = trhs >> 1;
     double acc[kSlots][4][2];
     int my_bi[kSlots], my_bj[kSlots];
 #pragma unroll
@@ -301,66 +265,79 @@ __global__ void __launch_bounds__(512, 1) k_schur_fused(BatchDev bd) {
             while (bi * (bi + 1) / 2 > t) --bi;
             bj = t - bi * (bi + 1) / 2;
         }
+        if (bi >= nb2) bi = 1 << 20;  // beyond this window's triangle
         my_bi[s] = bi; my_bj[s] = bj;
     }
     {
+        // Group ranges are aligned to 16-row blocks (k_solve_begin), so a block inside the range has both its tiles and the
+        // only partial block is the one holding the right-hand-side tile when it lies outside the range: three straight-line
+        // variants, no predicate inside a tensor-core loop.  The column stride is the constant kFMaxRs, so every fragment
+        // load of a block is base + immediate.
         int gi = 0;
-        int g = next_group(g0), rs = 0, t0 = 0, t1 = 0;
-        if (g < g1) { rs = grs[g]; t0 = gt0[g]; t1 = gt1[g]; }
+        int g = next_group(g0), t0 = 0, t1 = 0;
+        if (g < g1) { t0 = gt0[g]; t1 = gt1[g]; }
         KBA_PROF_DECL;
         for (; g < g1; ++gi) {
-            const int gn = next_group(g + 1);  // the next group's tile range is requested before this group's panel is awaited
-            int rsn = 0, t0n = 0, t1n = 0;
-            if (gn < g1) { rsn = grs[gn]; t0n = gt0[gn]; t1n = gt1[gn]; }
-            const int slot = gi & (kFStages - 1);
+            const int gn = next_group(g + 1);  // the next group's range is requested before this group's panel is awaited
+            int t0n = 0, t1n = 0;
+            if (gn < g1) { t0n = gt0[gn]; t1n = gt1[gn]; }
+            const int slot = gi % kFStages;
             KBA_PROF_T0;
             mbar_wait(&full[slot], (gi / kFStages) & 1);
             KBA_PROF_ACC(0);
-            const double* sb = stage + (size_t)slot * kFStageDoubles + (size_t)fc * rs + fr;
-            auto tile_row = [&](int i) -> int {  // panel row of tile i in this group, -1 if the group has no such rows
-                if (i >= t0 && i < t1) return 8 * (i - t0);
-                if (i == trhs) return 8 * (t1 - t0);
-                return -1;
-            };
+            const int b0 = t0 >> 1, b1 = t1 >> 1;                         // block range [b0, b1) of the group
+            const bool rhs_in = brhs >= b0 && brhs < b1;
+            const int rhs_row = 16 * (b1 - b0);  // panel row of the rhs tile when it lies outside the range
+            const double* sb = stage + (size_t)slot * kFStageDoubles + (size_t)fc * kFMaxRs + fr;
 #pragma unroll
             for (int s = 0; s < kSlots; ++s) {
                 const int bi = my_bi[s], bj = my_bj[s];
-                if (bi >= nb2) continue;
-                const int ri0 = tile_row(2 * bi), ri1 = tile_row(2 * bi + 1), rj0 = tile_row(2 * bj), rj1 = tile_row(2 * bj + 1);
-                if ((ri0 < 0 && ri1 < 0) || (rj0 < 0 && rj1 < 0)) continue;
-                const bool diag = bi == bj;
-                const double* pa0 = sb + max(ri0, 0);
-                const double* pa1 = sb + max(ri1, 0);
-                const double* pb0 = sb + max(rj0, 0);
-                const double* pb1 = sb + max(rj1, 0);
-                if (ri0 >= 0 && ri1 >= 0 && rj0 >= 0 && rj1 >= 0) {
+                if (bj < b0 || bj >= b1) continue;
+                if (bi >= b0 && bi < b1) {
+                    const double* pa = sb + 16 * (bi - b0);
+                    const double* pb = sb + 16 * (bj - b0);
+                    if (bi != bj) {
 #pragma unroll
-                    for (int kk = 0; kk < kGC; kk += 4) {
-                        const size_t o = (size_t)kk * rs;
-                        const double a0 = pa0[o], a1 = pa1[o], b0 = pb0[o], b1 = pb1[o];
-                        dmma(acc[s][0][0], acc[s][0][1], a0, b0);
-                        if (!diag) dmma(acc[s][1][0], acc[s][1][1], a0, b1);
-                        dmma(acc[s][2][0], acc[s][2][1], a1, b0);
-                        dmma(acc[s][3][0], acc[s][3][1], a1, b1);
+                        for (int kk = 0; kk < kGC; kk += 4) {
+                            const double a0 = pa[kk * kFMaxRs], a1 = pa[kk * kFMaxRs + 8], b0v = pb[kk * kFMaxRs], b1v = pb[kk * kFMaxRs + 8];
+                            dmma(acc[s][0][0], acc[s][0][1], a0, b0v);
+                            dmma(acc[s][1][0], acc[s][1][1], a0, b1v);
+                            dmma(acc[s][2][0], acc[s][2][1], a1, b0v);
+                            dmma(acc[s][3][0], acc[s][3][1], a1, b1v);
+                        }
+                    } else {
+#pragma unroll
+                        for (int kk = 0; kk < kGC; kk += 4) {
+                            const double a0 = pa[kk * kFMaxRs], a1 = pa[kk * kFMaxRs + 8];
+                            dmma(acc[s][0][0], acc[s][0][1], a0, a0);
+                            dmma(acc[s][2][0], acc[s][2][1], a1, a0);
+                            dmma(acc[s][3][0], acc[s][3][1], a1, a1);
+                        }
                     }
-                } else {  // a block on the edge of the group's row range: only the tile pairs that exist
-                    const bool p00 = ri0 >= 0 && rj0 >= 0, p01 = ri0 >= 0 && rj1 >= 0 && !diag, p10 = ri1 >= 0 && rj0 >= 0,
-                               p11 = ri1 >= 0 && rj1 >= 0;
-#pragma unroll 2
-                    for (int kk = 0; kk < kGC; kk += 4) {
-                        const size_t o = (size_t)kk * rs;
-                        const double a0 = pa0[o], a1 = pa1[o], b0 = pb0[o], b1 = pb1[o];
-                        if (p00) dmma(acc[s][0][0], acc[s][0][1], a0, b0);
-                        if (p01) dmma(acc[s][1][0], acc[s][1][1], a0, b1);
-                        if (p10) dmma(acc[s][2][0], acc[s][2][1], a1, b0);
-                        if (p11) dmma(acc[s][3][0], acc[s][3][1], a1, b1);
+                } else if (bi == brhs && !rhs_in) {  // the right-hand-side tile against the group's rows
+                    const double* pa = sb + rhs_row;
+                    const double* pb = sb + 16 * (bj - b0);
+                    if (trhs & 1) {
+#pragma unroll
+                        for (int kk = 0; kk < kGC; kk += 4) {
+                            const double a1 = pa[kk * kFMaxRs], b0v = pb[kk * kFMaxRs], b1v = pb[kk * kFMaxRs + 8];
+                            dmma(acc[s][2][0], acc[s][2][1], a1, b0v);
+                            dmma(acc[s][3][0], acc[s][3][1], a1, b1v);
+                        }
+                    } else {
+#pragma unroll
+                        for (int kk = 0; kk < kGC; kk += 4) {
+                            const double a0 = pa[kk * kFMaxRs], b0v = pb[kk * kFMaxRs], b1v = pb[kk * kFMaxRs + 8];
+                            dmma(acc[s][0][0], acc[s][0][1], a0, b0v);
+                            dmma(acc[s][1][0], acc[s][1][1], a0, b1v);
+                        }
                     }
                 }
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(&empty[slot]);
             KBA_PROF_ACC(1);
-            g = gn; rs = rsn; t0 = t0n; t1 = t1n;
+            g = gn; t0 = t0n; t1 = t1n;
         }
         KBA_PROF_FLUSH(0);
     }

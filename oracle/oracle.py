@@ -23,10 +23,31 @@ def build(force=False):
     return _LIB_PATH
 
 
+def use_native_build():
+    """bench.py's CPU legs: compile the oracle with -O3 -march=native for the host this process runs
+    on -- into a temporary directory, so that a library tuned for one machine never travels to another -- and load that
+    instead of the portable -O2 build.  Must be called before the first lib().  Falls back to the portable build (and
+    says so) when the compiler is missing.  Returns the description of the build for the bench line."""
+    global _LIB_PATH
+    import tempfile
+    if _lib is not None:
+        raise RuntimeError("use_native_build() must be called before the oracle library is loaded")
+    out = os.path.join(tempfile.mkdtemp(prefix="kba_oracle_native_"), "libkba_oracle_native.so")
+    cmd = ["gcc", "-O3", "-march=native", "-std=gnu11", "-fPIC", "-fopenmp", "-I" + os.path.join(_HERE, "..", "include"), "-shared",
+           "-o", out, os.path.join(_HERE, "kba_oracle.c"), os.path.join(_HERE, "lidar_oracle.c"), "-lm"]
+    try:
+        subprocess.check_call(cmd, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+    except (OSError, subprocess.CalledProcessError):
+        return "gcc -O2 (portable build; native build failed)"
+    _LIB_PATH = out
+    return "gcc -O3 -march=native -fopenmp, built on this host"
+
+
 def lib():
     global _lib
     if _lib is None:
-        build()
+        if _LIB_PATH.endswith("libkba_oracle.so"):
+            build()
         _lib = C.CDLL(_LIB_PATH)
         dp = c_double_p
         _lib.kbo_solve_window.argtypes = [C.POINTER(KbaWindow), C.POINTER(KbaOptions), C.POINTER(KbaResult), C.c_int]
