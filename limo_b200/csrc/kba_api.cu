@@ -18,6 +18,7 @@
 using namespace kba;
 
 static thread_local std::string g_last_error;
+static thread_local bool g_force_host_pack = false;  // kba_eval: needs the host-side observation permutation
 static int fail(int code, const std::string& msg) {
     g_last_error = msg;
     return code;
@@ -92,6 +93,14 @@ struct kba_batch {
     Staged<uint8_t> kf_fixed;
     Staged<int> lm_ptr, obs_kf, obs_cam, obs_lm, kf_ptr, pm_lm, pm_cam, chunk_lm0, chunk_lm1, chunk_k0, chunk_k1, lm_orig, obs_orig;
     Staged<int> grp_k0, grp_k1;
+    // device-side packing (kba_pack.cu): the caller's arrays are uploaded as they are, the sorted layout is built by kernels
+    bool device_pack = false;
+    Staged<int> r_lm_ptr, r_obs_kf, r_obs_cam, r_gp_lm;
+    Staged<float> r_obs_u, r_obs_v, r_obs_d;
+    Staged<double> r_lm_pos, r_lm_weight;
+    Staged<double> lm_user;            // landmark results in the caller's order (device + pinned)
+    Staged<uint8_t> rej_user;
+    PackRaw raw;
     Staged<int> obs_rank;
     Staged<float> obs_u, obs_v, obs_d, pm_u, pm_v, pm_d;
     // outputs
@@ -127,6 +136,8 @@ struct kba_batch {
         pm_lm.release(); pm_cam.release(); chunk_lm0.release(); chunk_lm1.release(); chunk_k0.release(); chunk_k1.release();
         lm_orig.release(); obs_orig.release(); obs_rank.release(); obs_u.release(); obs_v.release();
         grp_k0.release(); grp_k1.release();
+        r_lm_ptr.release(); r_obs_kf.release(); r_obs_cam.release(); r_gp_lm.release(); r_obs_u.release(); r_obs_v.release();
+        r_obs_d.release(); r_lm_pos.release(); r_lm_weight.release(); lm_user.release(); rej_user.release();
         obs_d.release(); pm_u.release(); pm_v.release(); pm_d.release(); state.release(); log.release();
         pose_out[0].release(); pose_out[1].release(); lm_out[0].release(); lm_out[1].release(); lm_active.release();
         n_active.release(); jac_obs.release(); plane_out[0].release(); plane_out[1].release();
@@ -283,6 +294,50 @@ static void fill_window(kba_batch* b, int wi, const kba_window* w) {
         b->grp_k0.h[d.grp_off + c] = k0;
         b->grp_k1.h[d.grp_off + c] = k1;
     }
+}
+
+// device-pack mode: the caller's arrays are copied as they are into the pinned staging buffers (one memcpy per array)
+static void fill_window_raw(kba_batch* b, int wi, const kba_window* w) {
+    const WinDesc& d = b->desc_h[wi];
+    memcpy(b->pose0.h + 7 * (size_t)d.kf_off, w->kf_pose, sizeof(double) * 7 * w->n_kf);
+    memcpy(b->kf_fixed.h + d.kf_off, w->kf_fixed, w->n_kf);
+    for (int k = 0; k < w->n_kf; ++k) {
+        double* pl = b->plane0.h + 4 * (size_t)(d.kf_off + k);
+        if (w->kf_plane) memcpy(pl, w->kf_plane + 4 * k, 4 * sizeof(double));
+        else { pl[0] = 0; pl[1] = 0; pl[2] = 1; pl[3] = 0; }
+    }
+    for (int c = 0; c < w->n_cam; ++c) {
+        double* o = b->cam.h + kCamStride * (size_t)(d.cam_off + c);
+        quat_to_rot<double>(w->cam_pose + 7 * c, o);
+        o[9] = w->cam_pose[7 * c + 4]; o[10] = w->cam_pose[7 * c + 5]; o[11] = w->cam_pose[7 * c + 6];
+        o[12] = w->cam_intr[3 * c]; o[13] = w->cam_intr[3 * c + 1]; o[14] = w->cam_intr[3 * c + 2]; o[15] = 0;
+    }
+    const size_t nl = (size_t)w->n_lm, no = (size_t)w->n_obs;
+    memcpy(b->r_lm_pos.h + 3 * (size_t)d.lm_off, w->lm_pos, 3 * nl * sizeof(double));
+    memcpy(b->r_lm_weight.h + d.lm_off, w->lm_weight, nl * sizeof(double));
+    int* lp = b->r_lm_ptr.h + d.lm_off + wi;
+    if (nl) memcpy(lp, w->lm_obs_ptr, (nl + 1) * sizeof(int)); else lp[0] = 0;
+    memcpy(b->r_obs_kf.h + d.obs_off, w->obs_kf, no * sizeof(int));
+    if (w->obs_cam) memcpy(b->r_obs_cam.h + d.obs_off, w->obs_cam, no * sizeof(int));
+    else memset(b->r_obs_cam.h + d.obs_off, 0, no * sizeof(int));
+    memcpy(b->r_obs_u.h + d.obs_off, w->obs_u, no * sizeof(float));
+    memcpy(b->r_obs_v.h + d.obs_off, w->obs_v, no * sizeof(float));
+    memcpy(b->r_obs_d.h + d.obs_off, w->obs_d, no * sizeof(float));
+    if (w->n_gp) {
+        memcpy(b->r_gp_lm.h + d.gp_off, w->gp_lm, w->n_gp * sizeof(int));
+        memcpy(b->gp_kf.h + d.gp_off, w->gp_kf, w->n_gp * sizeof(int));
+        memcpy(b->gp_weight.h + d.gp_off, w->gp_weight, w->n_gp * sizeof(double));
+    }
+    int max_rank = 0;  // several cameras of a rig seeing the landmark in one keyframe (observations are sorted by keyframe)
+    for (int j = 0; j < w->n_lm; ++j) {
+        int rank = 0;
+        for (int o = w->lm_obs_ptr[j] + 1; o < w->lm_obs_ptr[j + 1]; ++o) {
+            rank = (w->obs_kf[o] == w->obs_kf[o - 1]) ? rank + 1 : 0;
+            max_rank = std::max(max_rank, rank);
+        }
+    }
+    b->desc_h[wi].max_rank = max_rank;
+    b->desc.h[wi].max_rank = max_rank;
 }
 
 // reduced-system rows a window can have given its constant keyframes (k_solve_begin may leave out more)
@@ -472,6 +527,7 @@ int kba_batch_create(kba_handle* h, int32_t n_windows, const kba_window* w, kba_
         bd.eval_tiles_jac = std::max(1, knob("KBA_EVAL_TILES_JAC", 8));
         bd.eval_tiles_cost = std::max(1, knob("KBA_EVAL_TILES_COST", 8));
         bd.eval_min_blocks = knob("KBA_EVAL_MIN_BLOCKS", 2);
+        bd.eval_cs = knob("KBA_EVAL_CS", 0);
         bd.solve_row_major = knob("KBA_SOLVE_ROW_MAJOR", 0);
         bd.solve_tiled = (nr_cap_max <= 192 && !bd.solve_row_major) ? 1 : 0;
         // a single SM's FP64 rate bounds the one-CTA factorisation of a large system: with few windows spread it
@@ -479,19 +535,32 @@ int kba_batch_create(kba_handle* h, int32_t n_windows, const kba_window* w, kba_
         bd.solve_split = bd.solve_tiled ? 0 : knob("KBA_SOLVE_SPLIT", split_dflt);
     }
     bd.bs_parts = (bd.max_lm + 15) / 16;
+    {   // device-side packing: fused batches whose landmark keys fit the sort (KBA_DEVICE_PACK=0: host packing as in round 1)
+        const char* pe = std::getenv("KBA_DEVICE_PACK");
+        b->device_pack = bd.fused && !g_force_host_pack && bd.max_lm <= pack_max_landmarks() && !(pe && std::atoi(pe) == 0);
+    }
+    const bool hp = !b->device_pack;  // pinned host mirrors of the sorted layout are only needed when the host builds it
     int bad = 0;
     bad |= b->desc.alloc(n_windows, true);
     bad |= b->pose0.alloc(7 * kf, true); bad |= b->plane0.alloc(4 * kf, true); bad |= b->kf_fixed.alloc(kf, true);
     bad |= b->cam.alloc(kCamStride * cam, true);
-    bad |= b->lm0.alloc(3 * lm, true); bad |= b->lm_weight.alloc(lm, true); bad |= b->lm_ptr.alloc(lm + n_windows, true);
-    bad |= b->obs_kf.alloc(obs, true); bad |= b->obs_cam.alloc(obs, true); bad |= b->obs_lm.alloc(obs, true);
-    bad |= b->obs_u.alloc(obs, true); bad |= b->obs_v.alloc(obs, true); bad |= b->obs_d.alloc(obs, true);
-    bad |= b->kf_ptr.alloc(kf + n_windows, true); bad |= b->pm_lm.alloc(obs, true); bad |= b->pm_cam.alloc(obs, true);
-    bad |= b->pm_u.alloc(obs, true); bad |= b->pm_v.alloc(obs, true); bad |= b->pm_d.alloc(obs, true);
-    bad |= b->chunk_lm0.alloc(chunks, true); bad |= b->chunk_lm1.alloc(chunks, true);
-    bad |= b->chunk_k0.alloc(chunks, true); bad |= b->chunk_k1.alloc(chunks, true);
-    bad |= b->lm_orig.alloc(lm, true); bad |= b->obs_orig.alloc(obs, true); bad |= b->obs_rank.alloc(obs, true);
-    bad |= b->grp_k0.alloc(groups, true); bad |= b->grp_k1.alloc(groups, true);
+    bad |= b->lm0.alloc(3 * lm, hp); bad |= b->lm_weight.alloc(lm, hp); bad |= b->lm_ptr.alloc(lm + n_windows, hp);
+    bad |= b->obs_kf.alloc(obs, hp); bad |= b->obs_cam.alloc(obs, hp); bad |= b->obs_lm.alloc(obs, hp);
+    bad |= b->obs_u.alloc(obs, hp); bad |= b->obs_v.alloc(obs, hp); bad |= b->obs_d.alloc(obs, hp);
+    bad |= b->kf_ptr.alloc(kf + n_windows, hp); bad |= b->pm_lm.alloc(obs, hp); bad |= b->pm_cam.alloc(obs, hp);
+    bad |= b->pm_u.alloc(obs, hp); bad |= b->pm_v.alloc(obs, hp); bad |= b->pm_d.alloc(obs, hp);
+    bad |= b->chunk_lm0.alloc(chunks, hp); bad |= b->chunk_lm1.alloc(chunks, hp);
+    bad |= b->chunk_k0.alloc(chunks, hp); bad |= b->chunk_k1.alloc(chunks, hp);
+    bad |= b->lm_orig.alloc(lm, hp); bad |= b->obs_rank.alloc(obs, hp);
+    if (hp) bad |= b->obs_orig.alloc(obs, true);
+    bad |= b->grp_k0.alloc(groups, hp); bad |= b->grp_k1.alloc(groups, hp);
+    if (b->device_pack) {
+        bad |= b->r_lm_ptr.alloc(lm + n_windows, true); bad |= b->r_obs_kf.alloc(obs, true); bad |= b->r_obs_cam.alloc(obs, true);
+        bad |= b->r_obs_u.alloc(obs, true); bad |= b->r_obs_v.alloc(obs, true); bad |= b->r_obs_d.alloc(obs, true);
+        bad |= b->r_lm_pos.alloc(3 * lm, true); bad |= b->r_lm_weight.alloc(lm, true); bad |= b->r_gp_lm.alloc(gp, true);
+        bad |= b->lm_user.alloc(3 * lm, true); bad |= b->rej_user.alloc(lm, true);
+        bad |= b->dev_alloc(&b->raw.lm_inv, lm);
+    }
     bad |= b->dev_alloc(&bd.grp_t0, groups); bad |= b->dev_alloc(&bd.grp_t1, groups); bad |= b->dev_alloc(&bd.grp_rs, groups);
 #ifdef KBA_PROF
     bad |= b->dev_alloc(&bd.prof, 16);
@@ -505,11 +574,11 @@ int kba_batch_create(kba_handle* h, int32_t n_windows, const kba_window* w, kba_
     }
     bad |= b->dev_alloc(&bd.chunk_t0, chunks); bad |= b->dev_alloc(&bd.chunk_t1, chunks); bad |= b->dev_alloc(&bd.obs_row, obs);
     bad |= b->state.alloc(n_windows, true); bad |= b->log.alloc((size_t)n_windows * kIterLogCap, true);
-    for (int q = 0; q < 2; ++q) { bad |= b->pose_out[q].alloc(7 * kf, true); bad |= b->lm_out[q].alloc(3 * lm, true); }
-    bad |= b->lm_active.alloc(lm, true); bad |= b->n_active.alloc(1, true); bad |= b->jac_obs.alloc(1, true);
+    for (int q = 0; q < 2; ++q) { bad |= b->pose_out[q].alloc(7 * kf, true); bad |= b->lm_out[q].alloc(3 * lm, hp); }
+    bad |= b->lm_active.alloc(lm, hp); bad |= b->n_active.alloc(1, true); bad |= b->jac_obs.alloc(1, true);
     // device-only scratch
     bad |= b->plane_out[0].alloc(4 * kf, true); bad |= b->plane_out[1].alloc(4 * kf, true);
-    bad |= b->gp_lm.alloc(gp, true); bad |= b->gp_kf.alloc(gp, true); bad |= b->gp_weight.alloc(gp, true); bad |= b->gp_of_lm.alloc(lm, true); bad |= b->gp_shared.alloc(gp, true);
+    bad |= b->gp_lm.alloc(gp, hp); bad |= b->gp_kf.alloc(gp, true); bad |= b->gp_weight.alloc(gp, true); bad |= b->gp_of_lm.alloc(lm, hp); bad |= b->gp_shared.alloc(gp, hp);
     bad |= b->dev_alloc(&bd.gp_lin, 14 * gp); bad |= b->dev_alloc(&bd.vgp, 30 * gp);
     bad |= b->dev_alloc(&bd.gp_cost_x, n_windows); bad |= b->dev_alloc(&bd.gp_cost_c, n_windows);
     bad |= b->dev_alloc(&bd.off_pose, kf); bad |= b->dev_alloc(&bd.off_dir, kf); bad |= b->dev_alloc(&bd.off_dist, kf);
@@ -521,7 +590,7 @@ int kba_batch_create(kba_handle* h, int32_t n_windows, const kba_window* w, kba_
     bad |= b->dev_alloc(&bd.trim_reject, lm);
     bad |= b->dev_alloc(&bd.res, 3 * obs); bad |= b->dev_alloc(&bd.jp, 18 * obs);
     if (!bd.fused) bad |= b->dev_alloc(&bd.jl, 9 * obs);  // fused path: J_l is re-formed from J_p by its consumers
-    else bad |= b->dev_alloc(&bd.vobs, 18 * obs);         // ... and V is kept per observation, unpadded
+    else { bad |= b->dev_alloc(&bd.vobs, 18 * obs); bad |= b->dev_alloc(&bd.lm_run, lm); }  // ... and V is kept per observation, unpadded
     bad |= b->dev_alloc(&bd.cost_part_x, (size_t)n_windows * bd.cost_parts); bad |= b->dev_alloc(&bd.cost_part_c, (size_t)n_windows * bd.cost_parts);
     bad |= b->dev_alloc(&bd.bs_part, (size_t)n_windows * bd.bs_parts * 4);
     bad |= b->dev_alloc(&bd.sred, (size_t)soff * bd.p_split); bad |= b->dev_alloc(&bd.amat, (size_t)soff);
@@ -547,11 +616,18 @@ int kba_batch_create(kba_handle* h, int32_t n_windows, const kba_window* w, kba_
     bd.gp_lm = b->gp_lm.d; bd.gp_kf = b->gp_kf.d; bd.gp_weight = b->gp_weight.d; bd.gp_of_lm = b->gp_of_lm.d; bd.gp_shared = b->gp_shared.d;
     bd.n_active = b->n_active.d;
     bd.jac_obs = b->jac_obs.d;
+    if (b->device_pack) {
+        PackRaw& r = b->raw;
+        r.lm_ptr = b->r_lm_ptr.d; r.obs_kf = b->r_obs_kf.d; r.obs_cam = b->r_obs_cam.d;
+        r.obs_u = b->r_obs_u.d; r.obs_v = b->r_obs_v.d; r.obs_d = b->r_obs_d.d;
+        r.lm_pos = b->r_lm_pos.d; r.lm_weight = b->r_lm_weight.d; r.gp_lm = b->r_gp_lm.d; r.obs_orig = nullptr;
+    }
     {   // failures from here on must give the allocations back
         cudaError_t e = cudaMemset(bd.jac_obs, 0, sizeof(unsigned long long));
         if (e == cudaSuccess) e = cudaEventCreate(&b->ev_a);
         if (e == cudaSuccess) e = cudaEventCreate(&b->ev_b);
         if (e == cudaSuccess) e = configure_kernels(nr_cap_max);
+        if (e == cudaSuccess && b->device_pack) e = configure_pack();
         if (e != cudaSuccess) { b->release(); delete b; return fail(KBA_ERR_CUDA, cudaGetErrorString(e)); }
     }
     *out = b;
@@ -586,7 +662,8 @@ int kba_batch_upload(kba_batch* b, int32_t n_windows, const kba_window* w) {
         memcpy(b->desc_h[i].speed_v_before, w[i].speed_v_before, sizeof(double) * 3);
         memcpy(b->desc_h[i].speed_T_origin_before, w[i].speed_T_origin_before, sizeof(double) * 7);
         b->desc.h[i] = b->desc_h[i];
-        fill_window(b, i, &w[i]);
+        if (b->device_pack) fill_window_raw(b, i, &w[i]);
+        else fill_window(b, i, &w[i]);
     };
     {
         const char* e = std::getenv("KBA_HOST_THREADS");
@@ -630,6 +707,18 @@ int kba_batch_upload(kba_batch* b, int32_t n_windows, const kba_window* w) {
         for (int i = 0; i < n_windows; ++i) { b->desc_h[i].panel_off = (long long)i * b->bd.panel_cap; b->desc.h[i].panel_off = b->desc_h[i].panel_off; }
     }
     cudaStream_t s = b->h->stream;
+    if (b->device_pack) {  // the caller's arrays as they are (~33 B per observation), then the packing kernels
+        CU(b->desc.upload(s)); CU(b->pose0.upload(s)); CU(b->plane0.upload(s)); CU(b->kf_fixed.upload(s)); CU(b->cam.upload(s));
+        CU(b->r_lm_pos.upload(s)); CU(b->r_lm_weight.upload(s)); CU(b->r_lm_ptr.upload(s));
+        CU(b->r_obs_kf.upload(s)); CU(b->r_obs_cam.upload(s)); CU(b->r_obs_u.upload(s)); CU(b->r_obs_v.upload(s)); CU(b->r_obs_d.upload(s));
+        CU(b->r_gp_lm.upload(s)); CU(b->gp_kf.upload(s)); CU(b->gp_weight.upload(s));
+        launch_pack(b->bd, b->raw, s);
+        CU(cudaGetLastError());
+        const BatchDev& bd = b->bd;
+        b->h2d_bytes = sizeof(WinDesc) * bd.n_win + (7 + 4) * 8 * bd.tot_kf + bd.tot_kf + kCamStride * 8 * bd.tot_cam +
+                       (3 + 1) * 8 * bd.tot_lm + 4 * (bd.tot_lm + bd.n_win) + (2 * 4 + 3 * 4) * bd.tot_obs + (4 + 4 + 8) * bd.tot_gp;
+        return KBA_OK;
+    }
     CU(b->desc.upload(s)); CU(b->pose0.upload(s)); CU(b->plane0.upload(s)); CU(b->kf_fixed.upload(s)); CU(b->cam.upload(s));
     CU(b->lm0.upload(s)); CU(b->lm_weight.upload(s)); CU(b->lm_ptr.upload(s));
     CU(b->obs_kf.upload(s)); CU(b->obs_cam.upload(s)); CU(b->obs_lm.upload(s));
@@ -758,11 +847,16 @@ int kba_batch_download(kba_batch* b, kba_result* res) {
     cudaStream_t s = b->h->stream;
     CU(b->state.download(s)); CU(b->log.download(s));
     CU(b->pose_out[0].download(s)); CU(b->pose_out[1].download(s));
-    CU(b->lm_out[0].download(s)); CU(b->lm_out[1].download(s)); CU(b->lm_active.download(s));
+    const BatchDev& bd = b->bd;
+    if (b->device_pack) {  // landmarks come back in the caller's order: one kernel, one copy per array
+        launch_unpack_landmarks(bd, b->lm_user.d, b->rej_user.d, s);
+        CU(b->lm_user.download(s)); CU(b->rej_user.download(s));
+    } else {
+        CU(b->lm_out[0].download(s)); CU(b->lm_out[1].download(s)); CU(b->lm_active.download(s));
+    }
     CU(b->plane_out[0].download(s)); CU(b->plane_out[1].download(s));
     CU(wait_stream(b->h));
-    const BatchDev& bd = b->bd;
-    b->d2h_bytes = sizeof(WinState) * bd.n_win + 2 * (7 * 8 * bd.tot_kf + 3 * 8 * bd.tot_lm) + bd.tot_lm;
+    b->d2h_bytes = sizeof(WinState) * bd.n_win + 2 * (7 + 4) * 8 * bd.tot_kf + (b->device_pack ? 1 : 2) * 3 * 8 * bd.tot_lm + bd.tot_lm;
     for (int i = 0; i < bd.n_win; ++i) {
         const WinDesc& d = b->desc_h[i];
         const WinState& st = b->state.h[i];
@@ -770,10 +864,15 @@ int kba_batch_download(kba_batch* b, kba_result* res) {
         const int cur = st.cur;
         if (r.kf_pose) memcpy(r.kf_pose, b->pose_out[cur].h + 7 * (size_t)d.kf_off, sizeof(double) * 7 * d.n_kf);
         if (r.kf_plane) memcpy(r.kf_plane, b->plane_out[cur].h + 4 * (size_t)d.kf_off, sizeof(double) * 4 * d.n_kf);
-        const int* orig = b->lm_orig.h + d.lm_off;
-        if (r.lm_pos)
-            for (int j = 0; j < d.n_lm; ++j) memcpy(r.lm_pos + 3 * (size_t)orig[j], b->lm_out[cur].h + 3 * (size_t)(d.lm_off + j), 3 * sizeof(double));
-        if (r.lm_rejected) for (int j = 0; j < d.n_lm; ++j) r.lm_rejected[orig[j]] = !b->lm_active.h[d.lm_off + j];
+        if (b->device_pack) {
+            if (r.lm_pos) memcpy(r.lm_pos, b->lm_user.h + 3 * (size_t)d.lm_off, 3 * sizeof(double) * d.n_lm);
+            if (r.lm_rejected) memcpy(r.lm_rejected, b->rej_user.h + d.lm_off, d.n_lm);
+        } else {
+            const int* orig = b->lm_orig.h + d.lm_off;
+            if (r.lm_pos)
+                for (int j = 0; j < d.n_lm; ++j) memcpy(r.lm_pos + 3 * (size_t)orig[j], b->lm_out[cur].h + 3 * (size_t)(d.lm_off + j), 3 * sizeof(double));
+            if (r.lm_rejected) for (int j = 0; j < d.n_lm; ++j) r.lm_rejected[orig[j]] = !b->lm_active.h[d.lm_off + j];
+        }
         r.num_solves = st.n_solves;
         for (int q = 0; q < st.n_solves && q < KBA_MAX_SOLVES; ++q) {
             const SolveSummary& ss = st.solves[q];
@@ -865,7 +964,9 @@ int kba_solve_window(kba_handle* h, const kba_window* w, const kba_options* opt,
 int kba_eval(kba_handle* h, const kba_window* w, const kba_options* opt, kba_eval_out* out) {
     if (!h || !w || !opt || !out) return fail(KBA_ERR_BAD_ARG, "null argument to kba_eval");
     kba_batch* b = nullptr;
+    g_force_host_pack = true;  // the inspection entry point maps observations back to the caller's order on the host
     int rc = kba_batch_create(h, 1, w, &b);
+    g_force_host_pack = false;
     if (rc != KBA_OK) return rc;
     float ms;
     rc = kba_batch_jacobian_pass(b, opt, 1, &ms);

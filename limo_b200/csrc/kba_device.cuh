@@ -156,6 +156,7 @@ struct BatchDev {
     double* chol_w;           // [n_win][32*32] inverse of the current diagonal block's factor (split factorisation)
     double* chol_invd;        // [n_win][nr_cap_max] 1 / L_ii
     int eval_tiles_jac, eval_tiles_cost, eval_min_blocks;  // 256-observation tiles per CTA / CTAs per SM of k_eval_obs
+    int eval_cs;              // 1: streaming (evict-first) stores of the residual / Jacobian blocks
     double* bs_part;          // [n_win][bs_parts][4]: model_e, step_sq, xnorm_sq, gmax_e
     int bs_parts;
     int nr_cap_max;           // largest nr_cap in the batch = stride of scale_f / lambda_f / grad_f / delta_f
@@ -185,7 +186,12 @@ struct BatchDev {
     int* grp_t0;              // [tot_groups]
     int* grp_t1;
     int* grp_rs;              // [tot_groups] == 4 mod 16, 0: no free keyframe rows
-    double* vobs;             // [tot_obs][18] V_i = (J_p^T J_l) L^-T of every observation, 3 columns x 6 rows, unpadded
+    double* vobs;             // [18 * tot_obs] V_i = (J_p^T J_l) L^-T of every observation, unpadded.  Per landmark with
+                              //   observations [p0, p1), n = p1 - p0: column c of observation i at 18 (obs_off + p0) + 6 n c + 6 i
+                              //   (6 rows each), so a whole panel column of the landmark is ONE contiguous run
+    int4* lm_run;             // [tot_lm] {a, m, row, 0}: observations p0 + a .. p0 + a + m - 1 are the landmark's observations
+                              //   with variable poses and sit on consecutive reduced-system rows row, row + 6, ...;
+                              //   m = 0: none, m = -1: they do not form one such run (gaps, several cameras, plane rows)
     unsigned long long* prof; // [16] cycle counters of a KBA_PROF build (nullptr otherwise)
     int tot_groups;
     int* n_active;            // [1] windows still running (device counter)
@@ -318,11 +324,17 @@ __device__ inline bool eval_observation(const T* __restrict__ pose, const T* __r
 // Streaming form of eval_observation for the residual/Jacobian kernel: every Jacobian row is written to its SoA slot
 // as soon as it is formed, so at most one 3-vector m and the rotated point a stay live (64 registers -> 4 CTAs/SM).
 // res/jp/jl point at this observation's slot of component 0; `stride` is the component stride (total observations).
-template <typename T>
+// kJl: also store J_landmark (panel path); kCs: streaming (evict-first) stores -- the blocks are read back only after
+// hundreds of MB of other traffic, keeping them in L2 evicts what the next kernels would still hit
+template <typename T, bool kCs>
+__device__ __forceinline__ void lin_store(T* p, T v) {
+    if (kCs) __stcs(p, v); else *p = v;
+}
+template <typename T, bool kJl = true, bool kCs = false>
 __device__ inline bool eval_observation_store(const T* __restrict__ pose, const T* __restrict__ cam, const T p[3], T u,
                                               T v, T d, T wt, T b_repr, T b_depth, T* __restrict__ res,
                                               T* __restrict__ jp, T* __restrict__ jl, size_t stride, bool write_jp,
-                                              bool write_jl, T& half_rho_sum) {
+                                              T& half_rho_sum) {
     const T a0 = pose[0] * p[0] + pose[1] * p[1] + pose[2] * p[2];
     const T a1 = pose[3] * p[0] + pose[4] * p[1] + pose[5] * p[2];
     const T a2 = pose[6] * p[0] + pose[7] * p[1] + pose[8] * p[2];
@@ -344,9 +356,9 @@ __device__ inline bool eval_observation_store(const T* __restrict__ pose, const 
         cauchy<T>(b_depth, wt, rd * rd, hrd, sqd);
         half_rho_sum += hrd;
     }
-    res[0] = sq * ru;
-    res[stride] = sq * rv;
-    res[2 * stride] = sqd * rd;
+    lin_store<T, kCs>(res, sq * ru);
+    lin_store<T, kCs>(res + stride, sq * rv);
+    lin_store<T, kCs>(res + 2 * stride, sqd * rd);
     const T fz = f * iz * sq;
 #pragma unroll
     for (int i = 0; i < 3; ++i) {
@@ -356,18 +368,18 @@ __device__ inline bool eval_observation_store(const T* __restrict__ pose, const 
         else { m0 = sqd * cam[6]; m1 = sqd * cam[7]; m2 = sqd * cam[8]; }
         if (write_jp) {
             T* o = jp + (size_t)(6 * i) * stride;
-            o[0] = T(-2) * (m1 * a2 - m2 * a1);
-            o[stride] = T(-2) * (m2 * a0 - m0 * a2);
-            o[2 * stride] = T(-2) * (m0 * a1 - m1 * a0);
-            o[3 * stride] = m0;
-            o[4 * stride] = m1;
-            o[5 * stride] = m2;
+            lin_store<T, kCs>(o, T(-2) * (m1 * a2 - m2 * a1));
+            lin_store<T, kCs>(o + stride, T(-2) * (m2 * a0 - m0 * a2));
+            lin_store<T, kCs>(o + 2 * stride, T(-2) * (m0 * a1 - m1 * a0));
+            lin_store<T, kCs>(o + 3 * stride, m0);
+            lin_store<T, kCs>(o + 4 * stride, m1);
+            lin_store<T, kCs>(o + 5 * stride, m2);
         }
-        if (write_jl) {
+        if (kJl) {
             T* q = jl + (size_t)(3 * i) * stride;
-            q[0] = m0 * pose[0] + m1 * pose[3] + m2 * pose[6];
-            q[stride] = m0 * pose[1] + m1 * pose[4] + m2 * pose[7];
-            q[2 * stride] = m0 * pose[2] + m1 * pose[5] + m2 * pose[8];
+            lin_store<T, kCs>(q, m0 * pose[0] + m1 * pose[3] + m2 * pose[6]);
+            lin_store<T, kCs>(q + stride, m0 * pose[1] + m1 * pose[4] + m2 * pose[7]);
+            lin_store<T, kCs>(q + 2 * stride, m0 * pose[2] + m1 * pose[5] + m2 * pose[8]);
         }
     }
     return true;
@@ -398,6 +410,11 @@ __device__ inline void stage_window(const WinDesc& wd, const double* __restrict_
 __device__ inline void write_rt(double* rt12, const double* p7) {
     quat_to_rot<double>(p7, rt12);
     rt12[9] = p7[4]; rt12[10] = p7[5]; rt12[11] = p7[6];
+}
+
+// V_i of observation o (window-local index) of a landmark with observations [p0, p1): address of column c
+__device__ __forceinline__ size_t vobs_index(size_t obs_off, int p0, int p1, int o, int c) {
+    return 18 * (obs_off + (size_t)p0) + (size_t)(6 * (p1 - p0)) * c + (size_t)6 * (o - p0);
 }
 
 // ---- mbarrier / bulk-copy (TMA) primitives ------------------------------------------------------------------------------

@@ -108,7 +108,7 @@ __global__ void __launch_bounds__(256) k_solve_begin(BatchDev bd, SolveParams sp
         bd.obs_row[oo] = act ? bd.off_pose[wd.kf_off + bd.obs_kf[oo]] : -1;
     }
     // 8-row tile range of the reduced system each landmark chunk touches (landmarks are sorted by first keyframe)
-    for (int c = threadIdx.x; c < wd.n_chunks; c += blockDim.x) {
+    for (int c = threadIdx.x; c < (bd.fused ? 0 : wd.n_chunks); c += blockDim.x) {
         int r0 = 1 << 30, r1 = -1;
         for (int k = bd.chunk_k0[wd.chunk_off + c]; k <= bd.chunk_k1[wd.chunk_off + c]; ++k) {
             const int off = bd.off_pose[wd.kf_off + k], od = bd.off_dir[wd.kf_off + k], oz = bd.off_dist[wd.kf_off + k];
@@ -118,6 +118,30 @@ __global__ void __launch_bounds__(256) k_solve_begin(BatchDev bd, SolveParams sp
         }
         bd.chunk_t0[wd.chunk_off + c] = (r1 < 0) ? 0 : r0 / 8;
         bd.chunk_t1[wd.chunk_off + c] = (r1 < 0) ? 0 : (r1 + 7) / 8;
+    }
+    // fused path: does a landmark's set of observations with variable poses form ONE run of consecutive reduced-system rows
+    // (a track without gaps over free keyframes, one camera per keyframe)?  Then each of its three panel columns is one
+    // contiguous segment and the Schur kernel fetches it with a single bulk copy (BatchDev::lm_run).  Fixed for the solve.
+    if (bd.fused) {
+        __syncthreads();  // obs_row is complete
+        for (int j = threadIdx.x; j < wd.n_lm; j += blockDim.x) {
+            const int o0 = lm_ptr[j], o1 = lm_ptr[j + 1];
+            int n_start = 0, n_valid = 0, bad = 0, a = 0, row_a = 0, prev = -2;
+            for (int o = o0; o < o1; ++o) {
+                const size_t oo = (size_t)wd.obs_off + o;
+                const int r = bd.obs_row[oo];
+                if (r >= 0) {
+                    ++n_valid;
+                    if (prev < 0) { if (n_start++ == 0) { a = o - o0; row_a = r; } }
+                    else if (r != prev + 6) bad = 1;
+                    if (bd.obs_rank[oo] != 0) bad = 1;
+                }
+                prev = r;
+            }
+            int4 run = make_int4(0, 0, 0, 0);
+            if (n_valid > 0) run = (bad || n_start != 1) ? make_int4(0, -1, 0, 0) : make_int4(a, n_valid, row_a, 0);
+            bd.lm_run[wd.lm_off + j] = run;
+        }
     }
     // fused path: 8-row tile range and shared-memory row stride (== 4 mod 16) of each 8-landmark group
     if (bd.fused) {
@@ -177,7 +201,7 @@ __global__ void __launch_bounds__(256) k_panel_zero(BatchDev bd) {
 //   kJac = false: cost only, at the candidate point
 // Algorithmic HBM bytes per observation (FP64, with depth row): 20 read + 240 written.
 // =====================================================================================================================
-template <bool kJac, int kMinBlocks, typename TLin>
+template <bool kJac, int kMinBlocks, typename TLin, bool kJl = true, bool kCs = false>
 __global__ void __launch_bounds__(256, kMinBlocks) k_eval_obs(BatchDev bd, SolveParams sp, int tiles) {
     // A CTA walks `tiles` consecutive 256-observation tiles of one window with a two-deep software pipeline: while tile
     // t is evaluated, the measurement / landmark loads of tile t+1 and the landmark-index load of tile t+2 are in
@@ -218,7 +242,6 @@ __global__ void __launch_bounds__(256, kMinBlocks) k_eval_obs(BatchDev bd, Solve
         act = bd.lm_active[L];
     }
     stage_window_bulk(wd, bd.rt[buf], bd.cam, s_pose, s_cam, &s_bar);  // poses (R | t) and cameras: two bulk copies
-    const bool write_jl = !bd.fused;  // fused path: consumers form J_l = (translation columns of J_p) R themselves
     if (kF32) {
         for (int i = threadIdx.x; i < wd.n_kf * kPoseStride; i += blockDim.x) s_pose_f[i] = (float)s_pose[i];
         for (int i = threadIdx.x; i < wd.n_cam * kCamStride; i += blockDim.x) s_cam_f[i] = (float)s_cam[i];
@@ -265,16 +288,16 @@ __global__ void __launch_bounds__(256, kMinBlocks) k_eval_obs(BatchDev bd, Solve
                     float* resf = reinterpret_cast<float*>(bd.res) + o;
                     float* jpf = reinterpret_cast<float*>(bd.jp) + o;
                     float* jlf = reinterpret_cast<float*>(bd.jl) + o;
-                    eval_observation_store<float>(
+                    eval_observation_store<float, kJl, kCs>(
                         s_pose_f + kPoseStride * k, s_cam_f + kCamStride * c, pf, u, v, d, (float)wgt,
                         (float)(sp.reprojection_thres * sp.reprojection_thres), (float)(sp.depth_thres * sp.depth_thres),
-                        resf, jpf, jlf, (size_t)bd.tot_obs, row >= 0 || !write_jl, write_jl, hrf);
+                        resf, jpf, jlf, (size_t)bd.tot_obs, row >= 0 || !kJl, hrf);
                 }
             } else if (kJac) {  // rows are stored to their SoA slots as they are formed
-                ok = eval_observation_store<double>(
+                ok = eval_observation_store<double, kJl, kCs>(
                     s_pose + kPoseStride * k, s_cam + kCamStride * c, p, (double)u, (double)v, (double)d, wgt,
                     sp.reprojection_thres * sp.reprojection_thres, sp.depth_thres * sp.depth_thres, bd.res + o, bd.jp + o,
-                    bd.jl + o, (size_t)bd.tot_obs, row >= 0 || !write_jl, write_jl, hr);
+                    bd.jl + o, (size_t)bd.tot_obs, row >= 0 || !kJl, hr);
             } else {
                 double r[3], raw[2];
                 ok = eval_observation<double, false>(
@@ -313,11 +336,25 @@ template <bool kJac>
 static void launch_eval_obs(const BatchDev& bd, const SolveParams& sp, cudaStream_t s) {
     const int tiles = kJac ? bd.eval_tiles_jac : bd.eval_tiles_cost;
     const dim3 g((bd.max_obs + 256 * tiles - 1) / (256 * tiles), bd.n_win);
-    const int mb = kJac ? bd.eval_min_blocks : 4;
-    if (kJac && bd.precision == 1) k_eval_obs<kJac, 2, float><<<g, 256, 0, s>>>(bd, sp, tiles);
-    else if (mb == 2) k_eval_obs<kJac, 2, double><<<g, 256, 0, s>>>(bd, sp, tiles);
-    else if (mb == 3) k_eval_obs<kJac, 3, double><<<g, 256, 0, s>>>(bd, sp, tiles);
-    else k_eval_obs<kJac, 4, double><<<g, 256, 0, s>>>(bd, sp, tiles);
+    if (!kJac) { k_eval_obs<false, 4, double><<<g, 256, 0, s>>>(bd, sp, tiles); return; }
+    const int mb = bd.eval_min_blocks;
+    // fused path (kJl = false): J_l is not materialised, its consumers form it as (translation columns of J_p) R
+    if (bd.precision == 1) {
+        if (bd.fused) k_eval_obs<true, 2, float, false><<<g, 256, 0, s>>>(bd, sp, tiles);
+        else k_eval_obs<true, 2, float, true><<<g, 256, 0, s>>>(bd, sp, tiles);
+    } else if (!bd.fused) {
+        if (mb == 2) k_eval_obs<true, 2, double, true><<<g, 256, 0, s>>>(bd, sp, tiles);
+        else if (mb == 3) k_eval_obs<true, 3, double, true><<<g, 256, 0, s>>>(bd, sp, tiles);
+        else k_eval_obs<true, 4, double, true><<<g, 256, 0, s>>>(bd, sp, tiles);
+    } else if (bd.eval_cs) {
+        if (mb == 2) k_eval_obs<true, 2, double, false, true><<<g, 256, 0, s>>>(bd, sp, tiles);
+        else if (mb == 3) k_eval_obs<true, 3, double, false, true><<<g, 256, 0, s>>>(bd, sp, tiles);
+        else k_eval_obs<true, 4, double, false, true><<<g, 256, 0, s>>>(bd, sp, tiles);
+    } else {
+        if (mb == 2) k_eval_obs<true, 2, double, false><<<g, 256, 0, s>>>(bd, sp, tiles);
+        else if (mb == 3) k_eval_obs<true, 3, double, false><<<g, 256, 0, s>>>(bd, sp, tiles);
+        else k_eval_obs<true, 4, double, false><<<g, 256, 0, s>>>(bd, sp, tiles);
+    }
 }
 
 // =====================================================================================================================
@@ -1569,8 +1606,8 @@ __global__ void __launch_bounds__(256) k_backsub(BatchDev bd) {
     }
 }
 
-// Fused path: sum_i V_i^T delta_f,i from the compact per-observation V (18 doubles, k_obs_v2): each lane reads its
-// observation's 144 contiguous bytes with nine 128-bit loads.
+// Fused path: sum_i V_i^T delta_f,i from the compact per-observation V (k_obs_v2; landmark-column-major): each lane reads
+// its observation's three 48-byte column segments with nine 128-bit loads, consecutive lanes consecutive segments.
 __global__ void __launch_bounds__(256) k_backsub_v(BatchDev bd) {
     const int w = blockIdx.y;
     const WinState& st = bd.state[w];
@@ -1594,17 +1631,18 @@ __global__ void __launch_bounds__(256) k_backsub_v(BatchDev bd) {
         for (int o = o0 + hl; o < o1; o += 16) {
             const int off = bd.obs_row[base + o];  // row of the observation's pose block (k_solve_begin), -1: constant
             if (off < 0) continue;
-            const double2* v = reinterpret_cast<const double2*>(bd.vobs + 18 * (base + o));
             double d[6];
 #pragma unroll
             for (int r = 0; r < 6; ++r) d[r] = delta_f[off + r];
 #pragma unroll
-            for (int c = 0; c < 3; ++c)
+            for (int c = 0; c < 3; ++c) {
+                const double2* v = reinterpret_cast<const double2*>(bd.vobs + vobs_index(base, o0, o1, o, c));
 #pragma unroll
                 for (int h = 0; h < 3; ++h) {
-                    const double2 x = v[3 * c + h];
+                    const double2 x = v[h];
                     t[c] += x.x * d[2 * h] + x.y * d[2 * h + 1];
                 }
+            }
         }
         const int gl = (wd.n_gp > 0) ? bd.gp_of_lm[L] : -1;
         if (gl >= 0 && hl < 10) {  // row `hl` of the gp block's 10 x 3 V

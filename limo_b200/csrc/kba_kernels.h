@@ -36,6 +36,54 @@ struct LaunchCfg {
     double *x_sred = nullptr, *x_bkf = nullptr, *x_cost = nullptr;  // window-wide sums (receive buffers of the exchange)
 };
 
+// window arrays exactly as the caller passes them (landmark-major CSR in the caller's landmark order), batch-flat on the
+// device: input of the packing kernels (kba_pack.cu)
+struct PackRaw {
+    const int* lm_ptr = nullptr;      // [tot_lm + n_win]
+    const int* obs_kf = nullptr;      // [tot_obs]
+    const int* obs_cam = nullptr;
+    const float* obs_u = nullptr, *obs_v = nullptr, *obs_d = nullptr;
+    const double* lm_pos = nullptr;   // [tot_lm*3]
+    const double* lm_weight = nullptr;
+    const int* gp_lm = nullptr;       // [tot_gp] caller landmark index
+    int* lm_inv = nullptr;            // [tot_lm] scratch: caller index -> sorted position
+    int* obs_orig = nullptr;          // [tot_obs] optional: sorted slot -> caller observation index
+};
+// device-resident track store of a persistent sliding window (kba_track_*, include/kba_b200.h): keyframe poses / planes,
+// the measurements of every pushed keyframe in one arena, landmark positions / weights by caller-assigned slot
+struct TrackDev {
+    double* kf_pose = nullptr;   // [kf_cap*7]
+    double* kf_plane = nullptr;  // [kf_cap*4]
+    int* m_off = nullptr;        // [kf_cap] first measurement of the keyframe in the arena
+    int* m_cnt = nullptr;        // [kf_cap]
+    int* m_lm = nullptr;         // [m_cap] landmark slot
+    int* m_cam = nullptr;        // [m_cap] camera index
+    float* m_u = nullptr, *m_v = nullptr, *m_d = nullptr;
+    double* lm_pos = nullptr;    // [lm_cap*3]
+    double* lm_weight = nullptr; // [lm_cap]
+    int* sel_index = nullptr;    // [lm_cap] position of the landmark in the current selection, -1 otherwise (all -1 between solves)
+    int* cursor = nullptr;       // [lm window capacity] scratch
+    long long* key = nullptr;    // [obs window capacity] scratch: (keyframe index, arena index) of each gathered observation
+    int kf_cap = 0, lm_cap = 0, m_cap = 0;
+};
+// per-solve selection, device copies of the caller's small lists
+struct TrackSel {
+    const int* kf_slot = nullptr;    // [n_kf] ascending keyframe id
+    const unsigned char* kf_fixed = nullptr;
+    const int* lm_slot = nullptr;    // [n_lm] ascending landmark id
+    int n_kf = 0, n_lm = 0, max_meas = 0;
+};
+// builds the window's raw CSR (PackRaw inputs of batch `bd`, window 0) from the track store; returns nothing: desc[0].n_obs
+// is written on the device
+void launch_track_gather(const BatchDev& bd, const PackRaw& raw_out, const TrackDev& td, const TrackSel& sel, cudaStream_t s);
+// results of window 0 back into the track store
+void launch_track_writeback(const BatchDev& bd, const TrackDev& td, const TrackSel& sel, cudaStream_t s);
+
+cudaError_t configure_pack();
+int pack_max_landmarks();
+void launch_pack(const BatchDev& bd, const PackRaw& raw, cudaStream_t s);
+void launch_unpack_landmarks(const BatchDev& bd, double* lm_user, unsigned char* rejected_user, cudaStream_t s);
+
 cudaError_t configure_kernels(int nr_cap_max);
 void launch_reset(const BatchDev& bd, const LaunchCfg& lc, cudaStream_t s);
 int launch_pass(const BatchDev& bd, const SolveParams& sp, const LaunchCfg& lc, Counters* cnt, cudaStream_t s);

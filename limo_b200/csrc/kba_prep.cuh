@@ -207,8 +207,9 @@ __global__ void __launch_bounds__(256) k_obs_v(BatchDev bd, int round) {
     }
 }
 
-// Fused path: V_i = (J_p^T J_l) L^-T per observation, written compactly (18 doubles: 3 columns x 6 rows) -- the fused Schur
-// kernel copies these straight into its shared-memory panels and the back substitution reads them again.  J_l is formed
+// Fused path: V_i = (J_p^T J_l) L^-T per observation, written compactly (18 doubles: 3 columns x 6 rows; layout: BatchDev::vobs,
+// column-major per landmark) -- the fused Schur kernel copies whole landmark columns straight into its shared-memory panels
+// and the back substitution reads them again.  J_l is formed
 // as (translation columns of J_p) R(keyframe) from the staged rotations; W = J_l L^-T first keeps the dependency chains short.
 // HBM per observation: 144 B of J_p read + 144 B written.
 __global__ void __launch_bounds__(256) k_obs_v2(BatchDev bd) {
@@ -235,10 +236,13 @@ __global__ void __launch_bounds__(256) k_obs_v2(BatchDev bd) {
     const size_t o = (size_t)wd.obs_off + (have ? i : 0), T = (size_t)bd.tot_obs;
     const int row0 = have ? bd.obs_row[o] : -1;  // -1: constant pose or trimmed landmark
     double jp[18], li[6];
-    int kf = 0;
+    int kf = 0, p0 = 0, p1 = 0;
     if (row0 >= 0) {
         kf = bd.obs_kf[o];
-        const double* lp = bd.lm_linv + 6 * (size_t)(wd.lm_off + bd.obs_lm[o]);
+        const int j = bd.obs_lm[o];
+        const int* lm_ptr = bd.lm_ptr + wd.lm_off + w;
+        p0 = lm_ptr[j]; p1 = lm_ptr[j + 1];
+        const double* lp = bd.lm_linv + 6 * (size_t)(wd.lm_off + j);
 #pragma unroll
         for (int q = 0; q < 6; ++q) li[q] = lp[q];
 #pragma unroll
@@ -256,15 +260,16 @@ __global__ void __launch_bounds__(256) k_obs_v2(BatchDev bd) {
         wm[3 * r + 1] = l0 * li[1] + l1 * li[2];
         wm[3 * r + 2] = l0 * li[3] + l1 * li[4] + l2 * li[5];
     }
-    double2* out = reinterpret_cast<double2*>(bd.vobs + 18 * o);  // 144 B per observation, 16-byte aligned
 #pragma unroll
-    for (int c = 0; c < 3; ++c)
+    for (int c = 0; c < 3; ++c) {  // 48 contiguous bytes per column; consecutive threads = consecutive observations of the landmark
+        double2* out = reinterpret_cast<double2*>(bd.vobs + vobs_index((size_t)wd.obs_off, p0, p1, i, c));
 #pragma unroll
         for (int h = 0; h < 3; ++h) {
             const int r0 = 2 * h, r1 = 2 * h + 1;  // V[r][c] = sum_k J_p[k][r] W[k][c]
-            out[3 * c + h] = make_double2(jp[r0] * wm[c] + jp[6 + r0] * wm[3 + c] + jp[12 + r0] * wm[6 + c],
-                                          jp[r1] * wm[c] + jp[6 + r1] * wm[3 + c] + jp[12 + r1] * wm[6 + c]);
+            out[h] = make_double2(jp[r0] * wm[c] + jp[6 + r0] * wm[3 + c] + jp[12 + r0] * wm[6 + c],
+                                  jp[r1] * wm[c] + jp[6 + r1] * wm[3 + c] + jp[12 + r1] * wm[6 + c]);
         }
+    }
 }
 
 // ground-plane V rows into the chunk panels: one thread per (gp residual, row of its 10 x 3 block)

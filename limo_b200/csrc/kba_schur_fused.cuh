@@ -2,13 +2,15 @@
 //
 //   k_obs_v2 (kba_prep.cuh, one thread per observation, full occupancy) has written V_i = (J_p^T J_l) L^-T compactly:
 //   18 doubles per observation (3 columns x 6 rows), no padding.
-//   producers (4 warps)  : per group of 8 landmarks the panel (24 columns x the group's reduced-system rows, column-major,
-//                          zeros included) is assembled in shared memory by ASYNCHRONOUS copies: every lane owns one
-//                          observation and issues nine 16-byte cp.async from the compact V straight to the panel
-//                          positions of its pose rows, plus the z row; the stage's "full" mbarrier is armed with
-//                          cp.async.mbarrier.arrive, so no producer thread ever waits for data and the ring runs four groups
-//                          ahead.  Windows with ground-plane rows or several cameras per keyframe (rows that ADD onto
-//                          others) take a synchronous variant of the same loop.
+//   producers (4 warps, each assembling whole groups on its own: four panels under construction at any time):
+//                          per group of 8 landmarks the panel (24 columns x the group's reduced-system rows, column-major,
+//                          zeros included) is assembled in shared memory by ASYNCHRONOUS copies.  V is stored
+//                          landmark-column-major, and a track without gaps sits on consecutive rows, so a landmark's panel
+//                          column is ONE bulk copy (cp.async.bulk, 48 B per observation, complete_tx on the stage's "full"
+//                          mbarrier): 24 bulk copies + the z rows per group, issued by 32 lanes, nobody waits for data and
+//                          the ring runs five groups ahead.  Landmarks whose rows are not one run fall back to nine 16-byte
+//                          cp.async per observation; windows with ground-plane rows or several cameras per keyframe (rows
+//                          that ADD onto others) take a synchronous variant of the same loop.
 //   consumers (12 warps) : Sred += V V^T on the FP64 tensor cores (mma.sync m8n8k4).  The whole lower triangle lives in
 //                          the consumers' registers as 16x16 blocks (2x2 tiles: one shared-memory load per DMMA); only
 //                          the tile pairs inside the group's row range are multiplied.
@@ -68,7 +70,7 @@ __device__ __forceinline__ void reg_dec() { asm volatile("setmaxnreg.dec.sync.al
 template <int N>
 __device__ __forceinline__ void reg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
 
-constexpr size_t schur_fused_smem() { return (size_t)kFStages * kFStageDoubles * sizeof(double) + 16 * sizeof(uint64_t); }
+constexpr size_t schur_fused_smem() { return (size_t)kFStages * kFStageDoubles * sizeof(double) + 24 * sizeof(uint64_t); }
 
 // KBA_PROF build: cycles per role (lane 0 of every warp, summed over CTAs into BatchDev::prof) --
 //   consumers: [0] waiting for a full panel, [1] multiplying;  producers: [4] waiting for an empty stage, [5] zero fill +
@@ -104,7 +106,8 @@ __global__ void __launch_bounds__(512, 1) k_schur_fused(BatchDev bd) {
     const int* gt0 = bd.grp_t0 + wd.grp_off;
     const int* gt1 = bd.grp_t1 + wd.grp_off;
     if (tid == 0) {
-        for (int i = 0; i < kFStages; ++i) { mbar_init(&full[i], 128); mbar_init(&empty[i], kFConsumerWarps); }
+        for (int i = 0; i < kFStages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], kFConsumerWarps); }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // the barriers are armed by bulk copies (async proxy) too
     }
     __syncthreads();
     auto next_group = [&](int g) { while (g < g1 && grs[g] == 0) ++g; return g; };
@@ -113,133 +116,144 @@ __global__ void __launch_bounds__(512, 1) k_schur_fused(BatchDev bd) {
         // =============================== producers ===============================
         if (kSlots == 7) reg_dec<56>(); else reg_dec<104>();
 
-        const int ptid = tid - 32 * kFConsumerWarps;
+        // Each producer warp assembles WHOLE groups on its own (group sequence number gi -> warp gi % 4), so four panels are
+        // being built at any time and no CTA-level barrier is needed.  Lane roles inside a warp: lanes 0..23 own one panel
+        // column each (landmark lane / 3 of the group, column lane % 3) and fetch it with ONE bulk copy when the landmark's
+        // rows form a run (BatchDev::lm_run); lanes 24..31 own the z row of landmark lane - 24.
+        // A one-deep register pipeline keeps the next group's meta data in flight (no load result is consumed in the
+        // iteration that issues it): P1 = this warp's next group, P0 = the group being assembled.
+        const int pw = warp - kFConsumerWarps;
         const int* lm_ptr = bd.lm_ptr + wd.lm_off + w;
         const size_t base = (size_t)wd.obs_off, TG = (size_t)bd.tot_gp;
-        // rows that ADD onto others (ground-plane rows, further cameras of a rig) cannot be async copies
-        const bool sync_path = wd.n_gp > 0 || wd.max_rank > 0;
-        // Two-deep register pipeline in front of the copies: P2 (group g+2) observation range; P1 (group g+1) this lane's
-        // observation (row, landmark, rank), the group's tile range and the validity of "its" landmark (lanes 0..7);
-        // P0 (group g): zero the stage, issue the copies, arm the barrier.  No load result is consumed in the iteration that
-        // issues it.
-        int a_ob = 0, a_oe = 0, b_ob = 0, b_oe = 0, c_ob = 0, c_oe = 0;
-        int m1_o = 0, m1_row = -1, m1_lm = 0, m1_rank = 0, m0_o = 0, m0_row = -1, m0_lm = 0, m0_rank = 0;
-        int rs1 = 0, t01 = 0, t11 = 0, rs0 = 0, t00 = 0, t10 = 0;
-        int act1 = 0, p01 = 0, p11 = 0, act0 = 0, p00 = 0, p10 = 0;  // lanes 0..7: lm_active and CSR bounds of landmark 8 g + lane
-        int gi = 0;
+        const bool sync_path = wd.n_gp > 0 || wd.max_rank > 0;  // rows that ADD onto others cannot be async copies
+        const int cj = lane / 3, cc = lane - 3 * cj;  // column lanes
+        const int zj = lane - 24;                      // z lanes
+        int g1_ = -1, rs1 = 0, t01 = 0, t11 = 0, act1 = 0, p01 = 0, p11 = 0;
+        int4 run1 = make_int4(0, 0, 0, 0);
         KBA_PROF_DECL;
-        for (int gg = g0 - 2; gg < g1; ++gg) {
-            {   // ---- P2
-                const int g = gg + 2;
-                if (g >= g0 && g < g1) {
-                    a_ob = lm_ptr[g * kLG];
-                    a_oe = lm_ptr[min(wd.n_lm, g * kLG + kLG)];
-                }
+        // (gi, g) enumerates the non-empty groups of this CTA in order; the warp takes every 4th
+        auto load_meta = [&](int g) {  // P1 loads for group g
+            g1_ = g; act1 = 0; run1 = make_int4(0, 0, 0, 0); p01 = p11 = 0;
+            if (g >= g1) return;
+            rs1 = grs[g]; t01 = gt0[g]; t11 = gt1[g];
+            if (lane < 24) {
+                const int j = g * kLG + cj;
+                if (j < wd.n_lm) { run1 = bd.lm_run[wd.lm_off + j]; p01 = lm_ptr[j]; p11 = lm_ptr[j + 1]; }
+            } else {
+                const int j = g * kLG + zj;
+                if (j < wd.n_lm) { act1 = bd.lm_active[wd.lm_off + j]; p01 = lm_ptr[j]; p11 = lm_ptr[j + 1]; }
             }
-            {   // ---- P1 (b_* = observation range of group gg + 1)
-                const int g = gg + 1;
-                m1_row = -1; act1 = 0;
-                if (g >= g0 && g < g1) {
-                    rs1 = grs[g]; t01 = gt0[g]; t11 = gt1[g];
-                    m1_o = b_ob + ptid;
-                    if (m1_o < b_oe) {
-                        const size_t oo = base + m1_o;
-                        m1_row = bd.obs_row[oo]; m1_lm = bd.obs_lm[oo]; m1_rank = bd.obs_rank[oo];
-                    }
-                    const int j = g * kLG + ptid;
-                    if (ptid < kLG && j < wd.n_lm) { act1 = bd.lm_active[wd.lm_off + j]; p01 = lm_ptr[j]; p11 = lm_ptr[j + 1]; }
-                }
+        };
+        auto nth_group = [&](int g, int n) {  // the n-th non-empty group at or after g (n >= 0), g1 if none
+            g = next_group(g);
+            for (; n > 0 && g < g1; --n) g = next_group(g + 1);
+            return g;
+        };
+        int g = nth_group(g0, pw), gi = pw;
+        load_meta(g);
+        while (g < g1) {
+            // ---- shift: P1 -> P0, issue the loads of this warp's next group
+            const int rs = rs1, t0 = t01, t1 = t11, act0 = act1, p00 = p01, p10 = p11;
+            const int4 run0 = run1;
+            const int gnext = nth_group(g + 1, 3);
+            load_meta(gnext);
+            // ---- P0
+            const int slot = gi % kFStages;
+            KBA_PROF_T0;
+            if (gi >= kFStages) mbar_wait(&empty[slot], ((gi / kFStages) - 1) & 1);
+            KBA_PROF_ACC(0);
+            double* sb = stage + (size_t)slot * kFStageDoubles;
+            {   // rs = rows of this group's panel (multiple of 8); the column stride is the constant kFMaxRs
+                const int h = rs >> 1;
+                for (int c = 0; c < kGC; ++c)
+                    for (int r2 = lane; r2 < h; r2 += 32) reinterpret_cast<double2*>(sb + (size_t)c * kFMaxRs)[r2] = make_double2(0.0, 0.0);
             }
-            if (gg >= g0 && rs0 != 0) {   // ---- P0
-                const int g = gg, rs = rs0, t0 = t00, t1 = t10;
-                const int slot = gi % kFStages;
-                KBA_PROF_T0;
-                if (gi >= kFStages) mbar_wait(&empty[slot], ((gi / kFStages) - 1) & 1);
-                KBA_PROF_ACC(0);
-                double* sb = stage + (size_t)slot * kFStageDoubles;
-                {   // rs = rows of this group's panel (multiple of 8); the column stride is the constant kFMaxRs
-                    const int h = rs >> 1;
-                    for (int i = ptid; i < kGC * h; i += 128) {
-                        const int c = i / h, r2 = i - c * h;
-                        reinterpret_cast<double2*>(sb + (size_t)c * kFMaxRs)[r2] = make_double2(0.0, 0.0);
-                    }
+            // does every landmark of the group have its rows in one run that starts on an even panel row?
+            const bool no_run = lane < 24 && (run0.y < 0 || (run0.y > 0 && ((run0.z - 8 * t0) & 1)));
+            const bool bulk = __ballot_sync(0xffffffffu, no_run) == 0u && !sync_path;
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // the zeros (generic proxy) before the bulk copies (async proxy)
+            __syncwarp();
+            KBA_PROF_ACC(1);
+            const int j0 = g * kLG, j1 = min(wd.n_lm, j0 + kLG);
+            const int ob = lm_ptr[j0], oe = lm_ptr[j1];
+            const int rl = (trhs >= t0 && trhs < t1) ? n_f - 8 * t0 : 8 * (t1 - t0) + (n_f - 8 * trhs);  // t0, t1: block aligned
+            if (bulk) {
+                if (lane < 24 && run0.y > 0) {  // one bulk copy: the landmark's column, 6 rows per observation of the run
+                    const uint32_t bytes = (uint32_t)(48 * run0.y);
+                    asm volatile("mbarrier.expect_tx.relaxed.cta.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(&full[slot])), "r"(bytes) : "memory");
+                    tma_load_1d(sb + (size_t)(3 * cj + cc) * kFMaxRs + (run0.z - 8 * t0),
+                                bd.vobs + vobs_index(base, p00, p10, p00 + run0.x, cc), bytes, &full[slot]);
                 }
-                producer_sync();  // the stage is zero before any copy lands in it
-                KBA_PROF_ACC(1);
-                const int j0 = g * kLG;
-                const int rl = (trhs >= t0 && trhs < t1) ? n_f - 8 * t0 : 8 * (t1 - t0) + (n_f - 8 * trhs);  // t0, t1: block aligned
-                auto copy_obs = [&](int o, int row, int jj) {  // 3 columns x 6 rows of one observation, asynchronously
-                    const double* src = bd.vobs + 18 * (base + o);
-                    double* dst = sb + (size_t)(3 * jj) * kFMaxRs + (row - 8 * t0);
-                    if (((row - 8 * t0) & 1) == 0) {
-#pragma unroll
-                        for (int c = 0; c < 3; ++c)
-#pragma unroll
-                            for (int h = 0; h < 3; ++h) cp_async16(dst + c * kFMaxRs + 2 * h, src + 6 * c + 2 * h);
-                    } else {
-#pragma unroll
-                        for (int c = 0; c < 3; ++c)
-#pragma unroll
-                            for (int r = 0; r < 6; ++r) cp_async8(dst + c * kFMaxRs + r, src + 6 * c + r);
-                    }
-                };
-                if (m0_row >= 0 && m0_rank == 0) copy_obs(m0_o, m0_row, m0_lm - j0);
-                for (int o = c_ob + kFObs + ptid; o < c_oe; o += kFObs) {  // groups of more than 128 observations (rare)
+            } else {  // per observation: nine 16-byte (or eighteen 8-byte) async copies
+                for (int o = ob + lane; o < oe; o += 32) {
                     const size_t oo = base + o;
                     const int row = bd.obs_row[oo];
-                    if (row >= 0 && bd.obs_rank[oo] == 0) copy_obs(o, row, bd.obs_lm[oo] - j0);
-                }
-                const bool zvalid = ptid < kLG && act0 && p10 > p00;
-                if (zvalid) {  // right-hand-side row z_j
-                    const double* zz = bd.lm_z + 3 * (size_t)(wd.lm_off + j0 + ptid);
-                    double* col = sb + (size_t)(3 * ptid) * kFMaxRs + rl;
-                    cp_async8(col, zz); cp_async8(col + kFMaxRs, zz + 1); cp_async8(col + 2 * kFMaxRs, zz + 2);
-                }
-                if (!sync_path) {
-                    cp_async_arrive(&full[slot]);  // this thread's arrival fires when its copies have landed
-                } else {
-                    cp_async_commit();
-                    cp_async_wait<0>();
-                    producer_sync();
-                    for (int round = 1; round <= wd.max_rank; ++round) {  // further cameras of a rig: add onto the same rows
-                        for (int o = c_ob + ptid; o < c_oe; o += kFObs) {
-                            const size_t oo = base + o;
-                            const int row = bd.obs_row[oo];
-                            if (row < 0 || bd.obs_rank[oo] != round) continue;
-                            const double* src = bd.vobs + 18 * oo;
-                            double* dst = sb + (size_t)(3 * (bd.obs_lm[oo] - j0)) * kFMaxRs + (row - 8 * t0);
-                            for (int c = 0; c < 3; ++c)
-                                for (int r = 0; r < 6; ++r) dst[c * kFMaxRs + r] += src[6 * c + r];
-                        }
-                        producer_sync();
-                    }
-                    if (wd.n_gp > 0 && ptid < 80) {  // ground-plane rows: 8 landmarks x 10 rows, added onto the pose rows
-                        const int jj = ptid / 10, r = ptid - 10 * jj, j = j0 + jj;
-                        const int L = wd.lm_off + j;
-                        if (j < wd.n_lm && bd.lm_active[L] && lm_ptr[j + 1] > lm_ptr[j]) {
-                            const int gl = bd.gp_of_lm[L];
-                            if (gl >= 0) {
-                                const size_t G = (size_t)wd.gp_off + gl;
-                                const int row = gp_row(bd, wd, bd.gp_kf[G], r);
-                                if (row >= 0) {
-                                    double* q = sb + (size_t)(3 * jj) * kFMaxRs + (row - 8 * t0);
-                                    q[0] += bd.vgp[(3 * r + 0) * TG + G];
-                                    q[kFMaxRs] += bd.vgp[(3 * r + 1) * TG + G];
-                                    q[2 * kFMaxRs] += bd.vgp[(3 * r + 2) * TG + G];
-                                }
-                            }
+                    if (row < 0 || bd.obs_rank[oo] != 0) continue;
+                    const int lm = bd.obs_lm[oo], q0 = lm_ptr[lm], q1 = lm_ptr[lm + 1];
+                    double* dst = sb + (size_t)(3 * (lm - j0)) * kFMaxRs + (row - 8 * t0);
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) {
+                        const double* src = bd.vobs + vobs_index(base, q0, q1, o, c);
+                        if (((row - 8 * t0) & 1) == 0) {
+#pragma unroll
+                            for (int h = 0; h < 3; ++h) cp_async16(dst + c * kFMaxRs + 2 * h, src + 2 * h);
+                        } else {
+#pragma unroll
+                            for (int r = 0; r < 6; ++r) cp_async8(dst + c * kFMaxRs + r, src + r);
                         }
                     }
-                    mbar_arrive(&full[slot]);  // release: this thread's panel writes are visible to the consumers' acquire
                 }
-                KBA_PROF_ACC(2);
-                ++gi;
             }
-            KBA_PROF_T0;
-            // ---- shift the pipeline registers
-            c_ob = b_ob; c_oe = b_oe; b_ob = a_ob; b_oe = a_oe;
-            m0_o = m1_o; m0_row = m1_row; m0_lm = m1_lm; m0_rank = m1_rank;
-            rs0 = rs1; t00 = t01; t10 = t11; act0 = act1; p00 = p01; p10 = p11;
+            if (lane >= 24 && act0 && p10 > p00) {  // right-hand-side row z_j
+                const double* zz = bd.lm_z + 3 * (size_t)(wd.lm_off + j0 + zj);
+                double* col = sb + (size_t)(3 * zj) * kFMaxRs + rl;
+                cp_async8(col, zz); cp_async8(col + kFMaxRs, zz + 1); cp_async8(col + 2 * kFMaxRs, zz + 2);
+            }
+            if (!sync_path) {
+                // every lane: "count my outstanding cp.async into this phase" (increments the pending count now, decrements on
+                // completion); then ONE arrival per warp -- the phase completes when the copies and the bulk bytes have landed
+                asm volatile("cp.async.mbarrier.arrive.shared::cta.b64 [%0];" ::"r"(smem_u32(&full[slot])) : "memory");
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&full[slot]);
+            } else {
+                cp_async_commit();
+                cp_async_wait<0>();
+                __syncwarp();
+                for (int round = 1; round <= wd.max_rank; ++round) {  // further cameras of a rig: add onto the same rows
+                    for (int o = ob + lane; o < oe; o += 32) {
+                        const size_t oo = base + o;
+                        const int row = bd.obs_row[oo];
+                        if (row < 0 || bd.obs_rank[oo] != round) continue;
+                        const int lm = bd.obs_lm[oo], q0 = lm_ptr[lm], q1 = lm_ptr[lm + 1];
+                        double* dst = sb + (size_t)(3 * (lm - j0)) * kFMaxRs + (row - 8 * t0);
+                        for (int c = 0; c < 3; ++c) {
+                            const double* src = bd.vobs + vobs_index(base, q0, q1, o, c);
+                            for (int r = 0; r < 6; ++r) dst[c * kFMaxRs + r] += src[r];
+                        }
+                    }
+                    __syncwarp();
+                }
+                if (wd.n_gp > 0) {  // ground-plane rows: 8 landmarks x 10 rows, added onto the pose rows
+                    for (int it = lane; it < 80; it += 32) {
+                        const int jj = it / 10, r = it - 10 * jj, j = j0 + jj;
+                        const int L = wd.lm_off + j;
+                        if (j >= wd.n_lm || !bd.lm_active[L] || lm_ptr[j + 1] <= lm_ptr[j]) continue;
+                        const int gl = bd.gp_of_lm[L];
+                        if (gl < 0) continue;
+                        const size_t G = (size_t)wd.gp_off + gl;
+                        const int row = gp_row(bd, wd, bd.gp_kf[G], r);
+                        if (row < 0) continue;
+                        double* q = sb + (size_t)(3 * jj) * kFMaxRs + (row - 8 * t0);
+                        q[0] += bd.vgp[(3 * r + 0) * TG + G];
+                        q[kFMaxRs] += bd.vgp[(3 * r + 1) * TG + G];
+                        q[2 * kFMaxRs] += bd.vgp[(3 * r + 2) * TG + G];
+                    }
+                }
+                __syncwarp();  // the warp's panel writes are ordered before lane 0's releasing arrival
+                if (lane == 0) mbar_arrive(&full[slot]);
+            }
+            KBA_PROF_ACC(2);
+            g = gnext; gi += 4;
         }
         cp_async_commit();
         cp_async_wait<0>();

@@ -33,14 +33,15 @@ def use_native_build():
     if _lib is not None:
         raise RuntimeError("use_native_build() must be called before the oracle library is loaded")
     out = os.path.join(tempfile.mkdtemp(prefix="kba_oracle_native_"), "libkba_oracle_native.so")
-    cmd = ["gcc", "-O3", "-march=native", "-std=gnu11", "-fPIC", "-fopenmp", "-I" + os.path.join(_HERE, "..", "include"), "-shared",
+    # -ffp-contract=off: same arithmetic as the portable build (the lidar oracle is compared bit for bit)
+    cmd = ["gcc", "-O3", "-march=native", "-ffp-contract=off", "-std=gnu11", "-fPIC", "-fopenmp", "-I" + os.path.join(_HERE, "..", "include"), "-shared",
            "-o", out, os.path.join(_HERE, "kba_oracle.c"), os.path.join(_HERE, "lidar_oracle.c"), "-lm"]
     try:
         subprocess.check_call(cmd, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
     except (OSError, subprocess.CalledProcessError):
         return "gcc -O2 (portable build; native build failed)"
     _LIB_PATH = out
-    return "gcc -O3 -march=native -fopenmp, built on this host"
+    return "gcc -O3 -march=native -ffp-contract=off -fopenmp, built on this host"
 
 
 def lib():

@@ -309,3 +309,22 @@ def test_edge_case_windows_match_oracle(handle, oracle, case):
     if case == "ragged":
         empty = np.diff(win.lm_obs_ptr) == 0
         assert empty.sum() == 4 and np.array_equal(rg.lm_pos[:win.n_lm][empty], win.lm_pos[empty])
+
+
+def test_device_packing_equals_host_packing(handle, monkeypatch):
+    """the packing kernels (kba_pack.cu: landmark sort by (first, last) keyframe, CSR, keyframe-major copy, ground-plane
+    mapping, group ranges, caller-order download) against the host packer of round 1 (KBA_DEVICE_PACK=0): the same sorted
+    layout, hence bit-identical solves -- mono + depth windows, ground-plane windows, ragged CSR rows, a two-camera rig"""
+    from tests import edge_windows as ew
+    wins = [synth.make_window(2, n_kf=12, n_lm=700, n_obs=6000, seed=3), synth.make_window(3, seed=41, n_kf=8, n_lm=300, n_obs=1800, gp_frac=0.2),
+            ew.CASES["ragged"](), synth.make_window(1, seed=9)]
+    dev = handle.solve_batch(wins)
+    monkeypatch.setenv("KBA_DEVICE_PACK", "0")
+    host = handle.solve_batch(wins)
+    for a, b, w in zip(dev, host, wins):
+        assert a.c.status == 0 and b.c.status == 0
+        assert [s.num_iterations for s in a.solves] == [s.num_iterations for s in b.solves]
+        assert np.array_equal(a.kf_pose, b.kf_pose)
+        assert np.array_equal(a.lm_pos[:w.n_lm], b.lm_pos[:w.n_lm])
+        assert np.array_equal(a.lm_rejected[:w.n_lm], b.lm_rejected[:w.n_lm])
+        assert a.c.final_cost == b.c.final_cost
