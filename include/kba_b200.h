@@ -257,6 +257,49 @@ void kba_shard_comm_destroy(kba_shard_comm* c);
  * whole window.  Afterwards kba_batch_solve is a collective call: every rank must make it. */
 int kba_batch_set_shard(kba_batch* b, kba_shard_comm* comm, int32_t lm_begin, int32_t lm_total);
 
+/* ---- persistent, device-resident sliding window ------------------------------------------------------------
+ * The reference rebuilds the whole ceres::Problem for every solve() (bundle_adjuster_keyframes.cpp:635-637) and kba_solve_window
+ * re-packs and re-uploads the whole window likewise.  A kba_track keeps what push() has seen on the device instead:
+ *   - every pushed keyframe's pose, plane and measurements (landmark slot, camera, u, v, d) in one arena, uploaded ONCE at push;
+ *   - landmark positions / weights by caller-assigned dense slot (the caller keeps LandmarkId -> slot), updated in place by solves.
+ * kba_track_solve() then takes only the small per-solve lists (which keyframe slots are active, in ascending id order, with their
+ * fixation; which landmark slots are selected, in ascending id order; the ground-plane attachments; the regulariser scalars),
+ * gathers the window's CSR ON THE DEVICE (k_track_* in kba_pack.cu), packs and solves it exactly like kba_solve_window, writes
+ * poses / planes / landmarks back into the store and returns them.  The window it builds is, array for array, the one the caller
+ * would have passed to kba_solve_window, so the results are bit-identical (tests/test_track.py).
+ * Capacities are fixed at creation; a window beyond `win_*` must go through kba_solve_window.  Not thread-safe (one handle). */
+typedef struct kba_track kba_track;
+typedef struct kba_track_caps {
+    int32_t max_keyframes;     /* keyframe slots in the store (active or not)        */
+    int32_t max_landmarks;     /* landmark slots                                      */
+    int32_t max_measurements;  /* arena entries over all stored keyframes             */
+    int32_t win_keyframes;     /* largest window: keyframes (<= 30: fused path)       */
+    int32_t win_landmarks;     /*                 selected landmarks                  */
+    int32_t win_observations;  /*                 observations                        */
+    int32_t win_ground;        /*                 ground-plane residuals              */
+} kba_track_caps;
+int kba_track_create(kba_handle* h, const kba_track_caps* caps, int32_t n_cam, const double* cam_intr, const double* cam_pose,
+                     kba_track** out);
+void kba_track_destroy(kba_track* t);
+/* push(): keyframe `kf_slot` (re-usable after kba_track_drop_keyframe) with pose, plane (4, may be NULL) and its measurements */
+int kba_track_push_keyframe(kba_track* t, int32_t kf_slot, const double* pose7, const double* plane4, int32_t n_meas,
+                            const int32_t* lm_slot, const int32_t* cam, const float* u, const float* v, const float* d);
+int kba_track_drop_keyframe(kba_track* t, int32_t kf_slot);  /* its arena space is reclaimed by compaction when needed */
+/* landmark state the host changes outside a solve: initial positions of new landmarks (push(), cpp:318-319), weights and
+ * positions touched by the caller; any of pos / weight may be NULL */
+int kba_track_set_landmarks(kba_track* t, int32_t n, const int32_t* lm_slot, const double* pos3, const double* weight);
+int kba_track_set_keyframe_pose(kba_track* t, int32_t kf_slot, const double* pose7, const double* plane4);
+/* the same for n keyframes with ONE copy (pose7s [n*7], plane4s [n*4] or NULL): what solve() sends for its active keyframes */
+int kba_track_set_keyframe_poses(kba_track* t, int32_t n, const int32_t* kf_slot, const double* pose7s, const double* plane4s);
+/* one solve() on the stored window; `sel` carries sizes, the scalar members and the ground-plane lists of kba_window (gp_lm =
+ * index into lm_slot), its keyframe / landmark / observation arrays are ignored; scale_weight < 0 asks for the reference's own rule
+ * (cpp:703-716: 1000, or 1000 / (depth + ground-plane residuals) beyond ten of them; plane_dist_fixed by cpp:722-728), evaluated
+ * on the device from the gathered window so that the host need not visit a single observation.  Results: res->kf_pose / kf_plane [n_kf],
+ * res->lm_pos / lm_rejected [n_lm] in selection order. */
+int kba_track_solve(kba_track* t, int32_t n_kf, const int32_t* kf_slot, const uint8_t* kf_fixed, int32_t n_lm, const int32_t* lm_slot,
+                    const kba_window* sel, const kba_options* opt, kba_result* res);
+int kba_track_transfer_bytes(kba_track* t, int64_t* h2d_last_solve, int64_t* d2h_last_solve, int64_t* h2d_pushes_total);
+
 /* ---- landmark initialisation of push() for a whole window ------------------------------------------
  * Replaces, for all landmarks of `w` at once, what BundleAdjusterKeyframes::push() does per new landmark on the host:
  * the first observation with a lidar depth (d >= 0) is back-projected (bundle_adjuster_keyframes.cpp:332-355); without

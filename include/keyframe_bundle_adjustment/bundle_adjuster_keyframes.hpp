@@ -5,6 +5,7 @@
 // around it live where the reference keeps them: internal/definitions.hpp, keyframe.hpp, landmark_selector.hpp,
 // landmark_selection_schemes.hpp, matches_msg_types/*.hpp.
 #pragma once
+#include <array>
 #include <exception>
 #include <map>
 #include <memory>
@@ -17,6 +18,7 @@
 #include "landmark_selector.hpp"
 
 struct kba_handle;
+struct kba_track;
 
 namespace keyframe_bundle_adjustment {
 
@@ -68,6 +70,14 @@ public:
     bool calculateLandmark(const Keyframe& kf, const LandmarkId& lId, v3& posAbs);
     bool calculateLandmark(const LandmarkId& lId, v3& posAbs);
     void set_solver_time(double solver_time_sec) { this->solver_time_sec = solver_time_sec; }
+    // Not in the reference: keep the pushed keyframes on the device (kba_track_*, include/kba_b200.h) so that solve() sends only
+    // the lists of active keyframes / selected landmarks instead of re-packing and re-uploading the window (the reference
+    // rebuilds its ceres::Problem per call, cpp:635-637).  On by default; windows the device-resident store cannot take (more than
+    // 30 keyframes, ground-plane residuals, a camera that was not there at the first push) fall back to the rebuild path.
+    void set_persistent_window(bool on) { persistent_window_ = on; }
+    // host -> device bytes of the last solve() (either path) and of all push() calls so far (persistent path)
+    long long lastSolveUploadBytes() const { return last_solve_h2d_; }
+    long long pushUploadBytes() const { return push_h2d_; }
     void updateLabels(const Tracklets& t, double shrubbery_weight = 1.);
 
     std::map<KeyframeId, Keyframe::Ptr> keyframes_;
@@ -87,6 +97,18 @@ private:
                           Keyframe* speed_prior_for);
     kba_handle* handle_{nullptr};  // replaces std::shared_ptr<ceres::Problem> problem_
     double solver_time_sec;
+    // persistent device-resident window
+    bool ensureHandle();
+    bool trackPush(const Keyframe& kf);
+    bool solveTracked(const std::vector<Keyframe*>& kfs, const std::vector<LandmarkId>& lm_ids, std::string& report);
+    kba_track* track_{nullptr};
+    bool persistent_window_{true}, track_failed_{false};
+    std::map<KeyframeId, int> kf_slot_;
+    std::map<LandmarkId, int> lm_slot_;
+    std::vector<int> free_kf_slots_;
+    std::vector<std::array<double, 10>> track_cams_;  // camera values (f, pp, pose_camera_vehicle) the track was created with
+    std::set<LandmarkId> new_landmarks_, dirty_weights_;
+    long long last_solve_h2d_{0}, push_h2d_{0};
 };
 
 }  // namespace keyframe_bundle_adjustment

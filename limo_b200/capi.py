@@ -8,7 +8,8 @@ import os
 
 import numpy as np
 
-from .capi_types import (KbaCounters, KbaEvalOut, KbaLidarOptions, KbaOptions, KbaResult, KbaWindow, Result, c_double_p, c_int32_p)
+from .capi_types import (KbaCounters, KbaEvalOut, KbaLidarOptions, KbaOptions, KbaResult, KbaTrackCaps, KbaWindow, Result, Window,
+                         c_double_p, c_int32_p)
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("KBA_LIB_PATH") or os.path.join(_HERE, "libkba_b200.so")  # KBA_LIB_PATH: instrumented builds
@@ -19,7 +20,8 @@ SYMBOLS = ["kba_version", "kba_last_error", "kba_default_options", "kba_create",
            "kba_batch_solve", "kba_batch_download", "kba_batch_transfer_bytes", "kba_batch_jacobian_pass", "kba_batch_destroy",
            "kba_get_counters", "kba_enable_kernel_timing", "kba_lidar_default_options", "kba_lidar_depth",
            "kba_shard_unique_id", "kba_shard_comm_create", "kba_shard_comm_destroy", "kba_batch_set_shard",
-           "kba_init_landmarks"]
+           "kba_init_landmarks", "kba_track_create", "kba_track_destroy", "kba_track_push_keyframe", "kba_track_drop_keyframe",
+           "kba_track_set_landmarks", "kba_track_set_keyframe_pose", "kba_track_set_keyframe_poses", "kba_track_solve", "kba_track_transfer_bytes"]
 
 
 class KbaError(RuntimeError):
@@ -60,6 +62,18 @@ def lib():
         L.kba_shard_comm_destroy.restype = None
         L.kba_batch_set_shard.argtypes = [vp, vp, C.c_int32, C.c_int32]
         L.kba_init_landmarks.argtypes = [vp, C.POINTER(KbaWindow), c_double_p, C.POINTER(C.c_uint8), C.POINTER(C.c_float)]
+        ip, u8p = C.POINTER(C.c_int32), C.POINTER(C.c_uint8)
+        L.kba_track_create.argtypes = [vp, C.POINTER(KbaTrackCaps), C.c_int32, c_double_p, c_double_p, C.POINTER(vp)]
+        L.kba_track_destroy.argtypes = [vp]
+        L.kba_track_destroy.restype = None
+        L.kba_track_push_keyframe.argtypes = [vp, C.c_int32, c_double_p, c_double_p, C.c_int32, ip, ip, C.POINTER(C.c_float),
+                                              C.POINTER(C.c_float), C.POINTER(C.c_float)]
+        L.kba_track_drop_keyframe.argtypes = [vp, C.c_int32]
+        L.kba_track_set_landmarks.argtypes = [vp, C.c_int32, ip, c_double_p, c_double_p]
+        L.kba_track_set_keyframe_pose.argtypes = [vp, C.c_int32, c_double_p, c_double_p]
+        L.kba_track_set_keyframe_poses.argtypes = [vp, C.c_int32, ip, c_double_p, c_double_p]
+        L.kba_track_solve.argtypes = [vp, C.c_int32, ip, u8p, C.c_int32, ip, C.POINTER(KbaWindow), C.POINTER(KbaOptions), C.POINTER(KbaResult)]
+        L.kba_track_transfer_bytes.argtypes = [vp, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
         L.kba_lidar_default_options.argtypes = [C.POINTER(KbaLidarOptions)]
         L.kba_lidar_default_options.restype = None
         fp = C.POINTER(C.c_float)
@@ -138,6 +152,70 @@ class Batch:
             self.close()
         except Exception:
             pass
+
+
+class Track:
+    """Persistent, device-resident sliding window (kba_track_*): keyframes are uploaded once when pushed, a solve sends only
+    the lists of active keyframe slots and selected landmark slots."""
+
+    def __init__(self, handle, cam_intr, cam_pose, max_keyframes, max_landmarks, max_measurements, win_keyframes,
+                 win_landmarks, win_observations, win_ground=0):
+        self.handle = handle
+        caps = KbaTrackCaps(max_keyframes, max_landmarks, max_measurements, win_keyframes, win_landmarks, win_observations, win_ground)
+        intr = np.ascontiguousarray(cam_intr, dtype=np.float64).reshape(-1, 3)
+        pose = np.ascontiguousarray(cam_pose, dtype=np.float64).reshape(-1, 7)
+        self._p = C.c_void_p()
+        _check(lib().kba_track_create(handle._p, C.byref(caps), len(intr), intr.ctypes.data_as(c_double_p),
+                                      pose.ctypes.data_as(c_double_p), C.byref(self._p)))
+
+    @staticmethod
+    def _i32(a):
+        a = np.ascontiguousarray(a, dtype=np.int32)
+        return a, a.ctypes.data_as(C.POINTER(C.c_int32))
+
+    def push_keyframe(self, slot, pose7, lm_slot, u, v, d, cam=None, plane4=None):
+        fp = C.POINTER(C.c_float)
+        pose = np.ascontiguousarray(pose7, dtype=np.float64)
+        pl = None if plane4 is None else np.ascontiguousarray(plane4, dtype=np.float64)
+        lm, lmp = self._i32(lm_slot)
+        cm, cmp_ = (None, C.cast(None, C.POINTER(C.c_int32))) if cam is None else self._i32(cam)
+        uu, vv, dd = (np.ascontiguousarray(x, dtype=np.float32) for x in (u, v, d))
+        _check(lib().kba_track_push_keyframe(self._p, int(slot), pose.ctypes.data_as(c_double_p),
+                                             C.cast(None, c_double_p) if pl is None else pl.ctypes.data_as(c_double_p), len(lm), lmp, cmp_,
+                                             uu.ctypes.data_as(fp), vv.ctypes.data_as(fp), dd.ctypes.data_as(fp)))
+
+    def drop_keyframe(self, slot):
+        _check(lib().kba_track_drop_keyframe(self._p, int(slot)))
+
+    def set_landmarks(self, lm_slot, pos=None, weight=None):
+        lm, lmp = self._i32(lm_slot)
+        p = None if pos is None else np.ascontiguousarray(pos, dtype=np.float64).reshape(-1, 3)
+        w = None if weight is None else np.ascontiguousarray(weight, dtype=np.float64)
+        _check(lib().kba_track_set_landmarks(self._p, len(lm), lmp, C.cast(None, c_double_p) if p is None else p.ctypes.data_as(c_double_p),
+                                             C.cast(None, c_double_p) if w is None else w.ctypes.data_as(c_double_p)))
+
+    def solve(self, kf_slots, kf_fixed, lm_slots, opt=None, **scalars):
+        """scalars: scale_kf0, scale_kf1, scale_weight, scale_value, plane_reg_weight, plane_dist_fixed, gp_lm, gp_kf, gp_weight"""
+        kf, kfp = self._i32(kf_slots)
+        lm, lmp = self._i32(lm_slots)
+        fx = np.ascontiguousarray(kf_fixed, dtype=np.uint8)
+        n_kf, n_lm = len(kf), len(lm)
+        sel = Window(np.tile([1.0, 0, 0, 0, 0, 0, 0], (n_kf, 1)), fx, [[1.0, 0, 0]], [[1.0, 0, 0, 0, 0, 0, 0]], np.zeros((n_lm, 3)),
+                     np.ones(n_lm), np.zeros(n_lm + 1, dtype=np.int32), [], [], [], [], **scalars)
+        res = Result(sel, 256)
+        _check(lib().kba_track_solve(self._p, n_kf, kfp, fx.ctypes.data_as(C.POINTER(C.c_uint8)), n_lm, lmp, C.byref(sel.c),
+                                     C.byref(opt or default_options()), C.byref(res.c)))
+        return res
+
+    def transfer_bytes(self):
+        a, b, c = C.c_int64(), C.c_int64(), C.c_int64()
+        _check(lib().kba_track_transfer_bytes(self._p, C.byref(a), C.byref(b), C.byref(c)))
+        return a.value, b.value, c.value
+
+    def close(self):
+        if self._p:
+            lib().kba_track_destroy(self._p)
+            self._p = C.c_void_p()
 
 
 SHARD_ID_BYTES = 128

@@ -46,7 +46,10 @@ BundleAdjusterKeyframes::BundleAdjusterKeyframes() : solver_time_sec(0.2) {
     landmark_selector_ = std::make_unique<LandmarkSelector>();
     landmark_selector_->addScheme(LandmarkRejectionSchemeCheirality::create());  // cpp:116-118
 }
-BundleAdjusterKeyframes::~BundleAdjusterKeyframes() { if (handle_) kba_destroy(handle_); }
+BundleAdjusterKeyframes::~BundleAdjusterKeyframes() {
+    if (track_) kba_track_destroy(track_);
+    if (handle_) kba_destroy(handle_);
+}
 
 void BundleAdjusterKeyframes::push(const std::vector<Keyframe>& kfs) { for (const auto& kf : kfs) push(kf); }
 
@@ -61,9 +64,12 @@ void BundleAdjusterKeyframes::push(const Keyframe& kf) {  // cpp:289-329
             const bool success = has_depth ? calculateLandmark(kf, m.first, p) : calculateLandmark(m.first, p);
             if (!success) continue;
             landmarks_.insert(std::make_pair(m.first, std::make_shared<Landmark>(p, has_depth)));
+            new_landmarks_.insert(m.first);
         }
         active_landmark_ids_.insert(m.first);
     }
+    // the device-resident store gets the keyframe lazily, at the next solve() (trackPush): callers may still edit the stored
+    // copy before (mono_lidar.cpp sets the pose prior after push)
 }
 
 bool BundleAdjusterKeyframes::calculateLandmark(const Keyframe& kf, const LandmarkId& lId, v3& posAbs) {  // cpp:332-355
@@ -105,7 +111,7 @@ void BundleAdjusterKeyframes::updateLabels(const Tracklets& t, double shrubbery_
     landmark_selector_->setOutlier(outlier_ids);
     for (const auto& track : t.tracks) {
         if (!active_landmark_ids_.count(track.id)) continue;
-        if (labels_["shrubbery"].count(track.label)) landmarks_.at(track.id)->weight = shrubbery_weight;
+        if (labels_["shrubbery"].count(track.label)) { landmarks_.at(track.id)->weight = shrubbery_weight; dirty_weights_.insert(track.id); }
         landmarks_.at(track.id)->is_ground_plane = labels_["ground"].count(track.label) > 0;
     }
 }
@@ -184,9 +190,7 @@ void BundleAdjusterKeyframes::deactivateKeyframes(int min_num_connecting_landmar
 // robust_optimization::solveTrimmed (:765, :886).
 std::string BundleAdjusterKeyframes::runWindow(const std::vector<Keyframe*>& kfs, const std::vector<LandmarkId>& lm_ids,
                                                bool motion_only, Keyframe* speed_kf) {
-    if (!handle_) {
-        if (kba_create(&handle_, 0) != KBA_OK) throw std::runtime_error(std::string("kba_b200: ") + kba_last_error());
-    }
+    ensureHandle();
     std::vector<double> kf_pose, kf_plane, cam_intr, cam_pose, lm_pos, lm_weight, gp_weight;
     std::vector<uint8_t> kf_fixed;
     std::vector<int32_t> lm_obs_ptr{0}, obs_kf, obs_cam, gp_lm, gp_kf;
@@ -294,6 +298,9 @@ std::string BundleAdjusterKeyframes::runWindow(const std::vector<Keyframe*>& kfs
     kba_result r{};
     r.kf_pose = out_pose.data(); r.kf_plane = out_plane.data(); r.lm_pos = out_lm.data();
     if (kba_solve_window(handle_, &w, &opt, &r) != KBA_OK) throw std::runtime_error(std::string("kba_b200: ") + kba_last_error());
+    // what the rebuild path uploads: the window's arrays as passed (kba_batch_transfer_bytes reports the same for a batch)
+    last_solve_h2d_ = (long long)(kf_pose.size() + kf_plane.size() + lm_pos.size() + lm_weight.size() + cam_intr.size() + cam_pose.size()) * 8 +
+                      (long long)(lm_obs_ptr.size() + 2 * obs_kf.size()) * 4 + (long long)obs_u.size() * 12 + (long long)kf_fixed.size();
 
     for (size_t k = 0; k < kfs.size(); ++k) {  // the reference optimises in place (cpp:554-557, 592-593)
         std::copy_n(out_pose.begin() + 7 * k, 7, kfs[k]->pose_.begin());
@@ -327,7 +334,159 @@ std::string BundleAdjusterKeyframes::solve() {  // cpp:629-767
     std::vector<Keyframe*> kfs;
     for (const auto& id : active_keyframe_ids_) kfs.push_back(keyframes_.at(id).get());
     std::vector<LandmarkId> lm_ids(selected_landmark_ids_.begin(), selected_landmark_ids_.end());
+    std::string report;
+    if (persistent_window_ && !track_failed_ && solveTracked(kfs, lm_ids, report)) return report;
     return runWindow(kfs, lm_ids, false, nullptr);
+}
+
+// ---- persistent device-resident window ---------------------------------------------------------------------------------------
+bool BundleAdjusterKeyframes::ensureHandle() {
+    if (!handle_ && kba_create(&handle_, 0) != KBA_OK) throw std::runtime_error(std::string("kba_b200: ") + kba_last_error());
+    return true;
+}
+
+namespace {
+std::array<double, 10> camera_value(const Camera& c) {
+    std::array<double, 10> k{{c.focal_length, c.principal_point[0], c.principal_point[1]}};
+    std::copy(c.pose_camera_vehicle.begin(), c.pose_camera_vehicle.end(), k.begin() + 3);
+    return k;
+}
+constexpr int kTrackKeyframes = 256, kTrackLandmarks = 1 << 17, kTrackMeasurements = 1 << 21;
+constexpr int kTrackWinKeyframes = 30, kTrackWinLandmarks = 16384, kTrackWinObservations = 1 << 18;
+}  // namespace
+
+// the keyframe's measurements go to the device ONCE (landmark slot, camera, u, v, d in measurements_ order: landmark id, then
+// camera id -- the order addKeyframeToProblem enumerates, cpp:564-627); false: this keyframe cannot live in the store
+bool BundleAdjusterKeyframes::trackPush(const Keyframe& kf) {
+    ensureHandle();
+    if (!track_) {  // created from the cameras of the first keyframe that reaches it
+        std::vector<double> intr, pose;
+        for (const auto& c : kf.cameras_) {
+            const auto v = camera_value(*c.second);
+            if (std::find(track_cams_.begin(), track_cams_.end(), v) != track_cams_.end()) continue;
+            track_cams_.push_back(v);
+            intr.insert(intr.end(), v.begin(), v.begin() + 3);
+            pose.insert(pose.end(), v.begin() + 3, v.end());
+        }
+        kba_track_caps caps{kTrackKeyframes, kTrackLandmarks, kTrackMeasurements, kTrackWinKeyframes, kTrackWinLandmarks, kTrackWinObservations, 0};
+        if (kba_track_create(handle_, &caps, int(track_cams_.size()), intr.data(), pose.data(), &track_) != KBA_OK) return false;
+        for (int i = kTrackKeyframes - 1; i >= 0; --i) free_kf_slots_.push_back(i);
+    }
+    std::map<CameraId, int> cam_of;
+    for (const auto& c : kf.cameras_) {
+        const auto it = std::find(track_cams_.begin(), track_cams_.end(), camera_value(*c.second));
+        if (it == track_cams_.end()) return false;  // a camera the store does not know
+        cam_of[c.first] = int(it - track_cams_.begin());
+    }
+    if (free_kf_slots_.empty()) {  // reclaim the slots of the oldest keyframes that are no longer active
+        for (auto it = kf_slot_.begin(); it != kf_slot_.end() && free_kf_slots_.size() < 32;) {
+            if (active_keyframe_ids_.count(it->first)) { ++it; continue; }
+            kba_track_drop_keyframe(track_, it->second);
+            free_kf_slots_.push_back(it->second);
+            it = kf_slot_.erase(it);
+        }
+        if (free_kf_slots_.empty()) return false;
+    }
+    std::vector<int32_t> lm, cam;
+    std::vector<float> u, v, d;
+    for (const auto& m : kf.measurements_) {
+        auto it = lm_slot_.find(m.first);
+        if (it == lm_slot_.end()) {
+            if (int(lm_slot_.size()) >= kTrackLandmarks) return false;
+            it = lm_slot_.emplace(m.first, int(lm_slot_.size())).first;
+        }
+        for (const auto& cm : m.second) {
+            lm.push_back(it->second); cam.push_back(cam_of.at(cm.first));
+            u.push_back(cm.second.u); v.push_back(cm.second.v); d.push_back(cm.second.d);
+        }
+    }
+    const int slot = free_kf_slots_.back();
+    double plane[4] = {kf.local_ground_plane_.direction[0], kf.local_ground_plane_.direction[1], kf.local_ground_plane_.direction[2], kf.local_ground_plane_.distance};
+    if (kba_track_push_keyframe(track_, slot, kf.pose_.data(), plane, int(lm.size()), lm.data(), cam.data(), u.data(), v.data(), d.data()) != KBA_OK) return false;
+    free_kf_slots_.pop_back();
+    kf_slot_[kf.timestamp_] = slot;
+    return true;
+}
+
+// solve() on the device-resident window: only the selection goes up.  false: not possible for this window (caller rebuilds).
+bool BundleAdjusterKeyframes::solveTracked(const std::vector<Keyframe*>& kfs, const std::vector<LandmarkId>& lm_ids, std::string& report) {
+    if (int(kfs.size()) > kTrackWinKeyframes || int(lm_ids.size()) > kTrackWinLandmarks) return false;
+    for (const auto lm_id : lm_ids)
+        if (landmarks_.at(lm_id)->is_ground_plane) return false;  // ground-plane residuals: plane blocks, rebuild path
+    for (const Keyframe* kf : kfs)
+        if (!kf_slot_.count(kf->timestamp_) && !trackPush(*kf)) { track_failed_ = true; return false; }
+    // state the host may have changed since the last solve: poses / planes of the active keyframes, new landmarks, weights
+    const int n_kf = int(kfs.size()), n_lm = int(lm_ids.size());
+    std::vector<int32_t> kf_slots, lm_slots;
+    std::vector<uint8_t> fixed;
+    std::vector<double> poses, planes;
+    for (const Keyframe* kf : kfs) {
+        kf_slots.push_back(kf_slot_.at(kf->timestamp_));
+        fixed.push_back(kf->fixation_status_ == Keyframe::FixationStatus::Pose);
+        poses.insert(poses.end(), kf->pose_.begin(), kf->pose_.end());
+        planes.insert(planes.end(), kf->local_ground_plane_.direction.begin(), kf->local_ground_plane_.direction.end());
+        planes.push_back(kf->local_ground_plane_.distance);
+    }
+    if (kba_track_set_keyframe_poses(track_, n_kf, kf_slots.data(), poses.data(), planes.data()) != KBA_OK) { track_failed_ = true; return false; }
+    {
+        std::vector<int32_t> slots; std::vector<double> pos, wgt;
+        for (const auto id : new_landmarks_) {
+            auto it = lm_slot_.find(id);
+            if (it == lm_slot_.end()) continue;  // created, but its keyframe has not reached the store yet
+            const Landmark& lm = *landmarks_.at(id);
+            slots.push_back(it->second); pos.insert(pos.end(), lm.pos.begin(), lm.pos.end()); wgt.push_back(lm.weight);
+        }
+        if (!slots.empty() && kba_track_set_landmarks(track_, int(slots.size()), slots.data(), pos.data(), wgt.data()) != KBA_OK) { track_failed_ = true; return false; }
+        for (const auto id : std::set<LandmarkId>(new_landmarks_)) if (lm_slot_.count(id)) new_landmarks_.erase(id);
+        slots.clear(); wgt.clear();
+        for (const auto id : dirty_weights_) { auto it = lm_slot_.find(id); if (it != lm_slot_.end()) { slots.push_back(it->second); wgt.push_back(landmarks_.at(id)->weight); } }
+        if (!slots.empty() && kba_track_set_landmarks(track_, int(slots.size()), slots.data(), nullptr, wgt.data()) != KBA_OK) { track_failed_ = true; return false; }
+        dirty_weights_.clear();
+    }
+    for (const auto id : lm_ids) {
+        auto it = lm_slot_.find(id);
+        if (it == lm_slot_.end()) return false;  // selected but never measured by a stored keyframe: let the rebuild path decide
+        lm_slots.push_back(it->second);
+    }
+    kba_window sel{};
+    sel.n_kf = n_kf; sel.n_lm = n_lm;
+    sel.scale_kf0 = 0; sel.scale_kf1 = 1;
+    sel.scale_weight = -1.;  // the reference's rule (cpp:703-716), evaluated on the device from the gathered window
+    sel.scale_value = n_kf > 1 ? (kfs[1]->getEigenPose() * kfs[0]->getEigenPose().inverse()).translation().norm() : 0.;
+    kba_options opt;
+    kba_default_options(&opt);
+    opt.depth_thres = outlier_rejection_options_.depth_thres;
+    opt.reprojection_thres = outlier_rejection_options_.reprojection_thres;
+    opt.depth_quantile = outlier_rejection_options_.depth_quantile;
+    opt.reprojection_quantile = outlier_rejection_options_.reprojection_quantile;
+    opt.num_rounds_option = outlier_rejection_options_.num_iterations;
+    opt.solver_time_sec = solver_time_sec;
+    std::vector<double> out_pose(7 * size_t(n_kf)), out_plane(4 * size_t(n_kf)), out_lm(3 * size_t(n_lm) + 3);
+    kba_result r{};
+    r.kf_pose = out_pose.data(); r.kf_plane = out_plane.data(); r.lm_pos = out_lm.data();
+    const int rc = kba_track_solve(track_, n_kf, kf_slots.data(), fixed.data(), n_lm, lm_slots.data(), &sel, &opt, &r);
+    if (rc == KBA_ERR_CAPACITY) return false;  // e.g. more observations than the store's window capacity: rebuild
+    if (rc != KBA_OK) throw std::runtime_error(std::string("kba_b200: ") + kba_last_error());
+    int64_t h2d = 0, d2h = 0, pushes = 0;
+    kba_track_transfer_bytes(track_, &h2d, &d2h, &pushes);
+    push_h2d_ = (long long)pushes;
+    last_solve_h2d_ = (long long)h2d + (long long)n_kf * (7 + 4) * 8;  // the selection lists + the active keyframes' poses
+    for (int k = 0; k < n_kf; ++k) std::copy_n(out_pose.begin() + 7 * k, 7, kfs[k]->pose_.begin());  // in place, as the reference (cpp:554-557)
+    for (int j = 0; j < n_lm; ++j) std::copy_n(out_lm.begin() + 3 * j, 3, landmarks_.at(lm_ids[j])->pos.begin());
+    static const char* term[] = {"CONVERGENCE", "NO_CONVERGENCE", "FAILURE"};
+    std::stringstream ss;
+    ss << "Merged summaries:\n";
+    for (int i = 0; i < r.num_solves; ++i) {
+        const kba_solve_summary& s = r.solves[i];
+        ss << "--------------------------------------------------\nIteration No." << i << "\n"
+           << "Residual blocks " << s.num_residual_blocks << ", landmarks " << s.num_landmarks << "; initial cost "
+           << s.initial_cost << ", final cost " << s.final_cost << ", iterations " << s.num_iterations << " (successful "
+           << s.num_successful_steps << "), termination " << term[s.termination < 3 ? s.termination : 2] << "\n";
+    }
+    if (r.status != KBA_OK) ss << "\nsolver did not finish (kba status " << r.status << "): the last accepted iterate was written back\n";
+    ss << "\nDuration solveTrimmed=" << r.time_sec << " sec (device-resident window)\n";
+    report = ss.str();
+    return true;
 }
 
 std::string BundleAdjusterKeyframes::adjustPoseOnly(Keyframe& kf) {  // cpp:820-888

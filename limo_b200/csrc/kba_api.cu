@@ -149,6 +149,37 @@ struct kba_batch {
     }
 };
 
+// persistent, device-resident window (kba_track_*, at the end of this file)
+struct kba_track {
+    kba_handle* h = nullptr;
+    kba_track_caps caps{};
+    int n_cam = 0;
+    kba_batch* batch = nullptr;            // one window of capacity shape; its raw arrays are filled by the gather kernels
+    TrackDev td{};
+    int* arena_i[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};      // [buffer][lm, cam]
+    float* arena_f[2][3] = {{nullptr, nullptr, nullptr}, {nullptr, nullptr, nullptr}};  // [buffer][u, v, d]
+    int arena_cur = 0, arena_used = 0;
+    std::vector<int> m_off, m_cnt;         // host mirror of the arena layout
+    std::vector<char> kf_live;
+    std::vector<void*> dev;
+    Staged<int> p_lm, p_cam, sel_kf, sel_lm, lay;  // pinned staging: one push / one selection / arena layout
+    Staged<float> p_u, p_v, p_d;
+    Staged<uint8_t> sel_fixed;
+    Staged<double> p_dbl;                  // poses / landmark values on their way to the store
+    Staged<int> p_slot;                    // ... and the slots they go to
+    int push_cap = 0, set_cap = 0;
+    int64_t h2d_solve = 0, d2h_solve = 0, h2d_push = 0;
+    template <typename T> int alloc(T** p, size_t n) {
+        void* q = nullptr;
+        if (cudaMalloc(&q, std::max<size_t>(n, 1) * sizeof(T)) != cudaSuccess) return 1;
+        dev.push_back(q); *p = (T*)q; return 0;
+    }
+    void point_arena() {
+        td.m_lm = arena_i[arena_cur][0]; td.m_cam = arena_i[arena_cur][1];
+        td.m_u = arena_f[arena_cur][0]; td.m_v = arena_f[arena_cur][1]; td.m_d = arena_f[arena_cur][2];
+    }
+};
+
 static int validate_window(const kba_window* w, std::string& why) {
     if (!w) { why = "null window"; return KBA_ERR_BAD_ARG; }
     if (w->n_kf < 0 || w->n_lm < 0 || w->n_obs < 0 || w->n_gp < 0 || w->n_cam < 1) { why = "negative size"; return KBA_ERR_BAD_ARG; }
@@ -915,7 +946,7 @@ void kba_batch_destroy(kba_batch* b) {
         unsigned long long c[16];
         cudaMemcpy(c, b->bd.prof, sizeof c, cudaMemcpyDeviceToHost);
         fprintf(stderr, "[kba prof] fused Schur kernel, cycles summed over warps: consumers wait %llu multiply %llu | producers "
-                "wait-empty %llu zero+copy-wait %llu scatter %llu\n", c[0], c[1], c[4], c[5], c[6]);
+                "wait-empty %llu set-up %llu copies %llu\n", c[0], c[1], c[4], c[5], c[6]);
     }
 #endif
     b->release();
@@ -1011,4 +1042,263 @@ int kba_eval(kba_handle* h, const kba_window* w, const kba_options* opt, kba_eva
     return KBA_OK;
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// persistent, device-resident window (include/kba_b200.h, kba_track_*)
+// ---------------------------------------------------------------------------------------------------------------------
+void kba_track_destroy(kba_track* t) {
+    if (!t) return;
+    cudaStreamSynchronize(t->h->stream);
+    if (t->batch) kba_batch_destroy(t->batch);
+    for (void* p : t->dev) cudaFree(p);
+    t->p_lm.release(); t->p_cam.release(); t->sel_kf.release(); t->sel_lm.release(); t->lay.release();
+    t->p_u.release(); t->p_v.release(); t->p_d.release(); t->sel_fixed.release(); t->p_dbl.release(); t->p_slot.release();
+    delete t;
+}
+
+int kba_track_create(kba_handle* h, const kba_track_caps* c, int32_t n_cam, const double* cam_intr, const double* cam_pose, kba_track** out) {
+    if (!h || !c || !out || !cam_intr || !cam_pose || n_cam < 1) return fail(KBA_ERR_BAD_ARG, "bad argument to kba_track_create");
+    if (c->max_keyframes < 3 || c->max_landmarks < 1 || c->max_measurements < 1 || c->win_keyframes < 3 || c->win_landmarks < 1 ||
+        c->win_observations < 1 || c->win_ground < 0 || c->win_ground > c->win_landmarks)
+        return fail(KBA_ERR_BAD_ARG, "kba_track_create: capacities");
+    if ((c->win_ground > 0 ? 10 : 6) * c->win_keyframes + 1 > 184 || c->win_keyframes > kFusedMaxKf || c->win_landmarks > pack_max_landmarks())
+        return fail(KBA_ERR_CAPACITY, "kba_track_create: the stored window must fit the fused path (<= 184 reduced rows: 30 keyframes, "
+                                      "18 with ground-plane blocks; <= 32768 landmarks) -- larger windows go through kba_solve_window");
+    CU(cudaSetDevice(h->device));
+    kba_track* t = new kba_track();
+    t->h = h; t->caps = *c; t->n_cam = n_cam;
+    // capacity batch from a dummy window of the largest shape (landmark 0 carries every observation)
+    {
+        const int K = c->win_keyframes, L = c->win_landmarks, O = c->win_observations, G = c->win_ground;
+        std::vector<double> pose(7 * (size_t)K, 0.0), plane(4 * (size_t)K, 0.0), lmp(3 * (size_t)L, 0.0), lmw(L, 1.0), gw(std::max(G, 1), 1.0);
+        std::vector<uint8_t> fixed(K, 0);
+        std::vector<int32_t> ptr(L + 1, O), okf(O, 1), gl(std::max(G, 1), 0), gk(std::max(G, 1), 1);
+        std::vector<float> u(O, 0.f), v(O, 0.f), d(O, -1.f);
+        for (int k = 0; k < K; ++k) { pose[7 * k] = 1.0; plane[4 * k + 2] = 1.0; }
+        for (int j = 0; j < L; ++j) lmp[3 * j + 2] = 10.0;
+        for (int g = 0; g < G; ++g) gl[g] = g;
+        fixed[0] = 1; ptr[0] = 0;
+        kba_window w{};
+        w.n_kf = K; w.n_cam = n_cam; w.n_lm = L; w.n_obs = O; w.n_gp = G;
+        w.kf_pose = pose.data(); w.kf_fixed = fixed.data(); w.kf_plane = plane.data(); w.cam_intr = cam_intr; w.cam_pose = cam_pose;
+        w.lm_pos = lmp.data(); w.lm_weight = lmw.data(); w.lm_obs_ptr = ptr.data(); w.obs_kf = okf.data(); w.obs_u = u.data();
+        w.obs_v = v.data(); w.obs_d = d.data(); w.gp_lm = gl.data(); w.gp_kf = gk.data(); w.gp_weight = gw.data();
+        w.plane_reg_weight = G > 0 ? 10.0 : 0.0;
+        const int rc = kba_batch_create(h, 1, &w, &t->batch);
+        if (rc != KBA_OK) { delete t; return rc; }
+        if (!t->batch->device_pack) { kba_track_destroy(t); return fail(KBA_ERR_CAPACITY, "kba_track_create: device packing is disabled (KBA_FUSED / KBA_DEVICE_PACK)"); }
+    }
+    int bad = 0;
+    TrackDev& td = t->td;
+    td.kf_cap = c->max_keyframes; td.lm_cap = c->max_landmarks; td.m_cap = c->max_measurements;
+    bad |= t->alloc(&td.kf_pose, 7 * (size_t)td.kf_cap); bad |= t->alloc(&td.kf_plane, 4 * (size_t)td.kf_cap);
+    bad |= t->alloc(&td.m_off, td.kf_cap); bad |= t->alloc(&td.m_cnt, td.kf_cap);
+    for (int b2 = 0; b2 < 2; ++b2) {
+        for (int q = 0; q < 2; ++q) bad |= t->alloc(&t->arena_i[b2][q], td.m_cap);
+        for (int q = 0; q < 3; ++q) bad |= t->alloc(&t->arena_f[b2][q], td.m_cap);
+    }
+    bad |= t->alloc(&td.lm_pos, 3 * (size_t)td.lm_cap); bad |= t->alloc(&td.lm_weight, td.lm_cap); bad |= t->alloc(&td.sel_index, td.lm_cap);
+    bad |= t->alloc(&td.cursor, c->win_landmarks); bad |= t->alloc(&td.key, c->win_observations); bad |= t->alloc(&td.n_depth, 1);
+    t->push_cap = std::min(c->max_measurements, 1 << 16);
+    bad |= t->p_lm.alloc(t->push_cap, true); bad |= t->p_cam.alloc(t->push_cap, true); bad |= t->p_u.alloc(t->push_cap, true);
+    bad |= t->p_v.alloc(t->push_cap, true); bad |= t->p_d.alloc(t->push_cap, true);
+    bad |= t->sel_kf.alloc(c->win_keyframes, true); bad |= t->sel_fixed.alloc(c->win_keyframes, true); bad |= t->sel_lm.alloc(c->win_landmarks, true);
+    bad |= t->lay.alloc(2 * (size_t)td.kf_cap, true);
+    t->set_cap = std::max(c->win_landmarks, 64);  // rows per staged scatter (landmarks or keyframes)
+    bad |= t->p_dbl.alloc(7 * (size_t)t->set_cap, true); bad |= t->p_slot.alloc(t->set_cap, true);
+    if (bad) { kba_track_destroy(t); return fail(KBA_ERR_CUDA, "kba_track_create: out of memory"); }
+    t->point_arena();
+    t->m_off.assign(td.kf_cap, 0); t->m_cnt.assign(td.kf_cap, 0); t->kf_live.assign(td.kf_cap, 0);
+    cudaStream_t s = h->stream;
+    CU(cudaMemsetAsync(td.sel_index, 0xff, sizeof(int) * (size_t)td.lm_cap, s));
+    CU(cudaMemsetAsync(td.m_cnt, 0, sizeof(int) * (size_t)td.kf_cap, s));
+    CU(cudaMemsetAsync(td.lm_weight, 0, sizeof(double) * (size_t)td.lm_cap, s));
+    CU(cudaStreamSynchronize(s));
+    *out = t;
+    return KBA_OK;
+}
+
+static int track_upload_layout(kba_track* t) {  // arena offsets / counts of every keyframe slot
+    const int K = t->td.kf_cap;
+    memcpy(t->lay.h, t->m_off.data(), K * sizeof(int));
+    memcpy(t->lay.h + K, t->m_cnt.data(), K * sizeof(int));
+    cudaStream_t s = t->h->stream;
+    CU(cudaMemcpyAsync(t->td.m_off, t->lay.h, K * sizeof(int), cudaMemcpyHostToDevice, s));
+    CU(cudaMemcpyAsync(t->td.m_cnt, t->lay.h + K, K * sizeof(int), cudaMemcpyHostToDevice, s));
+    CU(cudaStreamSynchronize(s));  // the pinned layout buffer is reused by the next call
+    t->h2d_push += 2 * K * (int64_t)sizeof(int);
+    return KBA_OK;
+}
+
+static int track_compact(kba_track* t) {  // live keyframes copied, in slot order, into the other arena
+    const int other = 1 - t->arena_cur;
+    cudaStream_t s = t->h->stream;
+    int used = 0;
+    for (int k = 0; k < t->td.kf_cap; ++k) {
+        if (!t->kf_live[k] || t->m_cnt[k] == 0) { if (!t->kf_live[k]) t->m_cnt[k] = 0; continue; }
+        const size_t n = (size_t)t->m_cnt[k], o = (size_t)t->m_off[k];
+        for (int q = 0; q < 2; ++q) CU(cudaMemcpyAsync(t->arena_i[other][q] + used, t->arena_i[t->arena_cur][q] + o, n * sizeof(int), cudaMemcpyDeviceToDevice, s));
+        for (int q = 0; q < 3; ++q) CU(cudaMemcpyAsync(t->arena_f[other][q] + used, t->arena_f[t->arena_cur][q] + o, n * sizeof(float), cudaMemcpyDeviceToDevice, s));
+        t->m_off[k] = used;
+        used += (int)n;
+    }
+    t->arena_cur = other; t->arena_used = used;
+    t->point_arena();
+    return KBA_OK;
+}
+
+int kba_track_push_keyframe(kba_track* t, int32_t slot, const double* pose7, const double* plane4, int32_t n, const int32_t* lm,
+                            const int32_t* cam, const float* u, const float* v, const float* d) {
+    if (!t || !pose7 || n < 0 || slot < 0 || slot >= t->td.kf_cap || (n > 0 && (!lm || !u || !v || !d)))
+        return fail(KBA_ERR_BAD_ARG, "bad argument to kba_track_push_keyframe");
+    if (t->kf_live[slot]) return fail(KBA_ERR_BAD_ARG, "kba_track_push_keyframe: slot in use (drop it first)");
+    for (int i = 0; i < n; ++i)
+        if (lm[i] < 0 || lm[i] >= t->td.lm_cap || (cam && (cam[i] < 0 || cam[i] >= t->n_cam))) return fail(KBA_ERR_BAD_ARG, "kba_track_push_keyframe: landmark slot / camera out of range");
+    CU(cudaSetDevice(t->h->device));
+    if (t->arena_used + n > t->td.m_cap) {
+        const int rc = track_compact(t);
+        if (rc != KBA_OK) return rc;
+        if (t->arena_used + n > t->td.m_cap) return fail(KBA_ERR_CAPACITY, "kba_track_push_keyframe: measurement arena full");
+    }
+    cudaStream_t s = t->h->stream;
+    for (int i0 = 0; i0 < n; i0 += t->push_cap) {  // staged through pinned memory in chunks
+        const int m = std::min(t->push_cap, n - i0);
+        memcpy(t->p_lm.h, lm + i0, m * sizeof(int));
+        if (cam) memcpy(t->p_cam.h, cam + i0, m * sizeof(int)); else memset(t->p_cam.h, 0, m * sizeof(int));
+        memcpy(t->p_u.h, u + i0, m * sizeof(float)); memcpy(t->p_v.h, v + i0, m * sizeof(float)); memcpy(t->p_d.h, d + i0, m * sizeof(float));
+        const size_t o = (size_t)t->arena_used + i0;
+        CU(cudaMemcpyAsync(t->td.m_lm + o, t->p_lm.h, m * sizeof(int), cudaMemcpyHostToDevice, s));
+        CU(cudaMemcpyAsync(t->td.m_cam + o, t->p_cam.h, m * sizeof(int), cudaMemcpyHostToDevice, s));
+        CU(cudaMemcpyAsync(t->td.m_u + o, t->p_u.h, m * sizeof(float), cudaMemcpyHostToDevice, s));
+        CU(cudaMemcpyAsync(t->td.m_v + o, t->p_v.h, m * sizeof(float), cudaMemcpyHostToDevice, s));
+        CU(cudaMemcpyAsync(t->td.m_d + o, t->p_d.h, m * sizeof(float), cudaMemcpyHostToDevice, s));
+        CU(cudaStreamSynchronize(s));
+    }
+    t->m_off[slot] = t->arena_used; t->m_cnt[slot] = n; t->kf_live[slot] = 1;
+    t->arena_used += n;
+    t->h2d_push += (int64_t)n * 20 + 11 * 8;
+    const int rc = track_upload_layout(t);
+    if (rc != KBA_OK) return rc;
+    return kba_track_set_keyframe_pose(t, slot, pose7, plane4);
+}
+
+int kba_track_drop_keyframe(kba_track* t, int32_t slot) {
+    if (!t || slot < 0 || slot >= t->td.kf_cap) return fail(KBA_ERR_BAD_ARG, "bad argument to kba_track_drop_keyframe");
+    t->kf_live[slot] = 0;  // the arena space is reclaimed by the next compaction
+    return KBA_OK;
+}
+
+// rows of `width` doubles into their store slots: staged through pinned memory, one copy + one scatter kernel per chunk
+static int track_scatter(kba_track* t, double* dst, int cap_slots, int n, const int32_t* slot, const double* src, int width) {
+    cudaStream_t s = t->h->stream;
+    for (int i0 = 0; i0 < n; i0 += t->set_cap) {
+        const int m = std::min(t->set_cap, n - i0);
+        for (int i = 0; i < m; ++i)
+            if (slot[i0 + i] < 0 || slot[i0 + i] >= cap_slots) return fail(KBA_ERR_BAD_ARG, "kba_track: slot out of range");
+        memcpy(t->p_slot.h, slot + i0, m * sizeof(int));
+        memcpy(t->p_dbl.h, src + (size_t)width * i0, (size_t)width * m * sizeof(double));
+        CU(cudaMemcpyAsync(t->p_slot.d, t->p_slot.h, m * sizeof(int), cudaMemcpyHostToDevice, s));
+        CU(cudaMemcpyAsync(t->p_dbl.d, t->p_dbl.h, (size_t)width * m * sizeof(double), cudaMemcpyHostToDevice, s));
+        launch_scatter_rows(dst, t->p_slot.d, t->p_dbl.d, m, width, s);
+        CU(cudaStreamSynchronize(s));  // the staging buffers are reused
+    }
+    return KBA_OK;
+}
+
+int kba_track_set_keyframe_poses(kba_track* t, int32_t n, const int32_t* slot, const double* pose7s, const double* plane4s) {
+    if (!t || n < 0 || (n > 0 && (!slot || !pose7s))) return fail(KBA_ERR_BAD_ARG, "bad argument to kba_track_set_keyframe_poses");
+    CU(cudaSetDevice(t->h->device));
+    int rc = track_scatter(t, t->td.kf_pose, t->td.kf_cap, n, slot, pose7s, 7);
+    if (rc == KBA_OK && plane4s) rc = track_scatter(t, t->td.kf_plane, t->td.kf_cap, n, slot, plane4s, 4);
+    return rc;
+}
+
+int kba_track_set_keyframe_pose(kba_track* t, int32_t slot, const double* pose7, const double* plane4) {
+    static const double kNoPlane[4] = {0., 0., 1., 0.};
+    return kba_track_set_keyframe_poses(t, 1, &slot, pose7, plane4 ? plane4 : kNoPlane);
+}
+
+int kba_track_set_landmarks(kba_track* t, int32_t n, const int32_t* slot, const double* pos3, const double* weight) {
+    if (!t || n < 0 || (n > 0 && !slot)) return fail(KBA_ERR_BAD_ARG, "bad argument to kba_track_set_landmarks");
+    CU(cudaSetDevice(t->h->device));
+    int rc = KBA_OK;
+    if (pos3) rc = track_scatter(t, t->td.lm_pos, t->td.lm_cap, n, slot, pos3, 3);
+    if (rc == KBA_OK && weight) rc = track_scatter(t, t->td.lm_weight, t->td.lm_cap, n, slot, weight, 1);
+    t->h2d_push += (int64_t)n * ((pos3 ? 24 : 0) + (weight ? 8 : 0) + 4);
+    return rc;
+}
+
+int kba_track_solve(kba_track* t, int32_t n_kf, const int32_t* kf_slot, const uint8_t* kf_fixed, int32_t n_lm, const int32_t* lm_slot,
+                    const kba_window* sel, const kba_options* opt, kba_result* res) {
+    if (!t || !kf_slot || !kf_fixed || !lm_slot || !sel || !opt || !res) return fail(KBA_ERR_BAD_ARG, "null argument to kba_track_solve");
+    const kba_track_caps& c = t->caps;
+    if (n_kf < 3) return fail(KBA_ERR_NOT_ENOUGH_KF, "kba_track_solve: fewer than 3 keyframes");
+    if (n_kf > c.win_keyframes || n_lm > c.win_landmarks || n_lm < 0 || sel->n_gp < 0 || sel->n_gp > c.win_ground)
+        return fail(KBA_ERR_CAPACITY, "kba_track_solve: window larger than the capacities given to kba_track_create");
+    long long n_meas = 0;
+    int max_meas = 0, n_free = 0;
+    for (int k = 0; k < n_kf; ++k) {
+        if (kf_slot[k] < 0 || kf_slot[k] >= t->td.kf_cap || !t->kf_live[kf_slot[k]]) return fail(KBA_ERR_BAD_ARG, "kba_track_solve: keyframe slot not pushed");
+        n_meas += t->m_cnt[kf_slot[k]]; max_meas = std::max(max_meas, t->m_cnt[kf_slot[k]]);
+        n_free += kf_fixed[k] ? 0 : 1;
+    }
+    if (n_meas > c.win_observations) return fail(KBA_ERR_CAPACITY, "kba_track_solve: more observations than win_observations");
+    for (int j = 0; j < n_lm; ++j)
+        if (lm_slot[j] < 0 || lm_slot[j] >= t->td.lm_cap) return fail(KBA_ERR_BAD_ARG, "kba_track_solve: landmark slot out of range");
+    for (int g = 0; g < sel->n_gp; ++g)
+        if (!sel->gp_lm || !sel->gp_kf || !sel->gp_weight || sel->gp_lm[g] < 0 || sel->gp_lm[g] >= n_lm || sel->gp_kf[g] < 0 || sel->gp_kf[g] >= n_kf)
+            return fail(KBA_ERR_BAD_ARG, "kba_track_solve: ground-plane index out of range");
+    const bool planes = sel->n_gp > 0 || sel->plane_reg_weight > 0;
+    if (planes && c.win_ground == 0) return fail(KBA_ERR_CAPACITY, "kba_track_solve: the track was created without ground-plane capacity");
+    kba_batch* b = t->batch;
+    CU(cudaSetDevice(t->h->device));
+    cudaStream_t s = t->h->stream;
+    // ---- the window descriptor of this solve (n_obs is written by the gather kernels)
+    WinDesc& d = b->desc_h[0];
+    d.n_kf = n_kf; d.n_lm = n_lm; d.n_obs = 0; d.n_gp = sel->n_gp;
+    d.n_chunks = (n_lm + 31) / 32; d.n_groups = (n_lm + 7) / 8;
+    d.scale_kf0 = sel->scale_kf0; d.scale_kf1 = sel->scale_kf1; d.scale_weight = sel->scale_weight; d.scale_value = sel->scale_value;
+    d.plane_reg_weight = sel->plane_reg_weight; d.plane_dist_fixed = sel->plane_dist_fixed; d.landmarks_fixed = 0;
+    d.speed_kf = 0; d.speed_weight = 0; d.speed_dt = 1;
+    d.max_rank = t->n_cam > 1 ? t->n_cam - 1 : 0;  // a rig may see a landmark from several cameras of one keyframe
+    if (d.scale_weight != 0 && (d.scale_kf0 < 0 || d.scale_kf0 >= n_kf || d.scale_kf1 < 0 || d.scale_kf1 >= n_kf))
+        return fail(KBA_ERR_BAD_ARG, "kba_track_solve: scale regulariser keyframe out of range");
+    b->desc.h[0] = d;
+    b->lc.max_rank = d.max_rank;
+    b->lc.fused_slots = ((planes ? 10 : 6) * n_free + 1 <= 176) ? 6 : 7;
+    memcpy(t->sel_kf.h, kf_slot, n_kf * sizeof(int)); memcpy(t->sel_fixed.h, kf_fixed, n_kf);
+    memcpy(t->sel_lm.h, lm_slot, n_lm * sizeof(int));
+    if (sel->n_gp) {
+        memcpy(b->r_gp_lm.h, sel->gp_lm, sel->n_gp * sizeof(int)); memcpy(b->gp_kf.h, sel->gp_kf, sel->n_gp * sizeof(int));
+        memcpy(b->gp_weight.h, sel->gp_weight, sel->n_gp * sizeof(double));
+    }
+    CU(b->desc.upload(s));
+    CU(cudaMemcpyAsync(t->sel_kf.d, t->sel_kf.h, n_kf * sizeof(int), cudaMemcpyHostToDevice, s));
+    CU(cudaMemcpyAsync(t->sel_fixed.d, t->sel_fixed.h, n_kf, cudaMemcpyHostToDevice, s));
+    CU(cudaMemcpyAsync(t->sel_lm.d, t->sel_lm.h, n_lm * sizeof(int), cudaMemcpyHostToDevice, s));
+    if (sel->n_gp) { CU(b->r_gp_lm.upload(s)); CU(b->gp_kf.upload(s)); CU(b->gp_weight.upload(s)); }
+    t->h2d_solve = (int64_t)sizeof(WinDesc) + n_kf * 5 + n_lm * 4 + sel->n_gp * 16;
+    // ---- gather the CSR from the store, pack, solve, write back
+    TrackSel ts;
+    ts.kf_slot = t->sel_kf.d; ts.kf_fixed = t->sel_fixed.d; ts.lm_slot = t->sel_lm.d; ts.n_kf = n_kf; ts.n_lm = n_lm; ts.max_meas = max_meas;
+    ts.auto_scale = sel->scale_weight < 0 ? 1 : 0;
+    launch_track_gather(b->bd, b->raw, t->td, ts, s);
+    launch_pack(b->bd, b->raw, s);
+    CU(cudaGetLastError());
+    int rc = kba_batch_solve(b, opt);
+    if (rc != KBA_OK) return rc;
+    launch_track_writeback(b->bd, t->td, ts, s);
+    rc = kba_batch_download(b, res);
+    t->d2h_solve = (int64_t)b->d2h_bytes;
+    return rc;
+}
+
+int kba_track_transfer_bytes(kba_track* t, int64_t* h2d, int64_t* d2h, int64_t* push) {
+    if (!t) return fail(KBA_ERR_BAD_ARG, "null track");
+    if (h2d) *h2d = t->h2d_solve;
+    if (d2h) *d2h = t->d2h_solve;
+    if (push) *push = t->h2d_push;
+    return KBA_OK;
+}
+
 }  // extern "C"
+

@@ -64,6 +64,7 @@ struct TrackDev {
     int* sel_index = nullptr;    // [lm_cap] position of the landmark in the current selection, -1 otherwise (all -1 between solves)
     int* cursor = nullptr;       // [lm window capacity] scratch
     long long* key = nullptr;    // [obs window capacity] scratch: (keyframe index, arena index) of each gathered observation
+    int* n_depth = nullptr;      // [1] gathered observations with a lidar depth (d > 0): the depth residual blocks of the window
     int kf_cap = 0, lm_cap = 0, m_cap = 0;
 };
 // per-solve selection, device copies of the caller's small lists
@@ -72,10 +73,12 @@ struct TrackSel {
     const unsigned char* kf_fixed = nullptr;
     const int* lm_slot = nullptr;    // [n_lm] ascending landmark id
     int n_kf = 0, n_lm = 0, max_meas = 0;
+    int auto_scale = 0;              // 1: scale-regulariser weight by the reference rule (cpp:703-716) from the gathered window
 };
 // builds the window's raw CSR (PackRaw inputs of batch `bd`, window 0) from the track store; returns nothing: desc[0].n_obs
 // is written on the device
 void launch_track_gather(const BatchDev& bd, const PackRaw& raw_out, const TrackDev& td, const TrackSel& sel, cudaStream_t s);
+void launch_scatter_rows(double* dst, const int* slot, const double* src, int n, int width, cudaStream_t s);
 // results of window 0 back into the track store
 void launch_track_writeback(const BatchDev& bd, const TrackDev& td, const TrackSel& sel, cudaStream_t s);
 

@@ -228,6 +228,7 @@ __global__ void __launch_bounds__(256) k_track_begin(BatchDev bd, PackRaw raw, T
         r_cnt[i] = 0;
         td.cursor[i] = 0;
     }
+    if (i == 0) *td.n_depth = 0;
 }
 
 // pass 0: observations per selected landmark; pass 1: scatter behind the CSR pointers (order fixed afterwards by k_track_sort)
@@ -240,7 +241,11 @@ __global__ void __launch_bounds__(256) k_track_scatter(PackRaw raw, TrackDev td,
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         const int j = td.sel_index[td.m_lm[m0 + i]];
         if (j < 0) continue;
-        if (kPass == 0) { atomicAdd(&r_cnt[j], 1); continue; }
+        if (kPass == 0) {
+            atomicAdd(&r_cnt[j], 1);
+            if (td.m_d[m0 + i] > 0.0f) atomicAdd(td.n_depth, 1);
+            continue;
+        }
         const int pos = raw.lm_ptr[j] + atomicAdd(&td.cursor[j], 1);
         r_kf[pos] = k; r_cam[pos] = td.m_cam[m0 + i];
         r_u[pos] = td.m_u[m0 + i]; r_v[pos] = td.m_v[m0 + i]; r_d[pos] = td.m_d[m0 + i];
@@ -248,7 +253,7 @@ __global__ void __launch_bounds__(256) k_track_scatter(PackRaw raw, TrackDev td,
     }
 }
 
-__global__ void __launch_bounds__(1024) k_track_scan(BatchDev bd, TrackSel sel, const int* r_cnt, int* r_lm_ptr) {
+__global__ void __launch_bounds__(1024) k_track_scan(BatchDev bd, TrackDev td, TrackSel sel, const int* r_cnt, int* r_lm_ptr) {
     __shared__ int s_scan[1024];
     const int tid = threadIdx.x, nth = blockDim.x, n = sel.n_lm;
     int carry = 0;
@@ -267,7 +272,18 @@ __global__ void __launch_bounds__(1024) k_track_scan(BatchDev bd, TrackSel sel, 
         __syncthreads();
         carry += tot;
     }
-    if (tid == 0) { r_lm_ptr[0] = 0; bd.desc[0].n_obs = carry; }
+    if (tid == 0) {
+        r_lm_ptr[0] = 0;
+        WinDesc& d = bd.desc[0];
+        d.n_obs = carry;
+        if (sel.auto_scale) {  // addScaleRegularization's weight (bundle_adjuster_keyframes.cpp:703-716) and the plane-distance rule (:722-728)
+            const int n_depth = *td.n_depth, n_gp = d.n_gp;
+            double wgt = 1000.0;
+            if (n_depth > 10 || n_gp > 10) wgt = (n_gp < 30) ? 1000.0 / ((double)n_depth + (double)n_gp) : 0.0;
+            d.scale_weight = wgt;
+            d.plane_dist_fixed = n_depth < 10;
+        }
+    }
 }
 
 // a landmark's observations in (keyframe, arena) order = (keyframe, camera id) order of the caller: insertion sort, <= a few dozen
@@ -305,6 +321,17 @@ __global__ void __launch_bounds__(256) k_track_writeback(BatchDev bd, TrackDev t
     }
 }
 
+// dst[slot[i]][0..width) = src[i][0..width): host-staged rows into their store slots (poses, planes, landmark values)
+__global__ void __launch_bounds__(256) k_scatter_rows(double* dst, const int* slot, const double* src, int n, int width) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n * width) return;
+    const int r = i / width, c = i - r * width;
+    dst[(size_t)slot[r] * width + c] = src[i];
+}
+void launch_scatter_rows(double* dst, const int* slot, const double* src, int n, int width, cudaStream_t s) {
+    if (n > 0) k_scatter_rows<<<(n * width + 255) / 256, 256, 0, s>>>(dst, slot, src, n, width);
+}
+
 void launch_track_gather(const BatchDev& bd, const PackRaw& raw, const TrackDev& td, const TrackSel& sel, cudaStream_t s) {
     // the PackRaw pointers are const views of buffers this batch owns: the gather is what fills them
     int* r_lm_ptr = const_cast<int*>(raw.lm_ptr);
@@ -316,7 +343,7 @@ void launch_track_gather(const BatchDev& bd, const PackRaw& raw, const TrackDev&
     k_track_begin<<<(n + 255) / 256, 256, 0, s>>>(bd, raw, td, sel, r_pos, r_w, r_cnt);
     const dim3 gm((sel.max_meas + 255) / 256 > 0 ? (sel.max_meas + 255) / 256 : 1, sel.n_kf);
     k_track_scatter<0><<<gm, 256, 0, s>>>(raw, td, sel, r_cnt, r_kf, r_cam, r_u, r_v, r_d);
-    k_track_scan<<<1, 1024, 0, s>>>(bd, sel, r_cnt, r_lm_ptr);
+    k_track_scan<<<1, 1024, 0, s>>>(bd, td, sel, r_cnt, r_lm_ptr);
     k_track_scatter<1><<<gm, 256, 0, s>>>(raw, td, sel, r_cnt, r_kf, r_cam, r_u, r_v, r_d);
     k_track_sort<<<(sel.n_lm + 255) / 256, 256, 0, s>>>(td, sel, r_lm_ptr, r_kf, r_cam, r_u, r_v, r_d);
 }

@@ -7,8 +7,10 @@
 //                          zeros included) is assembled in shared memory by ASYNCHRONOUS copies.  V is stored
 //                          landmark-column-major, and a track without gaps sits on consecutive rows, so a landmark's panel
 //                          column is ONE bulk copy (cp.async.bulk, 48 B per observation, complete_tx on the stage's "full"
-//                          mbarrier): 24 bulk copies + the z rows per group, issued by 32 lanes, nobody waits for data and
-//                          the ring runs five groups ahead.  Landmarks whose rows are not one run fall back to nine 16-byte
+//                          mbarrier): 24 bulk copies + the z rows per group, nobody waits for data and the ring runs five
+//                          groups ahead.  Measured alternatives (profiles/r02_schur_fused.md): zero segments as bulk copies too
+//                          (no stores by the SM at all: slower, a warp issues its bulk copies one lane after the other, ~65
+//                          cycles each), 16-byte cp.async per lane instead of bulk copies (equal or slower).  Landmarks whose rows are not one run fall back to nine 16-byte
 //                          cp.async per observation; windows with ground-plane rows or several cameras per keyframe (rows
 //                          that ADD onto others) take a synchronous variant of the same loop.
 //   consumers (12 warps) : Sred += V V^T on the FP64 tensor cores (mma.sync m8n8k4).  The whole lower triangle lives in

@@ -301,6 +301,57 @@ static void test_camera_object_per_keyframe() {
     for (int k = 0; k < n_kf && ok; ++k) CHECK(b.keyframes_.at(k)->getEigenPose().isApprox(gt[k], 1e-3));
 }
 
+// push a keyframe, solve, push the next ... with the device-resident window (default) and with the rebuild-per-call path: the
+// same poses and landmarks bit for bit after every solve, and a fraction of the upload per solve
+static void test_persistent_window_equals_rebuild() {
+    const int n_kf = 14;
+    std::vector<Eigen::Vector3d> lms;
+    for (int i = 0; i < 160; ++i) lms.push_back(Eigen::Vector3d(-3. + 0.041 * ((i * 37) % 151), -1.5 + 0.023 * ((i * 53) % 131), 5. + 0.07 * ((i * 29) % 113)));
+    std::vector<Eigen::Isometry3d> gt(n_kf);
+    gt[0] = Eigen::Isometry3d::Identity();
+    for (int k = 1; k < n_kf; ++k) { gt[k] = gt[k - 1]; gt[k].translate(Eigen::Vector3d(0.04 * (k % 3), 0.015, -0.3)); gt[k].rotate(Eigen::AngleAxisd(0.008, Eigen::Vector3d(0., 1., 0.))); }
+    const Camera proto(600., Eigen::Vector2d(300., 200.), Eigen::Isometry3d::Identity());
+    Tracklets ts;
+    for (int k = 0; k < n_kf; ++k) ts.stamps.push_back(k);
+    ts.tracks.resize(lms.size());
+    for (size_t i = 0; i < lms.size(); ++i) {
+        ts.tracks[i].id = i;
+        for (int k = 0; k < n_kf; ++k) {
+            const Eigen::Vector3d lm_cam = gt[k] * lms[i];
+            Eigen::Vector3d proj = proto.getIntrinsicMatrix() * lm_cam;
+            proj /= proj[2];
+            const float du = 0.3f * float((int(i) * 7 + k * 3) % 5 - 2), dv = 0.3f * float((int(i) * 3 + k * 5) % 5 - 2);  // deterministic pixel noise
+            ts.tracks[i].feature_points.push_back(FeaturePoint(float(proj[0]) + du, float(proj[1]) + dv, (i % 3 == 0) ? float(lm_cam[2]) : -1.f));
+        }
+    }
+    BundleAdjusterKeyframes a, b;
+    b.set_persistent_window(false);
+    a.set_solver_time(20.); b.set_solver_time(20.);
+    long long up_a = 0, up_b = 0;
+    int solves = 0;
+    for (int k = 0; k < n_kf; ++k) {
+        Eigen::Isometry3d start = gt[k];
+        if (k >= 2) start.translate(Eigen::Vector3d(0.02, -0.015, 0.03));
+        const auto fix = k == 0 ? Keyframe::FixationStatus::Pose : (k == 1 ? Keyframe::FixationStatus::Scale : Keyframe::FixationStatus::None);
+        for (BundleAdjusterKeyframes* adj : {&a, &b})
+            adj->push(Keyframe(k, ts, std::make_shared<Camera>(600., Eigen::Vector2d(300., 200.), Eigen::Isometry3d::Identity()), start, fix));
+        if (k < 3) continue;
+        for (BundleAdjusterKeyframes* adj : {&a, &b}) { adj->deactivateKeyframes(3, 4, 8); adj->solve(); }
+        ++solves;
+        up_a += a.lastSolveUploadBytes(); up_b += b.lastSolveUploadBytes();
+        bool same = true;
+        for (const auto& id : a.active_keyframe_ids_) same = same && a.keyframes_.at(id)->pose_ == b.keyframes_.at(id)->pose_;
+        for (const auto& id : a.selected_landmark_ids_) same = same && a.landmarks_.at(id)->pos == b.landmarks_.at(id)->pos;
+        CHECK(same);
+        CHECK(a.active_keyframe_ids_ == b.active_keyframe_ids_ && a.selected_landmark_ids_ == b.selected_landmark_ids_);
+    }
+    CHECK(solves == n_kf - 3);
+    CHECK(up_a > 0 && up_a * 10 < up_b);  // < 10 % of the rebuild path's bytes per solve
+    CHECK(a.pushUploadBytes() > 0);
+    std::printf("persistent window: %lld B per solve on average (rebuild path %lld B), %lld B for all pushes\n", up_a / solves, up_b / solves, a.pushUploadBytes());
+    for (int k = 0; k < n_kf; ++k) CHECK(a.keyframes_.at(k)->getEigenPose().isApprox(gt[k], 2e-2));
+}
+
 int main(int argc, char** argv) {
     const bool gpu = argc > 1 && std::strcmp(argv[1], "gpu") == 0;
     test_triangulator();
@@ -309,7 +360,7 @@ int main(int argc, char** argv) {
     test_landmark_selector();
     test_voxel_selector();
     test_add_depth_selector();
-    if (gpu) { test_solve(false); test_solve(true); test_motion_only(); test_camera_object_per_keyframe(); }
+    if (gpu) { test_solve(false); test_solve(true); test_motion_only(); test_camera_object_per_keyframe(); test_persistent_window_equals_rebuild(); }
     std::printf("%s: %d failed checks\n", gpu ? "gpu" : "cpu", g_fail);
     return g_fail ? 1 : 0;
 }
