@@ -36,12 +36,21 @@ METRIC = "BA windows/s (30 KF, 3k LM, 40k obs)"
 # keyframe index (4) + landmark data (~3); writes residual 3x8 + J_pose 3x6x8 [+ J_landmark 3x3x8].  Since round 2 the
 # small-window path does not materialise J_landmark (its consumers re-form it as J_pose[:, 3:6] R): 259 - 72 = 187 B.
 FUSED = os.environ.get("KBA_FUSED", "1") != "0"
-B_OBS_ALGORITHMIC = 187.0 if FUSED else 259.0
-# dram__bytes_read.sum + dram__bytes_write.sum of one k_eval_obs<true> launch / its observations, from the ncu --set full
+# One-kernel linearisation (kba_linearize.cuh, default): the Jacobian is never materialised; the kernel reads the measurements
+# and writes V_i = (J_p^T J_l) L^-T (144 B per observation) plus the landmark blocks.  SURVEY.md 8(d) gives the algorithmic
+# bytes of such a fused kernel: reads 16 + 2.7, writes E_ij 144 per observation + (C_j 48 + g_j 24) per landmark = 5.4 -> 168 B.
+LIN1 = FUSED and os.environ.get("KBA_LINEARIZE", "1") != "0"
+B_OBS_ALGORITHMIC = 168.0 if LIN1 else (187.0 if FUSED else 259.0)
+# dram__bytes_read.sum + dram__bytes_write.sum of one launch of that kernel / its observations, from the ncu --set full
 # capture summarised in profiles/ (re-measured whenever the kernel changes)
-B_OBS_DRAM_MEASURED = 201.0 if FUSED else 277.0
-TRAFFIC_SOURCE = ("ncu --set full, profiles/r02_ncu_summary.md" if FUSED else
+B_OBS_DRAM_MEASURED = 176.0 if LIN1 else (199.0 if FUSED else 277.0)
+TRAFFIC_SOURCE = ("ncu --set full, profiles/r02_ncu_summary.md (k_linearize)" if LIN1 else
+                  "ncu --set full, profiles/r02_ncu_summary.md (k_eval_obs<true>, J_landmark not materialised)" if FUSED else
                   "ncu --set full, profiles/r01_v11_ncu_summary.md: (0.200 GB read + 1.293 GB written) / 5.39 M observations")
+KERNEL_NAME = ("k_linearize (residual/Jacobian + landmark blocks + V rows, one kernel)" if LIN1 else "k_eval_obs<true> (residual/Jacobian)")
+ALG_NOTE = ("SURVEY 8(d), fused Hessian kernel: 18.7 B read + 144 B (E_ij) written per observation + 72 B per landmark; the Jacobian "
+            "stays in registers.  The kernel is FP64-issue bound, not HBM bound: see profiles/r02_ncu_summary.md" if LIN1 else
+            "19 B read + 168 B written (residual 24 + J_pose 144); J_landmark (72 B) is not materialised" if FUSED else "SURVEY 8(d): 259 B/obs")
 CONFIG2 = "config 2: 30 KF / 3000 LM / 40000 obs, mono + lidar depth, FP64"
 
 
@@ -543,8 +552,8 @@ def main():
                        "parallelism": "independent windows per GPU (no data-path collective)" if world > 1 else "1 GPU",
                        "lm_iterations_per_window_mean": float(np.mean(iters)),
                        "lm_iterations_per_window_max": int(np.max(iters)),
-                       "l2_policy": "inputs larger than L2 (%.1f GB of residual / Jacobian blocks per pass)"
-                                    % (args.batch * n_obs_win * (B_OBS_ALGORITHMIC - 19) / 1e9),
+                       "l2_policy": "inputs larger than L2 (%.1f GB of V blocks written and re-read per pass)"
+                                    % (args.batch * n_obs_win * 144.0 / 1e9),
                        "all_windows_finished": bool(done), "all_final_solves_converged": bool(converged)},
             "e2e": {"value": total_windows / (ms_e2e * 1e-3), "unit": "windows/s",
                     "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
@@ -552,15 +561,13 @@ def main():
                     "host_pack_upload_ms_per_step": 1e3 * t_up / args.steps,
                     "download_ms_per_step": 1e3 * t_dn / args.steps},
             "gpu_launches": int(cnt.launches_total),
-            "roofline": {"kernel": "k_eval_obs<true> (residual/Jacobian)", "bound": "hbm", "achieved": jac_gbs,
+            "roofline": {"kernel": KERNEL_NAME, "bound": "hbm", "achieved": jac_gbs,
                          "peak": peak, "unit": "GB/s", "frac": (jac_gbs / peak) if jac_gbs else None,
                          "peak_source": peak_src,
                          "traffic": B_OBS_DRAM_MEASURED * cnt.jacobian_obs / max(cnt.launches_jacobian, 1),
                          "traffic_unit": "bytes per launch", "traffic_source": TRAFFIC_SOURCE,
                          "algorithmic_bytes_per_obs": B_OBS_ALGORITHMIC,
-                         "algorithmic_note": "19 B read + 168 B written (residual 24 + J_pose 144); J_landmark (72 B) is not materialised "
-                                             "since round 2 -- with SURVEY 8(d)'s 259 B/obs the same launches would read %.0f GB/s"
-                                             % ((jac_gbs or 0) * 259.0 / B_OBS_ALGORITHMIC) if FUSED else "SURVEY 8(d): 259 B/obs",
+                         "algorithmic_note": ALG_NOTE,
                          "launch_ms_mean": cnt.ms_jacobian / max(cnt.launches_jacobian, 1),
                          "launches": int(cnt.launches_jacobian), "share_of_timed_region": cnt.ms_jacobian / ms,
                          "obs_per_launch_mean": cnt.jacobian_obs / max(cnt.launches_jacobian, 1)},

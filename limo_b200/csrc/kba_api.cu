@@ -552,7 +552,8 @@ int kba_batch_create(kba_handle* h, int32_t n_windows, const kba_window* w, kba_
         else if (std::getenv("KBA_P_SPLIT")) bd.p_split = std::max(1, std::min(p, max_chunks));
         b->lc.fused_slots = (max_rows_free <= 176) ? 6 : 7;
     }
-    bd.cost_parts = (bd.max_obs + 255) / 256;
+    bd.cost_parts = (bd.max_obs + 223) / 224;  // >= CTAs of k_linearize (224 observations each) and 256-observation tiles of k_eval_obs
+    { const char* le = std::getenv("KBA_LINEARIZE"); b->lc.lin_fused = !(le && std::atoi(le) == 0); }
     {  // tuning knobs of the residual/Jacobian kernel (defaults measured on B200)
         auto knob = [](const char* name, int dflt) { const char* e = std::getenv(name); return e ? std::atoi(e) : dflt; };
         bd.eval_tiles_jac = std::max(1, knob("KBA_EVAL_TILES_JAC", 8));
@@ -804,6 +805,10 @@ int kba_batch_solve(kba_batch* b, const kba_options* opt) {
     h->ev_used = 0;
     lc.ev_pool = h->ev_pool.data(); lc.ev_cap = (int)h->ev_pool.size(); lc.ev_used = &h->ev_used;
     CU(cudaMemsetAsync(b->bd.jac_obs, 0, sizeof(unsigned long long), s));
+    // the evaluation kernels write the cost slots of the CTAs they launch and rely on the others being zero; the slot layout
+    // differs between k_linearize and k_eval_obs (a batch may be solved with either: kba_options.precision)
+    CU(cudaMemsetAsync(b->bd.cost_part_x, 0, sizeof(double) * (size_t)b->bd.n_win * b->bd.cost_parts, s));
+    CU(cudaMemsetAsync(b->bd.cost_part_c, 0, sizeof(double) * (size_t)b->bd.n_win * b->bd.cost_parts, s));
     CU(cudaEventRecord(b->ev_a, s));
     launch_reset(b->bd, lc, s);
     // upper bound on passes: every solve needs (iterations + 2) passes, plus one pass per trimming step
@@ -816,6 +821,10 @@ int kba_batch_solve(kba_batch* b, const kba_options* opt) {
         if (launch_pass(b->bd, sp, lc, &h->counters, s)) {  // message set by the exchange
             cudaEventRecord(b->ev_b, s);
             return KBA_ERR_NCCL;
+        }
+        if (pass < 2) {  // a launch that fails fails in the first pass: do not let the windows spin to the safety cap
+            const cudaError_t le = cudaGetLastError();
+            if (le != cudaSuccess) { cudaEventRecord(b->ev_b, s); cudaStreamSynchronize(s); return fail(KBA_ERR_CUDA, std::string("kernel launch failed in kba_batch_solve: ") + cudaGetErrorString(le)); }
         }
         if ((pass + 1) % check_every == 0 || pass + 1 == max_passes) {
             launch_count_active(b->bd, s);

@@ -11,9 +11,11 @@
 #include "kba_kernels.h"
 #include "kba_regularisers.cuh"
 #include "kba_prep.cuh"
+#include "kba_linearize.cuh"
 
 #include <cfloat>
 #include <cstdio>
+#include <cstdlib>
 #include <cmath>
 #include <type_traits>
 
@@ -342,18 +344,22 @@ static void launch_eval_obs(const BatchDev& bd, const SolveParams& sp, cudaStrea
     if (bd.precision == 1) {
         if (bd.fused) k_eval_obs<true, 2, float, false><<<g, 256, 0, s>>>(bd, sp, tiles);
         else k_eval_obs<true, 2, float, true><<<g, 256, 0, s>>>(bd, sp, tiles);
+        LCHK("k_eval_obs");
     } else if (!bd.fused) {
         if (mb == 2) k_eval_obs<true, 2, double, true><<<g, 256, 0, s>>>(bd, sp, tiles);
         else if (mb == 3) k_eval_obs<true, 3, double, true><<<g, 256, 0, s>>>(bd, sp, tiles);
         else k_eval_obs<true, 4, double, true><<<g, 256, 0, s>>>(bd, sp, tiles);
+        LCHK("k_eval_obs");
     } else if (bd.eval_cs) {
         if (mb == 2) k_eval_obs<true, 2, double, false, true><<<g, 256, 0, s>>>(bd, sp, tiles);
         else if (mb == 3) k_eval_obs<true, 3, double, false, true><<<g, 256, 0, s>>>(bd, sp, tiles);
         else k_eval_obs<true, 4, double, false, true><<<g, 256, 0, s>>>(bd, sp, tiles);
+        LCHK("k_eval_obs");
     } else {
         if (mb == 2) k_eval_obs<true, 2, double, false><<<g, 256, 0, s>>>(bd, sp, tiles);
         else if (mb == 3) k_eval_obs<true, 3, double, false><<<g, 256, 0, s>>>(bd, sp, tiles);
         else k_eval_obs<true, 4, double, false><<<g, 256, 0, s>>>(bd, sp, tiles);
+        LCHK("k_eval_obs");
     }
 }
 
@@ -2117,6 +2123,15 @@ __global__ void k_reset_state(BatchDev bd, int rounds_total_override, int min_la
 // =====================================================================================================================
 // launch wrappers
 // =====================================================================================================================
+int launch_check_enabled() {
+    static const int on = [] { const char* e = getenv("KBA_LAUNCH_CHECK"); return (e && e[0] == '1') ? 1 : 0; }();
+    return on;
+}
+static cudaError_t g_launch_check_first = cudaSuccess;
+void launch_check_report(const char* kernel, cudaError_t e) {
+    if (g_launch_check_first == cudaSuccess) fprintf(stderr, "[kba] launch of %s failed: %s\n", kernel, cudaGetErrorString(e));
+    g_launch_check_first = e;
+}
 static inline size_t schur_smem() { return (size_t)2 * kKC * kGS * sizeof(double); }
 static inline size_t schur_tma_smem() { return (size_t)2 * kStageDoubles * sizeof(double); }
 static inline size_t solve_smem(int ld) { return ((size_t)5 * ld + kNB + kNB * (kNB + 1) + (size_t)(ld + 8) * kPanelStride) * sizeof(double); }
@@ -2126,65 +2141,101 @@ static inline size_t solve_tiled_smem(int ld) {
     return ((size_t)5 * ld + kNB + kNB * (kNB + 1) + (size_t)nt * (nt + 1) / 2 * 64) * sizeof(double);
 }
 
+// Opt-in dynamic shared memory of the solve kernels.  The attribute is per function (per device), not per batch: a later,
+// smaller batch must never lower what an earlier, larger batch still launches with (a persistent window next to one-shot
+// solves did exactly that: "invalid argument" at the next launch) -- so the sizes only ever grow, per device.
 cudaError_t configure_kernels(int nr_cap_max) {
-    cudaError_t e = cudaFuncSetAttribute(k_schur_syrk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)schur_smem());
+    static int hi_tiled[64] = {0}, hi_rows[64] = {0};
+    static bool fixed_done[64] = {false};
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
     if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(k_schur_syrk_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)schur_tma_smem());
-    if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(k_schur_fused<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)schur_fused_smem());
-    if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(k_schur_fused<7>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)schur_fused_smem());
-    if (e != cudaSuccess) return e;
-    if (nr_cap_max <= 192) {
+    dev &= 63;
+    if (!fixed_done[dev]) {
+        e = cudaFuncSetAttribute(k_schur_syrk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)schur_smem());
+        if (e != cudaSuccess) return e;
+        e = cudaFuncSetAttribute(k_schur_syrk_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)schur_tma_smem());
+        if (e != cudaSuccess) return e;
+        e = cudaFuncSetAttribute(k_schur_fused<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)schur_fused_smem());
+        if (e != cudaSuccess) return e;
+        e = cudaFuncSetAttribute(k_schur_fused<7>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)schur_fused_smem());
+        if (e != cudaSuccess) return e;
+        fixed_done[dev] = true;
+    }
+    if (nr_cap_max <= 192 && nr_cap_max > hi_tiled[dev]) {
         e = cudaFuncSetAttribute(k_reduced_solve<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  (int)solve_tiled_smem(nr_cap_max));
         if (e != cudaSuccess) return e;
+        hi_tiled[dev] = nr_cap_max;
     }
-    e = cudaFuncSetAttribute(k_chol_trail, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)trail_smem(nr_cap_max));
-    if (e != cudaSuccess) return e;
-    return cudaFuncSetAttribute(k_reduced_solve<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)solve_smem(nr_cap_max));
+    if (nr_cap_max > hi_rows[dev]) {
+        e = cudaFuncSetAttribute(k_chol_trail, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)trail_smem(nr_cap_max));
+        if (e != cudaSuccess) return e;
+        e = cudaFuncSetAttribute(k_reduced_solve<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)solve_smem(nr_cap_max));
+        if (e != cudaSuccess) return e;
+        hi_rows[dev] = nr_cap_max;
+    }
+    return cudaSuccess;
 }
 
 void launch_reset(const BatchDev& bd, const LaunchCfg& lc, cudaStream_t s) {
-    k_reset_state<<<bd.n_win, 256, 0, s>>>(bd, lc.rounds_override, lc.min_landmarks_for_trimming, lc.num_rounds_option);
+    k_reset_state<<<bd.n_win, 256, 0, s>>>(bd, lc.rounds_override, lc.min_landmarks_for_trimming, lc.num_rounds_option); LCHK("k_reset_state");
 }
 
 int launch_pass(const BatchDev& bd, const SolveParams& sp, const LaunchCfg& lc, Counters* cnt, cudaStream_t s) {
     const int B = bd.n_win;
     const dim3 g_obs((bd.max_obs + 255) / 256, B);
     const dim3 g_lm((bd.max_lm + 7) / 8, B);
-    k_panel_zero<<<dim3(64, B), 256, 0, s>>>(bd);
-    k_solve_begin<<<B, 256, 0, s>>>(bd, sp);
+    k_panel_zero<<<dim3(64, B), 256, 0, s>>>(bd); LCHK("k_panel_zero");
+    k_solve_begin<<<B, 256, 0, s>>>(bd, sp); LCHK("k_solve_begin");
     const bool timed = lc.time_jacobian && lc.ev_pool && *lc.ev_used + 2 <= lc.ev_cap;
-    if (timed) cudaEventRecord(lc.ev_pool[(*lc.ev_used)++], s);
-    launch_eval_obs<true>(bd, sp, s);
-    if (timed) cudaEventRecord(lc.ev_pool[(*lc.ev_used)++], s);
-    if (bd.tot_gp > 0) k_gp_eval<true><<<B, 256, 0, s>>>(bd, sp);
-    k_pose_hessian<<<dim3(bd.max_kf, B), 256, 0, s>>>(bd, sp);
+    // one-kernel linearisation (kba_linearize.cuh): fused path, FP64, at most one observation per (landmark, keyframe)
+    const bool lin1 = bd.fused && lc.lin_fused && bd.precision == 0 && lc.max_rank == 0;
+    if (lin1) {
+        if (bd.tot_gp > 0) k_gp_eval<true><<<B, 256, 0, s>>>(bd, sp);
+        LCHK("k_gp_eval");
+        if (timed) cudaEventRecord(lc.ev_pool[(*lc.ev_used)++], s);
+        k_linearize<<<dim3((bd.max_obs + kLinTile - 1) / kLinTile, B), kLinThreads, 0, s>>>(bd, sp); LCHK("k_linearize");
+        if (timed) cudaEventRecord(lc.ev_pool[(*lc.ev_used)++], s);
+        k_pose_hessian<<<dim3(bd.max_kf, B), 256, 0, s>>>(bd, sp); LCHK("k_pose_hessian");
+    } else {
+        if (timed) cudaEventRecord(lc.ev_pool[(*lc.ev_used)++], s);
+        launch_eval_obs<true>(bd, sp, s);
+        if (timed) cudaEventRecord(lc.ev_pool[(*lc.ev_used)++], s);
+        if (bd.tot_gp > 0) k_gp_eval<true><<<B, 256, 0, s>>>(bd, sp);
+        LCHK("k_gp_eval");
+        k_pose_hessian<<<dim3(bd.max_kf, B), 256, 0, s>>>(bd, sp); LCHK("k_pose_hessian");
+    }
     if (bd.fused) {
-        k_landmark_reduce<true><<<dim3((bd.max_lm + 15) / 16, B), 256, 0, s>>>(bd, sp);
-        k_obs_v2<<<g_obs, 256, 0, s>>>(bd);
+        if (!lin1) {
+            k_landmark_reduce<true><<<dim3((bd.max_lm + 15) / 16, B), 256, 0, s>>>(bd, sp); LCHK("k_landmark_reduce");
+            k_obs_v2<<<g_obs, 256, 0, s>>>(bd); LCHK("k_obs_v2");
+        }
         const dim3 gf(bd.p_split, B);
         if (lc.fused_slots == 7) k_schur_fused<7><<<gf, 512, schur_fused_smem(), s>>>(bd);
         else k_schur_fused<6><<<gf, 512, schur_fused_smem(), s>>>(bd);
+        LCHK("k_schur_fused");
     } else {
-        k_landmark_reduce<false><<<dim3((bd.max_lm + 15) / 16, B), 256, 0, s>>>(bd, sp);
+        k_landmark_reduce<false><<<dim3((bd.max_lm + 15) / 16, B), 256, 0, s>>>(bd, sp); LCHK("k_landmark_reduce");
         for (int round = 0; round <= lc.max_rank; ++round) k_obs_v<<<g_obs, 256, 0, s>>>(bd, round);
+        LCHK("k_obs_v");
         if (bd.tot_gp > 0) k_gp_panel<<<dim3((bd.max_gp * 10 + 255) / 256, B), 256, 0, s>>>(bd);
+        LCHK("k_gp_panel");
     }
     if (bd.fused) {
     } else if (lc.small_syrk) {
-        k_schur_syrk_tma<<<dim3(bd.p_split, B), 512, schur_tma_smem(), s>>>(bd);
+        k_schur_syrk_tma<<<dim3(bd.p_split, B), 512, schur_tma_smem(), s>>>(bd); LCHK("k_schur_syrk_tma");
     } else {
         const int nb = lc.nr_cap_max / 64;
-        k_schur_syrk<<<dim3(nb * (nb + 1) / 2, bd.p_split, B), 256, schur_smem(), s>>>(bd);
+        k_schur_syrk<<<dim3(nb * (nb + 1) / 2, bd.p_split, B), 256, schur_smem(), s>>>(bd); LCHK("k_schur_syrk");
     }
     const dim3 g_red((lc.nr_cap_max * lc.nr_cap_max + 255) / 256, B);
     BatchDev bc = bd;  // consumer view of the reduced system
     if (bd.sharded) {
         // the one exchange of the linearisation: reduced system (Schur sums + right-hand side), pose blocks, cost at x
         if (bd.p_split > 1) k_sred_reduce<<<g_red, 256, 0, s>>>(bd, 1);
-        k_shard_flags<<<1, 32, 0, s>>>(bd, 0);
+        LCHK("k_sred_reduce");
+        k_shard_flags<<<1, 32, 0, s>>>(bd, 0); LCHK("k_shard_flags");
         // out of place: a pass that does not re-linearise (rejected step) leaves bkf / cost_part_x untouched, and summing
         // an already summed buffer again would scale it by the number of ranks
         const LaunchCfg::WinDescHost& wh = lc.shard_win;
@@ -2193,46 +2244,48 @@ int launch_pass(const BatchDev& bd, const SolveParams& sp, const LaunchCfg& lc, 
         rc |= lc.xchg.allreduce(lc.xchg.user, bd.cost_part_x, lc.x_cost, bd.cost_parts, 0, s);
         rc |= lc.xchg.allreduce(lc.xchg.user, bd.xs + 8, bd.xs + 8, 2, 0, s);
         if (rc) return rc;
-        k_shard_flags<<<1, 32, 0, s>>>(bd, 1);
+        k_shard_flags<<<1, 32, 0, s>>>(bd, 1); LCHK("k_shard_flags");
         bc.sred = lc.x_sred; bc.bkf = lc.x_bkf; bc.cost_part_x = lc.x_cost;  // the solve reads the window-wide sums
-        k_sred_reduce<<<g_red, 256, 0, s>>>(bc, 2);
+        k_sred_reduce<<<g_red, 256, 0, s>>>(bc, 2); LCHK("k_sred_reduce");
     } else if (bd.p_split > 1) {
-        k_sred_reduce<<<g_red, 256, 0, s>>>(bd, 0);
+        k_sred_reduce<<<g_red, 256, 0, s>>>(bd, 0); LCHK("k_sred_reduce");
     }
     if (bd.solve_tiled) {
-        k_reduced_solve<true><<<B, 512, solve_tiled_smem(lc.nr_cap_max), s>>>(bc, sp, 0);
+        k_reduced_solve<true><<<B, 512, solve_tiled_smem(lc.nr_cap_max), s>>>(bc, sp, 0); LCHK("k_reduced_solve");
     } else if (!bd.solve_split) {
-        k_reduced_solve<false><<<B, 512, solve_smem(lc.nr_cap_max), s>>>(bc, sp, 0);
+        k_reduced_solve<false><<<B, 512, solve_smem(lc.nr_cap_max), s>>>(bc, sp, 0); LCHK("k_reduced_solve");
     } else {  // few large windows: the factorisation is spread over the GPU, one 32-column block at a time
-        k_reduced_solve<false><<<B, 512, solve_smem(lc.nr_cap_max), s>>>(bc, sp, 1);
+        k_reduced_solve<false><<<B, 512, solve_smem(lc.nr_cap_max), s>>>(bc, sp, 1); LCHK("k_reduced_solve");
         const int strips = (lc.nr_cap_max + 7) / 8;
         for (int kb = 0; kb < lc.nr_cap_max; kb += kNB) {
-            k_chol_diag<<<B, 32, 0, s>>>(bc, kb);
-            k_chol_panel<<<dim3((strips + 15) / 16, B), 512, 0, s>>>(bc, kb);
-            k_chol_trail<<<dim3(bd.solve_split, B), 512, trail_smem(lc.nr_cap_max), s>>>(bc, kb);
+            k_chol_diag<<<B, 32, 0, s>>>(bc, kb); LCHK("k_chol_diag");
+            k_chol_panel<<<dim3((strips + 15) / 16, B), 512, 0, s>>>(bc, kb); LCHK("k_chol_panel");
+            k_chol_trail<<<dim3(bd.solve_split, B), 512, trail_smem(lc.nr_cap_max), s>>>(bc, kb); LCHK("k_chol_trail");
         }
-        k_reduced_solve<false><<<B, 512, solve_smem(lc.nr_cap_max), s>>>(bc, sp, 2);
+        k_reduced_solve<false><<<B, 512, solve_smem(lc.nr_cap_max), s>>>(bc, sp, 2); LCHK("k_reduced_solve");
     }
     if (bd.fused) k_backsub_v<<<dim3((bd.max_lm + 15) / 16, B), 256, 0, s>>>(bd);
     else k_backsub<<<dim3((bd.max_lm + 15) / 16, B), 256, 0, s>>>(bd);
+    LCHK("k_backsub");
     launch_eval_obs<false>(bd, sp, s);
     if (bd.tot_gp > 0) k_gp_eval<false><<<B, 256, 0, s>>>(bd, sp);
+    LCHK("k_gp_eval");
     if (bd.sharded) {  // model decrease / step norm / candidate cost over all ranks
-        k_shard_scalars<<<1, 256, 0, s>>>(bd);
+        k_shard_scalars<<<1, 256, 0, s>>>(bd); LCHK("k_shard_scalars");
         int rc = lc.xchg.allreduce(lc.xchg.user, bd.xs, bd.xs, 5, 0, s);
         rc |= lc.xchg.allreduce(lc.xchg.user, bd.xs + 5, bd.xs + 5, 1, 1, s);
         if (rc) return rc;
     }
-    k_lm_update<<<(B * 32 + 127) / 128, 128, 0, s>>>(bd, sp);
-    k_trim_eval<<<g_lm, 256, 0, s>>>(bd, sp);
+    k_lm_update<<<(B * 32 + 127) / 128, 128, 0, s>>>(bd, sp); LCHK("k_lm_update");
+    k_trim_eval<<<g_lm, 256, 0, s>>>(bd, sp); LCHK("k_trim_eval");
     if (bd.sharded) {  // quantiles are taken over the landmarks of all ranks
-        k_shard_trim_scatter<<<(bd.max_lm + 255) / 256, 256, 0, s>>>(bd);
+        k_shard_trim_scatter<<<(bd.max_lm + 255) / 256, 256, 0, s>>>(bd); LCHK("k_shard_trim_scatter");
         if (int rc = lc.xchg.allreduce(lc.xchg.user, bd.trim_send, bd.trim_glob, 3LL * bd.lm_total, 0, s)) return rc;
     }
-    k_trim_select<<<B, 512, 0, s>>>(bd, sp);
+    k_trim_select<<<B, 512, 0, s>>>(bd, sp); LCHK("k_trim_select");
     if (cnt) {
         const int gp = bd.tot_gp > 0 ? 1 : 0;
-        const int prep = 2 + (lc.max_rank + 1) + gp;  // pose blocks, landmark blocks, V rows
+        const int prep = lin1 ? 1 : 2 + (bd.fused ? 1 : lc.max_rank + 1 + gp);  // pose blocks [, landmark blocks, V rows]
         const int split = (!bd.solve_tiled && bd.solve_split) ? 1 + 3 * ((lc.nr_cap_max + kNB - 1) / kNB) : 0;
         cnt->launches_total += 1 + 1 + 1 + gp + prep + 1 + (bd.p_split > 1 ? 1 : 0) + 1 + split + 1 + 1 + gp + 1 + 2;
         cnt->launches_jacobian += 1; cnt->launches_prep += prep + gp; cnt->launches_schur += 1; cnt->launches_solve += 2;
@@ -2243,7 +2296,7 @@ int launch_pass(const BatchDev& bd, const SolveParams& sp, const LaunchCfg& lc, 
 
 void launch_count_active(const BatchDev& bd, cudaStream_t s) {
     cudaMemsetAsync(bd.n_active, 0, sizeof(int), s);
-    k_count_active<<<(bd.n_win + 127) / 128, 128, 0, s>>>(bd);
+    k_count_active<<<(bd.n_win + 127) / 128, 128, 0, s>>>(bd); LCHK("k_count_active");
 }
 
 // stand-alone residual/Jacobian pass at the uploaded state (parity + roofline measurement)
@@ -2276,10 +2329,11 @@ void launch_expand_jl(const BatchDev& bd, double* out, cudaStream_t s) {
     const int n = (int)bd.tot_obs;
     if (bd.precision) k_expand_jl<float><<<(n + 255) / 256, 256, 0, s>>>(bd, reinterpret_cast<float*>(out));
     else k_expand_jl<double><<<(n + 255) / 256, 256, 0, s>>>(bd, out);
+    LCHK("k_expand_jl");
 }
 void launch_force_linearize(const BatchDev& bd, cudaStream_t s) {
-    k_solve_begin<<<bd.n_win, 256, 0, s>>>(bd, SolveParams{});  // layout (off_pose) for the eval entry point
-    k_force_linearize<<<(bd.n_win + 127) / 128, 128, 0, s>>>(bd);
+    k_solve_begin<<<bd.n_win, 256, 0, s>>>(bd, SolveParams{}); LCHK("k_solve_begin");  // layout (off_pose) for the eval entry point
+    k_force_linearize<<<(bd.n_win + 127) / 128, 128, 0, s>>>(bd); LCHK("k_force_linearize");
 }
 
 }  // namespace kba

@@ -6,6 +6,18 @@
 
 namespace kba {
 
+// KBA_LAUNCH_CHECK=1 (debugging): every kernel launch is followed by cudaGetLastError() and a failing one is named on stderr.
+// Off by default: kba_batch_solve checks once per solve.
+int launch_check_enabled();
+void launch_check_report(const char* kernel, cudaError_t e);
+#define LCHK(name)                                                                       \
+    do {                                                                                 \
+        if (kba::launch_check_enabled()) {                                               \
+            const cudaError_t lchk_e_ = cudaGetLastError();                              \
+            if (lchk_e_ != cudaSuccess) kba::launch_check_report(name, lchk_e_);         \
+        }                                                                                \
+    } while (0)
+
 struct Counters {
     long long launches_total = 0;
     long long launches_jacobian = 0, launches_prep = 0, launches_schur = 0, launches_solve = 0, launches_backsub = 0,
@@ -25,6 +37,7 @@ struct LaunchCfg {
     int nr_cap_max = 64;
     int max_rank = 0;         // largest observation rank in the batch (multi-camera rigs)
     bool small_syrk = false;  // every window has <= 184 reduced rows: register-resident Schur kernel
+    bool lin_fused = true;    // fused path: evaluation + landmark blocks + V rows in one kernel (k_linearize); KBA_LINEARIZE=0: three kernels
     int fused_slots = 6;      // fused Schur kernel instance: 6 accumulator blocks per warp (<= 176 rows) or 7 (<= 184)
     int rounds_override = -1, min_landmarks_for_trimming = 100, num_rounds_option = 1;
     bool time_jacobian = false;

@@ -330,6 +330,7 @@ __global__ void __launch_bounds__(256) k_scatter_rows(double* dst, const int* sl
 }
 void launch_scatter_rows(double* dst, const int* slot, const double* src, int n, int width, cudaStream_t s) {
     if (n > 0) k_scatter_rows<<<(n * width + 255) / 256, 256, 0, s>>>(dst, slot, src, n, width);
+    LCHK("k_scatter_rows");
 }
 
 void launch_track_gather(const BatchDev& bd, const PackRaw& raw, const TrackDev& td, const TrackSel& sel, cudaStream_t s) {
@@ -340,17 +341,17 @@ void launch_track_gather(const BatchDev& bd, const PackRaw& raw, const TrackDev&
     double* r_pos = const_cast<double*>(raw.lm_pos); double* r_w = const_cast<double*>(raw.lm_weight);
     int* r_cnt = raw.lm_inv;  // scratch until the packing kernels overwrite it
     const int n = sel.n_kf > sel.n_lm ? sel.n_kf : sel.n_lm;
-    k_track_begin<<<(n + 255) / 256, 256, 0, s>>>(bd, raw, td, sel, r_pos, r_w, r_cnt);
+    k_track_begin<<<(n + 255) / 256, 256, 0, s>>>(bd, raw, td, sel, r_pos, r_w, r_cnt); LCHK("k_track_begin");
     const dim3 gm((sel.max_meas + 255) / 256 > 0 ? (sel.max_meas + 255) / 256 : 1, sel.n_kf);
-    k_track_scatter<0><<<gm, 256, 0, s>>>(raw, td, sel, r_cnt, r_kf, r_cam, r_u, r_v, r_d);
-    k_track_scan<<<1, 1024, 0, s>>>(bd, td, sel, r_cnt, r_lm_ptr);
-    k_track_scatter<1><<<gm, 256, 0, s>>>(raw, td, sel, r_cnt, r_kf, r_cam, r_u, r_v, r_d);
-    k_track_sort<<<(sel.n_lm + 255) / 256, 256, 0, s>>>(td, sel, r_lm_ptr, r_kf, r_cam, r_u, r_v, r_d);
+    k_track_scatter<0><<<gm, 256, 0, s>>>(raw, td, sel, r_cnt, r_kf, r_cam, r_u, r_v, r_d); LCHK("k_track_scatter");
+    k_track_scan<<<1, 1024, 0, s>>>(bd, td, sel, r_cnt, r_lm_ptr); LCHK("k_track_scan");
+    k_track_scatter<1><<<gm, 256, 0, s>>>(raw, td, sel, r_cnt, r_kf, r_cam, r_u, r_v, r_d); LCHK("k_track_scatter");
+    k_track_sort<<<(sel.n_lm + 255) / 256, 256, 0, s>>>(td, sel, r_lm_ptr, r_kf, r_cam, r_u, r_v, r_d); LCHK("k_track_sort");
 }
 
 void launch_track_writeback(const BatchDev& bd, const TrackDev& td, const TrackSel& sel, cudaStream_t s) {
     const int n = sel.n_kf > sel.n_lm ? sel.n_kf : sel.n_lm;
-    k_track_writeback<<<(n + 255) / 256, 256, 0, s>>>(bd, td, sel);
+    k_track_writeback<<<(n + 255) / 256, 256, 0, s>>>(bd, td, sel); LCHK("k_track_writeback");
 }
 
 cudaError_t configure_pack() {
@@ -363,16 +364,17 @@ void launch_pack(const BatchDev& bd, const PackRaw& raw, cudaStream_t s) {
     const int B = bd.n_win;
     int np = 1;
     while (np < bd.max_lm) np <<= 1;
-    k_pack_sort<<<B, 1024, (size_t)np * sizeof(unsigned), s>>>(bd, raw);
-    k_pack_obs<<<dim3((bd.max_lm + 7) / 8, B), 256, 0, s>>>(bd, raw);
-    k_pack_kf_count<<<B, 256, 0, s>>>(bd);
-    k_pack_kf_fill<<<dim3(bd.max_kf, B), 256, 0, s>>>(bd);
+    k_pack_sort<<<B, 1024, (size_t)np * sizeof(unsigned), s>>>(bd, raw); LCHK("k_pack_sort");
+    k_pack_obs<<<dim3((bd.max_lm + 7) / 8, B), 256, 0, s>>>(bd, raw); LCHK("k_pack_obs");
+    k_pack_kf_count<<<B, 256, 0, s>>>(bd); LCHK("k_pack_kf_count");
+    k_pack_kf_fill<<<dim3(bd.max_kf, B), 256, 0, s>>>(bd); LCHK("k_pack_kf_fill");
     if (bd.tot_gp > 0) k_pack_gp<<<dim3((bd.max_gp + 255) / 256, B), 256, 0, s>>>(bd, raw);
-    k_pack_groups<<<dim3(((bd.max_lm + 7) / 8 + 255) / 256, B), 256, 0, s>>>(bd);
+    LCHK("k_pack_gp");
+    k_pack_groups<<<dim3(((bd.max_lm + 7) / 8 + 255) / 256, B), 256, 0, s>>>(bd); LCHK("k_pack_groups");
 }
 
 void launch_unpack_landmarks(const BatchDev& bd, double* lm_user, unsigned char* rejected_user, cudaStream_t s) {
-    k_unpack_landmarks<<<dim3((bd.max_lm + 255) / 256, bd.n_win), 256, 0, s>>>(bd, lm_user, rejected_user);
+    k_unpack_landmarks<<<dim3((bd.max_lm + 255) / 256, bd.n_win), 256, 0, s>>>(bd, lm_user, rejected_user); LCHK("k_unpack_landmarks");
 }
 
 }  // namespace kba

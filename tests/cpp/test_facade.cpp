@@ -354,13 +354,20 @@ static void test_persistent_window_equals_rebuild() {
 
 int main(int argc, char** argv) {
     const bool gpu = argc > 1 && std::strcmp(argv[1], "gpu") == 0;
+    std::setvbuf(stdout, nullptr, _IOLBF, 0);  // progress survives an abort
     test_triangulator();
     test_landmark_creation();
     test_bookkeeping();
     test_landmark_selector();
     test_voxel_selector();
     test_add_depth_selector();
-    if (gpu) { test_solve(false); test_solve(true); test_motion_only(); test_camera_object_per_keyframe(); test_persistent_window_equals_rebuild(); }
+    if (gpu) {
+        std::printf("solve\n"); test_solve(false);
+        std::printf("solve_depth\n"); test_solve(true);
+        std::printf("motion_only\n"); test_motion_only();
+        std::printf("camera_object_per_keyframe\n"); test_camera_object_per_keyframe();
+        std::printf("persistent_window_equals_rebuild\n"); test_persistent_window_equals_rebuild();
+    }
     std::printf("%s: %d failed checks\n", gpu ? "gpu" : "cpu", g_fail);
     return g_fail ? 1 : 0;
 }

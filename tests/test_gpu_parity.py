@@ -24,7 +24,7 @@ def handle():
     h.close()
 
 
-def _compare_solves(res_gpu, res_cpu, win, label="", iter_slack=0, lm_p95=1e-6, lm_max=0.1):
+def _compare_solves(res_gpu, res_cpu, win, label="", iter_slack=0, lm_p95=1e-6, lm_max=0.1, lm_outliers=0):
     assert res_gpu.c.status == 0, label
     assert res_gpu.c.num_solves == res_cpu.c.num_solves, label
     for a, b in zip(res_gpu.solves, res_cpu.solves):
@@ -45,7 +45,8 @@ def _compare_solves(res_gpu, res_cpu, win, label="", iter_slack=0, lm_p95=1e-6, 
     assert dq <= 1e-7, (label, dq)
     # Landmarks seen twice with almost no parallax are nearly unobservable along the ray (condition ~1e10), so rounding
     # differences show up there first; north_star's tolerances are on poses and cost.  Typical landmarks agree to 1e-6.
-    assert np.percentile(dl, 95) <= lm_p95 and dl.max() <= lm_max, (label, np.percentile(dl, 95), dl.max())
+    # lm_outliers: how many such landmarks may exceed lm_max (a 20 000-landmark window holds a few with condition > 1e14)
+    assert np.percentile(dl, 95) <= lm_p95 and (dl > lm_max).sum() <= lm_outliers, (label, np.percentile(dl, 95), dl.max())
 
 
 def test_eval_matches_oracle(handle, oracle):
@@ -243,6 +244,17 @@ def test_large_window_generic_path_matches_oracle(handle, oracle):
     rg = handle.solve_window(win)
     rc = oracle.solve_window(win, num_threads=8)
     _compare_solves(rg, rc, win, "config5-small")
+
+
+def test_config5_full_window_matches_oracle(handle, oracle):
+    """BASELINE config 5 at full size (100 keyframes / 20 000 landmarks / ~300 000 observations, 594 reduced rows): the
+    split factorisation (k_chol_*) and the generic Schur kernel against the oracle at north_star's tolerances"""
+    import os
+    win = synth.make_window(5)
+    assert (win.n_kf, win.n_lm) == (100, 20000) and win.n_obs > 290000
+    rg = handle.solve_window(win)
+    rc = oracle.solve_window(win, num_threads=min(32, os.cpu_count() or 8))
+    _compare_solves(rg, rc, win, "config5-full", lm_outliers=3)
 
 
 def test_sharded_solve_with_one_rank_equals_plain_solve(handle):
