@@ -548,11 +548,14 @@ int kba_batch_create(kba_handle* h, int32_t n_windows, const kba_window* w, kba_
         // KBA_P_SPLIT pins the number of CTAs a window's landmark groups are split over.  The partial Schur sums are folded in
         // a fixed order, so results are bit-reproducible for a given split; the default split follows the batch size.
         if (const char* pe = std::getenv("KBA_P_SPLIT")) { if (std::atoi(pe) > 0) p = std::atoi(pe); }
+        // (a CTA of the fused Schur kernel takes at least 8 landmark groups of a window, see schur_split in kba_schur_fused.cuh: the
+        // partition of a window then does not depend on how many CTAs the batch was given)
         if (bd.fused) bd.p_split = std::max(1, std::min(p, max_groups));
         else if (std::getenv("KBA_P_SPLIT")) bd.p_split = std::max(1, std::min(p, max_chunks));
         b->lc.fused_slots = (max_rows_free <= 176) ? 6 : 7;
     }
-    bd.cost_parts = (bd.max_obs + 223) / 224;  // >= CTAs of k_linearize (224 observations each) and 256-observation tiles of k_eval_obs
+    // cost partials: one per CTA of k_linearize (8 warp tiles each, at most max_obs / 16 + 2 tiles) or per 256-observation tile of k_eval_obs
+    bd.cost_parts = std::max((bd.max_obs + 255) / 256, (bd.max_obs / 16 + 2 + 7) / 8);
     { const char* le = std::getenv("KBA_LINEARIZE"); b->lc.lin_fused = !(le && std::atoi(le) == 0); }
     {  // tuning knobs of the residual/Jacobian kernel (defaults measured on B200)
         auto knob = [](const char* name, int dflt) { const char* e = std::getenv(name); return e ? std::atoi(e) : dflt; };
@@ -594,6 +597,7 @@ int kba_batch_create(kba_handle* h, int32_t n_windows, const kba_window* w, kba_
         bad |= b->dev_alloc(&b->raw.lm_inv, lm);
     }
     bad |= b->dev_alloc(&bd.grp_t0, groups); bad |= b->dev_alloc(&bd.grp_t1, groups); bad |= b->dev_alloc(&bd.grp_rs, groups);
+    bad |= b->dev_alloc(&bd.lin_tile, (size_t)(obs / 16) + 2 * (size_t)n_windows + 2);
 #ifdef KBA_PROF
     bad |= b->dev_alloc(&bd.prof, 16);
     if (!bad) cudaMemset(bd.prof, 0, 16 * sizeof(unsigned long long));
@@ -789,6 +793,7 @@ int kba_batch_solve(kba_batch* b, const kba_options* opt) {
     if (opt->num_trim_rounds > 6 || (opt->num_trim_rounds < 0 && opt->num_rounds_option > 6))
         return fail(KBA_ERR_CAPACITY, "at most 6 trimming rounds (KBA_MAX_SOLVES = 8 inner solves incl. one retry and the final solve)");
     b->bd.precision = opt->precision;
+    b->bd.lin1 = (b->bd.fused && b->lc.lin_fused && opt->precision == 0 && b->lc.max_rank == 0) ? 1 : 0;
     kba_handle* h = b->h;
     CU(cudaSetDevice(h->device));
     cudaStream_t s = h->stream;
@@ -865,18 +870,21 @@ int kba_batch_set_shard(kba_batch* b, kba_shard_comm* comm, int32_t lm_begin, in
     if (bd.sharded) return fail(KBA_ERR_BAD_ARG, "kba_batch_set_shard called twice");
     const WinDesc& d = b->desc_h[0];
     int bad = 0;
-    bad |= b->dev_alloc(&bd.xs, 16);
+    const kba::Exchange xchg = kba_shard_exchange(comm);
+    const size_t n_x = (size_t)d.nr_cap * d.nr_cap + (size_t)d.n_kf * 27 + (size_t)bd.cost_parts + 2;
+    bad |= b->dev_alloc(&bd.xs, 16 + (size_t)xchg.world);
     bad |= b->dev_alloc(&bd.trim_send, 3 * (size_t)lm_total); bad |= b->dev_alloc(&bd.trim_glob, 3 * (size_t)lm_total);
     bad |= b->dev_alloc(&bd.reject_glob, (size_t)lm_total);
-    bad |= b->dev_alloc(&b->lc.x_sred, (size_t)d.nr_cap * d.nr_cap);
-    bad |= b->dev_alloc(&b->lc.x_bkf, (size_t)d.n_kf * 27); bad |= b->dev_alloc(&b->lc.x_cost, (size_t)bd.cost_parts);
+    bad |= b->dev_alloc(&bd.x_send, n_x); bad |= b->dev_alloc(&bd.x_recv, n_x);
     if (bad) return fail(KBA_ERR_CUDA, "out of device memory (shard buffers)");
     cudaStream_t s = b->h->stream;
-    CU(cudaMemsetAsync(bd.xs, 0, 16 * sizeof(double), s));
+    CU(cudaMemsetAsync(bd.xs, 0, (16 + (size_t)xchg.world) * sizeof(double), s));
     CU(cudaMemsetAsync(bd.trim_send, 0, 3 * (size_t)lm_total * sizeof(double), s));
-    CU(cudaMemsetAsync(b->lc.x_sred, 0, (size_t)d.nr_cap * d.nr_cap * sizeof(double), s));
+    CU(cudaMemsetAsync(bd.x_send, 0, n_x * sizeof(double), s));
+    CU(cudaMemsetAsync(bd.x_recv, 0, n_x * sizeof(double), s));
+    bd.shard_rank = xchg.rank; bd.shard_world = xchg.world;
     bd.sharded = 1; bd.lm_begin = lm_begin; bd.lm_total = lm_total;
-    b->lc.xchg = kba_shard_exchange(comm);
+    b->lc.xchg = xchg;
     b->lc.shard_win.nr_cap = d.nr_cap; b->lc.shard_win.n_kf = d.n_kf;
     return KBA_OK;
 }
@@ -1075,7 +1083,10 @@ int kba_track_create(kba_handle* h, const kba_track_caps* c, int32_t n_cam, cons
     CU(cudaSetDevice(h->device));
     kba_track* t = new kba_track();
     t->h = h; t->caps = *c; t->n_cam = n_cam;
-    // capacity batch from a dummy window of the largest shape (landmark 0 carries every observation)
+    // capacity batch from a dummy window of the largest shape.  The observations are spread evenly over the landmarks and, within
+    // a landmark, over the keyframes in ascending order: the packing kernels run once on this window (create = upload), and their
+    // per-landmark loops (insertion sort of a track, k_track_sort / k_pack_obs) are written for tracks of a few dozen
+    // observations -- one landmark carrying all 2^18 of them kept a single GPU thread busy for minutes.
     {
         const int K = c->win_keyframes, L = c->win_landmarks, O = c->win_observations, G = c->win_ground;
         std::vector<double> pose(7 * (size_t)K, 0.0), plane(4 * (size_t)K, 0.0), lmp(3 * (size_t)L, 0.0), lmw(L, 1.0), gw(std::max(G, 1), 1.0);
@@ -1085,7 +1096,12 @@ int kba_track_create(kba_handle* h, const kba_track_caps* c, int32_t n_cam, cons
         for (int k = 0; k < K; ++k) { pose[7 * k] = 1.0; plane[4 * k + 2] = 1.0; }
         for (int j = 0; j < L; ++j) lmp[3 * j + 2] = 10.0;
         for (int g = 0; g < G; ++g) gl[g] = g;
-        fixed[0] = 1; ptr[0] = 0;
+        fixed[0] = 1;
+        for (int j = 0; j <= L; ++j) ptr[j] = (int32_t)(((long long)O * j) / L);
+        for (int j = 0; j < L; ++j) {
+            const int n = ptr[j + 1] - ptr[j];
+            for (int i = 0; i < n; ++i) okf[ptr[j] + i] = (n <= K) ? i : (int32_t)(((long long)i * K) / n);  // non-decreasing
+        }
         kba_window w{};
         w.n_kf = K; w.n_cam = n_cam; w.n_lm = L; w.n_obs = O; w.n_gp = G;
         w.kf_pose = pose.data(); w.kf_fixed = fixed.data(); w.kf_plane = plane.data(); w.cam_intr = cam_intr; w.cam_pose = cam_pose;

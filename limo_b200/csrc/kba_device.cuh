@@ -69,7 +69,7 @@ struct WinState {
     int solve_failed;      // reduced Cholesky / finiteness failure of the current step
     int log_n;
     int n_solves;
-    int pad;
+    int n_lin_tiles;       // warp tiles of k_linearize (built by k_solve_begin for the active landmarks of this solve)
     double radius, decrease_factor;
     double x_cost, x_norm, gmax;
     // pose-side scalars of the current step (written by the reduced solve)
@@ -143,8 +143,11 @@ struct BatchDev {
     // ---- one window sharded by landmark blocks over several GPUs (kba_shard.cu) ----
     int sharded;              // 1: this batch holds ONE window's shard; sums cross the ranks through LaunchCfg::xchg
     int lm_begin, lm_total;   // first landmark of this rank's block / landmarks of the whole window (caller's order)
-    double* xs;               // [16] exchanged scalars: 0 model, 1 step^2, 2 |x|^2, 3 candidate cost, 4 eval-failed flag,
-                              //      5 gradient max-norm (MAX), 8 eval_failed at x, 9 landmark block not PD
+    int shard_rank, shard_world;
+    double* xs;               // [16 + world] exchanged scalars (ONE sum all-reduce after the back substitution): 0 model, 1 step^2,
+                              //      2 |x|^2, 3 candidate cost, 4 eval-failed flag, 16 + r: gradient max-norm of rank r
+    double* x_send;           // [nr_cap^2 + 27 n_kf + cost_parts + 2] packed linearisation of this rank (k_shard_pack) and
+    double* x_recv;           //      its sum over the ranks (ONE all-reduce per linearisation)
     double* trim_send;        // [3][lm_total] this rank's trimming values (+2, 0 where not owned), all-reduced into
     double* trim_glob;        // [3][lm_total]
     uint8_t* reject_glob;     // [lm_total]
@@ -192,6 +195,9 @@ struct BatchDev {
     int4* lm_run;             // [tot_lm] {a, m, row, 0}: observations p0 + a .. p0 + a + m - 1 are the landmark's observations
                               //   with variable poses and sit on consecutive reduced-system rows row, row + 6, ...;
                               //   m = 0: none, m = -1: they do not form one such run (gaps, several cameras, plane rows)
+    int lin1;                 // 1: this solve linearises with k_linearize (fused path, FP64, <= 1 observation per landmark and keyframe);
+                              //    set per solve by kba_batch_solve.  Also: the cost at x is evaluated at iteration zero only
+    int2* lin_tile;           // [tot_obs / 16 + 2 n_win + 2] warp tiles of k_linearize: {first observation, count <= 32} (kba_linearize.cuh)
     unsigned long long* prof; // [16] cycle counters of a KBA_PROF build (nullptr otherwise)
     int tot_groups;
     int* n_active;            // [1] windows still running (device counter)

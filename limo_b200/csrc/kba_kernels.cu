@@ -32,6 +32,7 @@ __global__ void __launch_bounds__(256) k_solve_begin(BatchDev bd, SolveParams sp
     __shared__ int s_has[kMaxKf];
     __shared__ int s_plane[kMaxKf];  // keyframe's plane blocks are referenced by a ground-plane residual
     __shared__ int s_cnt[3];
+    __shared__ int s_tile_ptr[1025];
     for (int k = threadIdx.x; k < wd.n_kf; k += blockDim.x) { s_has[k] = 0; s_plane[k] = 0; }
     if (threadIdx.x < 3) s_cnt[threadIdx.x] = 0;
     __syncthreads();
@@ -145,6 +146,7 @@ __global__ void __launch_bounds__(256) k_solve_begin(BatchDev bd, SolveParams sp
             bd.lm_run[wd.lm_off + j] = run;
         }
     }
+    if (bd.fused) build_lin_tiles(bd, wd, st, w, s_tile_ptr);  // warp tiles of k_linearize over the active landmarks
     // fused path: 8-row tile range and shared-memory row stride (== 4 mod 16) of each 8-landmark group
     if (bd.fused) {
         const int trhs = st.n_f >> 3;
@@ -918,12 +920,14 @@ __global__ void __launch_bounds__(256) k_sred_reduce(BatchDev bd, int mode) {
     double* sp0 = bd.sred + wd.s_off * (size_t)bd.p_split;
     const size_t pstride = (size_t)ld * ld;
     double s = 0.0;
+    int used = bd.p_split;  // partials that were written: all of them, or (fused Schur kernel) those of the CTAs that own groups
+    if (bd.fused) { int per; schur_split(wd.n_groups, bd.p_split, per, used); }
     if (mode == 2) s = sp0[idx];
     else
-    for (int p0 = 0; p0 < bd.p_split; p0 += 16) {  // 16 independent loads in flight, summed in slot order
+    for (int p0 = 0; p0 < used; p0 += 16) {  // 16 independent loads in flight, summed in slot order
         double v[16];
 #pragma unroll
-        for (int q = 0; q < 16; ++q) v[q] = (p0 + q < bd.p_split) ? sp0[(size_t)(p0 + q) * pstride + idx] : 0.0;
+        for (int q = 0; q < 16; ++q) v[q] = (p0 + q < used) ? sp0[(size_t)(p0 + q) * pstride + idx] : 0.0;
 #pragma unroll
         for (int q = 0; q < 16; ++q) s += v[q];
     }
@@ -973,10 +977,14 @@ __global__ void __launch_bounds__(512, 1) k_reduced_solve(BatchDev bd, SolvePara
     }
     if (stage != 2) {
     // ---- cost at x and evaluation failure (fresh linearisation only) ----
-    if (st.need_linearize && tid == 0) {
+    // cost at x: every fresh linearisation, or -- one-kernel linearisation -- at iteration zero only (k_lm_update carries the accepted
+    // candidate's cost over afterwards, kba_linearize.cuh)
+    const bool eval_cost = bd.lin1 ? (st.need_linearize && st.iter0) : (st.need_linearize != 0);
+    if (eval_cost && tid < 32) {  // warp 0: strided partial sums, then a butterfly (fixed shape)
         double c = 0.0;
-        for (int q = 0; q < bd.cost_parts; ++q) c += bd.cost_part_x[(size_t)w * bd.cost_parts + q];
-        st.x_cost = c;  // regulariser cost added below
+        for (int q = tid; q < bd.cost_parts; q += 32) c += bd.cost_part_x[(size_t)w * bd.cost_parts + q];
+        c = warp_sum(c);
+        if (tid == 0) st.x_cost = c;  // regulariser cost added below
     }
     __syncthreads();
     if (st.eval_failed) {  // only reachable at iteration zero: "Residual and Jacobian evaluation failed."
@@ -993,13 +1001,25 @@ __global__ void __launch_bounds__(512, 1) k_reduced_solve(BatchDev bd, SolvePara
         const int np = 1;  // with p_split > 1, k_sred_reduce has folded the partials into slot 0
         const int rows = kTiled ? ((n + 8) & ~7) : n + 1;  // tiled: whole tile rows, zero padded
         const bool done_by_reduce = !kTiled && (bd.p_split > 1 || bd.sharded) && !wd.landmarks_fixed;  // see k_sred_reduce
-        for (int idx = tid; idx < (done_by_reduce ? 0 : rows * ld); idx += nth) {
-            const int r = idx / ld, c = idx - r * ld;
-            if (kTiled ? (c >= rows || (c >> 3) > (r >> 3)) : (c > r || c >= n + 1)) continue;
-            double s = 0.0;
-            if (!wd.landmarks_fixed && c <= r && r <= n && !(r == n && c == n))  // motion-only: nothing was eliminated
-                for (int p = 0; p < np; ++p) s += sp0[p * pstride + (size_t)r * ld + c];
-            A(r, c) = -s;
+        // eight independent loads in flight per thread: the sums sit in L2, one load per iteration exposed its full latency
+        const int total = done_by_reduce ? 0 : rows * ld;
+        for (int idx0 = tid; idx0 < total; idx0 += 8 * nth) {
+            double v[8];
+            int rr[8], cc[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int idx = idx0 + u * nth;
+                const int r = idx / ld, c = idx - r * ld;
+                const bool skip = idx >= total || (kTiled ? (c >= rows || (c >> 3) > (r >> 3)) : (c > r || c >= n + 1));
+                rr[u] = skip ? -1 : r; cc[u] = c;
+                double s = 0.0;
+                if (!skip && !wd.landmarks_fixed && c <= r && r <= n && !(r == n && c == n))  // motion-only: nothing was eliminated
+                    for (int p = 0; p < np; ++p) s += sp0[p * pstride + (size_t)r * ld + c];
+                v[u] = s;
+            }
+#pragma unroll
+            for (int u = 0; u < 8; ++u)
+                if (rr[u] >= 0) A(rr[u], cc[u]) = -v[u];
         }
     }
     __syncthreads();
@@ -1110,9 +1130,9 @@ __global__ void __launch_bounds__(512, 1) k_reduced_solve(BatchDev bd, SolvePara
             const int off[1] = {bd.off_dir[wd.kf_off + k]}, sz[1] = {3};
             warp_add_block(A, s_fdiag, s_g, 3, r, 1, off, sz, J, lane);
         }
-        if (lane == 0 && st.need_linearize) st.x_cost += plane_chain_cost(wd, P, PL);
+        if (lane == 0 && eval_cost) st.x_cost += plane_chain_cost(wd, P, PL);
     }
-    if (tid == 0 && wd.n_gp > 0 && st.need_linearize) st.x_cost += bd.gp_cost_x[w];
+    if (tid == 0 && wd.n_gp > 0 && eval_cost) st.x_cost += bd.gp_cost_x[w];
     __syncthreads();
     // ---- regularisers (thread 0; a handful of residuals) ----
     if (tid == 0 && wd.scale_weight > 0) {
@@ -1121,7 +1141,7 @@ __global__ void __launch_bounds__(512, 1) k_reduced_solve(BatchDev bd, SolvePara
         scale_regulariser(P + 7 * (size_t)(wd.kf_off + wd.scale_kf1), P + 7 * (size_t)(wd.kf_off + wd.scale_kf0),
                           wd.scale_value, r, j1, j0);
         const double sq = sqrt(wd.scale_weight);  // TrivialLoss * weight: rho' = w
-        if (st.need_linearize) st.x_cost += 0.5 * wd.scale_weight * r * r;
+        if (eval_cost) st.x_cost += 0.5 * wd.scale_weight * r * r;
         const int o1 = bd.off_pose[wd.kf_off + wd.scale_kf1], o0 = bd.off_pose[wd.kf_off + wd.scale_kf0];
         double J[12]; int cols[12]; int m = 0;
         if (o1 >= 0) for (int a = 0; a < 6; ++a) { J[m] = sq * j1[a]; cols[m++] = o1 + a; }
@@ -1137,7 +1157,7 @@ __global__ void __launch_bounds__(512, 1) k_reduced_solve(BatchDev bd, SolvePara
     if (tid == 0 && wd.speed_weight > 0) {  // SpeedRegularizationVector2 of adjustPoseOnly (reference cpp:835-853)
         double r[3], J[18];
         speed_regulariser(bd.pose[st.cur] + 7 * (size_t)(wd.kf_off + wd.speed_kf), wd, r, J);
-        if (st.need_linearize) st.x_cost += 0.5 * wd.speed_weight * (r[0] * r[0] + r[1] * r[1] + r[2] * r[2]);
+        if (eval_cost) st.x_cost += 0.5 * wd.speed_weight * (r[0] * r[0] + r[1] * r[1] + r[2] * r[2]);
         const int o = bd.off_pose[wd.kf_off + wd.speed_kf];
         if (o >= 0) {
             const double wgt = wd.speed_weight;  // rho' = w: J^T J and J^T r scale by w
@@ -1746,22 +1766,32 @@ __global__ void __launch_bounds__(256) k_shard_scalars(BatchDev bd) {  // after 
         for (int q = 0; q < 8; ++q) { for (int e = 0; e < 4; ++e) t[e] += s_red[q][e]; t[4] = fmax(t[4], s_red[q][4]); }
         bd.xs[0] = t[0]; bd.xs[1] = t[1]; bd.xs[2] = t[2]; bd.xs[3] = t[3];
         bd.xs[4] = (st.phase == PH_ITERATE && st.eval_failed) ? 1.0 : 0.0;
-        bd.xs[5] = t[4];
+        // the gradient max-norm rides in the same SUM all-reduce: one slot per rank, the others contribute zero
+        for (int r = 0; r < bd.shard_world; ++r) bd.xs[16 + r] = (r == bd.shard_rank) ? t[4] : 0.0;
     }
 }
-__global__ void k_shard_flags(BatchDev bd, int post) {  // around the exchange that follows the linearisation kernels
+// The ONE exchange of a linearisation: [ reduced system (Schur sums + right-hand side) | pose blocks | cost partials at x |
+// evaluation-failed flag, landmark-block-not-PD flag ] packed into BatchDev::x_send, summed over the ranks into x_recv.
+// Out of place by construction: a pass that does not re-linearise (rejected step) packs the same local values again.
+__global__ void __launch_bounds__(256) k_shard_pack(BatchDev bd) {
+    const WinState& st = bd.state[0];
+    const WinDesc& wd = bd.desc[0];
+    const size_t n_s = (size_t)wd.nr_cap * wd.nr_cap, n_b = (size_t)wd.n_kf * 27, n_c = (size_t)bd.cost_parts;
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool on = st.phase == PH_ITERATE;
+    if (i < n_s) bd.x_send[i] = on ? bd.sred[i] : 0.0;
+    else if (i < n_s + n_b) bd.x_send[i] = on ? bd.bkf[i - n_s] : 0.0;
+    else if (i < n_s + n_b + n_c) bd.x_send[i] = on ? bd.cost_part_x[i - n_s - n_b] : 0.0;
+    else if (i == n_s + n_b + n_c) bd.x_send[i] = (on && st.eval_failed) ? 1.0 : 0.0;
+    else if (i == n_s + n_b + n_c + 1) bd.x_send[i] = (on && st.solve_failed) ? 1.0 : 0.0;
+}
+__global__ void k_shard_flags(BatchDev bd) {  // after the exchange: a failure on any rank is a failure of the window
     WinState& st = bd.state[0];
-    if (threadIdx.x != 0 || st.phase != PH_ITERATE) {
-        if (threadIdx.x == 0 && !post) { bd.xs[8] = 0.0; bd.xs[9] = 0.0; }
-        return;
-    }
-    if (!post) {
-        bd.xs[8] = st.eval_failed ? 1.0 : 0.0;
-        bd.xs[9] = st.solve_failed ? 1.0 : 0.0;
-    } else {
-        if (bd.xs[8] > 0.0) st.eval_failed = 1;
-        if (bd.xs[9] > 0.0 && !st.solve_failed) st.solve_failed = 1;
-    }
+    if (threadIdx.x != 0 || st.phase != PH_ITERATE) return;
+    const WinDesc& wd = bd.desc[0];
+    const double* f = bd.x_recv + (size_t)wd.nr_cap * wd.nr_cap + (size_t)wd.n_kf * 27 + bd.cost_parts;
+    if (f[0] > 0.0) st.eval_failed = 1;
+    if (f[1] > 0.0 && !st.solve_failed) st.solve_failed = 1;
 }
 // trimming values of this rank's landmarks into their slots of the window-wide array (0 = not mine, v + 2 otherwise)
 __global__ void __launch_bounds__(256) k_shard_trim_scatter(BatchDev bd) {
@@ -1793,7 +1823,9 @@ __global__ void __launch_bounds__(128) k_lm_update(BatchDev bd, SolveParams sp) 
     cand_sum = warp_sum(cand_sum);
     if (lane != 0) return;
     if (bd.sharded) {  // sums over all ranks (k_shard_scalars + all-reduce), identical on every rank
-        e_model = bd.xs[0]; e_step = bd.xs[1]; e_xn = bd.xs[2]; cand_sum = bd.xs[3]; e_g = bd.xs[5];
+        e_model = bd.xs[0]; e_step = bd.xs[1]; e_xn = bd.xs[2]; cand_sum = bd.xs[3];
+        e_g = 0.0;
+        for (int r = 0; r < bd.shard_world; ++r) e_g = fmax(e_g, bd.xs[16 + r]);
         if (bd.xs[4] > 0.0) st.eval_failed = 1;
     }
     if (st.solve_failed == 2) {  // evaluation failed at iteration zero
@@ -1877,6 +1909,7 @@ __global__ void __launch_bounds__(128) k_lm_update(BatchDev bd, SolveParams sp) 
     if (rel > sp.min_relative_decrease) {
         st.cur = 1 - st.cur;
         st.need_linearize = 1; st.iter0 = 0; st.last_successful = 1;
+        if (bd.lin1) st.x_cost = cand;  // the accepted candidate is the next x: its cost is known (ceres: x_cost = candidate_cost)
         sum.num_successful_steps++;
         const double t = 2.0 * rel - 1.0;
         st.radius = fmin(sp.max_radius, st.radius / fmax(1.0 / 3.0, 1.0 - t * t * t));
@@ -2190,12 +2223,12 @@ int launch_pass(const BatchDev& bd, const SolveParams& sp, const LaunchCfg& lc, 
     k_solve_begin<<<B, 256, 0, s>>>(bd, sp); LCHK("k_solve_begin");
     const bool timed = lc.time_jacobian && lc.ev_pool && *lc.ev_used + 2 <= lc.ev_cap;
     // one-kernel linearisation (kba_linearize.cuh): fused path, FP64, at most one observation per (landmark, keyframe)
-    const bool lin1 = bd.fused && lc.lin_fused && bd.precision == 0 && lc.max_rank == 0;
+    const bool lin1 = bd.lin1 != 0;
     if (lin1) {
         if (bd.tot_gp > 0) k_gp_eval<true><<<B, 256, 0, s>>>(bd, sp);
         LCHK("k_gp_eval");
         if (timed) cudaEventRecord(lc.ev_pool[(*lc.ev_used)++], s);
-        k_linearize<<<dim3((bd.max_obs + kLinTile - 1) / kLinTile, B), kLinThreads, 0, s>>>(bd, sp); LCHK("k_linearize");
+        k_linearize<<<dim3((bd.max_obs / 16 + 2 + kLinWarps - 1) / kLinWarps, B), kLinThreads, 0, s>>>(bd, sp); LCHK("k_linearize");
         if (timed) cudaEventRecord(lc.ev_pool[(*lc.ev_used)++], s);
         k_pose_hessian<<<dim3(bd.max_kf, B), 256, 0, s>>>(bd, sp); LCHK("k_pose_hessian");
     } else {
@@ -2235,17 +2268,12 @@ int launch_pass(const BatchDev& bd, const SolveParams& sp, const LaunchCfg& lc, 
         // the one exchange of the linearisation: reduced system (Schur sums + right-hand side), pose blocks, cost at x
         if (bd.p_split > 1) k_sred_reduce<<<g_red, 256, 0, s>>>(bd, 1);
         LCHK("k_sred_reduce");
-        k_shard_flags<<<1, 32, 0, s>>>(bd, 0); LCHK("k_shard_flags");
-        // out of place: a pass that does not re-linearise (rejected step) leaves bkf / cost_part_x untouched, and summing
-        // an already summed buffer again would scale it by the number of ranks
         const LaunchCfg::WinDescHost& wh = lc.shard_win;
-        int rc = lc.xchg.allreduce(lc.xchg.user, bd.sred, lc.x_sred, (long long)wh.nr_cap * wh.nr_cap, 0, s);
-        rc |= lc.xchg.allreduce(lc.xchg.user, bd.bkf, lc.x_bkf, (long long)wh.n_kf * 27, 0, s);
-        rc |= lc.xchg.allreduce(lc.xchg.user, bd.cost_part_x, lc.x_cost, bd.cost_parts, 0, s);
-        rc |= lc.xchg.allreduce(lc.xchg.user, bd.xs + 8, bd.xs + 8, 2, 0, s);
-        if (rc) return rc;
-        k_shard_flags<<<1, 32, 0, s>>>(bd, 1); LCHK("k_shard_flags");
-        bc.sred = lc.x_sred; bc.bkf = lc.x_bkf; bc.cost_part_x = lc.x_cost;  // the solve reads the window-wide sums
+        const long long n_s = (long long)wh.nr_cap * wh.nr_cap, n_b = (long long)wh.n_kf * 27, n_x = n_s + n_b + bd.cost_parts + 2;
+        k_shard_pack<<<(unsigned)((n_x + 255) / 256), 256, 0, s>>>(bd); LCHK("k_shard_pack");
+        if (int rc = lc.xchg.allreduce(lc.xchg.user, bd.x_send, bd.x_recv, n_x, 0, s)) return rc;
+        k_shard_flags<<<1, 32, 0, s>>>(bd); LCHK("k_shard_flags");
+        bc.sred = bd.x_recv; bc.bkf = bd.x_recv + n_s; bc.cost_part_x = bd.x_recv + n_s + n_b;  // the solve reads the window-wide sums
         k_sred_reduce<<<g_red, 256, 0, s>>>(bc, 2); LCHK("k_sred_reduce");
     } else if (bd.p_split > 1) {
         k_sred_reduce<<<g_red, 256, 0, s>>>(bd, 0); LCHK("k_sred_reduce");
@@ -2272,9 +2300,8 @@ int launch_pass(const BatchDev& bd, const SolveParams& sp, const LaunchCfg& lc, 
     LCHK("k_gp_eval");
     if (bd.sharded) {  // model decrease / step norm / candidate cost over all ranks
         k_shard_scalars<<<1, 256, 0, s>>>(bd); LCHK("k_shard_scalars");
-        int rc = lc.xchg.allreduce(lc.xchg.user, bd.xs, bd.xs, 5, 0, s);
-        rc |= lc.xchg.allreduce(lc.xchg.user, bd.xs + 5, bd.xs + 5, 1, 1, s);
-        if (rc) return rc;
+        // model decrease, step / state norms, candidate cost, failure flag (sums) and one gradient-max slot per rank
+        if (int rc = lc.xchg.allreduce(lc.xchg.user, bd.xs, bd.xs, 16 + bd.shard_world, 0, s)) return rc;
     }
     k_lm_update<<<(B * 32 + 127) / 128, 128, 0, s>>>(bd, sp); LCHK("k_lm_update");
     k_trim_eval<<<g_lm, 256, 0, s>>>(bd, sp); LCHK("k_trim_eval");

@@ -31,6 +31,7 @@ struct Counters {
 struct Exchange {
     int (*allreduce)(void* user, const double* send, double* recv, long long count, int op, cudaStream_t s) = nullptr;
     void* user = nullptr;
+    int rank = 0, world = 1;
 };
 
 struct LaunchCfg {
@@ -46,7 +47,6 @@ struct LaunchCfg {
     int* ev_used = nullptr;
     Exchange xchg;  // used when BatchDev::sharded
     struct WinDescHost { int nr_cap = 0, n_kf = 0; } shard_win;  // shapes of the sharded window (host copy)
-    double *x_sred = nullptr, *x_bkf = nullptr, *x_cost = nullptr;  // window-wide sums (receive buffers of the exchange)
 };
 
 // window arrays exactly as the caller passes them (landmark-major CSR in the caller's landmark order), batch-flat on the

@@ -89,6 +89,16 @@ constexpr size_t schur_fused_smem() { return (size_t)kFStages * kFStageDoubles *
 #define KBA_PROF_FLUSH(base)
 #endif
 
+// Landmark groups per CTA and CTAs that own groups, for a window with n_groups groups in a batch launched with p_split CTAs per
+// window.  At least 8 groups per CTA: every CTA writes a whole partial triangle (up to 295 KB) that k_sred_reduce folds again --
+// one window alone spread over 148 CTAs spent 47 us per pass folding 148 partials.  Because of the floor the partition of a small
+// window is the same whether it is solved alone, in a batch or inside the capacity-sized batch of a persistent window
+// (kba_track_*), which keeps those paths bit-identical.
+__device__ __forceinline__ void schur_split(int n_groups, int p_split, int& per, int& used) {
+    per = max(8, (n_groups + p_split - 1) / p_split);
+    used = max(1, min(p_split, (n_groups + per - 1) / per));
+}
+
 template <int kSlots>
 __global__ void __launch_bounds__(512, 1) k_schur_fused(BatchDev bd) {
     const int w = blockIdx.y;
@@ -102,7 +112,9 @@ __global__ void __launch_bounds__(512, 1) k_schur_fused(BatchDev bd) {
     uint64_t* empty = full + kFStages;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int n_f = st.n_f, nt = (n_f + 8) >> 3, trhs = n_f >> 3;
-    const int per = (wd.n_groups + (int)gridDim.x - 1) / (int)gridDim.x;
+    int per, used;
+    schur_split(wd.n_groups, (int)gridDim.x, per, used);
+    if ((int)blockIdx.x >= used) return;  // k_sred_reduce folds the first `used` partials only
     const int g0 = blockIdx.x * per, g1 = min(wd.n_groups, g0 + per);
     const int* grs = bd.grp_rs + wd.grp_off;
     const int* gt0 = bd.grp_t0 + wd.grp_off;

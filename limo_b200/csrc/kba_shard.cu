@@ -69,6 +69,7 @@ kba::Exchange kba_shard_exchange(kba_shard_comm* c) {
     kba::Exchange x;
     x.allreduce = &shard_allreduce;
     x.user = c;
+    x.rank = c->rank; x.world = c->world;
     return x;
 }
 

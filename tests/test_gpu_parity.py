@@ -229,6 +229,21 @@ def test_full_size_properties(handle):
     assert rej.sum() > 0
 
 
+def test_small_batch_does_not_lower_a_live_batch_shared_memory(handle):
+    """the opt-in dynamic shared memory of the solve kernels is a per-function attribute: creating a batch with a smaller
+    reduced system while a larger one is alive (a persistent window next to one-shot solves) must not break the larger one"""
+    from limo_b200 import capi
+    big = synth.make_window(2, n_kf=30, n_lm=600, n_obs=6000, seed=3)
+    small = synth.make_window(1, seed=4)
+    b_big = handle.batch([big])
+    ref = handle.solve_window(big)
+    handle.solve_window(small)          # 5 keyframes: 64 reduced rows (the big batch uses 192)
+    b_big.solve(capi.default_options())
+    r = b_big.download()[0]
+    assert r.c.status == 0 and np.array_equal(r.kf_pose, ref.kf_pose)
+    b_big.close()
+
+
 def test_bad_arguments(handle):
     """error behaviour of the boundary: fewer than 3 keyframes -> NotEnoughKeyframes (reference cpp:630-632)"""
     from limo_b200 import capi
