@@ -43,7 +43,7 @@ LIN1 = FUSED and os.environ.get("KBA_LINEARIZE", "1") != "0"
 B_OBS_ALGORITHMIC = 168.0 if LIN1 else (187.0 if FUSED else 259.0)
 # dram__bytes_read.sum + dram__bytes_write.sum of one launch of that kernel / its observations, from the ncu --set full
 # capture summarised in profiles/ (re-measured whenever the kernel changes)
-B_OBS_DRAM_MEASURED = 176.0 if LIN1 else (199.0 if FUSED else 277.0)
+B_OBS_DRAM_MEASURED = 184.6 if LIN1 else (199.0 if FUSED else 277.0)
 TRAFFIC_SOURCE = ("ncu --set full, profiles/r02_ncu_summary.md (k_linearize)" if LIN1 else
                   "ncu --set full, profiles/r02_ncu_summary.md (k_eval_obs<true>, J_landmark not materialised)" if FUSED else
                   "ncu --set full, profiles/r01_v11_ncu_summary.md: (0.200 GB read + 1.293 GB written) / 5.39 M observations")
@@ -515,6 +515,12 @@ def main():
     done = done and all(r.c.status == 0 for _, rs in lanes[1:] for r in rs)
     clocks = sampler.stop()  # sampled over all timed regions
     h2d, d2h = batch.transfer_bytes()
+    # the materialising residual/Jacobian kernel alone (k_eval_obs<true>: what large windows, the FP32 mode and kba_eval run, and
+    # what k_linearize replaced on this path): every window active, 20 back-to-back launches between CUDA events, best of 3
+    jac_alone_ms = None
+    if rank == 0:
+        batch.jacobian_pass(opt, 5)
+        jac_alone_ms = min(batch.jacobian_pass(opt, 20) for _ in range(3)) / 20.0
     for _, h_, b_ in extra:
         b_.close()
         h_.close()
@@ -571,6 +577,12 @@ def main():
                          "launch_ms_mean": cnt.ms_jacobian / max(cnt.launches_jacobian, 1),
                          "launches": int(cnt.launches_jacobian), "share_of_timed_region": cnt.ms_jacobian / ms,
                          "obs_per_launch_mean": cnt.jacobian_obs / max(cnt.launches_jacobian, 1)},
+            "roofline_jacobian_kernel": {
+                "kernel": "k_eval_obs<true> alone (materialising residual/Jacobian kernel; not on the timed path of this workload)",
+                "bound": "hbm", "achieved": args.batch * n_obs_win * 187.0 / (jac_alone_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                "frac": args.batch * n_obs_win * 187.0 / (jac_alone_ms * 1e-3) / 1e9 / peak, "launch_ms": jac_alone_ms,
+                "algorithmic_bytes_per_obs": 187.0,
+                "note": "19 B read + 168 B written (residual 24 + J_pose 144; J_landmark = translation columns of J_pose x R is not stored)"},
             "host_cores": usable_cores(),
             "cpu_baseline": cpu_rec if cpu_rec else {"value": None, "unit": "windows/s", "cores": 0, "kind": "port", "sample": "skipped (--cpu-sample 0)"},
             "sub_records": sub,

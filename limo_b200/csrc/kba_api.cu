@@ -554,8 +554,8 @@ int kba_batch_create(kba_handle* h, int32_t n_windows, const kba_window* w, kba_
         else if (std::getenv("KBA_P_SPLIT")) bd.p_split = std::max(1, std::min(p, max_chunks));
         b->lc.fused_slots = (max_rows_free <= 176) ? 6 : 7;
     }
-    // cost partials: one per CTA of k_linearize (8 warp tiles each, at most max_obs / 16 + 2 tiles) or per 256-observation tile of k_eval_obs
-    bd.cost_parts = std::max((bd.max_obs + 255) / 256, (bd.max_obs / 16 + 2 + 7) / 8);
+    // cost partials: one per CTA of k_linearize (8 warp tiles each, kba_linearize.cuh: lin_tile_bound) or per 256-observation tile of k_eval_obs
+    bd.cost_parts = std::max((bd.max_obs + 255) / 256, (bd.max_obs / 16 + bd.max_lm / 32 + 4 + 7) / 8);
     { const char* le = std::getenv("KBA_LINEARIZE"); b->lc.lin_fused = !(le && std::atoi(le) == 0); }
     {  // tuning knobs of the residual/Jacobian kernel (defaults measured on B200)
         auto knob = [](const char* name, int dflt) { const char* e = std::getenv(name); return e ? std::atoi(e) : dflt; };
@@ -597,7 +597,7 @@ int kba_batch_create(kba_handle* h, int32_t n_windows, const kba_window* w, kba_
         bad |= b->dev_alloc(&b->raw.lm_inv, lm);
     }
     bad |= b->dev_alloc(&bd.grp_t0, groups); bad |= b->dev_alloc(&bd.grp_t1, groups); bad |= b->dev_alloc(&bd.grp_rs, groups);
-    bad |= b->dev_alloc(&bd.lin_tile, (size_t)(obs / 16) + 2 * (size_t)n_windows + 2);
+    bad |= b->dev_alloc(&bd.lin_tile, (size_t)(obs / 16) + (size_t)(lm / 32) + 4 * (size_t)n_windows + 4);
 #ifdef KBA_PROF
     bad |= b->dev_alloc(&bd.prof, 16);
     if (!bad) cudaMemset(bd.prof, 0, 16 * sizeof(unsigned long long));

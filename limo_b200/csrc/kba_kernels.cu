@@ -32,7 +32,7 @@ __global__ void __launch_bounds__(256) k_solve_begin(BatchDev bd, SolveParams sp
     __shared__ int s_has[kMaxKf];
     __shared__ int s_plane[kMaxKf];  // keyframe's plane blocks are referenced by a ground-plane residual
     __shared__ int s_cnt[3];
-    __shared__ int s_tile_ptr[1025];
+    __shared__ int s_tile_chunk[513];
     for (int k = threadIdx.x; k < wd.n_kf; k += blockDim.x) { s_has[k] = 0; s_plane[k] = 0; }
     if (threadIdx.x < 3) s_cnt[threadIdx.x] = 0;
     __syncthreads();
@@ -146,7 +146,7 @@ __global__ void __launch_bounds__(256) k_solve_begin(BatchDev bd, SolveParams sp
             bd.lm_run[wd.lm_off + j] = run;
         }
     }
-    if (bd.fused) build_lin_tiles(bd, wd, st, w, s_tile_ptr);  // warp tiles of k_linearize over the active landmarks
+    if (bd.fused) build_lin_tiles(bd, wd, st, w, s_tile_chunk);  // warp tiles of k_linearize over the active landmarks
     // fused path: 8-row tile range and shared-memory row stride (== 4 mod 16) of each 8-landmark group
     if (bd.fused) {
         const int trhs = st.n_f >> 3;
@@ -1225,24 +1225,41 @@ __global__ void __launch_bounds__(512, 1) k_reduced_solve(BatchDev bd, SolvePara
             }
             __syncthreads();
         }
-        for (int i = tid; i < m; i += nth) {
-            double x[kNB];
+        // Four lanes per row: lane a of a quad owns the columns c = 4 e + a.  Step q: the owner of column q scales it and
+        // hands it to the quad (one shuffle), every lane eliminates it from its own later columns -- the same operations on the
+        // same values in the same order as one thread per row, but 572 instead of 143 busy threads and a quarter of the
+        // dependent chain per thread (51 k -> cycles per solve of a 174-row system, profiles/).
+        {
+            const int quad = tid >> 2, qa = tid & 3;
+            const volatile double* vD = s_D;  // volatile: keeps the factor entries from being hoisted out of the row loop
+            for (int ib = 0; ib < m; ib += nth >> 2) {  // warp-uniform trip count: every lane takes part in the shuffles
+                const int i = ib + quad;
+                const bool live = i < m;
+                double x[kNB / 4];
 #pragma unroll
-            for (int c = 0; c < kNB; ++c) {
-                if constexpr (kTiled) x[c] = (c < nb) ? A(r0 + i, kb + c) : 0.0;
-                else x[c] = s_P[i * kPanelStride + c];
-            }
-            const volatile double* vD = s_D;  // volatile: keeps the 496 factor entries from being hoisted out of the row loop
+                for (int e = 0; e < kNB / 4; ++e) {
+                    const int c = 4 * e + qa;
+                    if constexpr (kTiled) x[e] = (live && c < nb) ? A(r0 + i, kb + c) : 0.0;
+                    else x[e] = live ? s_P[i * kPanelStride + c] : 0.0;
+                }
 #pragma unroll
-            for (int q = 0; q < kNB; ++q) {
-                x[q] *= s_inv[q];
+                for (int q = 0; q < kNB; ++q) {
+                    const int oe = q >> 2, oa = q & 3;
+                    double xq = x[oe] * s_inv[q];  // meaningful on the owner lane only
+                    xq = __shfl_sync(0xffffffffu, xq, (lane & ~3) | oa);
+                    if (qa == oa) x[oe] = xq;
 #pragma unroll
-                for (int c = q + 1; c < kNB; ++c) x[c] -= x[q] * vD[c * PS + q];
-            }
+                    for (int e = oe; e < kNB / 4; ++e) {
+                        const int c = 4 * e + qa;
+                        if (e > oe || qa > oa) x[e] -= xq * vD[c * PS + q];
+                    }
+                }
 #pragma unroll
-            for (int c = 0; c < kNB; ++c) {
-                if constexpr (kTiled) { if (c < nb) A(r0 + i, kb + c) = x[c]; }
-                else s_P[i * kPanelStride + c] = x[c];
+                for (int e = 0; e < kNB / 4; ++e) {
+                    const int c = 4 * e + qa;
+                    if constexpr (kTiled) { if (live && c < nb) A(r0 + i, kb + c) = x[e]; }
+                    else { if (live) s_P[i * kPanelStride + c] = x[e]; }
+                }
             }
         }
         __syncthreads();
@@ -1936,8 +1953,11 @@ __global__ void __launch_bounds__(256) k_trim_eval(BatchDev bd, SolveParams sp) 
     stage_window(wd, bd.pose[st.cur], bd.cam, s_pose, s_cam);
     __syncthreads();
     const int lane = threadIdx.x & 31;
-    const int j = blockIdx.x * 8 + (threadIdx.x >> 5);
-    if (j >= wd.n_lm) return;
+    // 64 landmarks per CTA (8 rounds of one landmark per warp): the kernel is launched in every pass and idles in all but the one or
+    // two trimming passes of a solve -- with 8 landmarks per CTA the idle launch of a 148-window batch alone cost 49 us per pass
+    for (int it = 0; it < 8; ++it) {
+    const int j = (blockIdx.x * 8 + it) * 8 + (threadIdx.x >> 5);
+    if (j >= wd.n_lm) continue;
     const int L = wd.lm_off + j;
     double m_d = -1.0, m_r = -1.0;
     if (bd.lm_active[L]) {
@@ -1973,6 +1993,7 @@ __global__ void __launch_bounds__(256) k_trim_eval(BatchDev bd, SolveParams sp) 
             m_g = fabs(pl[0] * px[0] + pl[1] * px[1] + pl[2] * px[2] + pl[3]);
         }
         bd.trim_val[2 * (size_t)bd.tot_lm + L] = m_g;
+    }
     }
 }
 
@@ -2218,7 +2239,7 @@ void launch_reset(const BatchDev& bd, const LaunchCfg& lc, cudaStream_t s) {
 int launch_pass(const BatchDev& bd, const SolveParams& sp, const LaunchCfg& lc, Counters* cnt, cudaStream_t s) {
     const int B = bd.n_win;
     const dim3 g_obs((bd.max_obs + 255) / 256, B);
-    const dim3 g_lm((bd.max_lm + 7) / 8, B);
+    const dim3 g_lm((bd.max_lm + 63) / 64, B);
     k_panel_zero<<<dim3(64, B), 256, 0, s>>>(bd); LCHK("k_panel_zero");
     k_solve_begin<<<B, 256, 0, s>>>(bd, sp); LCHK("k_solve_begin");
     const bool timed = lc.time_jacobian && lc.ev_pool && *lc.ev_used + 2 <= lc.ev_cap;
@@ -2228,7 +2249,7 @@ int launch_pass(const BatchDev& bd, const SolveParams& sp, const LaunchCfg& lc, 
         if (bd.tot_gp > 0) k_gp_eval<true><<<B, 256, 0, s>>>(bd, sp);
         LCHK("k_gp_eval");
         if (timed) cudaEventRecord(lc.ev_pool[(*lc.ev_used)++], s);
-        k_linearize<<<dim3((bd.max_obs / 16 + 2 + kLinWarps - 1) / kLinWarps, B), kLinThreads, 0, s>>>(bd, sp); LCHK("k_linearize");
+        k_linearize<<<dim3((lin_tile_bound(bd.max_obs, bd.max_lm) + kLinWarps - 1) / kLinWarps, B), kLinThreads, 0, s>>>(bd, sp); LCHK("k_linearize");
         if (timed) cudaEventRecord(lc.ev_pool[(*lc.ev_used)++], s);
         k_pose_hessian<<<dim3(bd.max_kf, B), 256, 0, s>>>(bd, sp); LCHK("k_pose_hessian");
     } else {

@@ -26,39 +26,54 @@ namespace kba {
 constexpr int kLinThreads = 256;
 constexpr int kLinWarps = kLinThreads / 32;
 
-// tiles of window w: at most n_obs / 16 + 2 (two consecutive tiles hold more than 32 observations), stored at
-// BatchDev::lin_tile + obs_off / 16 + 2 w as {first observation (window-local), observations}
-__device__ __forceinline__ size_t lin_tile_offset(const WinDesc& wd, int w) { return (size_t)(wd.obs_off / 16) + 2 * (size_t)w; }
+// tiles of window w: at most n_obs / 16 + n_lm / 32 + 4 (two consecutive tiles of a chunk hold more than 32 observations; every
+// chunk of >= 64 landmarks may end with a short one), stored at BatchDev::lin_tile + lin_tile_offset as {first observation
+// (window-local), observations}
+__host__ __device__ __forceinline__ int lin_tile_bound(int n_obs, int n_lm) { return n_obs / 16 + n_lm / 32 + 4; }
+__device__ __forceinline__ size_t lin_tile_offset(const WinDesc& wd, int w) {
+    return (size_t)(wd.obs_off / 16) + (size_t)(wd.lm_off / 32) + 4 * (size_t)w;
+}
 
-// called by k_solve_begin (one CTA per window): greedy packing by thread 0 over a shared-memory copy of the CSR pointers
-__device__ inline void build_lin_tiles(const BatchDev& bd, const WinDesc& wd, WinState& st, int w, int* s_ptr) {
-    constexpr int kChunk = 1024;
+// called by k_solve_begin (one CTA per window).  The tiling depends on the CSR only.  Greedy packing is sequential, so the
+// landmarks are cut into <= 512 chunks that are packed independently by one thread each (pass 1 counts, a scan places the
+// chunks, pass 2 writes): a serial pass over 3000 landmarks cost 270 us per solve begin, this one a few.
+__device__ inline void build_lin_tiles(const BatchDev& bd, const WinDesc& wd, WinState& st, int w, int* s_chunk /* [513] */) {
     const int* lm_ptr = bd.lm_ptr + wd.lm_off + w;
     int2* tiles = bd.lin_tile + lin_tile_offset(wd, w);
-    int n_tiles = 0, t_start = -1, t_cnt = 0;  // carried by thread 0
-    for (int j0 = 0; j0 < wd.n_lm; j0 += kChunk) {
-        const int nj = min(kChunk, wd.n_lm - j0);
-        __syncthreads();
-        for (int i = threadIdx.x; i <= nj; i += blockDim.x) s_ptr[i] = lm_ptr[j0 + i];
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            for (int i = 0; i < nj; ++i) {
-                const int o0 = s_ptr[i], k = s_ptr[i + 1] - o0;
-                if (k <= 0) continue;                       // no observations: invisible
-                if (k > 32) {                               // oversized (never on this path): ends the tile, is skipped
-                    if (t_cnt > 0) tiles[n_tiles++] = make_int2(t_start, t_cnt);
-                    t_cnt = 0;
-                    continue;
+    const int per = max(64, (wd.n_lm + 511) / 512);
+    const int n_chunks = (wd.n_lm + per - 1) / per;
+    for (int pass = 0; pass < 2; ++pass) {
+        for (int c = threadIdx.x; c < n_chunks; c += blockDim.x) {
+            const int j0 = c * per, j1 = min(wd.n_lm, j0 + per);
+            int n = 0, t_start = 0, t_cnt = 0;
+            int2* out = tiles + (pass ? s_chunk[c] : 0);
+            int o0 = lm_ptr[j0];
+            for (int j = j0; j < j1; ++j) {
+                const int o1 = lm_ptr[j + 1], k = o1 - o0;
+                if (k > 0) {
+                    const bool over = k > 32;  // oversized (never on this path): ends the tile, is skipped
+                    if (t_cnt > 0 && (over || t_cnt + k > 32)) { if (pass) out[n] = make_int2(t_start, t_cnt); ++n; t_cnt = 0; }
+                    if (!over) { if (t_cnt == 0) t_start = o0; t_cnt += k; }
                 }
-                if (t_cnt > 0 && t_cnt + k > 32) { tiles[n_tiles++] = make_int2(t_start, t_cnt); t_cnt = 0; }
-                if (t_cnt == 0) t_start = o0;
-                t_cnt += k;
+                o0 = o1;
             }
+            if (t_cnt > 0) { if (pass) out[n] = make_int2(t_start, t_cnt); ++n; }
+            if (!pass) s_chunk[c] = n;
         }
-    }
-    if (threadIdx.x == 0) {
-        if (t_cnt > 0) tiles[n_tiles++] = make_int2(t_start, t_cnt);
-        st.n_lin_tiles = n_tiles;
+        __syncthreads();
+        if (!pass) {
+            if (threadIdx.x == 0) {
+                int acc = 0;
+                for (int c = 0; c < n_chunks; ++c) { const int t = s_chunk[c]; s_chunk[c] = acc; acc += t; }
+                // windows this path does not serve (several observations per landmark and keyframe: more tile breaks than the
+                // bound allows for) get no tiles -- k_linearize is not launched for them (BatchDev::lin1)
+                if (acc > lin_tile_bound(wd.n_obs, wd.n_lm)) acc = 0;
+                st.n_lin_tiles = acc;
+                s_chunk[512] = acc;
+            }
+            __syncthreads();
+            if (s_chunk[512] == 0) return;
+        }
     }
 }
 
@@ -150,6 +165,12 @@ __global__ void __launch_bounds__(kLinThreads, 2) k_linearize(BatchDev bd, Solve
         for (int q = 0; q < 9; ++q) sw[q][lane] = cg[q];
         const int seg0 = p0 - tile.x;
         const int klen = p1 - p0;
+        // the stored Jacobi scaling of my landmark (past iteration zero): requested here, consumed after the segment sums
+        double tt_ld[3] = {0.0, 0.0, 0.0};
+        if (act && !st.iter0) {
+#pragma unroll
+            for (int e = 0; e < 3; ++e) tt_ld[e] = bd.lm_scale[3 * (size_t)L + e];
+        }
         __syncwarp();
         double (*st_)[33] = s_tot[warp];
         // lane seg0 + q of a landmark sums component q of its block in lane order (landmarks with fewer than 9 observations: several
@@ -188,7 +209,7 @@ __global__ void __launch_bounds__(kLinThreads, 2) k_linearize(BatchDev bd, Solve
             double tt[3], lam[3];
 #pragma unroll
             for (int e = 0; e < 3; ++e) {
-                tt[e] = st.iter0 ? 1.0 + sqrt(cd[e]) : bd.lm_scale[3 * (size_t)L + e];
+                tt[e] = st.iter0 ? 1.0 + sqrt(cd[e]) : tt_ld[e];
                 const double t2 = tt[e] * tt[e];
                 lam[e] = fmin(fmax(cd[e], sp.min_lm_diagonal * t2), sp.max_lm_diagonal * t2) * inv_radius;
             }
