@@ -557,6 +557,7 @@ int kba_batch_create(kba_handle* h, int32_t n_windows, const kba_window* w, kba_
     // cost partials: one per CTA of k_linearize (8 warp tiles each, kba_linearize.cuh: lin_tile_bound) or per 256-observation tile of k_eval_obs
     bd.cost_parts = std::max((bd.max_obs + 255) / 256, (bd.max_obs / 16 + bd.max_lm / 32 + 4 + 7) / 8);
     { const char* le = std::getenv("KBA_LINEARIZE"); b->lc.lin_fused = !(le && std::atoi(le) == 0); }
+    { const char* le = std::getenv("KBA_LIN_BLOCKS"); if (le && std::atoi(le) == 3) b->lc.lin_blocks = 3; }
     {  // tuning knobs of the residual/Jacobian kernel (defaults measured on B200)
         auto knob = [](const char* name, int dflt) { const char* e = std::getenv(name); return e ? std::atoi(e) : dflt; };
         bd.eval_tiles_jac = std::max(1, knob("KBA_EVAL_TILES_JAC", 8));

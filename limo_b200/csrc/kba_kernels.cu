@@ -2249,7 +2249,10 @@ int launch_pass(const BatchDev& bd, const SolveParams& sp, const LaunchCfg& lc, 
         if (bd.tot_gp > 0) k_gp_eval<true><<<B, 256, 0, s>>>(bd, sp);
         LCHK("k_gp_eval");
         if (timed) cudaEventRecord(lc.ev_pool[(*lc.ev_used)++], s);
-        k_linearize<<<dim3((lin_tile_bound(bd.max_obs, bd.max_lm) + kLinWarps - 1) / kLinWarps, B), kLinThreads, 0, s>>>(bd, sp); LCHK("k_linearize");
+        const dim3 g_lin((lin_tile_bound(bd.max_obs, bd.max_lm) + kLinWarps - 1) / kLinWarps, B);
+        if (lc.lin_blocks == 3) k_linearize<3><<<g_lin, kLinThreads, 0, s>>>(bd, sp);
+        else k_linearize<2><<<g_lin, kLinThreads, 0, s>>>(bd, sp);
+        LCHK("k_linearize");
         if (timed) cudaEventRecord(lc.ev_pool[(*lc.ev_used)++], s);
         k_pose_hessian<<<dim3(bd.max_kf, B), 256, 0, s>>>(bd, sp); LCHK("k_pose_hessian");
     } else {

@@ -39,6 +39,7 @@ struct LaunchCfg {
     int max_rank = 0;         // largest observation rank in the batch (multi-camera rigs)
     bool small_syrk = false;  // every window has <= 184 reduced rows: register-resident Schur kernel
     bool lin_fused = true;    // fused path: evaluation + landmark blocks + V rows in one kernel (k_linearize); KBA_LINEARIZE=0: three kernels
+    int lin_blocks = 2;       // CTAs per SM k_linearize is compiled for (KBA_LIN_BLOCKS: 2 or 3)
     int fused_slots = 6;      // fused Schur kernel instance: 6 accumulator blocks per warp (<= 176 rows) or 7 (<= 184)
     int rounds_override = -1, min_landmarks_for_trimming = 100, num_rounds_option = 1;
     bool time_jacobian = false;

@@ -77,7 +77,10 @@ __device__ inline void build_lin_tiles(const BatchDev& bd, const WinDesc& wd, Wi
     }
 }
 
-__global__ void __launch_bounds__(kLinThreads, 2) k_linearize(BatchDev bd, SolveParams sp) {
+// kMinBlocks: CTAs per SM the register allocation is sized for.  2: everything in registers (128 per thread); 3: 80 registers, the
+// Jacobian rows spill to local memory across the segment sums (KBA_LIN_BLOCKS, measured in profiles/r02_linearize.md)
+template <int kMinBlocks>
+__global__ void __launch_bounds__(kLinThreads, kMinBlocks) k_linearize(BatchDev bd, SolveParams sp) {
     const int w = blockIdx.y;
     WinState& st = bd.state[w];
     if (st.phase != PH_ITERATE) return;
@@ -97,8 +100,8 @@ __global__ void __launch_bounds__(kLinThreads, 2) k_linearize(BatchDev bd, Solve
     __shared__ __align__(16) double s_pose[kFusedMaxKf * kPoseStride];
     __shared__ __align__(16) double s_cam[kMaxCam * kCamStride];
     __shared__ __align__(8) uint64_t s_bar;
-    __shared__ double s_cg[kLinWarps][9][33];           // per warp: block contributions of its 32 observations
-    __shared__ double s_tot[kLinWarps][9][33];          //           their sums per landmark, at the landmark's first lane
+    __shared__ double s_cg[kLinWarps][9][33];           // per warp: block contributions of its 32 observations; then, in place at the
+                                                        // landmark's first lane, their sums
     __shared__ double s_red[kLinWarps];
     __shared__ int s_cnt[kLinWarps];
     const size_t base = (size_t)wd.obs_off;
@@ -158,9 +161,8 @@ __global__ void __launch_bounds__(kLinThreads, 2) k_linearize(BatchDev bd, Solve
         if (lane == 0) { s_red[warp] = cs; s_cnt[warp] = dn; }
     }
     if (!wd.landmarks_fixed) {  // (uniform per window) motion-only: the landmark blocks are constant, only the cost at x was needed
-        // ---- landmark blocks.  Lanes p0 - tile.x .. p1 - tile.x - 1 hold my landmark; the m-th landmark of the tile starts at
-        //      the m-th set bit of `starts`.  Lane (m, q) = 9 m + q (+ 32, ...) sums component q of landmark m in lane order.
-        double (*sw)[33] = s_cg[warp];  // row stride 33: the (landmark, component) lanes below hit different banks
+        // ---- landmark blocks.  Lanes seg0 .. seg0 + klen - 1 of the warp hold my landmark.
+        double (*sw)[33] = s_cg[warp];  // row stride 33: the lanes summing different components below hit different banks
 #pragma unroll
         for (int q = 0; q < 9; ++q) sw[q][lane] = cg[q];
         const int seg0 = p0 - tile.x;
@@ -172,23 +174,23 @@ __global__ void __launch_bounds__(kLinThreads, 2) k_linearize(BatchDev bd, Solve
             for (int e = 0; e < 3; ++e) tt_ld[e] = bd.lm_scale[3 * (size_t)L + e];
         }
         __syncwarp();
-        double (*st_)[33] = s_tot[warp];
         // lane seg0 + q of a landmark sums component q of its block in lane order (landmarks with fewer than 9 observations: several
-        // components per lane); the sums sit at [q][first lane of the landmark]
+        // components per lane) and leaves the sum at [q][first lane of the landmark] -- in place: component q of a landmark is read
+        // and written by this one lane only
         if (have) {
             for (int q = lane - seg0; q < 9; q += klen) {
                 double sacc = 0.0;
                 for (int l = seg0; l < seg0 + klen; ++l) sacc += sw[q][l];
-                st_[q][seg0] = sacc;
+                sw[q][seg0] = sacc;
             }
         }
         __syncwarp();
         if (act) {
             double c[6], g[3];
 #pragma unroll
-            for (int q = 0; q < 6; ++q) c[q] = st_[q][seg0];
+            for (int q = 0; q < 6; ++q) c[q] = sw[q][seg0];
 #pragma unroll
-            for (int q = 0; q < 3; ++q) g[q] = st_[6 + q][seg0];
+            for (int q = 0; q < 3; ++q) g[q] = sw[6 + q][seg0];
             const bool first = lane == seg0;  // writes the landmark's outputs
             // the landmark's ground-plane height residual (at most one) is one more row of its Jacobian
             const int gl = (wd.n_gp > 0) ? bd.gp_of_lm[L] : -1;
