@@ -50,6 +50,7 @@ struct kba_handle {
 // Wait for the handle's stream.  With KBA_BLOCKING_SYNC=1 (read at kba_create) the host thread sleeps on a blocking-sync
 // event instead of spinning on a core (cudaStreamSynchronize spins under the default scheduling policy): for several
 // handles per process / one process per GPU that share the box's cores with the packing threads.
+static cudaError_t wait_event(kba_handle*, cudaEvent_t ev) { return cudaEventSynchronize(ev); }
 static cudaError_t wait_stream(kba_handle* h) {
     if (!h->blocking_sync) return cudaStreamSynchronize(h->stream);  // lowest latency: the default for a lone handle
     if (!h->ev_block) {
@@ -116,7 +117,7 @@ struct kba_batch {
     LaunchCfg lc;
     size_t h2d_bytes = 0, d2h_bytes = 0;
     float last_solve_ms = 0.f;
-    cudaEvent_t ev_a = nullptr, ev_b = nullptr;
+    cudaEvent_t ev_a = nullptr, ev_b = nullptr, ev_poll = nullptr;
 
     template <typename T>
     int dev_alloc(T** p, size_t count) {
@@ -146,6 +147,7 @@ struct kba_batch {
         scratch.clear();
         if (ev_a) cudaEventDestroy(ev_a);
         if (ev_b) cudaEventDestroy(ev_b);
+        if (ev_poll) cudaEventDestroy(ev_poll);
     }
 };
 
@@ -663,6 +665,7 @@ int kba_batch_create(kba_handle* h, int32_t n_windows, const kba_window* w, kba_
         cudaError_t e = cudaMemset(bd.jac_obs, 0, sizeof(unsigned long long));
         if (e == cudaSuccess) e = cudaEventCreate(&b->ev_a);
         if (e == cudaSuccess) e = cudaEventCreate(&b->ev_b);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&b->ev_poll, (h->blocking_sync ? cudaEventBlockingSync : 0) | cudaEventDisableTiming);
         if (e == cudaSuccess) e = configure_kernels(nr_cap_max);
         if (e == cudaSuccess && b->device_pack) e = configure_pack();
         if (e != cudaSuccess) { b->release(); delete b; return fail(KBA_ERR_CUDA, cudaGetErrorString(e)); }
@@ -822,7 +825,7 @@ int kba_batch_solve(kba_batch* b, const kba_options* opt) {
     const int max_passes = rounds_max * (3 * opt->trim_solver_iterations + 4) + opt->final_solver_iterations + 8;
     const auto t0 = std::chrono::steady_clock::now();
     int check_every = 4;
-    bool timed_out = false;
+    bool timed_out = false, poll_pending = false;
     for (int pass = 0; pass < max_passes; ++pass) {
         if (launch_pass(b->bd, sp, lc, &h->counters, s)) {  // message set by the exchange
             cudaEventRecord(b->ev_b, s);
@@ -832,19 +835,29 @@ int kba_batch_solve(kba_batch* b, const kba_options* opt) {
             const cudaError_t le = cudaGetLastError();
             if (le != cudaSuccess) { cudaEventRecord(b->ev_b, s); cudaStreamSynchronize(s); return fail(KBA_ERR_CUDA, std::string("kernel launch failed in kba_batch_solve: ") + cudaGetErrorString(le)); }
         }
+        // Completion check without draining the queue: every `check_every` passes the active-window count is copied out behind an
+        // event, the next passes are enqueued at once, and the count is READ one check later.  The device never waits for the
+        // host (a synchronous poll emptied the queue 12-15 times per solve: ~1 ms of a 14 ms single-window solve); the price is
+        // up to `check_every` passes enqueued after the last window finished, in which every kernel exits at once.  In a sharded
+        // solve the state -- hence the count -- is identical on all ranks, so they still issue the same passes.
         if ((pass + 1) % check_every == 0 || pass + 1 == max_passes) {
+            if (poll_pending) {
+                CU(wait_event(h, b->ev_poll));
+                poll_pending = false;
+                if (b->n_active.h[0] == 0) break;
+                if (opt->solver_time_sec > 0 && !b->bd.sharded) {  // host safety cap, see below
+                    const double el = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+                    if (el > KBA_MAX_SOLVES * opt->solver_time_sec + 2.0) { timed_out = true; break; }
+                }
+            }
             launch_count_active(b->bd, s);
             CU(b->n_active.download(s));
-            CU(wait_stream(h));
-            if (b->n_active.h[0] == 0) break;
+            CU(cudaEventRecord(b->ev_poll, s));
+            poll_pending = true;
             // max_solver_time_in_seconds is applied PER INNER SOLVE on the device (k_lm_update, like ceres), which always
             // lets the final solve start; the host only guards against a stuck device with the budget of every possible
             // inner solve.  A sharded solve is collective: its ranks must issue the same passes, so no rank may leave on
             // its own clock (the iteration caps bound it).
-            if (opt->solver_time_sec > 0 && !b->bd.sharded) {
-                const double el = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
-                if (el > KBA_MAX_SOLVES * opt->solver_time_sec + 2.0) { timed_out = true; break; }
-            }
         }
     }
     if (timed_out) g_last_error = "kba_batch_solve: host safety cap reached, unfinished windows carry KBA_ERR_TIMEOUT in kba_result.status";

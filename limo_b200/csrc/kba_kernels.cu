@@ -2240,7 +2240,8 @@ int launch_pass(const BatchDev& bd, const SolveParams& sp, const LaunchCfg& lc, 
     const int B = bd.n_win;
     const dim3 g_obs((bd.max_obs + 255) / 256, B);
     const dim3 g_lm((bd.max_lm + 63) / 64, B);
-    k_panel_zero<<<dim3(64, B), 256, 0, s>>>(bd); LCHK("k_panel_zero");
+    if (!bd.fused) k_panel_zero<<<dim3(64, B), 256, 0, s>>>(bd);  // the fused path has no global V panels
+    LCHK("k_panel_zero");
     k_solve_begin<<<B, 256, 0, s>>>(bd, sp); LCHK("k_solve_begin");
     const bool timed = lc.time_jacobian && lc.ev_pool && *lc.ev_used + 2 <= lc.ev_cap;
     // one-kernel linearisation (kba_linearize.cuh): fused path, FP64, at most one observation per (landmark, keyframe)
@@ -2338,7 +2339,7 @@ int launch_pass(const BatchDev& bd, const SolveParams& sp, const LaunchCfg& lc, 
         const int gp = bd.tot_gp > 0 ? 1 : 0;
         const int prep = lin1 ? 1 : 2 + (bd.fused ? 1 : lc.max_rank + 1 + gp);  // pose blocks [, landmark blocks, V rows]
         const int split = (!bd.solve_tiled && bd.solve_split) ? 1 + 3 * ((lc.nr_cap_max + kNB - 1) / kNB) : 0;
-        cnt->launches_total += 1 + 1 + 1 + gp + prep + 1 + (bd.p_split > 1 ? 1 : 0) + 1 + split + 1 + 1 + gp + 1 + 2;
+        cnt->launches_total += (bd.fused ? 0 : 1) + 1 + 1 + gp + prep + 1 + (bd.p_split > 1 ? 1 : 0) + 1 + split + 1 + 1 + gp + 1 + 2;
         cnt->launches_jacobian += 1; cnt->launches_prep += prep + gp; cnt->launches_schur += 1; cnt->launches_solve += 2;
         cnt->launches_backsub += 1; cnt->launches_cost += 1 + gp; cnt->launches_update += 1; cnt->launches_trim += 2;
     }
