@@ -1,12 +1,18 @@
-// kba_kernels.cu -- sm_100a kernels of the window solver.  One LM "pass" over a batch of windows is
-//   k_panel_zero -> k_solve_begin -> k_eval_obs<true> (residual/Jacobian, HBM streaming) [-> k_gp_eval<true>]
-//   -> k_pose_hessian -> k_landmark_reduce -> k_obs_v [-> k_gp_panel]          (kba_prep.cuh: landmark blocks, V panels)
-//   -> k_schur_syrk_tma | k_schur_syrk (FP64 tensor-core SYRK) [-> k_sred_reduce]
+// kba_kernels.cu -- sm_100a kernels of the window solver.  One LM "pass" over a batch of windows is, for small windows
+// (every window <= 184 reduced rows and <= 32 keyframes: BASELINE configs 1-3),
+//   k_solve_begin [-> k_gp_eval<true>] -> k_linearize (kba_linearize.cuh: evaluation + landmark blocks + V rows, Jacobian in registers)
+//   -> k_pose_hessian -> k_schur_fused (kba_schur_fused.cuh: warp-specialised FP64 tensor-core SYRK over bulk-copied V columns)
+//   [-> k_sred_reduce] -> k_reduced_solve<tiled> -> k_backsub_v -> k_eval_obs<false> (candidate cost) [-> k_gp_eval<false>]
+//   -> k_lm_update -> k_trim_eval -> k_trim_select
+// and for large windows (BASELINE config 5), the FP32 mode or rigs with several observations per landmark and keyframe
+//   k_panel_zero -> k_solve_begin -> k_eval_obs<true> (materialised residual/Jacobian, HBM streaming) [-> k_gp_eval<true>]
+//   -> k_pose_hessian -> k_landmark_reduce -> k_obs_v | k_obs_v2 [-> k_gp_panel]   (kba_prep.cuh: landmark blocks, V panels)
+//   -> k_schur_syrk | k_schur_fused (FP64 tensor-core SYRK) [-> k_sred_reduce]
 //   -> k_reduced_solve (or, for large systems of small batches: stage 1, k_chol_diag/panel/trail per block, stage 2)
-//   -> k_backsub -> k_eval_obs<false> (candidate cost) [-> k_gp_eval<false>] -> k_lm_update -> k_trim_eval -> k_trim_select
-// with the k_shard_* kernels and NCCL all-reduces in between when one window is sharded over several GPUs (launch_pass).
-// Every kernel looks at the per-window state and returns immediately for windows that have nothing to do, so the
-// host launches a fixed sequence without synchronising per iteration.
+//   -> k_backsub -> k_eval_obs<false> [-> k_gp_eval<false>] -> k_lm_update -> k_trim_eval -> k_trim_select
+// with k_shard_pack / k_shard_scalars / k_shard_trim_scatter and three NCCL all-reduces in between when one window is sharded over
+// several GPUs (launch_pass).  Every kernel looks at the per-window state and returns immediately for windows that have nothing
+// to do, so the host launches a fixed sequence without synchronising per iteration.
 #include "kba_device.cuh"
 #include "kba_kernels.h"
 #include "kba_regularisers.cuh"
@@ -2092,6 +2098,21 @@ __global__ void __launch_bounds__(512) k_trim_select(BatchDev bd, SolveParams sp
         }
         const unsigned long long pivot = s_prefix;  // bit pattern of the value with rank `num`
         const int tie_keep = s_k;                   // ties with fewer than tie_keep smaller-index ties stay
+        // how many values equal the pivot?  Normally one (the pivot itself): then the O(n) index count below -- one thread walking
+        // every value, 50-100 us per group -- is not needed
+        __syncthreads();
+        if (threadIdx.x == 0) s_n = 0;
+        __syncthreads();
+        {
+            int ties = 0;
+            for (int j = threadIdx.x; j < n_items; j += blockDim.x) {
+                const double vj = val(j);
+                if (vj >= 0.0) ties += (((unsigned long long)__double_as_longlong(vj) & 0x7fffffffffffffffull) == pivot);
+            }
+            if (ties) atomicAdd(&s_n, ties);
+        }
+        __syncthreads();
+        const int n_ties = s_n;
         for (int j = threadIdx.x; j < n_items; j += blockDim.x) {
             const double vj = val(j);
             if (!(vj >= 0.0)) continue;
@@ -2101,7 +2122,7 @@ __global__ void __launch_bounds__(512) k_trim_select(BatchDev bd, SolveParams sp
             if (!reject) {
                 const int oj = oid(j);
                 int before = 0;
-                for (int k = 0; k < n_items; ++k) {
+                for (int k = 0; k < (n_ties > 1 ? n_items : 0); ++k) {
                     const double vk = val(k);
                     if (!(vk >= 0.0)) continue;
                     const unsigned long long kk = (unsigned long long)__double_as_longlong(vk) & 0x7fffffffffffffffull;

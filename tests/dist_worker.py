@@ -37,6 +37,15 @@ def main():
     # the data every rank would contribute to the exchanged reduced system: here the per-keyframe observation counts
     counts = np.bincount(sub.obs_kf, minlength=big.n_kf).astype(float)
     counts_sum = parallel.sum_over_ranks(counts)
+    # the packed scalar exchange of the sharded solve (kba_shard.cu / k_shard_scalars): ONE sum all-reduce carries the sums AND the
+    # gradient max-norm, as one slot per rank (the others contribute zero) -- the maximum is taken locally afterwards
+    g_mine = 0.25 + 0.5 * rank
+    xs = np.zeros(16 + world)
+    xs[:4] = [1.0 + rank, 2.0, 3.0 * rank, 4.0]
+    xs[16 + rank] = g_mine
+    xs_sum = np.asarray(parallel.sum_over_ranks(xs))
+    packed_ok = bool(xs_sum[16:].max() == max(0.25 + 0.5 * r for r in range(world)) and xs_sum[0] == sum(1.0 + r for r in range(world))
+                     and np.count_nonzero(xs_sum[4:16]) == 0)
     ok_slice = bool(np.array_equal(sub.lm_pos, big.lm_pos[j0:j1]) and np.array_equal(
         sub.obs_u, big.obs_u[big.lm_obs_ptr[j0]:big.lm_obs_ptr[j1]]))
     if rank == 0:
@@ -44,7 +53,7 @@ def main():
             json.dump(dict(world=world, ms_max=ms_max, all_ms=all_ms, n_windows=n_windows, cost_sum=cost_sum, seeds=seeds,
                            n_obs_total=n_obs_total, n_lm_total=n_lm_total, counts_sum=counts_sum,
                            counts_full=np.bincount(big.obs_kf, minlength=big.n_kf).tolist(),
-                           big=(big.n_obs, big.n_lm), ok_slice=ok_slice, shard0=(j0, j1, sub.n_obs)), f)
+                           big=(big.n_obs, big.n_lm), ok_slice=ok_slice, packed_ok=packed_ok, shard0=(j0, j1, sub.n_obs)), f)
     parallel.finalize()
 
 

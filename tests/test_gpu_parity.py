@@ -256,6 +256,19 @@ def test_one_kernel_linearisation_equals_three_kernels(handle, monkeypatch, case
     assert np.linalg.norm(a.kf_pose[:, 4:] - b.kf_pose[:, 4:], axis=1).max() <= 1e-8
 
 
+def test_many_landmarks_host_packed_small_window(handle, oracle):
+    """34 000 landmarks with short tracks in a 24-keyframe window: more landmarks than the device-side sort holds (32 768), so the
+    window is packed on the host, yet it is a small window (139 reduced rows) and linearised by k_linearize -- its tile builder
+    runs with 67 landmarks per chunk, twelve landmarks share a warp tile.  GPU vs oracle."""
+    win = synth.make_window(2, n_kf=24, n_lm=34000, n_obs=80000, seed=13)
+    assert win.n_lm > 32768
+    rg = handle.solve_window(win)
+    rc = oracle.solve_window(win, num_threads=8)
+    _compare_solves(rg, rc, win, "many landmarks", lm_outliers=17)  # 0.05 % of the landmarks (two-view tracks without parallax)
+    dl = np.linalg.norm(rg.lm_pos[:win.n_lm] - rc.lm_pos[:win.n_lm], axis=1)
+    assert np.percentile(dl, 99) <= 1e-6
+
+
 def test_small_batch_does_not_lower_a_live_batch_shared_memory(handle):
     """the opt-in dynamic shared memory of the solve kernels is a per-function attribute: creating a batch with a smaller
     reduced system while a larger one is alive (a persistent window next to one-shot solves) must not break the larger one"""

@@ -41,6 +41,7 @@ def test_world_size_2_gloo(tmp_path, oracle):
     # the landmark shards tile the large window exactly and their per-keyframe contributions add up
     assert [d["n_obs_total"], d["n_lm_total"]] == list(d["big"]) and d["ok_slice"]
     assert d["counts_sum"] == d["counts_full"]
+    assert d["packed_ok"]  # sums and the per-rank max slots through one sum all-reduce
 
 
 def test_landmark_ranges_balance():
