@@ -419,6 +419,9 @@ def main():
     windows = [base[i % n_distinct] for i in range(args.batch)]
     n_obs_win = windows[0].n_obs
 
+    # a stream of its own, not the legacy default stream: the library issues a solve as one CUDA graph (the passes are the body
+    # of a conditional WHILE node), and the legacy stream cannot be captured -- there it falls back to kernel-by-kernel launches
+    torch.cuda.set_stream(torch.cuda.Stream())
     stream = torch.cuda.current_stream()
     h = capi.Handle(local_rank, stream=stream.cuda_stream)
     opt = capi.default_options()

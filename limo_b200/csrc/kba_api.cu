@@ -117,7 +117,24 @@ struct kba_batch {
     LaunchCfg lc;
     size_t h2d_bytes = 0, d2h_bytes = 0;
     float last_solve_ms = 0.f;
-    cudaEvent_t ev_a = nullptr, ev_b = nullptr, ev_poll = nullptr;
+    cudaEvent_t ev_a = nullptr, ev_b = nullptr, ev_poll = nullptr, ev_poll2 = nullptr;
+    // The pass sequence as a CUDA graph (kba_batch_solve): mode 2 = ONE launch per solve, the passes are the body of a conditional
+    // WHILE node whose condition the device sets (k_loop_cond); mode 1 = a graph of `check_every` passes launched until the
+    // downloaded active-window count is zero.  Rebuilt when anything a kernel receives by value changes (`key`).
+    struct SolveGraph {
+        cudaGraph_t graph = nullptr;
+        cudaGraphExec_t exec = nullptr;
+        std::vector<unsigned char> key;
+        Counters per_pass;
+        int mode = 0, passes_per_launch = 0;
+        bool unusable = false;  // capture / instantiation failed once on this batch: the stream path is used from then on
+        void destroy() {
+            if (exec) cudaGraphExecDestroy(exec);
+            if (graph) cudaGraphDestroy(graph);
+            exec = nullptr; graph = nullptr; key.clear();
+        }
+    } sg;
+    Staged<int> loop_pass;  // passes the WHILE node has run (device counter + pinned copy)
 
     template <typename T>
     int dev_alloc(T** p, size_t count) {
@@ -148,6 +165,9 @@ struct kba_batch {
         if (ev_a) cudaEventDestroy(ev_a);
         if (ev_b) cudaEventDestroy(ev_b);
         if (ev_poll) cudaEventDestroy(ev_poll);
+        if (ev_poll2) cudaEventDestroy(ev_poll2);
+        sg.destroy();
+        loop_pass.release();
     }
 };
 
@@ -383,6 +403,97 @@ static int window_rows(const kba_window& w) {
 
 struct kba_shard_comm;
 kba::Exchange kba_shard_exchange(kba_shard_comm* c);  // kba_shard.cu
+
+// How the pass sequence of a solve is issued (KBA_GRAPH, read once):
+//   2 (default)  one CUDA graph launch per solve: the passes are the body of a conditional WHILE node, k_loop_cond sets the
+//                condition on the device -- no host polling, no pass enqueued after the last window finished, no launch gaps;
+//   1            a graph of four passes + the active-window count, launched until the count read back is zero;
+//   0            kernel by kernel on the stream (always used for sharded solves -- NCCL calls between the kernels --, with kernel
+//                timing on -- event pairs around the linearisation launches --, with KBA_LAUNCH_CHECK, or on the legacy stream).
+static int solve_graph_mode() {
+    static const int m = [] {
+        const char* e = getenv("KBA_GRAPH");
+        const int v = e ? atoi(e) : 2;
+        return (v < 0 || v > 2) ? 2 : v;
+    }();
+    return m;
+}
+
+template <typename T>
+static void key_append(std::vector<unsigned char>& k, const T& v) {
+    const unsigned char* p = reinterpret_cast<const unsigned char*>(&v);
+    k.insert(k.end(), p, p + sizeof(T));
+}
+
+// (re)builds b->sg for the given kernel arguments; false = not possible here (b->sg.unusable is set, the caller takes the stream path)
+static bool build_solve_graph(kba_batch* b, const SolveParams& sp, const LaunchCfg& lc, int mode, int max_passes, int check_every,
+                              const std::vector<unsigned char>& key) {
+    kba_batch::SolveGraph& g = b->sg;
+    g.destroy();
+    cudaStream_t s = b->h->stream;
+    Counters per{};
+    cudaError_t e = cudaSuccess;
+    bool capturing = false;
+    int rc_pass = 0;
+    if (mode == 2) {
+        cudaGraphConditionalHandle handle = 0;
+        cudaGraphNode_t node = nullptr;
+        cudaGraphNodeParams np = {};
+        e = cudaGraphCreate(&g.graph, 0);
+        if (e == cudaSuccess) e = cudaGraphConditionalHandleCreate(&handle, g.graph, 1, cudaGraphCondAssignDefault);
+        if (e == cudaSuccess) {
+            np.type = cudaGraphNodeTypeConditional;
+            np.conditional.handle = handle;
+            np.conditional.type = cudaGraphCondTypeWhile;
+            np.conditional.size = 1;
+            e = cudaGraphAddNode(&node, g.graph, nullptr, 0, &np);
+        }
+        if (e == cudaSuccess) e = cudaStreamBeginCaptureToGraph(s, np.conditional.phGraph_out[0], nullptr, nullptr, 0, cudaStreamCaptureModeThreadLocal);
+        if (e == cudaSuccess) {
+            capturing = true;
+            rc_pass = launch_pass(b->bd, sp, lc, &per, s);
+            launch_loop_cond(b->bd, (unsigned long long)handle, b->loop_pass.d, max_passes, s);
+            cudaGraph_t body = nullptr;
+            e = cudaStreamEndCapture(s, &body);
+            capturing = false;
+        }
+        g.passes_per_launch = 0;  // counted on the device
+    } else {
+        e = cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal);
+        if (e == cudaSuccess) {
+            capturing = true;
+            for (int i = 0; i < check_every && !rc_pass; ++i) rc_pass = launch_pass(b->bd, sp, lc, i == 0 ? &per : nullptr, s);
+            launch_count_active(b->bd, s);
+            b->n_active.download(s);
+            e = cudaStreamEndCapture(s, &g.graph);
+            capturing = false;
+        }
+        g.passes_per_launch = check_every;
+    }
+    if (capturing) { cudaGraph_t junk = nullptr; cudaStreamEndCapture(s, &junk); }
+    if (e == cudaSuccess && rc_pass) e = cudaErrorUnknown;
+    if (e == cudaSuccess) e = cudaGraphInstantiate(&g.exec, g.graph, 0);
+    if (e != cudaSuccess) {
+        if (getenv("KBA_GRAPH_VERBOSE")) fprintf(stderr, "kba: solve graph (mode %d) not available: %s -- stream launches\n", mode, cudaGetErrorString(e));
+        g.destroy();
+        g.unusable = true;
+        cudaGetLastError();  // the stream path starts with a clean error state
+        return false;
+    }
+    if (getenv("KBA_GRAPH_VERBOSE")) fprintf(stderr, "kba: solve graph built (mode %d, %lld launches per pass)\n", mode, per.launches_total);
+    g.key = key;
+    g.per_pass = per;
+    g.mode = mode;
+    return true;
+}
+
+static void add_pass_counters(Counters& c, const Counters& per, long long passes) {
+    c.launches_total += per.launches_total * passes; c.launches_jacobian += per.launches_jacobian * passes;
+    c.launches_prep += per.launches_prep * passes; c.launches_schur += per.launches_schur * passes;
+    c.launches_solve += per.launches_solve * passes; c.launches_backsub += per.launches_backsub * passes;
+    c.launches_cost += per.launches_cost * passes; c.launches_update += per.launches_update * passes;
+    c.launches_trim += per.launches_trim * passes;
+}
 
 extern "C" {
 
@@ -666,6 +777,8 @@ int kba_batch_create(kba_handle* h, int32_t n_windows, const kba_window* w, kba_
         if (e == cudaSuccess) e = cudaEventCreate(&b->ev_a);
         if (e == cudaSuccess) e = cudaEventCreate(&b->ev_b);
         if (e == cudaSuccess) e = cudaEventCreateWithFlags(&b->ev_poll, (h->blocking_sync ? cudaEventBlockingSync : 0) | cudaEventDisableTiming);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&b->ev_poll2, (h->blocking_sync ? cudaEventBlockingSync : 0) | cudaEventDisableTiming);
+        if (e == cudaSuccess && b->loop_pass.alloc(1, true)) e = cudaErrorMemoryAllocation;
         if (e == cudaSuccess) e = configure_kernels(nr_cap_max);
         if (e == cudaSuccess && b->device_pack) e = configure_pack();
         if (e != cudaSuccess) { b->release(); delete b; return fail(KBA_ERR_CUDA, cudaGetErrorString(e)); }
@@ -826,6 +939,59 @@ int kba_batch_solve(kba_batch* b, const kba_options* opt) {
     const auto t0 = std::chrono::steady_clock::now();
     int check_every = 4;
     bool timed_out = false, poll_pending = false;
+    // ---- graph paths (see solve_graph_mode) ----
+    int gmode = solve_graph_mode();
+    if (b->bd.sharded || h->kernel_timing || launch_check_enabled() || s == nullptr || b->sg.unusable) gmode = 0;
+    if (gmode) {
+        std::vector<unsigned char> key;
+        key.reserve(sizeof(BatchDev) + sizeof(SolveParams) + 64);
+        key_append(key, b->bd); key_append(key, sp); key_append(key, gmode); key_append(key, max_passes); key_append(key, s);
+        key_append(key, lc.nr_cap_max); key_append(key, lc.max_rank); key_append(key, (int)lc.small_syrk); key_append(key, (int)lc.lin_fused);
+        key_append(key, lc.lin_blocks); key_append(key, lc.fused_slots);
+        if (!(b->sg.exec && b->sg.key == key) && !build_solve_graph(b, sp, lc, gmode, max_passes, check_every, key)) gmode = 0;
+    }
+    if (gmode == 2) {
+        CU(cudaMemsetAsync(b->loop_pass.d, 0, sizeof(int), s));
+        CU(cudaGraphLaunch(b->sg.exec, s));
+        CU(b->loop_pass.download(s));
+        CU(cudaEventRecord(b->ev_b, s));
+        CU(b->jac_obs.download(s));
+        CU(wait_stream(h));
+        CU(cudaGetLastError());
+        CU(cudaEventElapsedTime(&b->last_solve_ms, b->ev_a, b->ev_b));
+        h->counters.jacobian_obs += (long long)b->jac_obs.h[0];
+        add_pass_counters(h->counters, b->sg.per_pass, b->loop_pass.h[0]);
+        h->counters.launches_total += b->loop_pass.h[0];  // k_loop_cond
+        return KBA_OK;
+    }
+    if (gmode == 1) {
+        cudaEvent_t evs[2] = {b->ev_poll, b->ev_poll2};
+        const int n_launch = (max_passes + check_every - 1) / check_every;
+        int launched = 0;
+        for (int g = 0; g < n_launch; ++g) {
+            CU(cudaGraphLaunch(b->sg.exec, s));
+            ++launched;
+            CU(cudaEventRecord(evs[g & 1], s));
+            if (g >= 1) {  // the count of the previous launch is read while this one runs (the device never waits for the host)
+                CU(wait_event(h, evs[(g - 1) & 1]));
+                if (b->n_active.h[0] == 0) break;
+                if (opt->solver_time_sec > 0) {
+                    const double el = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+                    if (el > KBA_MAX_SOLVES * opt->solver_time_sec + 2.0) { timed_out = true; break; }
+                }
+            }
+        }
+        if (timed_out) g_last_error = "kba_batch_solve: host safety cap reached, unfinished windows carry KBA_ERR_TIMEOUT in kba_result.status";
+        CU(cudaEventRecord(b->ev_b, s));
+        CU(b->jac_obs.download(s));
+        CU(wait_stream(h));
+        CU(cudaGetLastError());
+        CU(cudaEventElapsedTime(&b->last_solve_ms, b->ev_a, b->ev_b));
+        h->counters.jacobian_obs += (long long)b->jac_obs.h[0];
+        add_pass_counters(h->counters, b->sg.per_pass, (long long)launched * check_every);
+        h->counters.launches_total += launched;  // k_count_active
+        return KBA_OK;
+    }
     for (int pass = 0; pass < max_passes; ++pass) {
         if (launch_pass(b->bd, sp, lc, &h->counters, s)) {  // message set by the exchange
             cudaEventRecord(b->ev_b, s);

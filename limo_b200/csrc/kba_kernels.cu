@@ -30,7 +30,10 @@ namespace kba {
 // =====================================================================================================================
 // solve begin: program layout (which parameter blocks are in the reduced program) + LM state reset
 // =====================================================================================================================
-__global__ void __launch_bounds__(256) k_solve_begin(BatchDev bd, SolveParams sp) {
+// 1024 threads: the layout tables of a solve's first pass are dependent-load chains per landmark / observation (0.2 ms per
+// solve begin with 256 threads, three to four per trimmed solve: 5 % of a single-window solve)
+constexpr int kBeginThreads = 1024;
+__global__ void __launch_bounds__(kBeginThreads) k_solve_begin(BatchDev bd, SolveParams sp) {
     const int w = blockIdx.x;
     WinState& st = bd.state[w];
     if (st.phase != PH_SOLVE_BEGIN) return;
@@ -920,9 +923,20 @@ __global__ void __launch_bounds__(256) k_sred_reduce(BatchDev bd, int mode) {
     if (wd.landmarks_fixed) return;
     const int ld = wd.nr_cap, n = st.n_f;
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= (n + 1) * ld) return;
+    // tiled solve (<= 192 rows), mode 0: this kernel also writes A = -Sred in the tile-packed order of the solve kernel's shared
+    // memory (TiledMat), zero padding included, so that the single CTA of k_reduced_solve copies it linearly instead of gathering
+    // element by element (its assembly was 37 k of the kernel's 237 k cycles at 174 rows)
+    const bool pack = mode == 0 && bd.solve_tiled;
+    const int rows_t = (n + 8) & ~7;
+    if (idx >= (pack ? rows_t : n + 1) * ld) return;
     const int r = idx / ld, c = idx - r * ld;
-    if (c > r) return;
+    if (pack) {
+        if (c >= rows_t || (c >> 3) > (r >> 3)) return;
+        if (c > r || r > n) {  // padding inside the packed triangle
+            TiledMat{bd.amat + wd.s_off}(r, c) = -0.0;
+            return;
+        }
+    } else if (c > r) return;
     double* sp0 = bd.sred + wd.s_off * (size_t)bd.p_split;
     const size_t pstride = (size_t)ld * ld;
     double s = 0.0;
@@ -940,6 +954,7 @@ __global__ void __launch_bounds__(256) k_sred_reduce(BatchDev bd, int mode) {
     if (mode != 2) sp0[idx] = s;
     // row-major solve: A = -Sred is written here by the whole GPU instead of by the single CTA of the solve kernel
     if (mode != 1 && !bd.solve_tiled) bd.amat[wd.s_off + idx] = (r == n && c == n) ? 0.0 : -s;
+    if (pack) TiledMat{bd.amat + wd.s_off}(r, c) = (r == n && c == n) ? -0.0 : -s;
 }
 
 // stage 0: the whole solve in this one CTA.  Large reduced systems of small batches split it (launch_pass): stage 1 =
@@ -954,7 +969,7 @@ __global__ void __launch_bounds__(512, 1) k_reduced_solve(BatchDev bd, SolvePara
     const WinDesc& wd = bd.desc[w];
     const int tid = threadIdx.x, nth = blockDim.x;
     const int n = st.n_f, ld = wd.nr_cap;
-    extern __shared__ double sm[];
+    extern __shared__ __align__(16) double sm[];  // 16: the packed copy of A arrives in double2 units
     double* s_fdiag = sm;                 // [ld] squared column norms of J (f part)
     double* s_g = s_fdiag + ld;           // [ld] gradient J^T r (f part)
     double* s_y = s_g + ld;               // [ld]
@@ -1006,7 +1021,22 @@ __global__ void __launch_bounds__(512, 1) k_reduced_solve(BatchDev bd, SolvePara
         const size_t pstride = (size_t)ld * ld;
         const int np = 1;  // with p_split > 1, k_sred_reduce has folded the partials into slot 0
         const int rows = kTiled ? ((n + 8) & ~7) : n + 1;  // tiled: whole tile rows, zero padded
-        const bool done_by_reduce = !kTiled && (bd.p_split > 1 || bd.sharded) && !wd.landmarks_fixed;  // see k_sred_reduce
+        bool done_by_reduce = !kTiled && (bd.p_split > 1 || bd.sharded) && !wd.landmarks_fixed;  // see k_sred_reduce
+        if (kTiled && bd.p_split > 1 && !bd.sharded && !wd.landmarks_fixed) {
+            // k_sred_reduce left A tile-packed and padded in global memory (L2): a linear copy, 16 bytes per thread and load
+            const int ntr = rows >> 3;
+            const int n2 = ntr * (ntr + 1) / 2 * 32;  // double2 elements
+            const double2* src = reinterpret_cast<const double2*>(bd.amat + wd.s_off);
+            double2* dst = reinterpret_cast<double2*>(s_P);
+            for (int i0 = tid; i0 < n2; i0 += 4 * nth) {
+                double2 v[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) if (i0 + u * nth < n2) v[u] = src[i0 + u * nth];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) if (i0 + u * nth < n2) dst[i0 + u * nth] = v[u];
+            }
+            done_by_reduce = true;
+        }
         // eight independent loads in flight per thread: the sums sit in L2, one load per iteration exposed its full latency
         const int total = done_by_reduce ? 0 : rows * ld;
         for (int idx0 = tid; idx0 < total; idx0 += 8 * nth) {
@@ -1657,6 +1687,9 @@ __global__ void __launch_bounds__(256) k_backsub(BatchDev bd) {
 
 // Fused path: sum_i V_i^T delta_f,i from the compact per-observation V (k_obs_v2; landmark-column-major): each lane reads
 // its observation's three 48-byte column segments with nine 128-bit loads, consecutive lanes consecutive segments.
+// Measured and dropped (profiles/r02_graph_and_ab.md): requesting the V segments before obs_row has come back and the landmark's
+// L^-1 / z / g / lambda before the reduction (one round of memory latency instead of three) made a 296-window step 1.6 ms SLOWER --
+// the extra requests in flight evict what the neighbouring CTAs are about to read; the kernel stays as it is.
 __global__ void __launch_bounds__(256) k_backsub_v(BatchDev bd) {
     const int w = blockIdx.y;
     const WinState& st = bd.state[w];
@@ -2263,7 +2296,7 @@ int launch_pass(const BatchDev& bd, const SolveParams& sp, const LaunchCfg& lc, 
     const dim3 g_lm((bd.max_lm + 63) / 64, B);
     if (!bd.fused) k_panel_zero<<<dim3(64, B), 256, 0, s>>>(bd);  // the fused path has no global V panels
     LCHK("k_panel_zero");
-    k_solve_begin<<<B, 256, 0, s>>>(bd, sp); LCHK("k_solve_begin");
+    k_solve_begin<<<B, kBeginThreads, 0, s>>>(bd, sp); LCHK("k_solve_begin");
     const bool timed = lc.time_jacobian && lc.ev_pool && *lc.ev_used + 2 <= lc.ev_cap;
     // one-kernel linearisation (kba_linearize.cuh): fused path, FP64, at most one observation per (landmark, keyframe)
     const bool lin1 = bd.lin1 != 0;
@@ -2372,6 +2405,24 @@ void launch_count_active(const BatchDev& bd, cudaStream_t s) {
     k_count_active<<<(bd.n_win + 127) / 128, 128, 0, s>>>(bd); LCHK("k_count_active");
 }
 
+// Loop condition of the device-driven solve (kba_api.cu: the pass sequence is the body of a conditional WHILE node of a CUDA
+// graph).  Last kernel of the body: any window not done and the pass cap not reached -> run the body again.  The host launches the
+// graph once per solve and is not involved until every window has finished.
+__global__ void __launch_bounds__(256) k_loop_cond(BatchDev bd, cudaGraphConditionalHandle handle, int* pass, int max_passes) {
+    int active = 0;
+    for (int w = threadIdx.x; w < bd.n_win; w += blockDim.x) active += (bd.state[w].phase != PH_DONE) ? 1 : 0;
+    active = __syncthreads_count(active > 0);  // threads that saw an unfinished window (the host only tests for zero)
+    if (threadIdx.x == 0) {
+        const int p = *pass + 1;
+        *pass = p;
+        *bd.n_active = active;
+        cudaGraphSetConditional(handle, (active > 0 && p < max_passes) ? 1u : 0u);
+    }
+}
+void launch_loop_cond(const BatchDev& bd, unsigned long long handle, int* pass, int max_passes, cudaStream_t s) {
+    k_loop_cond<<<1, 256, 0, s>>>(bd, (cudaGraphConditionalHandle)handle, pass, max_passes);
+}
+
 // stand-alone residual/Jacobian pass at the uploaded state (parity + roofline measurement)
 __global__ void k_force_linearize(BatchDev bd) {
     const int w = blockIdx.x * blockDim.x + threadIdx.x;
@@ -2405,7 +2456,7 @@ void launch_expand_jl(const BatchDev& bd, double* out, cudaStream_t s) {
     LCHK("k_expand_jl");
 }
 void launch_force_linearize(const BatchDev& bd, cudaStream_t s) {
-    k_solve_begin<<<bd.n_win, 256, 0, s>>>(bd, SolveParams{}); LCHK("k_solve_begin");  // layout (off_pose) for the eval entry point
+    k_solve_begin<<<bd.n_win, kBeginThreads, 0, s>>>(bd, SolveParams{}); LCHK("k_solve_begin");  // layout (off_pose) for the eval entry point
     k_force_linearize<<<(bd.n_win + 127) / 128, 128, 0, s>>>(bd); LCHK("k_force_linearize");
 }
 

@@ -105,6 +105,7 @@ cudaError_t configure_kernels(int nr_cap_max);
 void launch_reset(const BatchDev& bd, const LaunchCfg& lc, cudaStream_t s);
 int launch_pass(const BatchDev& bd, const SolveParams& sp, const LaunchCfg& lc, Counters* cnt, cudaStream_t s);
 void launch_count_active(const BatchDev& bd, cudaStream_t s);
+void launch_loop_cond(const BatchDev& bd, unsigned long long handle, int* pass, int max_passes, cudaStream_t s);  // WHILE-node condition
 void launch_force_linearize(const BatchDev& bd, cudaStream_t s);
 void launch_jacobian_only(const BatchDev& bd, const SolveParams& sp, cudaStream_t s);
 void launch_expand_jl(const BatchDev& bd, double* out, cudaStream_t s);  // fused path: J_l as its consumers form it

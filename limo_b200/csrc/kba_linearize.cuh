@@ -34,6 +34,9 @@ __device__ __forceinline__ size_t lin_tile_offset(const WinDesc& wd, int w) {
     return (size_t)(wd.obs_off / 16) + (size_t)(wd.lm_off / 32) + 4 * (size_t)w;
 }
 
+// Measured and dropped (profiles/r02_graph_and_ab.md): a descriptor that also carries the first landmark and a segment-start mask,
+// so that a lane requests its landmark's data together with its observation's (no obs_lm -> lm_ptr round first), made the kernel
+// 1.5 % slower -- the bit arithmetic costs more than the dependent loads, which mostly hit L2.
 // called by k_solve_begin (one CTA per window).  The tiling depends on the CSR only.  Greedy packing is sequential, so the
 // landmarks are cut into <= 512 chunks that are packed independently by one thread each (pass 1 counts, a scan places the
 // chunks, pass 2 writes): a serial pass over 3000 landmarks cost 270 us per solve begin, this one a few.
