@@ -1689,7 +1689,7 @@ __global__ void __launch_bounds__(256) k_backsub(BatchDev bd) {
 // its observation's three 48-byte column segments with nine 128-bit loads, consecutive lanes consecutive segments.
 // Measured and dropped (profiles/r02_graph_and_ab.md): requesting the V segments before obs_row has come back and the landmark's
 // L^-1 / z / g / lambda before the reduction (one round of memory latency instead of three) made a 296-window step 1.6 ms SLOWER --
-// the extra requests in flight evict what the neighbouring CTAs are about to read; the kernel stays as it is.
+// not profiled further; the kernel stays as it is.
 __global__ void __launch_bounds__(256) k_backsub_v(BatchDev bd) {
     const int w = blockIdx.y;
     const WinState& st = bd.state[w];
