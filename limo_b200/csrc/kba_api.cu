@@ -135,6 +135,7 @@ struct kba_batch {
         }
     } sg;
     Staged<int> loop_pass;  // passes the WHILE node has run (device counter + pinned copy)
+    long long solves_done = 0;
 
     template <typename T>
     int dev_alloc(T** p, size_t count) {
@@ -417,6 +418,12 @@ static int solve_graph_mode() {
         return (v < 0 || v > 2) ? 2 : v;
     }();
     return m;
+}
+
+// KBA_SHARD_GRAPH=0: sharded solves stay on the stream path
+static bool shard_graph_enabled() {
+    static const bool on = [] { const char* e = getenv("KBA_SHARD_GRAPH"); return e ? atoi(e) != 0 : true; }();
+    return on;
 }
 
 template <typename T>
@@ -941,13 +948,18 @@ int kba_batch_solve(kba_batch* b, const kba_options* opt) {
     bool timed_out = false, poll_pending = false;
     // ---- graph paths (see solve_graph_mode) ----
     int gmode = solve_graph_mode();
-    if (b->bd.sharded || h->kernel_timing || launch_check_enabled() || s == nullptr || b->sg.unusable) gmode = 0;
+    if (h->kernel_timing || launch_check_enabled() || s == nullptr || b->sg.unusable) gmode = 0;
+    // Sharded solve: the NCCL all-reduces are captured with the kernels (flat graph, mode 1).  The first solve of a batch runs on
+    // the stream so that NCCL sets its connections up outside a capture; the active-window count is read BEFORE the next graph is
+    // launched (no look-ahead): it is identical on all ranks, and every rank must launch the same number of graphs.
+    const bool lockstep = b->bd.sharded != 0;
+    if (lockstep) gmode = (gmode && shard_graph_enabled() && b->solves_done > 0) ? 1 : 0;
     if (gmode) {
         std::vector<unsigned char> key;
         key.reserve(sizeof(BatchDev) + sizeof(SolveParams) + 64);
         key_append(key, b->bd); key_append(key, sp); key_append(key, gmode); key_append(key, max_passes); key_append(key, s);
         key_append(key, lc.nr_cap_max); key_append(key, lc.max_rank); key_append(key, (int)lc.small_syrk); key_append(key, (int)lc.lin_fused);
-        key_append(key, lc.lin_blocks); key_append(key, lc.fused_slots);
+        key_append(key, lc.lin_blocks); key_append(key, lc.fused_slots); key_append(key, lc.xchg.user);
         if (!(b->sg.exec && b->sg.key == key) && !build_solve_graph(b, sp, lc, gmode, max_passes, check_every, key)) gmode = 0;
     }
     if (gmode == 2) {
@@ -962,6 +974,7 @@ int kba_batch_solve(kba_batch* b, const kba_options* opt) {
         h->counters.jacobian_obs += (long long)b->jac_obs.h[0];
         add_pass_counters(h->counters, b->sg.per_pass, b->loop_pass.h[0]);
         h->counters.launches_total += b->loop_pass.h[0];  // k_loop_cond
+        b->solves_done++;
         return KBA_OK;
     }
     if (gmode == 1) {
@@ -972,7 +985,10 @@ int kba_batch_solve(kba_batch* b, const kba_options* opt) {
             CU(cudaGraphLaunch(b->sg.exec, s));
             ++launched;
             CU(cudaEventRecord(evs[g & 1], s));
-            if (g >= 1) {  // the count of the previous launch is read while this one runs (the device never waits for the host)
+            if (lockstep) {
+                CU(wait_event(h, evs[g & 1]));
+                if (b->n_active.h[0] == 0) break;
+            } else if (g >= 1) {  // the count of the previous launch is read while this one runs (the device never waits for the host)
                 CU(wait_event(h, evs[(g - 1) & 1]));
                 if (b->n_active.h[0] == 0) break;
                 if (opt->solver_time_sec > 0) {
@@ -990,6 +1006,7 @@ int kba_batch_solve(kba_batch* b, const kba_options* opt) {
         h->counters.jacobian_obs += (long long)b->jac_obs.h[0];
         add_pass_counters(h->counters, b->sg.per_pass, (long long)launched * check_every);
         h->counters.launches_total += launched;  // k_count_active
+        b->solves_done++;
         return KBA_OK;
     }
     for (int pass = 0; pass < max_passes; ++pass) {
@@ -1038,6 +1055,7 @@ int kba_batch_solve(kba_batch* b, const kba_options* opt) {
         CU(cudaEventElapsedTime(&ms, h->ev_pool[i], h->ev_pool[i + 1]));
         h->counters.ms_jacobian += ms;
     }
+    b->solves_done++;
     return KBA_OK;
 }
 

@@ -31,6 +31,7 @@ def main():
     parallel.init("nccl", torch.device("cuda", local_rank))
     win = synth.make_window(5, n_kf=40, n_lm=3000, n_obs=45000) if args.small else synth.make_window(5)
     sub, j0, j1 = parallel.shard_window(win, rank, world)
+    torch.cuda.set_stream(torch.cuda.Stream())  # not the legacy stream: the library captures the passes into a CUDA graph
     stream = torch.cuda.current_stream()
     h = capi.Handle(local_rank, stream=stream.cuda_stream)
     # NCCL id: rank 0 creates, torch.distributed broadcasts the 128 bytes
