@@ -1690,14 +1690,17 @@ __global__ void __launch_bounds__(256) k_backsub(BatchDev bd) {
 // Measured and dropped (profiles/r02_graph_and_ab.md): requesting the V segments before obs_row has come back and the landmark's
 // L^-1 / z / g / lambda before the reduction (one round of memory latency instead of three) made a 296-window step 1.6 ms SLOWER --
 // not profiled further; the kernel stays as it is.
-__global__ void __launch_bounds__(256) k_backsub_v(BatchDev bd) {
+// kLoop: the CTAs of a window stride over its 16-landmark units (grid.x < n_units, LaunchCfg::bs_grid); unit = partial-sum slot
+template <bool kLoop>
+__global__ void __launch_bounds__(256) k_backsub_v(BatchDev bd, int n_units) {
     const int w = blockIdx.y;
     const WinState& st = bd.state[w];
     if (st.phase != PH_ITERATE) return;
     const WinDesc& wd = bd.desc[w];
     __shared__ double s_red[16][4];
     const int hl = threadIdx.x & 15, grp = threadIdx.x >> 4;
-    const int j = blockIdx.x * 16 + grp;
+    for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
+    const int j = unit * 16 + grp;
     double model = 0.0, step_sq = 0.0, xn_sq = 0.0, gmax = 0.0;
     const bool have = j < wd.n_lm;
     const int L = wd.lm_off + (have ? j : 0);
@@ -1766,9 +1769,12 @@ __global__ void __launch_bounds__(256) k_backsub_v(BatchDev bd) {
     if (threadIdx.x == 0) {
         double a = 0, b = 0, c = 0, g = 0;
         for (int q = 0; q < 16; ++q) { a += s_red[q][0]; b += s_red[q][1]; c += s_red[q][2]; g = fmax(g, s_red[q][3]); }
-        double* out = bd.bs_part + ((size_t)w * bd.bs_parts + blockIdx.x) * 4;
+        double* out = bd.bs_part + ((size_t)w * bd.bs_parts + unit) * 4;
         out[0] = a; out[1] = b; out[2] = c; out[3] = g;
     }
+    if constexpr (!kLoop) break;
+    if (unit + (int)gridDim.x < n_units) __syncthreads();  // s_red is rewritten by the next unit
+    }  // units
 }
 
 // =====================================================================================================================
@@ -2286,6 +2292,18 @@ cudaError_t configure_kernels(int nr_cap_max) {
     return cudaSuccess;
 }
 
+// grid.x of a kernel whose CTAs stride over a window's units (k_linearize: 8 warp tiles, k_backsub_v: 16 landmarks).  Every pass is
+// launched for every window of the batch and the unit count is an upper bound, so with one CTA per unit most CTAs of a large batch
+// only find out that they have nothing to do; num/den of the units per window measured best on the headline workload (A/B in
+// profiles/r02_graph_and_ab.md: 296-window step 211.2 -> 202.9 ms).  Small batches keep one CTA per unit (latency: every SM busy).
+// `cfg`: -1 = this rule, 0 = one CTA per unit, > 0 = that many (KBA_LIN_GRID / KBA_BS_GRID).
+static int strided_grid(int cfg, int n_units, int num, int den, int n_win) {
+    if (cfg == 0) return n_units;
+    if (cfg > 0) return cfg < n_units ? cfg : n_units;
+    const int g = (n_units * num + den - 1) / den;
+    return ((long long)g * n_win >= 4 * 296 && g >= 1) ? g : n_units;  // at least four waves of 2 CTAs x 148 SMs remain
+}
+
 void launch_reset(const BatchDev& bd, const LaunchCfg& lc, cudaStream_t s) {
     k_reset_state<<<bd.n_win, 256, 0, s>>>(bd, lc.rounds_override, lc.min_landmarks_for_trimming, lc.num_rounds_option); LCHK("k_reset_state");
 }
@@ -2304,9 +2322,11 @@ int launch_pass(const BatchDev& bd, const SolveParams& sp, const LaunchCfg& lc, 
         if (bd.tot_gp > 0) k_gp_eval<true><<<B, 256, 0, s>>>(bd, sp);
         LCHK("k_gp_eval");
         if (timed) cudaEventRecord(lc.ev_pool[(*lc.ev_used)++], s);
-        const dim3 g_lin((lin_tile_bound(bd.max_obs, bd.max_lm) + kLinWarps - 1) / kLinWarps, B);
-        if (lc.lin_blocks == 3) k_linearize<3><<<g_lin, kLinThreads, 0, s>>>(bd, sp);
-        else k_linearize<2><<<g_lin, kLinThreads, 0, s>>>(bd, sp);
+        const int n_units = (lin_tile_bound(bd.max_obs, bd.max_lm) + kLinWarps - 1) / kLinWarps;
+        const dim3 g_lin(strided_grid(lc.lin_grid, n_units, 3, 10, B), B);  // CTAs of a window stride over its units
+        if ((int)g_lin.x < n_units) k_linearize<2, true><<<g_lin, kLinThreads, 0, s>>>(bd, sp, n_units);
+        else if (lc.lin_blocks == 3) k_linearize<3, false><<<g_lin, kLinThreads, 0, s>>>(bd, sp, n_units);
+        else k_linearize<2, false><<<g_lin, kLinThreads, 0, s>>>(bd, sp, n_units);
         LCHK("k_linearize");
         if (timed) cudaEventRecord(lc.ev_pool[(*lc.ev_used)++], s);
         k_pose_hessian<<<dim3(bd.max_kf, B), 256, 0, s>>>(bd, sp); LCHK("k_pose_hessian");
@@ -2371,7 +2391,12 @@ int launch_pass(const BatchDev& bd, const SolveParams& sp, const LaunchCfg& lc, 
         }
         k_reduced_solve<false><<<B, 512, solve_smem(lc.nr_cap_max), s>>>(bc, sp, 2); LCHK("k_reduced_solve");
     }
-    if (bd.fused) k_backsub_v<<<dim3((bd.max_lm + 15) / 16, B), 256, 0, s>>>(bd);
+    if (bd.fused) {
+        const int n_units = (bd.max_lm + 15) / 16;
+        const int gx = strided_grid(lc.bs_grid, n_units, 1, 3, B);
+        if (gx < n_units) k_backsub_v<true><<<dim3(gx, B), 256, 0, s>>>(bd, n_units);
+        else k_backsub_v<false><<<dim3(n_units, B), 256, 0, s>>>(bd, n_units);
+    }
     else k_backsub<<<dim3((bd.max_lm + 15) / 16, B), 256, 0, s>>>(bd);
     LCHK("k_backsub");
     launch_eval_obs<false>(bd, sp, s);

@@ -82,8 +82,13 @@ __device__ inline void build_lin_tiles(const BatchDev& bd, const WinDesc& wd, Wi
 
 // kMinBlocks: CTAs per SM the register allocation is sized for.  2: everything in registers (128 per thread); 3: 80 registers, the
 // Jacobian rows spill to local memory across the segment sums (KBA_LIN_BLOCKS, measured in profiles/r02_linearize.md)
-template <int kMinBlocks>
-__global__ void __launch_bounds__(kLinThreads, kMinBlocks) k_linearize(BatchDev bd, SolveParams sp) {
+// n_units = ceil(lin_tile_bound / kLinWarps): a unit is 8 consecutive warp tiles and owns cost slot `unit`.  The CTAs of a window
+// stride over the units (grid.x <= n_units; grid.x == n_units: one unit per CTA, the original launch): the tile bound is 1.7x the
+// tiles a window really has and every pass is launched for every window, so a smaller grid saves the CTAs that would only find out
+// that they have nothing to do (profiles/r02_ncu_summary.md, addendum) and stages the poses once for several units.
+// kLoop = false: grid.x == n_units, compiled without the loop (no loop-carried registers: the loop form spills 120 bytes).
+template <int kMinBlocks, bool kLoop>
+__global__ void __launch_bounds__(kLinThreads, kMinBlocks) k_linearize(BatchDev bd, SolveParams sp, int n_units) {
     const int w = blockIdx.y;
     WinState& st = bd.state[w];
     if (st.phase != PH_ITERATE) return;
@@ -96,10 +101,6 @@ __global__ void __launch_bounds__(kLinThreads, kMinBlocks) k_linearize(BatchDev 
     const bool want_cost = lin && st.iter0;
     if (wd.landmarks_fixed && !want_cost) return;       // motion-only window past iteration zero: the landmark blocks are constant
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if ((int)blockIdx.x * kLinWarps >= n_tiles) {       // no tile for this CTA: its cost slot still has to read zero
-        if (tid == 0 && want_cost) bd.cost_part_x[(size_t)w * bd.cost_parts + blockIdx.x] = 0.0;
-        return;
-    }
     __shared__ __align__(16) double s_pose[kFusedMaxKf * kPoseStride];
     __shared__ __align__(16) double s_cam[kMaxCam * kCamStride];
     __shared__ __align__(8) uint64_t s_bar;
@@ -107,10 +108,17 @@ __global__ void __launch_bounds__(kLinThreads, kMinBlocks) k_linearize(BatchDev 
                                                         // landmark's first lane, their sums
     __shared__ double s_red[kLinWarps];
     __shared__ int s_cnt[kLinWarps];
+    bool staged = false;
+    for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
+    if (unit * kLinWarps >= n_tiles) {                  // no tile in this unit: its cost slot still has to read zero
+        if (tid == 0 && want_cost) bd.cost_part_x[(size_t)w * bd.cost_parts + unit] = 0.0;
+        if constexpr (!kLoop) return;
+        continue;
+    }
     const size_t base = (size_t)wd.obs_off;
     const int* lm_ptr = bd.lm_ptr + wd.lm_off + w;
     // my observation: the loads are issued before the staging barrier so that their latency overlaps the bulk copy
-    const int t = blockIdx.x * kLinWarps + warp;
+    const int t = unit * kLinWarps + warp;
     int2 tile = make_int2(0, 0);
     if (t < n_tiles) tile = bd.lin_tile[lin_tile_offset(wd, w) + t];
     const bool have = lane < tile.y;
@@ -131,7 +139,10 @@ __global__ void __launch_bounds__(kLinThreads, kMinBlocks) k_linearize(BatchDev 
         wgt = bd.lm_weight[wd.lm_off + j];
     }
     const int L = wd.lm_off + j;
-    stage_window_bulk(wd, bd.rt[st.cur], bd.cam, s_pose, s_cam, &s_bar);
+    if (!staged) {  // (uniform per CTA) once: the poses do not change within a pass
+        stage_window_bulk(wd, bd.rt[st.cur], bd.cam, s_pose, s_cam, &s_bar);
+        staged = true;
+    }
     // ---- evaluate my observation; contributions to its landmark block
     double jp[18];
     bool ok = true;
@@ -286,9 +297,12 @@ __global__ void __launch_bounds__(kLinThreads, kMinBlocks) k_linearize(BatchDev 
         double s = 0.0;
         int cnt = 0;
         for (int q = 0; q < kLinWarps; ++q) { s += s_red[q]; cnt += s_cnt[q]; }
-        if (want_cost) bd.cost_part_x[(size_t)w * bd.cost_parts + blockIdx.x] = s;
+        if (want_cost) bd.cost_part_x[(size_t)w * bd.cost_parts + unit] = s;
         if (cnt) atomicAdd(bd.jac_obs, (unsigned long long)cnt);
     }
+    if constexpr (!kLoop) break;
+    if (unit + (int)gridDim.x < n_units) __syncthreads();  // s_red / s_cnt are rewritten by the next unit
+    }  // units
 }
 
 }  // namespace kba

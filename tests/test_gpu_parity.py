@@ -215,6 +215,28 @@ def test_batch_equals_single(handle, monkeypatch):
         assert s.c.final_cost == pytest.approx(b.c.final_cost, rel=1e-10)
 
 
+def test_strided_grids_are_bit_identical(handle, monkeypatch):
+    """k_linearize / k_backsub_v with their CTAs striding over a window's units (KBA_LIN_GRID / KBA_BS_GRID, read when a batch is
+    created; by default chosen from the batch size): every unit writes the same partial sums into the same slots whichever CTA
+    runs it, so any grid gives bit-identical results -- here one CTA per unit against 1, 3 and 7 CTAs per window"""
+    wins = [synth.make_window(1, seed=s) for s in (21, 22)] + [synth.make_window(2, n_kf=10, n_lm=300, n_obs=2500, seed=5),
+                                                               synth.make_window(3, seed=41, n_kf=8, n_lm=300, n_obs=1800, gp_frac=0.2)]
+    monkeypatch.setenv("KBA_LIN_GRID", "0")
+    monkeypatch.setenv("KBA_BS_GRID", "0")
+    ref = handle.solve_batch(wins)
+    for lg, bg in (("1", "1"), ("3", "2"), ("7", "5"), ("-1", "-1")):
+        monkeypatch.setenv("KBA_LIN_GRID", lg)
+        monkeypatch.setenv("KBA_BS_GRID", bg)
+        res = handle.solve_batch(wins)
+        for a, b, w in zip(ref, res, wins):
+            assert b.c.status == 0
+            assert np.array_equal(a.kf_pose, b.kf_pose) and np.array_equal(a.kf_plane, b.kf_plane), (lg, bg)
+            assert np.array_equal(a.lm_pos[:w.n_lm], b.lm_pos[:w.n_lm]), (lg, bg)
+            assert np.array_equal(a.lm_rejected[:w.n_lm], b.lm_rejected[:w.n_lm])
+            assert a.c.final_cost == b.c.final_cost
+            assert [x.num_iterations for x in a.solves] == [x.num_iterations for x in b.solves]
+
+
 def test_full_size_properties(handle):
     """size-independent properties at BASELINE config 2 scale: cost decreases, outputs finite, fixed keyframe untouched,
     rejected landmarks keep their position, repeat solve is bit-identical"""
