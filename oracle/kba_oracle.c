@@ -1145,6 +1145,15 @@ int kbo_trimmer_quantile(const double* values, int n, double q, unsigned char* r
     return n - (num < n ? num : n);
 }
 
+/* TrimmerFix::getOutliers (robust_optimization/include/robust_optimization/internal/trimmer_fix.hpp:38-47): residuals above a
+ * fixed threshold.  Not reachable from BundleAdjusterKeyframes::solve() (which uses the quantile trimmer, cpp:745-758); restated
+ * for the reference test Trimmers.TrimmerFix only. */
+int kbo_trimmer_fix(const double* values, int n, double threshold, unsigned char* rejected) {
+    int cnt = 0;
+    for (int i = 0; i < n; ++i) { rejected[i] = values[i] > threshold; cnt += rejected[i]; }
+    return cnt;
+}
+
 /* one rejection pass over the three residual groups; marks landmarks to remove */
 static void trim_round(program* P, const state_t* x, unsigned char* remove) {
     const kba_window* w = P->w;

@@ -64,6 +64,7 @@ void kbo_dir_plus(const double n[3], const double delta[3], double out[3]);
 /* TrimmerQuantile::getOutliers (trimmer_quantile.hpp:40-63); ties broken by index; returns number rejected,
  * writes rejected[i] = 1. */
 int kbo_trimmer_quantile(const double* values, int n, double quantile, unsigned char* rejected);
+int kbo_trimmer_fix(const double* values, int n, double threshold, unsigned char* rejected); /* trimmer_fix.hpp:38-47 */
 /* Triangulator::triangulate_rays (internal/triangulator.hpp:51-75): R_oc [n*9] row-major, t_oc [n*3], rays [n*3] (unit, camera frame). */
 void kbo_triangulate_rays(int n, const double* R_oc, const double* t_oc, const double* rays, double out[3]);
 

@@ -67,6 +67,8 @@ def lib():
         _lib.kbo_dir_plus.argtypes = [dp, dp, dp]
         _lib.kbo_trimmer_quantile.argtypes = [dp, C.c_int, C.c_double, C.POINTER(C.c_uint8)]
         _lib.kbo_trimmer_quantile.restype = C.c_int
+        _lib.kbo_trimmer_fix.argtypes = [dp, C.c_int, C.c_double, C.POINTER(C.c_uint8)]
+        _lib.kbo_trimmer_fix.restype = C.c_int
         _lib.kbo_triangulate_rays.argtypes = [C.c_int, dp, dp, dp, dp]
         fp = C.POINTER(C.c_float)
         _lib.kbo_lidar_default_options.argtypes = [C.POINTER(KbaLidarOptions)]
@@ -179,6 +181,13 @@ def trimmer_quantile(values, q):
     v, vp = _d(values)
     rej = np.zeros(max(len(v), 1), dtype=np.uint8)
     n = lib().kbo_trimmer_quantile(vp, len(v), float(q), rej.ctypes.data_as(C.POINTER(C.c_uint8)))
+    return n, rej[:len(v)].astype(bool)
+
+
+def trimmer_fix(values, threshold):
+    v, vp = _d(values)
+    rej = np.zeros(max(len(v), 1), dtype=np.uint8)
+    n = lib().kbo_trimmer_fix(vp, len(v), float(threshold), rej.ctypes.data_as(C.POINTER(C.c_uint8)))
     return n, rej[:len(v)].astype(bool)
 
 

@@ -92,6 +92,53 @@ def test_trimmer_quantile(oracle):
     assert n == 0 and not rej.any()
 
 
+def test_trimmer_fix(oracle):
+    """Trimmers.TrimmerFix (robust_optimization/test/robust_optimization.cpp:89-97): threshold 3.5 on makeData() -> the 10 outliers"""
+    n, rej = oracle.trimmer_fix(_trimmer_data(1), 3.5)
+    assert n == 10 and rej[:10].all() and not rej[10:].any()
+    n, rej = oracle.trimmer_fix([3.5, 3.5000001, -1.0], 3.5)       # strictly greater (trimmer_fix.hpp:41)
+    assert n == 1 and list(rej) == [False, True, False]
+
+
+def test_solve_trimmed_scalar_problem(oracle):
+    """Solve.trimmed (robust_optimization.cpp:134-156): one parameter x = 2, 90 residuals 3x and 10 constant residuals 10, ALL in
+    residual group 1, TrimmerQuantile 0.9, iterations {0, 2}.  Restated with the solveTrimmed outer loop (robust_solving.cpp:140-248)
+    around a scalar Levenberg-Marquardt step with ceres' Jacobi-scaled damping: one group is fewer than
+    minimum_number_residual_groups, so nothing is trimmed (robust_solving.cpp:19-21), the constant residuals have no gradient,
+    and the final solve drives x to 0 within the reference's 1e-3."""
+    x = 2.0
+    groups = {1: list(range(100))}                                   # residual index -> all in group 1
+    res = lambda x_: np.array([3.0 * x_] * 90 + [10.0] * 10)
+    jac = np.array([3.0] * 90 + [0.0] * 10)
+
+    def lm(x_, iters, radius=1e4):
+        for _ in range(iters):
+            r = res(x_)
+            g, h = jac @ r, jac @ jac
+            s2 = (1.0 / (1.0 + np.sqrt(h))) ** 2                     # Jacobi scaling as in the oracle (SURVEY A.5)
+            lam = min(max(h * s2, 1e-6), 1e32) / (radius * s2)
+            cand = x_ - g / (h + lam)
+            if (res(cand) ** 2).sum() < (r ** 2).sum():
+                x_, radius = cand, radius * 3.0
+            else:
+                radius /= 2.0
+        return x_
+
+    for iters in (0, 2):                                             # trimming rounds
+        c0 = (res(x) ** 2).sum()
+        x1 = lm(x, iters)
+        if c0 - (res(x1) ** 2).sum() <= 0.0:                         # retry rule, robust_solving.cpp:172-181
+            x1 = lm(x, 3 * iters)
+        x = x1
+        vals = np.array([np.abs(res(x)[idx]).max() for idx in groups.values()])
+        if len(vals) >= 30:                                          # minimum_number_residual_groups
+            n, rej = oracle.trimmer_quantile(vals, 0.9)
+            groups = {k: v for (k, v), r_ in zip(groups.items(), rej) if not r_}
+    assert len(groups) == 1                                          # nothing was removed
+    x = lm(x, 100)                                                   # final solve
+    assert abs(x) < 1e-3
+
+
 # ---- LandmarkCreator.CreateWithDepth ---------------------------------------------------------------------
 def test_landmark_creation_with_depth(oracle):
     """LandmarkCreator.CreateWithDepth (:1149-1210): depth back-projection recovers the landmark to 0.01 m"""
