@@ -409,8 +409,9 @@ kba::Exchange kba_shard_exchange(kba_shard_comm* c);  // kba_shard.cu
 //   2 (default)  one CUDA graph launch per solve: the passes are the body of a conditional WHILE node, k_loop_cond sets the
 //                condition on the device -- no host polling, no pass enqueued after the last window finished, no launch gaps;
 //   1            a graph of four passes + the active-window count, launched until the count read back is zero;
-//   0            kernel by kernel on the stream (always used for sharded solves -- NCCL calls between the kernels --, with kernel
-//                timing on -- event pairs around the linearisation launches --, with KBA_LAUNCH_CHECK, or on the legacy stream).
+//   0            kernel by kernel on the stream (always used with kernel timing on -- event pairs around the linearisation
+//                launches --, with KBA_LAUNCH_CHECK, or on the legacy default stream, which cannot be captured).
+// A sharded solve (NCCL all-reduces between the kernels) takes mode 1 from the second solve of its batch on, see kba_batch_solve.
 static int solve_graph_mode() {
     static const int m = [] {
         const char* e = getenv("KBA_GRAPH");
