@@ -49,7 +49,7 @@ TRAFFIC_SOURCE = ("ncu --set full, profiles/r02_ncu_summary.md (k_linearize)" if
                   "ncu --set full, profiles/r01_v11_ncu_summary.md: (0.200 GB read + 1.293 GB written) / 5.39 M observations")
 KERNEL_NAME = ("k_linearize (residual/Jacobian + landmark blocks + V rows, one kernel)" if LIN1 else "k_eval_obs<true> (residual/Jacobian)")
 ALG_NOTE = ("SURVEY 8(d), fused Hessian kernel: 18.7 B read + 144 B (E_ij) written per observation + 72 B per landmark; the Jacobian "
-            "stays in registers.  The kernel is FP64-issue bound, not HBM bound: see profiles/r02_ncu_summary.md" if LIN1 else
+            "stays in registers.  The kernel is bound by instruction latency at 16 warps per SM (issue slots 31 % used, FP64 pipe 24 % busy), not by HBM: see profiles/r02_ncu_summary.md" if LIN1 else
             "19 B read + 168 B written (residual 24 + J_pose 144); J_landmark (72 B) is not materialised" if FUSED else "SURVEY 8(d): 259 B/obs")
 CONFIG2 = "config 2: 30 KF / 3000 LM / 40000 obs, mono + lidar depth, FP64"
 
