@@ -2294,8 +2294,9 @@ cudaError_t configure_kernels(int nr_cap_max) {
 
 // grid.x of a kernel whose CTAs stride over a window's units (k_linearize: 8 warp tiles, k_backsub_v: 16 landmarks).  Every pass is
 // launched for every window of the batch and the unit count is an upper bound, so with one CTA per unit most CTAs of a large batch
-// only find out that they have nothing to do; num/den of the units per window measured best on the headline workload (A/B in
-// profiles/r02_graph_and_ab.md: 296-window step 211.2 -> 202.9 ms).  Small batches keep one CTA per unit (latency: every SM busy).
+// only find out that they have nothing to do; num/den of the units per window from the sweep on the headline workload
+// (profiles/r02_graph_and_ab.md: 296-window step 211.2 -> 202.9 ms at 3/10 and 1/3, 199.5 ms at 1/5 for k_linearize; k_backsub_v is
+// flat between 1/6 and 1/2).  Small batches keep one CTA per unit (latency: every SM busy).
 // `cfg`: -1 = this rule, 0 = one CTA per unit, > 0 = that many (KBA_LIN_GRID / KBA_BS_GRID).
 static int strided_grid(int cfg, int n_units, int num, int den, int n_win) {
     if (cfg == 0) return n_units;
@@ -2323,7 +2324,7 @@ int launch_pass(const BatchDev& bd, const SolveParams& sp, const LaunchCfg& lc, 
         LCHK("k_gp_eval");
         if (timed) cudaEventRecord(lc.ev_pool[(*lc.ev_used)++], s);
         const int n_units = (lin_tile_bound(bd.max_obs, bd.max_lm) + kLinWarps - 1) / kLinWarps;
-        const dim3 g_lin(strided_grid(lc.lin_grid, n_units, 3, 10, B), B);  // CTAs of a window stride over its units
+        const dim3 g_lin(strided_grid(lc.lin_grid, n_units, 1, 5, B), B);  // CTAs of a window stride over its units
         if ((int)g_lin.x < n_units) k_linearize<2, true><<<g_lin, kLinThreads, 0, s>>>(bd, sp, n_units);
         else if (lc.lin_blocks == 3) k_linearize<3, false><<<g_lin, kLinThreads, 0, s>>>(bd, sp, n_units);
         else k_linearize<2, false><<<g_lin, kLinThreads, 0, s>>>(bd, sp, n_units);
