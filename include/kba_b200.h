@@ -225,7 +225,11 @@ int kba_eval(kba_handle* h, const kba_window* w, const kba_options* opt, kba_eva
 /* --- device-resident batch (inputs stay in HBM between solves) --- */
 int kba_batch_create(kba_handle* h, int32_t n_windows, const kba_window* w, kba_batch** out);
 int kba_batch_upload(kba_batch* b, int32_t n_windows, const kba_window* w); /* re-upload state, same shapes */
-int kba_batch_solve(kba_batch* b, const kba_options* opt);                 /* resets to the uploaded state, solves */
+/* resets to the uploaded state and solves; returns when every window is done.  Issued as ONE CUDA graph launch (the
+ * Levenberg-Marquardt pass is the body of a conditional WHILE node, the device decides when the batch is done) unless the
+ * handle runs on the legacy default stream, which cannot be captured: give the handle a stream of its own (kba_create does,
+ * kba_set_stream with a created stream keeps it).  INTEGRATION.md lists the switches (KBA_GRAPH, ...). */
+int kba_batch_solve(kba_batch* b, const kba_options* opt);
 int kba_batch_download(kba_batch* b, kba_result* res);
 int kba_batch_transfer_bytes(kba_batch* b, int64_t* h2d_bytes, int64_t* d2h_bytes); /* of the last upload / download */
 int kba_batch_jacobian_pass(kba_batch* b, const kba_options* opt, int32_t repeats, float* ms_out); /* residual/Jacobian kernel only */
