@@ -2302,7 +2302,9 @@ static int strided_grid(int cfg, int n_units, int num, int den, int n_win) {
     if (cfg == 0) return n_units;
     if (cfg > 0) return cfg < n_units ? cfg : n_units;
     const int g = (n_units * num + den - 1) / den;
-    return ((long long)g * n_win >= 4 * 296 && g >= 1) ? g : n_units;  // at least four waves of 2 CTAs x 148 SMs remain
+    return ((long long)g * n_win >= 8 * 296 && g >= 1) ? g : n_units;  // at least eight waves of 2 CTAs x 148 SMs remain (a CTA
+                                                                        // now runs several units back to back: keep the last,
+                                                                        // partly filled wave a small share of the launch)
 }
 
 void launch_reset(const BatchDev& bd, const LaunchCfg& lc, cudaStream_t s) {
